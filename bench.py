@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Headline benchmark: parallelgen IAF audio samples/s on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            # CPU restatement of the reference
+
+Workload (config.workload): BASELINE configs[2] — parallel WaveNet 4-flow IAF student
+(parallel_wavenet.json, random init seed 12345), batch 8 x 7680 samples per GPU, synthetic
+mel ~ U[0,1), noise drawn on the device.  One "step" = one full forward of that batch
+(deconv stack, cond projections, 60 residual layers, 4 heads, quantise).  N > 1 shards
+independent clips across ranks (weak scaling, 8 clips per GPU); NCCL is used once, to
+broadcast the weight blob from rank 0, never in the timed loop.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'audio samples/sec (parallelgen IAF, 16 kHz)'
+UNIT = 'samples/s'
+CONFIGS = {'student': 'parallel_wavenet.json', 'clarinet': 'parallel_wavenet_gauss.json'}
+# algorithmic bytes of the fused residual layer per (sample, layer):
+# read l (64*4) + read cond (64*4) + write l (64*4)
+LAYER_BYTES_PER_SAMPLE = 768
+COND_FLOP_PER_SAMPLE_PLANE = 2 * 256 * 64
+
+
+def load_hparams(name):
+    from argparse import Namespace
+    with open(os.path.join(ROOT, 'nsynth_wavenet_b200', 'config_jsons', CONFIGS[name])) as f:
+        return Namespace(**json.load(f))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason sampling through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons)}
+
+
+def cpu_reference_run(hp, batch, frames, steps, warmup, seed=12345):
+    """Times the torch-CPU restatement of the reference's graph (oracle/torch_port.py) with
+    every host thread.  Returns (samples_per_s, ms_per_step, cores, sample description)."""
+    import torch
+    from oracle import torch_port, wavenet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = O.init_student_weights(hp, seed=seed)
+    port = torch_port.StudentPort(w, hp)
+    rng = np.random.default_rng(54321)
+    mel = rng.uniform(0, 1, (batch, frames, 80)).astype(np.float32)
+    T = O.iaf_length(frames, hp)
+    gauss = getattr(hp, 'loss_type', 'logistic') != 'logistic'
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if gauss:
+            z = rng.standard_normal((batch, T)).astype(np.float32)
+        else:
+            z = O.logistic_from_uniform(rng.uniform(1e-5, 1 - 1e-5, (batch, T))).astype(np.float32)
+        port.forward(mel, z, quantize=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    tot = float(np.sum(times))
+    return batch * T * len(times) / tot, 1e3 * tot / len(times), cores, \
+        '{} step(s) of {}x{} samples (full forward incl. noise draw), torch-CPU fp32, {} threads'.format(
+            len(times), batch, T, cores)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path restated (TF 1.x is not installable
+    here), bounded sample, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    hp = load_hparams(args.config)
+    # bounded: 1 clip of 7680 samples per step keeps K=10,W=3 within a few minutes
+    batch = args.ref_batch
+    v, ms, cores, sample = cpu_reference_run(hp, batch, args.frames, args.steps, max(1, args.warmup))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[2]: parallel WaveNet 4-flow IAF student ({}), '
+                               '8x7680 per GPU; reference arm runs a bounded sample of it on host '
+                               'cores'.format(CONFIGS[args.config])},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'rtf': v / 16000.0,
+        'note': 'TensorFlow 1.x is absent: this is the fp32 torch-CPU restatement of the '
+                'reference graph (oracle/torch_port.py), all host threads',
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='student', choices=list(CONFIGS))
+    ap.add_argument('--batch', type=int, default=8, help='clips per GPU')
+    ap.add_argument('--frames', type=int, default=39, help='mel frames per clip (39 -> 7680 samples)')
+    ap.add_argument('--engine', default=None, choices=[None, 'ffma', 'tc'])
+    ap.add_argument('--ref-batch', type=int, default=1)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nsynth_wavenet_b200 import IAFEngine, _lib
+    from oracle import wavenet_oracle as O  # weights init + cpu_baseline leg only
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+
+    hp = load_hparams(args.config)
+    # ---- weights: rank 0 initialises, NCCL broadcasts one flat blob (the only collective) ----
+    w0 = O.init_student_weights(hp, seed=12345)
+    names = list(w0)
+    if world > 1:
+        flat = torch.from_numpy(np.concatenate([w0[n].ravel() for n in names])).to(dev)
+        if rank != 0:
+            flat.zero_()
+        dist.broadcast(flat, src=0)
+        host = flat.cpu().numpy()
+        weights, off = {}, 0
+        for n in names:
+            sz = w0[n].size
+            weights[n] = host[off:off + sz].reshape(w0[n].shape)
+            off += sz
+    else:
+        weights = w0
+    eng = IAFEngine(hp, weights, device=local_rank, engine=args.engine)
+
+    B, F = args.batch, args.frames
+    T = eng.length(F)
+    rng = np.random.default_rng(54321 + rank)
+    mel_h = torch.from_numpy(rng.uniform(0, 1, (B, F, 80)).astype(np.float32)).pin_memory()
+    mel_d = mel_h.to(dev)
+    out = {k: torch.empty((B, T), dtype=torch.float32, device=dev)
+           for k in ('x', 'mean_tot', 'scale_tot', 'log_scale_tot')}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    lib = _lib.load()
+
+    def step(i):
+        eng.forward_device(mel_d, None, seed=1000 + i, quantize=True, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.nsw_kernel_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                      # evict L2 between timed iterations (not timed)
+        evs[i][0].record()
+        step(i)
+        evs[i][1].record()
+    barrier()
+    launches = lib.nsw_kernel_launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    gpu_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B * T * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the reference-facing host call, pinned host buffers, H2D + D2H inside ----
+    x_h = np.empty((B, T), np.float32)
+    x_pin = torch.from_numpy(x_h).pin_memory()
+    mel_np = mel_h.numpy()
+    for i in range(2):
+        eng.forward_host(mel_np, None, seed=i, quantize=True)
+    barrier()
+    names5 = ('x', 'mean_tot', 'scale_tot', 'log_scale_tot', 'rand_input')
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        _lib.check(lib.nsw_iaf_forward_host(eng._h, mel_h.data_ptr(), None, 2000 + i, B, F, 1,
+                                            x_pin.data_ptr(), None, None, None, None))
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T * args.steps / float(te.item())
+
+    # ---- roofline of the dominant kernel (iaf_layer_kernel), measured live with CUDA events
+    #      on the launch stream inside the library (separate profiled passes) ----
+    eng.set_profiling(True)
+    prof = []
+    for i in range(3):
+        flush.zero_()
+        step(i)
+        torch.cuda.synchronize()
+        prof.append(eng.last_timing())
+    eng.set_profiling(False)
+    stage = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
+    n_layers = int(sum(hp.num_iaf_layers))
+    n_planes = n_layers + len(hp.num_iaf_layers)
+    layer_launch_ms = stage['layers'] / n_layers
+    hbm_peak, tc_peak, peak_kind = measured_peaks()
+    layer_gbs = LAYER_BYTES_PER_SAMPLE * B * T / (layer_launch_ms * 1e-3) / 1e9
+    cond_tflops = COND_FLOP_PER_SAMPLE_PLANE * n_planes * B * T / (stage['cond'] * 1e-3) / 1e12
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {
+            'workload': 'configs[2]: parallel WaveNet 4-flow IAF student ({}), batch {}x{} samples '
+                        'per GPU, synthetic mel, device-drawn noise'.format(CONFIGS[args.config], B, T),
+            'clips_per_gpu': B, 'samples_per_clip': T, 'engine': eng.engine,
+            'l2': 'flushed between timed iterations (256 MB write)', 'parallelism': 'clips x{}'.format(world),
+        },
+        'rtf': value / 16000.0,
+        'rtf_per_gpu': value / 16000.0 / world,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * F * 80 * 4),
+                'd2h_bytes_per_step': int(B * T * 4)},
+        'gpu_launches': int(launches),
+        'clocks': sampler.summary(),
+        'roofline': {
+            'kernel': 'iaf_layer_kernel', 'bound': 'hbm', 'achieved': layer_gbs, 'peak': hbm_peak,
+            'unit': 'GB/s', 'frac': layer_gbs / hbm_peak, 'traffic': None,
+            'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
+            'bytes_per_launch': LAYER_BYTES_PER_SAMPLE * B * T, 'launch_ms': layer_launch_ms,
+            'share_of_step': stage['layers'] / stage['total'],
+        },
+        'roofline_cond_gemm': {
+            'kernel': 'conv_gemm (cond projections)', 'bound': 'tensor', 'achieved': cond_tflops,
+            'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': cond_tflops / tc_peak,
+            'note': 'algorithmic fp32-equivalent flops; the tcgen05 engine issues 3 bf16 MMAs per product',
+        },
+        'stage_ms': stage,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # bounded CPU sample (about cpu-seconds of work): single-clip forwards
+        v1, ms1, cores, _ = cpu_reference_run(hp, 1, F, 1, 1)
+        reps = int(max(1, min(20, args.cpu_seconds / (ms1 * 1e-3))))
+        v, ms, cores, sample = cpu_reference_run(hp, 1, F, reps, 0)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'sample': sample}
+    elif rank == 0:
+        line['cpu_baseline'] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,195 @@
+/*
+ * nsw.h — C ABI of libnsw_b200.so, the B200 (sm_100a) implementation of the
+ * bfs18/nsynth_wavenet generation hot path.
+ *
+ * The reference has no FFI layer: its boundary is the Python module API used by
+ * eval_parallel_wavenet.py / eval_wavenet.py (wavenet/parallelgen.py:11-51,
+ * wavenet/fastgen.py:61-169).  Each entry point below names the reference
+ * function whose device work it replaces; INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C types only; tensors are row-major fp32, activations [batch,time,chan]
+ *    exactly as in the reference (wavenet/masked.py:43).
+ *  - every call returns 0 on success, a negative NSW_E* code otherwise;
+ *    nsw_last_error() returns a thread-local message for the last failure.
+ *  - "_device" entry points take device pointers owned by the caller and enqueue
+ *    on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *    without synchronising.  "_host" entry points take host pointers, do the
+ *    H2D / D2H copies themselves and return after the result is in host memory.
+ *  - handles are not thread-safe; distinct handles may be used concurrently.
+ *  - weights are handed over as a list of named tensors using the reference's
+ *    TensorFlow variable names (the checkpoint contract), e.g.
+ *    "iaf_1/dilated_conv_3/W" [1,3,64,64], "iaf_share/trans_conv_2/kernel"
+ *    [1,80,256,256].  The library repacks them once at create time.
+ */
+#ifndef NSW_H_
+#define NSW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSW_OK 0
+#define NSW_EINVAL (-1)   /* bad argument / unsupported configuration        */
+#define NSW_ECUDA (-2)    /* CUDA runtime or driver error                    */
+#define NSW_EMISSING (-3) /* a required weight tensor is missing / misshaped */
+#define NSW_ETIMEOUT (-4) /* persistent kernel watchdog fired                */
+
+#define NSW_MAX_FLOWS 8
+#define NSW_MAX_DECONV 4
+
+/* loss_type: which noise the student consumes / which head the teacher has */
+#define NSW_LOSS_LOGISTIC 0 /* student 'logistic' (parallel_wavenet.py:303-304) */
+#define NSW_LOSS_GAUSS 1    /* 'gauss'                                          */
+#define NSW_LOSS_MOL 2      /* teacher 'mol' (wavenet.py:123-125)               */
+#define NSW_LOSS_CE 3       /* teacher 'ce'                                     */
+
+/* upsample_act (wavenet/masked.py:28-36) */
+#define NSW_ACT_TANH 0
+#define NSW_ACT_RELU 1
+#define NSW_ACT_LEAKY_RELU 2 /* alpha = 0.4 */
+
+/* engine selection for the dense contractions (cond projection, deconv) */
+#define NSW_ENGINE_FFMA 0 /* fp32 CUDA-core path, bit-for-bit fp32 products   */
+#define NSW_ENGINE_TC 1   /* tcgen05 split-bf16 (hi*hi + hi*lo + lo*hi)       */
+
+typedef struct nsw_tensor {
+  const char* name;    /* TF variable name, without ":0" and without EMA suffix */
+  const float* data;   /* host pointer, row-major                               */
+  int32_t ndim;
+  int64_t shape[4];
+} nsw_tensor;
+
+/* hparams of ParallelWavenet (config_jsons/parallel_wavenet*.json;
+ * parallel_wavenet.py:118-147) */
+typedef struct nsw_iaf_config {
+  int32_t num_flows;                       /* len(num_iaf_layers)            */
+  int32_t num_iaf_layers[NSW_MAX_FLOWS];
+  int32_t num_stages;                      /* dilation = 2^(i % num_stages)  */
+  int32_t filter_length;                   /* must be 3                      */
+  int32_t width;                           /* must be 64 (gate = width)      */
+  int32_t deconv_width;                    /* must be 256                    */
+  int32_t num_mel;                         /* 80                             */
+  int32_t num_deconv;                      /* len(deconv_config)             */
+  int32_t deconv_filter[NSW_MAX_DECONV];
+  int32_t deconv_stride[NSW_MAX_DECONV];
+  int32_t share_deconv;                    /* use_share_deconv || use_teacher_deconv */
+  int32_t loss_type;                       /* NSW_LOSS_LOGISTIC | NSW_LOSS_GAUSS */
+  int32_t upsample_act;
+  int32_t use_mu_law;
+  int32_t engine;                          /* NSW_ENGINE_*                   */
+} nsw_iaf_config;
+
+/* hparams of Wavenet / Fastgen (config_jsons/wavenet_*.json; wavenet.py:97-128,332-351) */
+typedef struct nsw_wavenet_config {
+  int32_t num_layers;
+  int32_t num_stages;
+  int32_t filter_length; /* must be 3 (masked.py:349) */
+  int32_t width;
+  int32_t gate_width;    /* 2*width if double_gate_width else width */
+  int32_t skip_width;
+  int32_t out_width;     /* 3*mol_mix | 2 | quant_chann */
+  int32_t deconv_width;
+  int32_t num_mel;
+  int32_t num_deconv;
+  int32_t deconv_filter[NSW_MAX_DECONV];
+  int32_t deconv_stride[NSW_MAX_DECONV];
+  int32_t loss_type;     /* NSW_LOSS_MOL | NSW_LOSS_GAUSS | NSW_LOSS_CE */
+  int32_t upsample_act;
+  int32_t use_mu_law;
+  int32_t engine;
+} nsw_wavenet_config;
+
+typedef struct nsw_iaf nsw_iaf;
+typedef struct nsw_fastgen nsw_fastgen;
+
+/* ---- library ------------------------------------------------------------ */
+int nsw_version(void);
+const char* nsw_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches claim is read from here, not estimated) */
+uint64_t nsw_kernel_launch_count(void);
+
+/* ---- parallel IAF student ------------------------------------------------
+ * replaces: parallelgen.load_parallelgen (parallelgen.py:11-19) = graph build of
+ * ParallelWavenet.feed_forward (parallel_wavenet.py:289-345) + _clip_quant_scale
+ * (:348-359), and the Saver.restore of parallelgen.py:30-41 (weights arrive as
+ * named tensors instead of a checkpoint path). */
+int nsw_iaf_create(const nsw_iaf_config* cfg, const nsw_tensor* tensors, int32_t n_tensors,
+                   int32_t device, nsw_iaf** out);
+void nsw_iaf_destroy(nsw_iaf* h);
+
+/* T = (F * prod(strides) / 2^(num_stages-1)) * 2^(num_stages-1)  (parallel_wavenet.py:302) */
+int64_t nsw_iaf_length(const nsw_iaf* h, int32_t num_frames);
+
+/* replaces: sess.run(fg_dict[...], {mel_in: mel}) (parallelgen.py:44).
+ * d_mel [B,F,num_mel]; d_z [B,T] noise or NULL (then drawn on device from `seed`
+ * with Philox: logistic log u - log(1-u), u~U[1e-5,1-1e-5], or N(0,1));
+ * outputs [B,T] each, any of them may be NULL:
+ *   d_x            feed_forward 'x' (after _clip_quant_scale iff quantize != 0)
+ *   d_mean_tot, d_scale_tot, d_log_scale_tot, d_rand_input  feed_forward dict  */
+int nsw_iaf_forward_device(nsw_iaf* h, const float* d_mel, const float* d_z, uint64_t seed,
+                           int32_t B, int32_t F, int32_t quantize, float* d_x, float* d_mean_tot,
+                           float* d_scale_tot, float* d_log_scale_tot, float* d_rand_input,
+                           void* stream);
+
+/* same with host buffers (pinned or pageable); H2D of mel (+z) and D2H of the
+ * requested outputs happen inside the call.  This is what parallelgen.synthesis
+ * calls. */
+int nsw_iaf_forward_host(nsw_iaf* h, const float* mel, const float* z, uint64_t seed, int32_t B,
+                         int32_t F, int32_t quantize, float* x, float* mean_tot, float* scale_tot,
+                         float* log_scale_tot, float* rand_input);
+
+/* kernel-level parity hooks -------------------------------------------------
+ * replaces: wavenet._deconv_stack (wavenet.py:46-73).  stack = 0 for the shared
+ * stack, else flow index.  d_mel_en [B, F*prod(strides), deconv_width] fp32. */
+int nsw_iaf_deconv_device(nsw_iaf* h, int32_t stack, const float* d_mel, int32_t B, int32_t F,
+                          float* d_mel_en, void* stream);
+/* after the next nsw_iaf_forward_*, copy the residual stream l [B,T,width] as it
+ * is after `layer` residual layers of `flow` (layer 0 = start_conv output) into
+ * d_l.  Pass d_l = NULL to clear. */
+int nsw_iaf_set_tap(nsw_iaf* h, int32_t flow, int32_t layer, float* d_l);
+/* bytes of device workspace currently held (grows with B*F) */
+size_t nsw_iaf_workspace_bytes(const nsw_iaf* h);
+/* per-stage device time of the last forward in ms (CUDA events on the launch
+ * stream): [0]=deconv, [1]=cond projection, [2]=residual layer kernels only,
+ * [3]=start conv + heads/affine, [4]=total.  Valid only after nsw_iaf_set_profiling(h,1). */
+int nsw_iaf_set_profiling(nsw_iaf* h, int32_t on);
+int nsw_iaf_last_timing(nsw_iaf* h, float ms[5]);
+
+/* ---- autoregressive teacher (fastgen) ------------------------------------
+ * replaces: fastgen.load_deconv_stack/encode (fastgen.py:61-88),
+ * load_fastgen + synthesis loop (fastgen.py:118-169) = Fastgen.sample
+ * (wavenet.py:379-514) with masked.causal_linear / linear (masked.py:328-405). */
+int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tensor* tensors,
+                       int32_t n_tensors, int32_t device, nsw_fastgen** out);
+void nsw_fastgen_destroy(nsw_fastgen* h);
+
+/* mel [B,F,num_mel] -> encoding [B, F*prod(strides), deconv_width] (fastgen.encode) */
+int nsw_fastgen_encode_device(nsw_fastgen* h, const float* d_mel, int32_t B, int32_t F,
+                              float* d_encoding, void* stream);
+int nsw_fastgen_encode_host(nsw_fastgen* h, const float* mel, int32_t B, int32_t F,
+                            float* encoding);
+
+/* the whole per-sample loop of fastgen.synthesis as ONE persistent kernel.
+ * d_encoding [B,T,deconv_width] (fed step by step with NO centre trim,
+ * fastgen.py:157); d_teacher_force [B,T] or NULL: if given the wav fed at step i
+ * is teacher_force[:, i-1] (0 at i = 0) instead of the model's own sample;
+ * outputs: d_audio [B,T] fp32 dequantised samples (may be NULL),
+ *          d_out [B,T,out_width] pre-sample parameters (may be NULL). */
+int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, int32_t B, int32_t T,
+                           const float* d_teacher_force, uint64_t seed, float* d_audio,
+                           float* d_out, void* stream);
+int nsw_fastgen_run_host(nsw_fastgen* h, const float* encoding, int32_t B, int32_t T,
+                         const float* teacher_force, uint64_t seed, float* audio, float* out);
+/* device time of the last nsw_fastgen_run_* persistent kernel in ms */
+int nsw_fastgen_last_timing(nsw_fastgen* h, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSW_H_ */

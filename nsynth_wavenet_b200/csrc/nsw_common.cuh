@@ -1,0 +1,158 @@
+// Shared host/device helpers for libnsw_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/nsw.h"
+
+namespace nsw {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define NSW_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ::nsw::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                 \
+                       cudaGetErrorString(e_));                                           \
+      return NSW_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+
+#define NSW_CHECK(cond, code, ...)                                                        \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::nsw::set_error(__VA_ARGS__);                                                      \
+      return (code);                                                                      \
+    }                                                                                     \
+  } while (0)
+
+#define NSW_TRY(expr)                                                                     \
+  do {                                                                                    \
+    int rc_ = (expr);                                                                     \
+    if (rc_ != NSW_OK) return rc_;                                                        \
+  } while (0)
+
+// ---- named-tensor lookup (TF variable names; EMA-shadow suffix tolerated) ----
+class TensorMap {
+ public:
+  TensorMap(const nsw_tensor* t, int n);
+  // returns NULL (and sets the error string) if missing or if numel mismatches
+  const float* get(const std::string& name, int64_t expect_numel) const;
+  bool has(const std::string& name) const { return map_.count(name) != 0; }
+
+ private:
+  std::map<std::string, const nsw_tensor*> map_;
+};
+
+// ---- device buffer that frees itself ----
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  int ensure(size_t n) {
+    if (n <= bytes) return NSW_OK;
+    release();
+    NSW_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return NSW_OK;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+int upload(DevBuf& buf, const void* host, size_t bytes);
+
+// deconv layer geometry shared by the IAF and fastgen handles
+//   out[o] = sum_q x[m-q] * K[r + q*s],  o + p = m*s + r   (masked.py:235-291)
+struct DeconvGeom {
+  int k, s, cin, cout, ntaps, p;
+  int mclip(int L) const { return (s * L - 1 + p) / s + 1; }  // GEMM rows per clip
+};
+
+#ifdef __CUDACC__
+// ------------------------------ device helpers ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// packed 2-wide fp32 FMA (SASS FFMA2): d.{x,y} += a.{x,y} * s
+__device__ __forceinline__ void ffma2_s(unsigned long long& d, unsigned long long a, float s) {
+  unsigned long long b;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(s));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned long long lds_u64(const void* p) {
+  unsigned long long r;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(smem_u32(p)));
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  uint32_t sz = valid ? 16u : 0u;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ float softplusf_acc(float v) {
+  // log(1 + e^v), stable on both tails (tf.nn.softplus)
+  return fmaxf(v, 0.0f) + log1pf(expf(-fabsf(v)));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == NSW_ACT_LEAKY_RELU) return v >= 0.0f ? v : 0.4f * v;
+  if (act == NSW_ACT_RELU) return fmaxf(v, 0.0f);
+  return tanhf(v);
+}
+
+// Philox4x32-10 (counter-based; one call gives 4 x 32 random bits)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// uniform in [1e-5, 1 - 1e-5] like tf.random_uniform(minval=1e-5, maxval=1-1e-5)
+__device__ __forceinline__ float u01_clipped(uint32_t r) {
+  float u = (static_cast<float>(r >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  return 1e-5f + u * (1.0f - 2e-5f);
+}
+#endif  // __CUDACC__
+
+}  // namespace nsw

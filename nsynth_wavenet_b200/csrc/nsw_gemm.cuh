@@ -1,0 +1,80 @@
+// "Conv-GEMM": the one dense contraction shape the generation path needs.
+//
+//   C[(clip, m), n] = sum_{tap < ntaps} sum_{c < cin}
+//                        X[clip, m + a_off + tap, c] * Bw[tap*cin + c, n]
+//   with X[clip, f, :] = 0 for f outside [0, L).
+//
+// * mel-conditioning 1x1 projections (masked.conv1d with filter_length 1 on mel_en,
+//   parallel_wavenet.py:237-243,259-261; wavenet.py:255-261,283-284): ntaps = 1,
+//   a_off = centre-trim offset of wavenet._condition (wavenet.py:76-85), all
+//   layers of a flow batched along n.
+// * transposed-conv upsampling (masked.trans_conv1d, masked.py:235-291): output
+//   phase r and input frame m give o = m*s + r - p; ntaps = k/s, a_off = -(ntaps-1),
+//   n = r*cout + co.
+//
+// Two engines implement it: fp32 CUDA cores (nsw_gemm_ffma.cu) and tcgen05
+// split-bf16 tensor cores (nsw_gemm_tc.cu).
+#pragma once
+#include "nsw_common.cuh"
+
+namespace nsw {
+
+struct ConvGemm {
+  int nclips;  // batch
+  int L;       // valid frames per clip in X
+  int cin;     // channels of X
+  int ntaps;
+  int a_off;
+  int mclip;  // GEMM rows per clip
+  int N;      // GEMM columns (multiple of 64)
+};
+
+enum EpiMode { EPI_PLANES = 0, EPI_DECONV = 1 };
+
+struct EpiParams {
+  int mode;
+  const float* bias;  // EPI_PLANES: [N]; EPI_DECONV: [cout]
+  // EPI_PLANES: out_f32[n/64][clip*mclip + m][n%64]
+  // EPI_DECONV: out_*[clip][o][co], o = m*s + n/cout - p in [0, Lout)
+  float* out_f32;
+  __nv_bfloat16* out_hi;  // optional bf16 split of the same values (hi + lo ~ fp32)
+  __nv_bfloat16* out_lo;
+  int s, p, cout, act, Lout;
+};
+
+// fp32 X [nclips, L, cin], fp32 Bw [ntaps*cin, N]
+int conv_gemm_ffma(const ConvGemm& g, const float* X, const float* Bw, const EpiParams& e,
+                   cudaStream_t stream);
+
+// bf16 split operands: X_hi/X_lo [nclips, L, cin], Bt_hi/Bt_lo [N, ntaps*cin] (K-major)
+int conv_gemm_tc(const ConvGemm& g, const __nv_bfloat16* X_hi, const __nv_bfloat16* X_lo,
+                 const __nv_bfloat16* Bt_hi, const __nv_bfloat16* Bt_lo, const EpiParams& e,
+                 cudaStream_t stream);
+bool conv_gemm_tc_supported(const ConvGemm& g);
+
+// host-side split of fp32 into bf16 hi + bf16 lo (round-to-nearest each)
+void split_bf16(const float* src, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
+
+// ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
+struct DeconvLayer {
+  DeconvGeom g;
+  DevBuf Bw;              // fp32 [ntaps*cin][s*cout]
+  DevBuf Bt_hi, Bt_lo;    // bf16 [s*cout][ntaps*cin] (tensor-core engine)
+  DevBuf bias;            // [cout]
+};
+
+struct DeconvStack {
+  std::vector<DeconvLayer> layers;
+  int act = NSW_ACT_TANH;
+  int total_stride = 1;
+  // prefix: "" (teacher), "iaf_share/", "iaf_3/"
+  int init(const TensorMap& tm, const std::string& prefix, int num_mel, int width, int n,
+           const int32_t* filt, const int32_t* stride, int act_kind, bool want_tc);
+  // mel [B,F,num_mel] -> out [B, F*total_stride, width]; intermediates live in `scratch`.
+  // engine FFMA: writes out_f32 (required).  engine TC: the last layer runs on tensor
+  // cores when supported and writes out_hi/out_lo (and out_f32 if non-NULL).
+  int forward(const float* d_mel, int B, int F, float* out_f32, __nv_bfloat16* out_hi,
+              __nv_bfloat16* out_lo, int engine, DevBuf& scratch, cudaStream_t stream) const;
+};
+
+}  // namespace nsw

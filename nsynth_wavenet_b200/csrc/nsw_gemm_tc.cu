@@ -1,0 +1,408 @@
+// tcgen05 engine of the conv-GEMM (see nsw_gemm.cuh): split-bf16 operands
+// (x = hi + lo, both bf16), fp32 accumulation in TMEM, three tensor-core products
+// per k-block (lo*hi + hi*lo + hi*hi; lo*lo ~ 2^-18 relative is dropped).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 3D for X, 2D for W; SWIZZLE_128B)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  epilogue: tcgen05.ld (32x32b.x32) -> bias/activation -> global stores
+// smem ring: 3 stages x {X_hi, X_lo [128 x 64], W_hi, W_lo [128 x 64]} bf16 = 64 KB/stage.
+// TMEM: two accumulator stages of 128 fp32 columns each, so the epilogue of tile i
+// overlaps the main loop of tile i+1.
+#include "nsw_gemm.cuh"
+
+#include <cuda.h>
+
+namespace nsw {
+
+namespace {
+
+constexpr int TBM = 128, TBN = 128, TBK = 64;
+constexpr int STAGES = 3;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TILE_BYTES = TBM * TBK * 2;          // 16 KB, one operand plane
+constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;        // 64 KB
+constexpr uint32_t TMEM_COLS = 2 * TBN;                 // 256
+constexpr long long WATCHDOG_CYCLES = 4000000000ll;     // ~2 s
+
+struct TcSmemTail {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+constexpr size_t TC_SMEM_BYTES = STAGES * STAGE_BYTES + sizeof(TcSmemTail) + 1024;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a wedged pipeline traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WATCHDOG_CYCLES) {
+      printf("nsw conv_gemm_tc: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (64 bf16 = 128 B per row,
+// 8-row groups 1024 B apart); field layout per the sm_100 UMMA descriptor.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);     // start address
+  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=TBN
+__device__ __forceinline__ uint32_t umma_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) |
+         ((uint32_t)(TBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// one output row, 32 consecutive columns starting at n (n % 32 == 0)
+__device__ __forceinline__ void store_row32(const ConvGemm& g, const EpiParams& e, int clip, int m,
+                                            int n, const float* v) {
+  if (m >= g.mclip || n >= g.N) return;
+  if (e.mode == EPI_PLANES) {
+    const size_t M = (size_t)g.nclips * g.mclip;
+    const size_t grow = (size_t)clip * g.mclip + m;
+    float* dst = e.out_f32 + ((size_t)(n >> 6) * M + grow) * 64 + (n & 63);
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      reinterpret_cast<float4*>(dst)[j] =
+          make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+    }
+  } else {
+    const int rr = n / e.cout, co = n - rr * e.cout;
+    const int o = m * e.s + rr - e.p;
+    if (o < 0 || o >= e.Lout) return;
+    const size_t off = ((size_t)clip * e.Lout + o) * e.cout + co;
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + co);
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      f[4 * j] = apply_act(v[4 * j] + b.x, e.act);
+      f[4 * j + 1] = apply_act(v[4 * j + 1] + b.y, e.act);
+      f[4 * j + 2] = apply_act(v[4 * j + 2] + b.z, e.act);
+      f[4 * j + 3] = apply_act(v[4 * j + 3] + b.w, e.act);
+    }
+    if (e.out_f32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(e.out_f32 + off)[j] =
+            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    }
+    if (e.out_hi) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          hi[i] = __float2bfloat16_rn(f[8 * j + i]);
+          lo[i] = __float2bfloat16_rn(f[8 * j + i] - __bfloat162float(hi[i]));
+        }
+        reinterpret_cast<uint4*>(e.out_hi + off)[j] = *reinterpret_cast<uint4*>(hi);
+        reinterpret_cast<uint4*>(e.out_lo + off)[j] = *reinterpret_cast<uint4*>(lo);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh,
+                    const __grid_constant__ CUtensorMap map_xl,
+                    const __grid_constant__ CUtensorMap map_wh,
+                    const __grid_constant__ CUtensorMap map_wl, ConvGemm g, EpiParams e,
+                    int tiles_per_clip, int n_tiles, int total_tiles) {
+  extern __shared__ unsigned char smem_dyn[];
+  // SWIZZLE_128B operand tiles need 1024 B alignment
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_per_tap = g.cin / TBK;
+  const int num_kb = g.ntaps * kb_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tail->tmem_full[a], 1);
+      mbar_init(&tail->tmem_empty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tail->tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int clip = mt / tiles_per_clip;
+        const int m0 = (mt - clip * tiles_per_clip) * TBM;
+        const int n0 = nt * TBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail->empty[stage], phase ^ 1);
+          const int tap = kb / kb_per_tap;
+          const int c0 = (kb - tap * kb_per_tap) * TBK;
+          const int frame0 = m0 + g.a_off + tap;  // may be negative: TMA zero-fills
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          mbar_expect_tx(&tail->full[stage], STAGE_BYTES);
+          tma_load_3d(sbase, &map_xh, &tail->full[stage], c0, frame0, clip);
+          tma_load_3d(sbase + TILE_BYTES, &map_xl, &tail->full[stage], c0, frame0, clip);
+          tma_load_2d(sbase + 2 * TILE_BYTES, &map_wh, &tail->full[stage], kb * TBK, n0);
+          tma_load_2d(sbase + 3 * TILE_BYTES, &map_wl, &tail->full[stage], kb * TBK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    const uint32_t idesc = umma_idesc();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tail->tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * TBN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&tail->full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint64_t xh = umma_desc_sw128(sbase);
+          const uint64_t xl = umma_desc_sw128(sbase + TILE_BYTES);
+          const uint64_t wh = umma_desc_sw128(sbase + 2 * TILE_BYTES);
+          const uint64_t wl = umma_desc_sw128(sbase + 3 * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TBK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 B per UMMA_K step
+            umma_bf16(d_tmem, xl + adv, wh + adv, idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, xh + adv, wl + adv, idesc, 1);
+            umma_bf16(d_tmem, xh + adv, wh + adv, idesc, 1);
+          }
+          umma_commit(&tail->empty[stage]);  // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tail->tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue ---------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int clip = mt / tiles_per_clip;
+      const int m = (mt - clip * tiles_per_clip) * TBM + q * 32 + lane;
+      const int n0 = nt * TBN;
+      const int as = it & 1;
+      mbar_wait(&tail->tmem_full[as], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TBN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TBN + c0), v);
+        store_row32(g, e, clip, m, n0 + c0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NSW_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    NSW_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, NSW_ECUDA,
+              "cuTensorMapEncodeTiled is not available from this driver");
+    cached = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *fn = cached;
+  return NSW_OK;
+}
+
+int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+             const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t gd[3], gs[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                   gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NSW_CHECK(r == CUDA_SUCCESS, NSW_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return NSW_OK;
+}
+
+}  // namespace
+
+bool conv_gemm_tc_supported(const ConvGemm& g) {
+  return g.cin % TBK == 0 && g.N % 64 == 0 && g.ntaps >= 1;
+}
+
+int conv_gemm_tc(const ConvGemm& g, const __nv_bfloat16* X_hi, const __nv_bfloat16* X_lo,
+                 const __nv_bfloat16* Bt_hi, const __nv_bfloat16* Bt_lo, const EpiParams& e,
+                 cudaStream_t stream) {
+  NSW_CHECK(conv_gemm_tc_supported(g), NSW_EINVAL, "conv_gemm_tc: unsupported shape cin=%d N=%d",
+            g.cin, g.N);
+  NSW_CHECK(X_hi && X_lo && Bt_hi && Bt_lo, NSW_EINVAL, "conv_gemm_tc: null operand");
+  if (e.mode == EPI_DECONV)
+    NSW_CHECK(e.cout % 32 == 0, NSW_EINVAL, "conv_gemm_tc: cout %d must be a multiple of 32", e.cout);
+  EncodeTiledFn enc;
+  NSW_TRY(get_encode_fn(&enc));
+  const int K = g.ntaps * g.cin;
+  CUtensorMap mxh, mxl, mwh, mwl;
+  {
+    const uint64_t dims[3] = {(uint64_t)g.cin, (uint64_t)g.L, (uint64_t)g.nclips};
+    const uint64_t strides[2] = {(uint64_t)g.cin * 2, (uint64_t)g.L * g.cin * 2};
+    const uint32_t box[3] = {TBK, TBM, 1};
+    NSW_TRY(make_map(enc, &mxh, X_hi, 3, dims, strides, box));
+    NSW_TRY(make_map(enc, &mxl, X_lo, 3, dims, strides, box));
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)g.N};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {TBK, TBN};
+    NSW_TRY(make_map(enc, &mwh, Bt_hi, 2, dims, strides, box));
+    NSW_TRY(make_map(enc, &mwl, Bt_lo, 2, dims, strides, box));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSW_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles_per_clip = (g.mclip + TBM - 1) / TBM;
+  const int n_tiles = (g.N + TBN - 1) / TBN;
+  const int total = g.nclips * tiles_per_clip * n_tiles;
+  const int grid = std::min(total, sms);
+  conv_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, g, e,
+                                                                  tiles_per_clip, n_tiles, total);
+  count_launch();
+  NSW_CUDA(cudaGetLastError());
+  return NSW_OK;
+}
+
+}  // namespace nsw

@@ -1,0 +1,261 @@
+"""Thin Python handles over the C ABI (include/nsw.h).
+
+`IAFEngine` stands where the reference builds a TF graph for
+ParallelWavenet.feed_forward (wavenet/parallelgen.py:11-19) and `FastgenEngine`
+where it builds Fastgen.sample + the deconv stack (wavenet/fastgen.py:61-66,118-125).
+Weights are dicts keyed by the reference's TF variable names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _get(hp, name, default):
+    return getattr(hp, name, default)
+
+
+def default_engine():
+    return os.environ.get('NSW_ENGINE', 'tc')
+
+
+def iaf_config(hp, num_mel=80, engine=None):
+    cfg = L.nsw_iaf_config()
+    layers = list(hp.num_iaf_layers)
+    if len(layers) > L.NSW_MAX_FLOWS:
+        raise ValueError('too many IAF flows')
+    cfg.num_flows = len(layers)
+    for i, n in enumerate(layers):
+        cfg.num_iaf_layers[i] = n
+    cfg.num_stages = hp.num_stages
+    cfg.filter_length = hp.filter_length
+    cfg.width = hp.width
+    cfg.deconv_width = hp.deconv_width
+    cfg.num_mel = num_mel
+    dc = list(hp.deconv_config)
+    cfg.num_deconv = len(dc)
+    for i, (fl, s) in enumerate(dc):
+        cfg.deconv_filter[i] = fl
+        cfg.deconv_stride[i] = s
+    # parallel_wavenet.py:130-135
+    cfg.share_deconv = int(bool(_get(hp, 'use_share_deconv', False) or
+                                _get(hp, 'use_teacher_deconv', False)))
+    cfg.loss_type = L.LOSS[_get(hp, 'loss_type', 'logistic')]  # parallel_wavenet.py:129
+    cfg.upsample_act = L.ACT[_get(hp, 'upsample_act', 'tanh')]
+    cfg.use_mu_law = int(bool(hp.use_mu_law))
+    cfg.engine = L.ENGINE[engine or default_engine()]
+    if _get(hp, 'use_resize_conv', False):
+        raise NotImplementedError('use_resize_conv is not used by any shipped config '
+                                  '(masked.py:294-322) and is not on the B200 path')
+    return cfg
+
+
+def wavenet_config(hp, num_mel=80, engine=None):
+    cfg = L.nsw_wavenet_config()
+    cfg.num_layers = hp.num_layers
+    cfg.num_stages = hp.num_stages
+    cfg.filter_length = hp.filter_length
+    cfg.width = hp.width
+    # wavenet.py:106,204
+    cfg.gate_width = 2 * hp.width if _get(hp, 'double_gate_width', True) else hp.width
+    cfg.skip_width = hp.skip_width
+    use_mu_law = bool(hp.use_mu_law)
+    qc = 2 ** 8 if use_mu_law else 2 ** 16
+    cfg.out_width = {'ce': qc, 'mol': 3 * _get(hp, 'mol_mix', 10), 'gauss': 2}[hp.loss_type]
+    cfg.deconv_width = hp.deconv_width
+    cfg.num_mel = num_mel
+    dc = list(hp.deconv_config)
+    cfg.num_deconv = len(dc)
+    for i, (fl, s) in enumerate(dc):
+        cfg.deconv_filter[i] = fl
+        cfg.deconv_stride[i] = s
+    cfg.loss_type = L.LOSS[hp.loss_type]
+    cfg.upsample_act = L.ACT[_get(hp, 'upsample_act', 'tanh')]
+    cfg.use_mu_law = int(use_mu_law)
+    cfg.engine = L.ENGINE[engine or default_engine()]
+    if _get(hp, 'use_resize_conv', False):
+        raise NotImplementedError('use_resize_conv is not on the B200 path')
+    return cfg
+
+
+def fold_weight_norm(weights):
+    """masked.get_kernel (masked.py:131-157): W = g * V / ||V||.  Returns a dict
+    with every (X_V, X_g) pair replaced by X so the engines only see plain kernels."""
+    out = {}
+    for name, v in weights.items():
+        if name.endswith('_V'):
+            base = name[:-2]
+            g = np.asarray(weights[base + '_g'], np.float64)
+            v64 = np.asarray(v, np.float64)
+            if base.endswith('/kernel'):  # deconv [1,k,Cout,Cin]: norm over (0,1,3)
+                nrm = np.sqrt((v64 ** 2).sum(axis=(0, 1, 3), keepdims=True))
+                out[base] = (v64 / nrm * g.reshape(1, 1, -1, 1)).astype(np.float32)
+            else:                          # conv [1,k,Cin,Cout]: norm over (0,1,2)
+                nrm = np.sqrt((v64 ** 2).sum(axis=(0, 1, 2), keepdims=True))
+                out[base] = (v64 / nrm * g.reshape(1, 1, 1, -1)).astype(np.float32)
+        elif not name.endswith('_g'):
+            out[name] = v
+    return out
+
+
+class IAFEngine:
+    """4-flow IAF student on one GPU."""
+
+    def __init__(self, hparams, weights, device=0, num_mel=80, engine=None):
+        self.lib = L.load()
+        self.hparams = hparams
+        self.device = device
+        self.num_mel = num_mel
+        self.engine = engine or default_engine()
+        cfg = iaf_config(hparams, num_mel, self.engine)
+        tensors, keep = L.make_tensors(fold_weight_norm(weights))
+        h = C.c_void_p()
+        L.check(self.lib.nsw_iaf_create(C.byref(cfg), tensors, len(tensors), device, C.byref(h)))
+        del keep
+        self._h = h
+        self.quant_chann = 2 ** 8 if hparams.use_mu_law else 2 ** 16
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.nsw_iaf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def length(self, num_frames):
+        return int(self.lib.nsw_iaf_length(self._h, num_frames))
+
+    def forward_host(self, mel, z=None, seed=0, quantize=True, want=('x',)):
+        """mel np[B,F,num_mel] (+ optional noise z np[B,T]) -> dict of np[B,T].
+        H2D and D2H copies happen inside the C call."""
+        mel = np.ascontiguousarray(mel, np.float32)
+        B, F, M = mel.shape
+        assert M == self.num_mel
+        T = self.length(F)
+        if z is not None:
+            z = np.ascontiguousarray(z, np.float32)
+            assert z.shape == (B, T), (z.shape, (B, T))
+        names = ('x', 'mean_tot', 'scale_tot', 'log_scale_tot', 'rand_input')
+        out = {n: (np.empty((B, T), np.float32) if n in want else None) for n in names}
+        L.check(self.lib.nsw_iaf_forward_host(
+            self._h, L.ptr(mel), L.ptr(z), seed, B, F, int(bool(quantize)),
+            *[L.ptr(out[n]) for n in names]))
+        return {n: v for n, v in out.items() if v is not None}
+
+    def forward_device(self, mel, z=None, seed=0, quantize=True, out=None, stream=None):
+        """torch CUDA tensors in, torch CUDA tensors out; enqueues on the current
+        torch stream (or `stream`) and does not synchronise."""
+        import torch
+        assert mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous()
+        B, F, _ = mel.shape
+        T = self.length(F)
+        names = ('x', 'mean_tot', 'scale_tot', 'log_scale_tot', 'rand_input')
+        if out is None:
+            out = {n: torch.empty((B, T), dtype=torch.float32, device=mel.device)
+                   for n in names[:4]}
+        if z is not None:
+            assert z.is_cuda and z.is_contiguous() and tuple(z.shape) == (B, T)
+        st = stream if stream is not None else torch.cuda.current_stream(mel.device).cuda_stream
+        L.check(self.lib.nsw_iaf_forward_device(
+            self._h, L.ptr(mel), L.ptr(z), seed, B, F, int(bool(quantize)),
+            *[L.ptr(out.get(n)) for n in names], st))
+        return out
+
+    def deconv_device(self, mel, stack=0):
+        import torch
+        B, F, _ = mel.shape
+        stride = int(np.prod([dc[1] for dc in self.hparams.deconv_config]))
+        enc = torch.empty((B, F * stride, self.hparams.deconv_width), dtype=torch.float32,
+                          device=mel.device)
+        st = torch.cuda.current_stream(mel.device).cuda_stream
+        L.check(self.lib.nsw_iaf_deconv_device(self._h, stack, L.ptr(mel), B, F, L.ptr(enc), st))
+        return enc
+
+    def set_tap(self, flow, layer, dst):
+        L.check(self.lib.nsw_iaf_set_tap(self._h, flow, layer, L.ptr(dst)))
+
+    def set_profiling(self, on):
+        L.check(self.lib.nsw_iaf_set_profiling(self._h, int(on)))
+
+    def last_timing(self):
+        ms = (C.c_float * 5)()
+        L.check(self.lib.nsw_iaf_last_timing(self._h, C.byref(ms)))
+        return dict(zip(('deconv', 'cond', 'layers', 'heads', 'total'), [float(v) for v in ms]))
+
+    def workspace_bytes(self):
+        return int(self.lib.nsw_iaf_workspace_bytes(self._h))
+
+
+class FastgenEngine:
+    """Teacher WaveNet: deconv encoder + persistent autoregressive kernel."""
+
+    def __init__(self, hparams, weights, device=0, num_mel=80, engine=None):
+        self.lib = L.load()
+        self.hparams = hparams
+        self.device = device
+        self.num_mel = num_mel
+        cfg = wavenet_config(hparams, num_mel, engine)
+        self.out_width = cfg.out_width
+        tensors, keep = L.make_tensors(fold_weight_norm(weights))
+        h = C.c_void_p()
+        L.check(self.lib.nsw_fastgen_create(C.byref(cfg), tensors, len(tensors), device,
+                                            C.byref(h)))
+        del keep
+        self._h = h
+        self.frame_shift = int(np.prod([dc[1] for dc in hparams.deconv_config]))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.nsw_fastgen_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode_host(self, mel):
+        mel = np.ascontiguousarray(mel, np.float32)
+        B, F, _ = mel.shape
+        enc = np.empty((B, F * self.frame_shift, self.hparams.deconv_width), np.float32)
+        L.check(self.lib.nsw_fastgen_encode_host(self._h, L.ptr(mel), B, F, L.ptr(enc)))
+        return enc
+
+    def run_host(self, encoding, teacher_force=None, seed=0, want_out=False):
+        encoding = np.ascontiguousarray(encoding, np.float32)
+        B, T, _ = encoding.shape
+        audio = np.empty((B, T), np.float32)
+        out = np.empty((B, T, self.out_width), np.float32) if want_out else None
+        if teacher_force is not None:
+            teacher_force = np.ascontiguousarray(teacher_force, np.float32)
+            assert teacher_force.shape == (B, T)
+        L.check(self.lib.nsw_fastgen_run_host(self._h, L.ptr(encoding), B, T,
+                                              L.ptr(teacher_force), seed, L.ptr(audio),
+                                              L.ptr(out)))
+        return (audio, out) if want_out else audio
+
+    def run_device(self, encoding, teacher_force=None, seed=0, want_out=False):
+        import torch
+        B, T, _ = encoding.shape
+        audio = torch.empty((B, T), dtype=torch.float32, device=encoding.device)
+        out = (torch.empty((B, T, self.out_width), dtype=torch.float32, device=encoding.device)
+               if want_out else None)
+        st = torch.cuda.current_stream(encoding.device).cuda_stream
+        L.check(self.lib.nsw_fastgen_run_device(self._h, L.ptr(encoding), B, T,
+                                                L.ptr(teacher_force), seed, L.ptr(audio),
+                                                L.ptr(out), st))
+        return (audio, out) if want_out else audio
+
+    def last_timing(self):
+        ms = C.c_float()
+        L.check(self.lib.nsw_fastgen_last_timing(self._h, C.byref(ms)))
+        return float(ms.value)

@@ -1,0 +1,108 @@
+"""Host-side logic of the drop-in modules (no GPU)."""
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+from scipy.io import wavfile
+
+from nsynth_wavenet_b200 import checkpoint as ckpt
+from nsynth_wavenet_b200 import engine
+from nsynth_wavenet_b200.auxilaries import mel_extractor, utils
+from nsynth_wavenet_b200.wavenet import fastgen, parallelgen
+
+
+def test_checkpoint_ema_shadow_preferred(tmp_path):
+    w = {'iaf_1/out1/W': np.ones((1, 1, 2, 2), np.float32)}
+    p = ckpt.save_weights(str(tmp_path / 'model.ckpt-1'), w, ema=True)
+    raw = dict(np.load(p))
+    raw['iaf_1/out1/W'] = np.zeros((1, 1, 2, 2), np.float32)  # stale non-EMA copy
+    np.savez(p, **raw)
+    got = ckpt.load_weights(str(tmp_path / 'model.ckpt-1'))
+    assert got['iaf_1/out1/W'].sum() == 4
+    assert ckpt.load_weights(str(tmp_path))['iaf_1/out1/W'].sum() == 4  # directory form
+
+
+def test_checkpoint_unshadowed_teacher_deconv(tmp_path):
+    # parallelgen.py:32-39: frozen deconv vars are restored from their plain names
+    p = str(tmp_path / 'c.npz')
+    np.savez(p, **{'iaf_share/trans_conv_1/kernel': np.full(3, 2.0, np.float32),
+                   'iaf_share/trans_conv_1/kernel/ExponentialMovingAverage': np.zeros(3, np.float32)})
+    hp = Namespace(use_teacher_deconv=True, use_resize_conv=False)
+    got = ckpt.load_weights(p, parallelgen._unshadowed(hp))
+    assert got['iaf_share/trans_conv_1/kernel'][0] == 2.0
+
+
+def test_missing_checkpoint_is_an_error(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        ckpt.load_weights(str(tmp_path / 'nope'))
+
+
+def test_shadow_dict_names():
+    class V:  # mimics tf.Variable.name
+        def __init__(self, n): self.name = n
+    d = fastgen.get_ema_shadow_dict([V('conv_start/W:0')])
+    assert list(d) == ['conv_start/W/ExponentialMovingAverage']
+    assert list(parallelgen.get_default_shadow_dict(['a/b'])) == ['a/b']
+
+
+def test_load_batch_pads_and_save_batch_roundtrip(tmp_path):
+    a = (np.sin(np.arange(1000) / 10) * 0.5).astype(np.float32)
+    b = a[:600]
+    pa, pb = str(tmp_path / 'a.wav'), str(tmp_path / 'b.wav')
+    wavfile.write(pa, 16000, (a * 32767).astype(np.int16))
+    wavfile.write(pb, 16000, (b * 32767).astype(np.int16))
+    batch = fastgen.load_batch([pa, pb], sample_length=-1)
+    assert batch.shape == (2, 1000) and np.all(batch[1, 600:] == 0)
+    assert fastgen.load_batch([pa, pb], sample_length=500).shape == (2, 500)
+    out = [str(tmp_path / 'o0.wav'), str(tmp_path / 'o1.wav')]
+    fastgen.save_batch(batch.astype(np.float32), out)
+    rate, data = wavfile.read(out[0])
+    assert rate == 16000 and data.dtype == np.float32 and len(data) == 1000
+    np.save(str(tmp_path / 'e.npy'), np.zeros((7, 3)))
+    np.save(str(tmp_path / 'f.npy'), np.zeros((5, 3)))
+    assert fastgen.load_batch([str(tmp_path / 'e.npy'), str(tmp_path / 'f.npy')]).shape == (14, 3)
+
+
+def test_mel_extractor_shapes_and_range():
+    y = np.random.default_rng(0).uniform(-0.5, 0.5, 154480).astype(np.float32)
+    m = mel_extractor.melspectrogram(y)
+    assert m.shape == (773, 80) and m.dtype == np.float32
+    assert m.min() >= 0 and m.max() <= 1
+    assert mel_extractor.batch_melspectrogram(y[None, :8000]).shape == (1, 41, 80)
+    basis = mel_extractor._build_mel_basis()
+    assert basis.shape == (80, 1025) and np.all(basis >= 0) and np.all(basis.sum(1) > 0)
+
+
+def test_mu_law_roundtrip_numpy():
+    x = np.linspace(-0.99, 0.99, 101)
+    q = utils.mu_law_numpy(x)
+    assert q.min() >= -128 and q.max() <= 127
+    assert np.abs(utils.inv_mu_law_numpy(q) - x).max() < 0.05
+
+
+def test_config_mapping(student_hp, clarinet_hp, teacher_hp):
+    c = engine.iaf_config(student_hp, engine='ffma')
+    assert (c.num_flows, list(c.num_iaf_layers)[:4], c.share_deconv, c.loss_type) == (4, [10, 10, 10, 30], 1, 0)
+    assert (c.deconv_filter[1], c.deconv_stride[1], c.upsample_act) == (80, 20, 2)
+    g = engine.iaf_config(clarinet_hp, engine='tc')
+    assert (g.share_deconv, g.loss_type, g.engine) == (0, 1, 1)   # parallel_wavenet.py:129-134
+    t = engine.wavenet_config(teacher_hp)
+    assert (t.gate_width, t.out_width, t.skip_width) == (512, 30, 256)
+    ce = Namespace(**{**vars(teacher_hp), 'loss_type': 'ce', 'use_mu_law': True})
+    delattr(ce, 'double_gate_width')
+    t2 = engine.wavenet_config(ce)
+    assert (t2.gate_width, t2.out_width) == (1024, 256)           # wavenet.py:106 default True
+
+
+def test_engine_fold_weight_norm_matches_oracle():
+    from oracle import wavenet_oracle as O
+    rng = np.random.default_rng(2)
+    w = {'x/W_V': rng.normal(size=(1, 3, 4, 5)).astype(np.float32),
+         'x/W_g': rng.uniform(0.5, 2, 5).astype(np.float32),
+         'y/kernel_V': rng.normal(size=(1, 4, 6, 3)).astype(np.float32),
+         'y/kernel_g': rng.uniform(0.5, 2, 6).astype(np.float32)}
+    a, b = engine.fold_weight_norm(w), O.fold_weight_norm(w)
+    assert set(a) == set(b) == {'x/W', 'y/kernel'}
+    for k in a:
+        assert np.allclose(a[k], b[k])

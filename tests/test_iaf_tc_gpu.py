@@ -1,0 +1,65 @@
+"""tcgen05 split-bf16 engine (cond projections + deconv layer 2 on tensor cores) against
+the same oracle vectors.  bf16 hi+lo carries ~16 mantissa bits, so this engine is held to
+the stated 1e-4 bar rather than the fp32 engine's 2e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+from conftest import GOLDEN_DIR, synth_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+KEYS = ('mean_tot', 'scale_tot', 'log_scale_tot')
+
+
+def make_engine(hp, engine, seed=12345, bias_std=0.02):
+    from nsynth_wavenet_b200 import IAFEngine
+    w = O.init_student_weights(hp, seed=seed, bias_std=bias_std)
+    return IAFEngine(hp, w, device=0, engine=engine), w
+
+
+def test_tc_engine_matches_golden_config1(student_hp):
+    eng, _ = make_engine(student_hp, 'tc')
+    g = np.load(os.path.join(GOLDEN_DIR, 'iaf_logistic_1x21.npz'))
+    out = eng.forward_host(g['mel'], g['z'], quantize=False, want=('x',) + KEYS)
+    errs = {k: float(np.abs(out[k] - g[k]).max()) for k in KEYS}
+    print('tc engine max-abs errors', errs)
+    for k in KEYS:
+        assert errs[k] < TOL, errs
+
+
+def test_tc_engine_first_layers_close_to_oracle(student_hp):
+    hp = student_hp
+    eng, w = make_engine(hp, 'tc')
+    mel, z = synth_inputs(hp, 1, 6)
+    taps = {}
+    O.student_feed_forward(w, hp, mel, z, np.float64, taps=taps)
+    buf = torch.empty((1, eng.length(6), 64), device='cuda')
+    for flow, layer in ((0, 1), (0, 10), (3, 30)):
+        eng.set_tap(flow, layer, buf)
+        eng.forward_host(mel, z, quantize=False)
+        err = np.abs(buf.cpu().numpy() - taps['iaf_{}/l{}'.format(flow + 1, layer)]).max()
+        assert err < TOL, (flow, layer, err)
+
+
+def test_tc_engine_clarinet_matches_golden(clarinet_hp):
+    eng, _ = make_engine(clarinet_hp, 'tc')
+    g = np.load(os.path.join(GOLDEN_DIR, 'iaf_gauss_2x6.npz'))
+    out = eng.forward_host(g['mel'], g['z'], quantize=False, want=KEYS)
+    for k in KEYS:
+        assert np.abs(out[k] - g[k]).max() < TOL, k
+
+
+def test_tc_and_ffma_engines_agree_at_full_size(student_hp):
+    hp = student_hp
+    a, _ = make_engine(hp, 'tc')
+    b, _ = make_engine(hp, 'ffma')
+    mel, z = synth_inputs(hp, 8, 39)
+    oa = a.forward_host(mel, z, quantize=False, want=KEYS)
+    ob = b.forward_host(mel, z, quantize=False, want=KEYS)
+    for k in KEYS:
+        assert np.abs(oa[k] - ob[k]).max() < TOL, k
+    assert np.all(oa['scale_tot'] > 0)
