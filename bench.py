@@ -131,6 +131,34 @@ def cpu_reference_run(hp, batch, frames, steps, warmup, seed=12345):
             len(times), batch, T, cores)
 
 
+def fastgen_bench(device, steps, hbm_peak):
+    """Teacher WaveNet (wavenet_mol.json, 30 layers, random init) free-running generation at
+    batch 1 through the persistent kernel; encoding resident in HBM, in-kernel RNG."""
+    import torch
+    from argparse import Namespace
+    from nsynth_wavenet_b200 import FastgenEngine
+    from oracle import wavenet_oracle as O
+    with open(os.path.join(ROOT, 'nsynth_wavenet_b200', 'config_jsons', 'wavenet_mol.json')) as f:
+        hp = Namespace(**json.load(f))
+    w = O.init_teacher_weights(hp, seed=12345)
+    eng = FastgenEngine(hp, w, device=device)
+    g = torch.Generator(device='cpu').manual_seed(1)
+    enc = (torch.rand((1, steps, 256), generator=g) * 2 - 1).to('cuda:%d' % device)
+    eng.run_device(enc[:, :2048], seed=1)       # warm-up
+    torch.cuda.synchronize()
+    eng.run_device(enc, seed=2)
+    torch.cuda.synchronize()
+    ms = eng.last_timing()
+    sps = steps / (ms * 1e-3)
+    weight_bytes = 32 * 128 * 9224 * 4          # per-step streamed weight blocks (all CTAs)
+    return {'metric': 'fastgen audio samples/sec (wavenet_mol.json, batch 1)', 'value': sps,
+            'unit': UNIT, 'rtf': sps / 16000.0, 'steps': steps, 'ms': ms,
+            'us_per_step': 1e3 * ms / steps,
+            'weight_stream_gbs': weight_bytes * sps / 1e9,
+            'weight_stream_frac_of_hbm': weight_bytes * sps / 1e9 / hbm_peak,
+            'note': 'includes the hoisted cond GEMM; weights stream L2/HBM -> smem every step'}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path restated (TF 1.x is not installable
     here), bounded sample, rank 0 only."""
@@ -170,6 +198,8 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=1)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-fastgen', action='store_true')
+    ap.add_argument('--fastgen-steps', type=int, default=32000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -322,6 +352,13 @@ def main():
         },
         'stage_ms': stage,
     }
+
+    # ---- secondary metric: autoregressive fastgen (BASELINE configs[1]), batch 1, rank 0 ----
+    if rank == 0 and not args.no_fastgen:
+        try:
+            line['fastgen'] = fastgen_bench(local_rank, args.fastgen_steps, hbm_peak)
+        except Exception as ex:  # reported, never silently dropped
+            line['fastgen'] = {'error': str(ex)[:300]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample (about cpu-seconds of work): single-clip forwards

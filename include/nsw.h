@@ -186,8 +186,15 @@ int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, int32_t B, i
                            float* d_out, void* stream);
 int nsw_fastgen_run_host(nsw_fastgen* h, const float* encoding, int32_t B, int32_t T,
                          const float* teacher_force, uint64_t seed, float* audio, float* out);
-/* device time of the last nsw_fastgen_run_* persistent kernel in ms */
+/* device time of the last nsw_fastgen_run_* (cond GEMM + persistent kernel) in ms */
 int nsw_fastgen_last_timing(nsw_fastgen* h, float* ms);
+/* TEST HOOK (host only, no CUDA): the create-time repacking of the TF-named tensors into
+ * the persistent kernel's per-(phase, CTA) weight blocks and the hoisted conditioning GEMM.
+ * sizes[0] = floats in `blocks`, sizes[1] = floats per block, sizes[2] = CTAs,
+ * sizes[3] = columns of cond_w.  blocks / cond_w / cond_b may be NULL to query sizes. */
+int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tensors,
+                          int32_t n_tensors, float* blocks, int64_t blocks_cap, float* cond_w,
+                          float* cond_b, int64_t* sizes);
 
 #ifdef __cplusplus
 }

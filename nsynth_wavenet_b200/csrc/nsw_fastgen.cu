@@ -1,32 +1,861 @@
-// Autoregressive teacher (fastgen) — placeholder entry points while the persistent
-// kernel is being brought up; every call fails loudly.
+// Autoregressive teacher WaveNet ("fastgen") as ONE persistent cooperative kernel.
+//
+// Replaces the per-sample Python -> Session.run loop of fastgen.synthesis
+// (wavenet/fastgen.py:147-168) and the one-timestep graph Fastgen.sample
+// (wavenet/wavenet.py:379-514) built from masked.causal_linear / masked.linear
+// (wavenet/masked.py:328-405).  The tf.FIFOQueue pairs of causal_linear become
+// per-layer circular buffers resident in HBM/L2.
+//
+// Work split: NC = 128 CTAs, each owning a fixed slice of every layer's outputs
+// (2 gate pairs = 4 rows of the dilated conv, 4 residual channels, 2 skip channels), so its
+// weight slice never changes; it is streamed from L2 through a 3-slot smem ring with
+// cp.async.bulk two phases ahead.  Per audio sample there are L+2 = 32 "phases", each ending
+// in one all-to-all exchange of a 768-float vector through an LL (value+tag in one 8-byte
+// word) buffer: no fences, no atomics, no grid barrier.
+//
+// Algebra that halves the number of exchanges (one per layer instead of two):
+//   d_i = W0_i l_{i-1}[t-2d] + W1_i l_{i-1}[t-d] + W2_i l_{i-1}[t] + b_i + cond_i[t]
+//   l_{i-1}[t] = l_{i-2}[t] + Wr_{i-1} g_{i-1} + br_{i-1}
+//   => W2_i l_{i-1}[t] = W2_i l_{i-2}[t] + (W2_i Wr_{i-1}) g_{i-1} + W2_i br_{i-1}
+// so phase i needs only g_{i-1} and l_{i-2}, both already exchanged; M_i = W2_i Wr_{i-1} is
+// precomputed in fp64 at create time.  The two past taps (2/3 of the dilated-conv work) only
+// depend on history and are computed in the slack while the exchange is in flight, and the
+// mel conditioning of the whole utterance is hoisted into one conv-GEMM (the reference
+// sketches the same hoist: Fastgen.cond_vars, wavenet.py:353-377).
 #include "nsw_gemm.cuh"
 
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+
+namespace nsw {
+namespace {
+
+constexpr int FW = 512;   // width
+constexpr int FM = 256;   // gate half (gate_width 512)
+constexpr int FS = 256;   // skip width
+constexpr int FD = 256;   // deconv width
+constexpr int NC = 128;   // CTAs
+constexpr int NT = 256;   // threads per CTA
+constexpr int MAX_O = 32;
+constexpr int MAX_PH = 40;
+
+// per-(phase, cta) weight block, in floats
+constexpr int OFF_D = 0;                    // 4 rows x 768: [W2 row (512) | M row (256)]
+constexpr int OFF_L = 4 * 768;              // 4 rows x 256: Wr rows of the previous layer
+constexpr int OFF_S = OFF_L + 4 * 256;      // 2 rows x 512: Ws rows of the previous layer / skip_start
+constexpr int OFF_C = OFF_S + 2 * 512;      // 8 consts: br[4], bs[2], pad[2]
+constexpr int OFF_P = OFF_C + 8;            // 4 rows x 1024: [W0 row (512) | W1 row (512)]
+constexpr int BLOCK_FLOATS = OFF_P + 4 * 1024;  // 9224
+constexpr uint32_t BLOCK_BYTES = BLOCK_FLOATS * 4;
+static_assert(BLOCK_BYTES % 16 == 0 && (OFF_P * 4) % 16 == 0, "bulk copy alignment");
+
+constexpr long long FG_WATCHDOG = 6000000000ll;  // ~3 s of SM clocks
+
+struct FgParams {
+  const float* blocks;          // [NPH][NC][BLOCK_FLOATS]
+  const float* cond;            // planes [(L*512+256)/64][T][64]
+  unsigned long long* xbuf;     // [NPH+1][256] tagged g / s' / h exchange slots
+  unsigned long long* hist;     // tagged l history rings
+  const int* hist_off;          // [L+1] entry offset of layer ph's ring
+  const int* dil;               // [L+1]
+  const float* wcs;             // conv_start W [3][512]
+  const float* bcs;             // [512]
+  const float* wo2t;            // out2 W transposed [O][256]
+  const float* bo2;             // [O]
+  const float* tf;              // teacher forcing [T] or NULL
+  float* audio;                 // [T] or NULL
+  float* out;                   // [T][O] or NULL
+  int T, L, O, loss_type;
+  unsigned long long seed;
+  float quant;                  // quant_chann
+};
+
+struct FgSmem {
+  float ring[3][BLOCK_FLOATS];
+  float wo2t[MAX_O * FM];
+  float wcs[3 * FW];
+  float bcs[FW];
+  float bo2[MAX_O];
+  float v[1024];        // [l_full (512) | g_full (256) | zeros (256)]
+  float hv[1024];       // [l[t-2d] | l[t-d]] of the next layer
+  float cnd[2][MAX_PH][4];
+  float red_d[4][2];
+  float red_l[4];
+  float red_s[2];
+  float red_p[4][2];
+  float pv[4];
+  float outv[MAX_O];
+  float gum[12];
+  float xnext;
+  unsigned long long mbar[3];
+};
+
+__device__ __forceinline__ void fg_die(const char* what) {
+  printf("nsw fastgen: watchdog in %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
+  __trap();
+}
+
+__device__ __forceinline__ float2 poll2(const unsigned long long* p, uint32_t tag) {
+  uint32_t a, b, c, d;
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                 : "l"(p)
+                 : "memory");
+    if (b == tag && d == tag) break;
+    if (++spins == 4096) {
+      spins = 0;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > FG_WATCHDOG) fg_die("exchange wait");
+    }
+  }
+  return make_float2(__uint_as_float(a), __uint_as_float(c));
+}
+__device__ __forceinline__ void publish(unsigned long long* p, float v, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)),
+               "r"(tag)
+               : "memory");
+}
+
+__device__ __forceinline__ void fg_mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins == 4096) {
+      spins = 0;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > FG_WATCHDOG) fg_die("weight ring wait");
+    }
+  }
+}
+__device__ __forceinline__ void bulk_load(float* dst, const float* src, uint32_t bytes,
+                                          unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// lane-strided dot product of nf4*128 floats: lane reads float4 at 128*i + 4*lane
+template <int NF4>
+__device__ __forceinline__ float dot_rows(const float* __restrict__ w, const float* __restrict__ x,
+                                          int lane) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NF4; ++i) {
+    const float4 ww = *reinterpret_cast<const float4*>(w + 128 * i + 4 * lane);
+    const float4 xx = *reinterpret_cast<const float4*>(x + 128 * i + 4 * lane);
+    a0 = fmaf(ww.x, xx.x, a0);
+    a1 = fmaf(ww.y, xx.y, a1);
+    a0 = fmaf(ww.z, xx.z, a0);
+    a1 = fmaf(ww.w, xx.w, a1);
+  }
+  return a0 + a1;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FgSmem& S = *reinterpret_cast<FgSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
+  const int L = P.L, NPH = L + 2, O = P.O, T = P.T;
+  const int nr = O / 3;
+
+  // ---------------- one-time setup ----------------
+  for (int i = tid; i < O * FM; i += NT) S.wo2t[i] = P.wo2t[i];
+  for (int i = tid; i < 3 * FW; i += NT) S.wcs[i] = P.wcs[i];
+  for (int i = tid; i < FW; i += NT) S.bcs[i] = P.bcs[i];
+  if (tid < O) S.bo2[tid] = P.bo2[tid];
+  for (int i = tid; i < 1024; i += NT) { S.v[i] = 0.f; S.hv[i] = 0.f; }
+  if (tid < 4) S.pv[tid] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < 3; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    S.xnext = 0.f;
+  }
+  __syncthreads();
+  const float* my_blocks = P.blocks + (size_t)c * BLOCK_FLOATS;
+  const size_t phase_stride = (size_t)NC * BLOCK_FLOATS;
+  if (tid == 0) {
+    bulk_load(S.ring[0], my_blocks, BLOCK_BYTES, &S.mbar[0]);                 // q = 0
+    bulk_load(S.ring[1], my_blocks + phase_stride, BLOCK_BYTES, &S.mbar[1]);  // q = 1
+  }
+  // conditioning slice of (t, phase i+1): 4 floats (layers) / 2 floats (out1)
+  auto load_cond = [&](int t, int i) -> float4 {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= T) return r;
+    if (i < L) {
+      const int n = i * 512 + 4 * c;
+      r = __ldg(reinterpret_cast<const float4*>(P.cond + ((size_t)(n >> 6) * T + t) * 64 + (n & 63)));
+    } else if (i == L + 1) {
+      const int n = L * 512 + 2 * c;
+      const float2 h = __ldg(reinterpret_cast<const float2*>(P.cond + ((size_t)(n >> 6) * T + t) * 64 + (n & 63)));
+      r.x = h.x; r.y = h.y;
+    }
+    return r;
+  };
+  if (tid < NPH) {
+    const float4 cc = load_cond(0, tid);
+    S.cnd[0][tid + 1][0] = cc.x; S.cnd[0][tid + 1][1] = cc.y;
+    S.cnd[0][tid + 1][2] = cc.z; S.cnd[0][tid + 1][3] = cc.w;
+  }
+
+  float x1 = 0.f, x2 = 0.f;  // inputs of the two previous steps (conv_start queues, rate 1)
+  float ls = 0.f;            // tid 4..7: my residual-stream channel 4c + tid-4
+  float sk = 0.f;            // tid 8,9: my skip channel 2c + tid-8
+  long long q = 0;           // global phase counter -> weight ring slot / parity
+  __syncthreads();
+
+  for (int t = 0; t < T; ++t) {
+    const uint32_t tag = (uint32_t)t + 1u;
+    // ---------------- local phase: conv_start on the fed-back sample ----------------
+    const float xin = S.xnext;  // written before the last __syncthreads of the previous step
+    {
+      const int k0 = tid, k1 = tid + 256;
+      S.v[k0] = fmaf(S.wcs[2 * FW + k0], xin, fmaf(S.wcs[FW + k0], x1, fmaf(S.wcs[k0], x2, S.bcs[k0])));
+      S.v[k1] = fmaf(S.wcs[2 * FW + k1], xin, fmaf(S.wcs[FW + k1], x1, fmaf(S.wcs[k1], x2, S.bcs[k1])));
+      S.v[512 + tid] = 0.f;  // no previous gate output at phase 1
+    }
+    x2 = x1;
+    x1 = xin;
+    float4 cnext = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < NPH) cnext = load_cond(t + 1, tid);  // consumed one step later
+    __syncthreads();
+    if (tid >= 4 && tid < 8) ls = S.v[4 * c + tid - 4];
+    const float(*cnd)[4] = S.cnd[t & 1];
+
+    for (int ph = 1; ph <= NPH; ++ph, ++q) {
+      const int slot = (int)(q % 3);
+      const uint32_t par = (uint32_t)((q / 3) & 1);
+      // ---- A. receive the previous phase's exchange ----
+      if (ph >= 2) {
+        if (ph <= L) {
+          const int d = P.dil[ph - 1];
+          const int R = 2 * d + 1;
+          const unsigned long long* hl = P.hist + P.hist_off[ph - 1] + (size_t)(t % R) * FW;
+          const float2 a = poll2(hl + 2 * tid, tag);
+          S.v[2 * tid] = a.x;
+          S.v[2 * tid + 1] = a.y;
+        }
+        if (tid < 128) {
+          const float2 g = poll2(P.xbuf + (size_t)(ph - 1) * 256 + 2 * tid, tag);
+          S.v[512 + 2 * tid] = g.x;
+          S.v[512 + 2 * tid + 1] = g.y;
+        }
+        __syncthreads();
+      }
+      // slot (q+2)%3 == (q-1)%3 was last read in phase q-1: free now
+      if (tid == 0) {
+        const long long qn = q + 2;
+        if (qn < (long long)T * NPH)
+          bulk_load(S.ring[qn % 3], my_blocks + (size_t)(qn % NPH) * phase_stride, BLOCK_BYTES,
+                    &S.mbar[qn % 3]);
+      }
+      fg_mbar_wait(&S.mbar[slot], par);
+      const float* blk = S.ring[slot];
+
+      // ---- C. critical compute ----
+      if (ph != L + 1) {
+        const int r = warp >> 1, half = warp & 1;
+        float a = dot_rows<3>(blk + OFF_D + r * 768 + half * 384, S.v + half * 384, lane);
+        float b = 0.f;
+        if (warp < 4 && ph <= L) b = dot_rows<2>(blk + OFF_L + warp * 256, S.v + 512, lane);
+        warp_sum2(a, b);
+        if (lane == 0) {
+          S.red_d[r][half] = a;
+          if (warp < 4) S.red_l[warp] = b;
+        }
+      } else if (warp < 2) {
+        float a = warp_sum(dot_rows<2>(blk + OFF_S + warp * 512, S.v + 512, lane));
+        if (lane == 0) S.red_s[warp] = a;
+      }
+      __syncthreads();
+      // ---- D. finalize + publish ----
+      if (ph <= L) {
+        if (tid < 2) {
+          const float ds = S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid] + S.pv[tid];
+          const float dt = S.red_d[2 + tid][0] + S.red_d[2 + tid][1] + cnd[ph][2 + tid] + S.pv[2 + tid];
+          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid, sigmoidf_acc(ds) * tanhf(dt), tag);
+        } else if (tid >= 4 && tid < 8) {
+          ls += S.red_l[tid - 4] + blk[OFF_C + tid - 4];
+          const int d = P.dil[ph];
+          const int R = 2 * d + 1;
+          publish(P.hist + P.hist_off[ph] + (size_t)(t % R) * FW + 4 * c + tid - 4, ls, tag);
+        }
+      } else if (ph == L + 1) {
+        if (tid >= 8 && tid < 10) {
+          sk = fmaxf(sk + S.red_s[tid - 8] + blk[OFF_C + 4 + tid - 8], 0.f);
+          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid - 8, sk, tag);
+        }
+      } else {  // ph == L + 2: h = relu(out1 . relu(s) + cond_out1)
+        if (tid < 2) {
+          const float h = fmaxf(S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid], 0.f);
+          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid, h, tag);
+        }
+      }
+
+      // ---- E. slack work while the exchange is in flight ----
+      // (i) skip accumulation of the previous layer (phase 1: skip_start on l_0)
+      if (ph <= L && warp < 2) {
+        float a = (ph == 1) ? dot_rows<4>(blk + OFF_S + warp * 512, S.v, lane)
+                            : dot_rows<2>(blk + OFF_S + warp * 512, S.v + 512, lane);
+        a = warp_sum(a);
+        if (lane == 0) S.red_s[warp] = a;
+      }
+      // (ii) past taps of the next phase's layer
+      const int nph = (ph == NPH) ? 1 : ph + 1;
+      const int nt = (ph == NPH) ? t + 1 : t;
+      const bool do_past = (nph <= L) && (nt < T);
+      if (do_past) {
+        const int d = P.dil[nph];
+        const int R = 2 * d + 1;
+        const unsigned long long* hb = P.hist + P.hist_off[nph];
+        float2 h2 = make_float2(0.f, 0.f), h1 = make_float2(0.f, 0.f);
+        if (nt - 2 * d >= 0) h2 = poll2(hb + (size_t)((nt - 2 * d) % R) * FW + 2 * tid, (uint32_t)(nt - 2 * d) + 1u);
+        if (nt - d >= 0) h1 = poll2(hb + (size_t)((nt - d) % R) * FW + 2 * tid, (uint32_t)(nt - d) + 1u);
+        S.hv[2 * tid] = h2.x;
+        S.hv[2 * tid + 1] = h2.y;
+        S.hv[512 + 2 * tid] = h1.x;
+        S.hv[512 + 2 * tid + 1] = h1.y;
+      }
+      if (ph == 1 && tid < NPH) {
+        float* dst = S.cnd[(t + 1) & 1][tid + 1];
+        dst[0] = cnext.x; dst[1] = cnext.y; dst[2] = cnext.z; dst[3] = cnext.w;
+      }
+      __syncthreads();
+      if (do_past) {
+        const int nslot = (int)((q + 1) % 3);
+        fg_mbar_wait(&S.mbar[nslot], (uint32_t)(((q + 1) / 3) & 1));
+        const float* nblk = S.ring[nslot];
+        const int r = warp >> 1, half = warp & 1;
+        float a = warp_sum(dot_rows<4>(nblk + OFF_P + r * 1024 + half * 512, S.hv + half * 512, lane));
+        if (lane == 0) S.red_p[r][half] = a;
+      }
+      if (ph <= L && tid >= 8 && tid < 10) {
+        const float add = S.red_s[tid - 8] + blk[OFF_C + 4 + tid - 8];
+        sk = (ph == 1) ? add : sk + add;
+      }
+      __syncthreads();
+      if (tid < 4) S.pv[tid] = do_past ? S.red_p[tid][0] + S.red_p[tid][1] : 0.f;
+      // S.pv is read after the next phase's __syncthreads
+    }
+
+    // ---------------- output head + sampler (every CTA, redundantly) ----------------
+    if (tid < 128) {
+      const float2 h = poll2(P.xbuf + (size_t)NPH * 256 + 2 * tid, tag);
+      S.v[512 + 2 * tid] = h.x;
+      S.v[512 + 2 * tid + 1] = h.y;
+    } else if (tid >= 224 && tid < 236) {
+      // noise for this step (Philox: counter = step, key = seed), off the critical path
+      const int j = tid - 224;
+      const uint4 rr = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)(j >> 2), 0x66617374u, 0u),
+                                     make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+      const uint32_t bits = (j & 3) == 0 ? rr.x : (j & 3) == 1 ? rr.y : (j & 3) == 2 ? rr.z : rr.w;
+      const float u = u01_clipped(bits);
+      if (P.loss_type == NSW_LOSS_MOL) {
+        // j < 10: Gumbel -log(-log u) (loss_func.py:168-171); j == 10: logistic noise (:182-183)
+        S.gum[j] = (j < 10) ? -logf(-logf(u)) : logf(u) - logf(1.0f - u);
+      } else {
+        S.gum[j] = u;
+      }
+    }
+    __syncthreads();
+    {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      if (warp < O) o0 = dot_rows<2>(S.wo2t + warp * FM, S.v + 512, lane);
+      if (warp + 8 < O) o1 = dot_rows<2>(S.wo2t + (warp + 8) * FM, S.v + 512, lane);
+      if (warp + 16 < O) o2 = dot_rows<2>(S.wo2t + (warp + 16) * FM, S.v + 512, lane);
+      if (warp + 24 < O) o3 = dot_rows<2>(S.wo2t + (warp + 24) * FM, S.v + 512, lane);
+      warp_sum2(o0, o1);
+      warp_sum2(o2, o3);
+      if (lane == 0) {
+        if (warp < O) S.outv[warp] = o0 + S.bo2[warp];
+        if (warp + 8 < O) S.outv[warp + 8] = o1 + S.bo2[warp + 8];
+        if (warp + 16 < O) S.outv[warp + 16] = o2 + S.bo2[warp + 16];
+        if (warp + 24 < O) S.outv[warp + 24] = o3 + S.bo2[warp + 24];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float Q = P.quant;
+      float x;
+      if (P.loss_type == NSW_LOSS_MOL) {
+        // loss_func.mol_sample (loss_func.py:154-186)
+        float best = -INFINITY;
+        int sel = 0;
+        for (int k = 0; k < nr; ++k) {
+          const float vv = S.outv[k] + S.gum[k];
+          if (vv > best) { best = vv; sel = k; }
+        }
+        const float mu = S.outv[nr + sel];
+        const float lsc = fminf(fmaxf(S.outv[2 * nr + sel], -7.0f), 7.0f);
+        x = fmaf(expf(lsc), S.gum[10], mu);
+      } else {
+        // loss_func.gauss_sample (loss_func.py:200-206), Box-Muller from two uniforms
+        const float n = sqrtf(-2.0f * logf(S.gum[0])) * cosf(6.283185307179586f * S.gum[1]);
+        x = fmaf(expf(fmaxf(S.outv[1], -7.0f)), n, S.outv[0]);
+      }
+      x = fminf(fmaxf(x, -1.0f), 1.0f - 2.0f / Q);
+      const float a = floorf(x * Q * 0.5f) / (Q * 0.5f);  // cast_quantize + inv_cast_quantize_numpy
+      const float fed = P.tf ? P.tf[t] : a;
+      S.xnext = fed;
+      if (c == 0 && P.audio) P.audio[t] = fed;
+    }
+    if (c == 0 && P.out && tid < O) P.out[(size_t)t * O + tid] = S.outv[tid];
+    __syncthreads();
+  }
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+}  // namespace
+}  // namespace nsw
+
+// ================================= host side =================================
 using namespace nsw;
 
 struct nsw_fastgen {
-  int dummy;
+  nsw_wavenet_config cfg;
+  int device = 0;
+  int L = 0, NPH = 0, O = 0, NPL = 0;  // NPL: cond planes of 64 columns
+  DeconvStack deconv;
+  DevBuf blocks, wcs, bcs, wo2t, bo2, cond_w, cond_wt_hi, cond_wt_lo, cond_b, hist_off, dil;
+  DevBuf xbuf, hist, cond, enc_split, scratch, stage_in, stage_tf, stage_audio, stage_out,
+      stage_mel, stage_enc;
+  size_t hist_entries = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
 };
 
-#define NSW_FG_NOT_YET()                                                          \
-  do {                                                                            \
-    set_error("fastgen persistent kernel is not part of this build yet");        \
-    return NSW_EINVAL;                                                            \
-  } while (0)
+namespace nsw_fg_host {
 
-extern "C" {
-int nsw_fastgen_create(const nsw_wavenet_config*, const nsw_tensor*, int32_t, int32_t,
-                       nsw_fastgen**) { NSW_FG_NOT_YET(); }
-void nsw_fastgen_destroy(nsw_fastgen* h) { delete h; }
-int nsw_fastgen_encode_device(nsw_fastgen*, const float*, int32_t, int32_t, float*, void*) {
-  NSW_FG_NOT_YET();
+struct FgPacked {
+  std::vector<float> blocks, wcs, bcs, wo2t, bo2, cond_w, cond_b;
+  std::vector<int> hist_off, dil;
+  size_t hist_entries = 0;
+};
+
+int fg_check_cfg(const nsw_wavenet_config& c) {
+  NSW_CHECK(c.width == FW && c.gate_width == 2 * FM && c.skip_width == FS && c.deconv_width == FD,
+            NSW_EINVAL,
+            "fastgen kernel is specialised for width=512, gate_width=512, skip_width=256, "
+            "deconv_width=256 (got %d, %d, %d, %d)",
+            c.width, c.gate_width, c.skip_width, c.deconv_width);
+  NSW_CHECK(c.filter_length == 3, NSW_EINVAL, "filter_length must be 3 (masked.py:349)");
+  NSW_CHECK(c.num_layers >= 2 && c.num_layers + 2 < MAX_PH, NSW_EINVAL, "bad num_layers %d", c.num_layers);
+  NSW_CHECK(c.loss_type == NSW_LOSS_MOL || c.loss_type == NSW_LOSS_GAUSS, NSW_EINVAL,
+            "fastgen: only mol / gauss heads are built (ce is a later row)");
+  NSW_CHECK(c.out_width >= 2 && c.out_width <= MAX_O, NSW_EINVAL, "bad out_width %d", c.out_width);
+  NSW_CHECK(!c.use_mu_law, NSW_EINVAL, "fastgen: mu-law input encoding is not built yet");
+  NSW_CHECK(c.num_stages >= 1 && c.num_stages <= 16, NSW_EINVAL, "bad num_stages");
+  return NSW_OK;
 }
-int nsw_fastgen_encode_host(nsw_fastgen*, const float*, int32_t, int32_t, float*) {
-  NSW_FG_NOT_YET();
+
+// all host-side repacking of the TF-named tensors into the kernel's layouts
+int fg_pack(const nsw_wavenet_config& cfg, const TensorMap& tm, FgPacked& pk) {
+  const int L = cfg.num_layers, NPH = L + 2, O = cfg.out_width;
+  const int G = 2 * FM;
+  std::vector<const float*> Wd(L + 1), bd(L + 1), Wc(L + 1), bc(L + 1), Wr(L + 1), br(L + 1),
+      Ws(L + 1), bs(L + 1);
+  for (int i = 1; i <= L; ++i) {
+    const std::string li = std::to_string(i);
+    Wd[i] = tm.get("dilated_conv_" + li + "/W", 3 * FW * G);  // [1,3,512,512] (j, cin, cout)
+    bd[i] = tm.get("dilated_conv_" + li + "/biases", G);
+    Wc[i] = tm.get("mel_cond_" + li + "/W", FD * G);          // [1,1,256,512]
+    bc[i] = tm.get("mel_cond_" + li + "/biases", G);
+    Wr[i] = tm.get("res_" + li + "/W", FM * FW);              // [1,1,256,512] (k, cout)
+    br[i] = tm.get("res_" + li + "/biases", FW);
+    Ws[i] = tm.get("skip_" + li + "/W", FM * FS);             // [1,1,256,256]
+    bs[i] = tm.get("skip_" + li + "/biases", FS);
+    if (!Wd[i] || !bd[i] || !Wc[i] || !bc[i] || !Wr[i] || !br[i] || !Ws[i] || !bs[i]) return NSW_EMISSING;
+  }
+  const float* wcs = tm.get("conv_start/W", 3 * FW);     // [1,3,1,512]
+  const float* bcs = tm.get("conv_start/biases", FW);
+  const float* wss = tm.get("skip_start/W", FW * FS);    // [1,1,512,256]
+  const float* bss = tm.get("skip_start/biases", FS);
+  const float* wo1 = tm.get("out1/W", FS * FS);          // [1,1,256,256]
+  const float* bo1 = tm.get("out1/biases", FS);
+  const float* wco = tm.get("mel_cond_out1/W", FD * FS); // [1,1,256,256]
+  const float* bco = tm.get("mel_cond_out1/biases", FS);
+  const float* wo2 = tm.get("out2/W", FS * O);           // [1,1,256,O]
+  const float* bo2 = tm.get("out2/biases", O);
+  if (!wcs || !bcs || !wss || !bss || !wo1 || !bo1 || !wco || !bco || !wo2 || !bo2) return NSW_EMISSING;
+
+  pk.wcs.assign(wcs, wcs + 3 * FW);
+  pk.bcs.assign(bcs, bcs + FW);
+  pk.wo2t.assign((size_t)O * FS, 0.f);
+  for (int k = 0; k < FS; ++k)
+    for (int o = 0; o < O; ++o) pk.wo2t[(size_t)o * FS + k] = wo2[(size_t)k * O + o];
+  pk.bo2.assign(bo2, bo2 + O);
+
+  pk.dil.assign(L + 1, 1);
+  pk.hist_off.assign(L + 1, 0);
+  size_t off = 0;
+  for (int i = 1; i <= L; ++i) {
+    pk.dil[i] = 1 << ((i - 1) % cfg.num_stages);
+    pk.hist_off[i] = (int)off;
+    off += (size_t)(2 * pk.dil[i] + 1) * FW;
+  }
+  pk.hist_entries = off;
+
+  auto drow = [](int c, int j) { return (j < 2) ? 2 * c + j : FM + 2 * c + (j - 2); };
+  // M_i = W2_i Wr_{i-1} (fp64), folded bias fb_i = W2_i br_{i-1}
+  pk.blocks.assign((size_t)NPH * NC * BLOCK_FLOATS, 0.f);
+  const int N = L * G + FS;
+  pk.cond_w.assign((size_t)FD * N, 0.f);
+  pk.cond_b.assign(N, 0.f);
+  std::vector<double> Mi((size_t)G * FM), fb(G);
+  std::vector<double> W2T((size_t)G * FW);  // [cout][cin] of tap 2
+  for (int i = 1; i <= L; ++i) {
+    const float* W0 = Wd[i];
+    const float* W1 = Wd[i] + (size_t)FW * G;
+    const float* W2 = Wd[i] + (size_t)2 * FW * G;
+    if (i >= 2) {
+      for (int cin = 0; cin < FW; ++cin)
+        for (int co = 0; co < G; ++co) W2T[(size_t)co * FW + cin] = W2[(size_t)cin * G + co];
+      // Mi[co][k] = sum_cin W2[cin][co] * Wr_{i-1}[k][cin]
+      for (int co = 0; co < G; ++co) {
+        const double* w2r = &W2T[(size_t)co * FW];
+        for (int k = 0; k < FM; ++k) {
+          const float* wr = Wr[i - 1] + (size_t)k * FW;
+          double acc = 0.0;
+          for (int cin = 0; cin < FW; ++cin) acc += w2r[cin] * (double)wr[cin];
+          Mi[(size_t)co * FM + k] = acc;
+        }
+        double accb = 0.0;
+        for (int cin = 0; cin < FW; ++cin) accb += w2r[cin] * (double)br[i - 1][cin];
+        fb[co] = accb;
+      }
+    }
+    for (int c = 0; c < NC; ++c) {
+      float* blk = &pk.blocks[((size_t)(i - 1) * NC + c) * BLOCK_FLOATS];
+      for (int j = 0; j < 4; ++j) {
+        const int co = drow(c, j);
+        float* d = blk + OFF_D + j * 768;
+        for (int k = 0; k < FW; ++k) d[k] = W2[(size_t)k * G + co];
+        if (i >= 2)
+          for (int k = 0; k < FM; ++k) d[FW + k] = (float)Mi[(size_t)co * FM + k];
+        float* p = blk + OFF_P + j * 1024;
+        for (int k = 0; k < FW; ++k) {
+          p[k] = W0[(size_t)k * G + co];
+          p[FW + k] = W1[(size_t)k * G + co];
+        }
+        // hoisted conditioning column + every static bias of this d row
+        const int n = (i - 1) * G + 4 * c + j;
+        for (int k = 0; k < FD; ++k) pk.cond_w[(size_t)k * N + n] = Wc[i][(size_t)k * G + co];
+        pk.cond_b[n] = (float)((double)bd[i][co] + (double)bc[i][co] + (i >= 2 ? fb[co] : 0.0));
+      }
+      if (i >= 2) {
+        for (int j = 0; j < 4; ++j) {
+          const int lc = 4 * c + j;
+          float* lrow = blk + OFF_L + j * 256;
+          for (int k = 0; k < FM; ++k) lrow[k] = Wr[i - 1][(size_t)k * FW + lc];
+          blk[OFF_C + j] = br[i - 1][lc];
+        }
+        for (int j = 0; j < 2; ++j) {
+          const int sc = 2 * c + j;
+          float* srow = blk + OFF_S + j * 512;
+          for (int k = 0; k < FM; ++k) srow[k] = Ws[i - 1][(size_t)k * FS + sc];
+          blk[OFF_C + 4 + j] = bs[i - 1][sc];
+        }
+      } else {
+        for (int j = 0; j < 2; ++j) {  // skip_start on l_0 (wavenet.py:444)
+          const int sc = 2 * c + j;
+          float* srow = blk + OFF_S + j * 512;
+          for (int k = 0; k < FW; ++k) srow[k] = wss[(size_t)k * FS + sc];
+          blk[OFF_C + 4 + j] = bss[sc];
+        }
+      }
+    }
+  }
+  for (int c = 0; c < NC; ++c) {
+    // phase L+1: last skip accumulation (skip_L), then relu
+    float* blk = &pk.blocks[((size_t)L * NC + c) * BLOCK_FLOATS];
+    for (int j = 0; j < 2; ++j) {
+      const int sc = 2 * c + j;
+      float* srow = blk + OFF_S + j * 512;
+      for (int k = 0; k < FM; ++k) srow[k] = Ws[L][(size_t)k * FS + sc];
+      blk[OFF_C + 4 + j] = bs[L][sc];
+    }
+    // phase L+2: out1 rows live in the "M" part of d rows 0,1
+    float* blk2 = &pk.blocks[((size_t)(L + 1) * NC + c) * BLOCK_FLOATS];
+    for (int j = 0; j < 2; ++j) {
+      const int oc = 2 * c + j;
+      float* d = blk2 + OFF_D + j * 768;
+      for (int k = 0; k < FS; ++k) d[FW + k] = wo1[(size_t)k * FS + oc];
+      const int n = L * G + 2 * c + j;
+      for (int k = 0; k < FD; ++k) pk.cond_w[(size_t)k * N + n] = wco[(size_t)k * FS + oc];
+      pk.cond_b[n] = bo1[oc] + bco[oc];
+    }
+  }
+  return NSW_OK;
 }
-int nsw_fastgen_run_device(nsw_fastgen*, const float*, int32_t, int32_t, const float*, uint64_t,
-                           float*, float*, void*) { NSW_FG_NOT_YET(); }
-int nsw_fastgen_run_host(nsw_fastgen*, const float*, int32_t, int32_t, const float*, uint64_t,
-                         float*, float*) { NSW_FG_NOT_YET(); }
-int nsw_fastgen_last_timing(nsw_fastgen*, float*) { NSW_FG_NOT_YET(); }
+
+}  // namespace nsw_fg_host
+using namespace nsw_fg_host;
+
+// test hook: host-only repacking, so the packing can be checked without a GPU
+extern "C" int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tensors,
+                                     int32_t n, float* blocks, int64_t blocks_cap, float* cond_w,
+                                     float* cond_b, int64_t* sizes) {
+  NSW_CHECK(cfg && tensors && sizes, NSW_EINVAL, "null argument");
+  NSW_TRY(fg_check_cfg(*cfg));
+  TensorMap tm(tensors, n);
+  FgPacked pk;
+  NSW_TRY(fg_pack(*cfg, tm, pk));
+  const int N = cfg->num_layers * 2 * FM + FS;
+  sizes[0] = (int64_t)pk.blocks.size();
+  sizes[1] = BLOCK_FLOATS;
+  sizes[2] = NC;
+  sizes[3] = N;
+  if (blocks) {
+    NSW_CHECK(blocks_cap >= (int64_t)pk.blocks.size(), NSW_EINVAL, "blocks buffer too small");
+    memcpy(blocks, pk.blocks.data(), pk.blocks.size() * sizeof(float));
+  }
+  if (cond_w) memcpy(cond_w, pk.cond_w.data(), pk.cond_w.size() * sizeof(float));
+  if (cond_b) memcpy(cond_b, pk.cond_b.data(), pk.cond_b.size() * sizeof(float));
+  return NSW_OK;
+}
+
+extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tensor* tensors,
+                                  int32_t n, int32_t device, nsw_fastgen** out) {
+  NSW_CHECK(cfg && tensors && out, NSW_EINVAL, "nsw_fastgen_create: null argument");
+  NSW_TRY(fg_check_cfg(*cfg));
+  NSW_CUDA(cudaSetDevice(device));
+  int coop = 0, sms = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  NSW_CHECK(coop && sms >= NC, NSW_EINVAL,
+            "fastgen needs cooperative launch and >= %d SMs (device has %d)", NC, sms);
+  TensorMap tm(tensors, n);
+  FgPacked pk;
+  NSW_TRY(fg_pack(*cfg, tm, pk));
+  nsw_fastgen* h = new nsw_fastgen();
+  h->cfg = *cfg;
+  h->device = device;
+  h->L = cfg->num_layers;
+  h->NPH = h->L + 2;
+  h->O = cfg->out_width;
+  const int N = h->L * 2 * FM + FS;
+  h->NPL = N / 64;
+  h->hist_entries = pk.hist_entries;
+  int rc = NSW_OK;
+  const bool want_tc = cfg->engine == NSW_ENGINE_TC;
+  auto up = [&](DevBuf& b, const void* p, size_t bytes) {
+    if (rc == NSW_OK) rc = upload(b, p, bytes);
+  };
+  up(h->blocks, pk.blocks.data(), pk.blocks.size() * 4);
+  up(h->wcs, pk.wcs.data(), pk.wcs.size() * 4);
+  up(h->bcs, pk.bcs.data(), pk.bcs.size() * 4);
+  up(h->wo2t, pk.wo2t.data(), pk.wo2t.size() * 4);
+  up(h->bo2, pk.bo2.data(), pk.bo2.size() * 4);
+  up(h->cond_b, pk.cond_b.data(), pk.cond_b.size() * 4);
+  up(h->hist_off, pk.hist_off.data(), pk.hist_off.size() * 4);
+  up(h->dil, pk.dil.data(), pk.dil.size() * 4);
+  if (want_tc) {
+    std::vector<float> bt((size_t)N * FD);
+    for (int k = 0; k < FD; ++k)
+      for (int nn = 0; nn < N; ++nn) bt[(size_t)nn * FD + k] = pk.cond_w[(size_t)k * N + nn];
+    std::vector<__nv_bfloat16> hi(bt.size()), lo(bt.size());
+    split_bf16(bt.data(), bt.size(), hi.data(), lo.data());
+    up(h->cond_wt_hi, hi.data(), hi.size() * 2);
+    up(h->cond_wt_lo, lo.data(), lo.size() * 2);
+  } else {
+    up(h->cond_w, pk.cond_w.data(), pk.cond_w.size() * 4);
+  }
+  if (rc == NSW_OK)
+    rc = h->deconv.init(tm, "", cfg->num_mel, FD, cfg->num_deconv, cfg->deconv_filter,
+                        cfg->deconv_stride, cfg->upsample_act, want_tc);
+  if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * 256 * 8);
+  if (rc == NSW_OK) rc = h->hist.ensure(h->hist_entries * 8);
+  if (rc == NSW_OK) {
+    cudaError_t e = cudaFuncSetAttribute(fastgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(FgSmem));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) {
+      set_error("nsw_fastgen_create: %s", cudaGetErrorString(e));
+      rc = NSW_ECUDA;
+    }
+  }
+  if (rc != NSW_OK) {
+    nsw_fastgen_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return NSW_OK;
+}
+
+extern "C" void nsw_fastgen_destroy(nsw_fastgen* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+extern "C" int nsw_fastgen_encode_device(nsw_fastgen* h, const float* d_mel, int32_t B, int32_t F,
+                                         float* d_encoding, void* stream) {
+  NSW_CHECK(h && d_mel && d_encoding, NSW_EINVAL, "null argument");
+  NSW_CHECK(B >= 1 && F >= 1, NSW_EINVAL, "bad batch/frames");
+  NSW_CUDA(cudaSetDevice(h->device));
+  // fp32 engine for the encoder output the caller sees (fastgen.encode returns fp32)
+  return h->deconv.forward(d_mel, B, F, d_encoding, nullptr, nullptr, NSW_ENGINE_FFMA, h->scratch,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int nsw_fastgen_encode_host(nsw_fastgen* h, const float* mel, int32_t B, int32_t F,
+                                       float* encoding) {
+  NSW_CHECK(h && mel && encoding, NSW_EINVAL, "null argument");
+  NSW_CUDA(cudaSetDevice(h->device));
+  const size_t nm = (size_t)B * F * h->cfg.num_mel * 4;
+  const size_t ne = (size_t)B * F * h->deconv.total_stride * FD * 4;
+  NSW_TRY(h->stage_mel.ensure(nm));
+  NSW_TRY(h->stage_enc.ensure(ne));
+  NSW_CUDA(cudaMemcpyAsync(h->stage_mel.p, mel, nm, cudaMemcpyHostToDevice, h->own_stream));
+  NSW_TRY(nsw_fastgen_encode_device(h, h->stage_mel.as<float>(), B, F, h->stage_enc.as<float>(),
+                                    h->own_stream));
+  NSW_CUDA(cudaMemcpyAsync(encoding, h->stage_enc.p, ne, cudaMemcpyDeviceToHost, h->own_stream));
+  NSW_CUDA(cudaStreamSynchronize(h->own_stream));
+  return NSW_OK;
+}
+
+extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, int32_t B, int32_t T,
+                                      const float* d_teacher_force, uint64_t seed, float* d_audio,
+                                      float* d_out, void* stream) {
+  NSW_CHECK(h && d_encoding, NSW_EINVAL, "null argument");
+  NSW_CHECK(B >= 1 && T >= 1, NSW_EINVAL, "bad batch/length %d/%d", B, T);
+  NSW_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->NPL * 64;
+  NSW_TRY(h->cond.ensure((size_t)h->NPL * T * 64 * sizeof(float)));
+  const bool tc = h->cfg.engine == NSW_ENGINE_TC;
+  if (tc) NSW_TRY(h->enc_split.ensure((size_t)T * FD * 2 * sizeof(__nv_bfloat16)));
+  NSW_CUDA(cudaEventRecord(h->ev0, st));
+  for (int b = 0; b < B; ++b) {
+    const float* enc = d_encoding + (size_t)b * T * FD;
+    // hoisted mel conditioning for the whole clip: [T,256] x [256, L*512+256], NO centre trim
+    // (fastgen.py:157 feeds encoding[:, i] directly)
+    ConvGemm g;
+    g.nclips = 1; g.L = T; g.cin = FD; g.ntaps = 1; g.a_off = 0; g.mclip = T; g.N = N;
+    EpiParams e{};
+    e.mode = EPI_PLANES;
+    e.bias = h->cond_b.as<float>();
+    e.out_f32 = h->cond.as<float>();
+    if (tc) {
+      __nv_bfloat16* hi = h->enc_split.as<__nv_bfloat16>();
+      __nv_bfloat16* lo = hi + (size_t)T * FD;
+      const size_t ne = (size_t)T * FD;
+      split_bf16_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(enc, hi, lo, ne);
+      count_launch();
+      NSW_TRY(conv_gemm_tc(g, hi, lo, h->cond_wt_hi.as<__nv_bfloat16>(),
+                           h->cond_wt_lo.as<__nv_bfloat16>(), e, st));
+    } else {
+      NSW_TRY(conv_gemm_ffma(g, enc, h->cond_w.as<float>(), e, st));
+    }
+    // queues start at zero (fastgen.py:150): tags 0 never match, values are never read
+    NSW_CUDA(cudaMemsetAsync(h->xbuf.p, 0, h->xbuf.bytes, st));
+    NSW_CUDA(cudaMemsetAsync(h->hist.p, 0, h->hist.bytes, st));
+    FgParams P;
+    P.blocks = h->blocks.as<float>();
+    P.cond = h->cond.as<float>();
+    P.xbuf = h->xbuf.as<unsigned long long>();
+    P.hist = h->hist.as<unsigned long long>();
+    P.hist_off = h->hist_off.as<int>();
+    P.dil = h->dil.as<int>();
+    P.wcs = h->wcs.as<float>();
+    P.bcs = h->bcs.as<float>();
+    P.wo2t = h->wo2t.as<float>();
+    P.bo2 = h->bo2.as<float>();
+    P.tf = d_teacher_force ? d_teacher_force + (size_t)b * T : nullptr;
+    P.audio = d_audio ? d_audio + (size_t)b * T : nullptr;
+    P.out = d_out ? d_out + (size_t)b * T * h->O : nullptr;
+    P.T = T;
+    P.L = h->L;
+    P.O = h->O;
+    P.loss_type = h->cfg.loss_type;
+    P.seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)b;
+    P.quant = 65536.0f;
+    void* args[] = {&P};
+    NSW_CUDA(cudaLaunchCooperativeKernel((void*)fastgen_kernel, dim3(NC), dim3(NT), args,
+                                         sizeof(FgSmem), st));
+    count_launch();
+  }
+  NSW_CUDA(cudaEventRecord(h->ev1, st));
+  return NSW_OK;
+}
+
+extern "C" int nsw_fastgen_run_host(nsw_fastgen* h, const float* encoding, int32_t B, int32_t T,
+                                    const float* teacher_force, uint64_t seed, float* audio,
+                                    float* out) {
+  NSW_CHECK(h && encoding, NSW_EINVAL, "null argument");
+  NSW_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->own_stream;
+  const size_t ne = (size_t)B * T * FD * 4, nt = (size_t)B * T * 4, no = (size_t)B * T * h->O * 4;
+  NSW_TRY(h->stage_in.ensure(ne));
+  NSW_TRY(h->stage_audio.ensure(nt));
+  if (teacher_force) NSW_TRY(h->stage_tf.ensure(nt));
+  if (out) NSW_TRY(h->stage_out.ensure(no));
+  NSW_CUDA(cudaMemcpyAsync(h->stage_in.p, encoding, ne, cudaMemcpyHostToDevice, st));
+  if (teacher_force)
+    NSW_CUDA(cudaMemcpyAsync(h->stage_tf.p, teacher_force, nt, cudaMemcpyHostToDevice, st));
+  NSW_TRY(nsw_fastgen_run_device(h, h->stage_in.as<float>(), B, T,
+                                 teacher_force ? h->stage_tf.as<float>() : nullptr, seed,
+                                 h->stage_audio.as<float>(), out ? h->stage_out.as<float>() : nullptr,
+                                 st));
+  if (audio) NSW_CUDA(cudaMemcpyAsync(audio, h->stage_audio.p, nt, cudaMemcpyDeviceToHost, st));
+  if (out) NSW_CUDA(cudaMemcpyAsync(out, h->stage_out.p, no, cudaMemcpyDeviceToHost, st));
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("fastgen kernel failed: %s", cudaGetErrorString(e));
+    return NSW_ECUDA;
+  }
+  return NSW_OK;
+}
+
+extern "C" int nsw_fastgen_last_timing(nsw_fastgen* h, float* ms) {
+  NSW_CHECK(h && ms, NSW_EINVAL, "null argument");
+  NSW_CUDA(cudaEventSynchronize(h->ev1));
+  NSW_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return NSW_OK;
 }
