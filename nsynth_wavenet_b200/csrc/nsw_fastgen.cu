@@ -78,13 +78,10 @@ struct FgSmem {
   float wcs[3 * FW];
   float bcs[FW];
   float bo2[MAX_O];
-  float v[1024];        // [l_full (512) | g_full (256) | zeros (256)]
+  float v[2][1024];     // double-buffered [l_full (512) | g_full (256) | zeros (256)]
   float hv[1024];       // [l[t-2d] | l[t-d]] of the next layer
   float cnd[2][MAX_PH][4];
   float red_d[4][2];
-  float red_l[4];
-  float red_s[2];
-  float red_p[4][2];
   float pv[4];
   float outv[MAX_O];
   float gum[12];
@@ -182,6 +179,22 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b) {
   }
 }
 
+__device__ __forceinline__ uint4 ldv4(const unsigned long long* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.0f * sigmoid_fast(2.0f * x) - 1.0f; }
+
+// Thread roles inside a phase (after the critical section):
+//   warps 0-3 "slack group": skip accumulation + the two past taps of the NEXT layer
+//   warps 4-7 "poll group" : weight prefetch + receive the exchange for the NEXT phase
+// so the exchange latency overlaps the slack work.  lane 0 of warp w<4 owns residual channel
+// 4c+w (register ls), lane 0 of warp w<2 owns skip channel 2c+w (register sk).
 __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FgSmem& S = *reinterpret_cast<FgSmem*>(smem_raw);
@@ -194,7 +207,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   for (int i = tid; i < 3 * FW; i += NT) S.wcs[i] = P.wcs[i];
   for (int i = tid; i < FW; i += NT) S.bcs[i] = P.bcs[i];
   if (tid < O) S.bo2[tid] = P.bo2[tid];
-  for (int i = tid; i < 1024; i += NT) { S.v[i] = 0.f; S.hv[i] = 0.f; }
+  for (int i = tid; i < 1024; i += NT) { S.v[0][i] = 0.f; S.v[1][i] = 0.f; S.hv[i] = 0.f; }
   if (tid < 4) S.pv[tid] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < 3; ++s)
@@ -230,152 +243,161 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   }
 
   float x1 = 0.f, x2 = 0.f;  // inputs of the two previous steps (conv_start queues, rate 1)
-  float ls = 0.f;            // tid 4..7: my residual-stream channel 4c + tid-4
-  float sk = 0.f;            // tid 8,9: my skip channel 2c + tid-8
+  float ls = 0.f, sk = 0.f;
   long long q = 0;           // global phase counter -> weight ring slot / parity
+  int vb = 0;                // which S.v buffer the current phase reads
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
     const uint32_t tag = (uint32_t)t + 1u;
-    // ---------------- local phase: conv_start on the fed-back sample ----------------
+    // ---------------- conv_start on the fed-back sample (every CTA, full vector) ----------
     const float xin = S.xnext;  // written before the last __syncthreads of the previous step
     {
+      float* vc = S.v[vb];
       const int k0 = tid, k1 = tid + 256;
-      S.v[k0] = fmaf(S.wcs[2 * FW + k0], xin, fmaf(S.wcs[FW + k0], x1, fmaf(S.wcs[k0], x2, S.bcs[k0])));
-      S.v[k1] = fmaf(S.wcs[2 * FW + k1], xin, fmaf(S.wcs[FW + k1], x1, fmaf(S.wcs[k1], x2, S.bcs[k1])));
-      S.v[512 + tid] = 0.f;  // no previous gate output at phase 1
+      vc[k0] = fmaf(S.wcs[2 * FW + k0], xin, fmaf(S.wcs[FW + k0], x1, fmaf(S.wcs[k0], x2, S.bcs[k0])));
+      vc[k1] = fmaf(S.wcs[2 * FW + k1], xin, fmaf(S.wcs[FW + k1], x1, fmaf(S.wcs[k1], x2, S.bcs[k1])));
+      vc[512 + tid] = 0.f;  // no previous gate output at phase 1
     }
     x2 = x1;
     x1 = xin;
     float4 cnext = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < NPH) cnext = load_cond(t + 1, tid);  // consumed one step later
-    __syncthreads();
-    if (tid >= 4 && tid < 8) ls = S.v[4 * c + tid - 4];
     const float(*cnd)[4] = S.cnd[t & 1];
 
-    for (int ph = 1; ph <= NPH; ++ph, ++q) {
+    for (int ph = 1; ph <= NPH; ++ph, ++q, vb ^= 1) {
+      __syncthreads();  // S1: S.v[vb], S.pv, S.cnd complete; S.hv and S.v[vb^1] free
+      const float* v = S.v[vb];
+      if (ph == 1 && warp < 4 && lane == 0) ls = v[4 * c + warp];
       const int slot = (int)(q % 3);
       const uint32_t par = (uint32_t)((q / 3) & 1);
-      // ---- A. receive the previous phase's exchange ----
-      if (ph >= 2) {
-        if (ph <= L) {
-          const int d = P.dil[ph - 1];
-          const int R = 2 * d + 1;
-          const unsigned long long* hl = P.hist + P.hist_off[ph - 1] + (size_t)(t % R) * FW;
-          const float2 a = poll2(hl + 2 * tid, tag);
-          S.v[2 * tid] = a.x;
-          S.v[2 * tid + 1] = a.y;
-        }
-        if (tid < 128) {
-          const float2 g = poll2(P.xbuf + (size_t)(ph - 1) * 256 + 2 * tid, tag);
-          S.v[512 + 2 * tid] = g.x;
-          S.v[512 + 2 * tid + 1] = g.y;
-        }
-        __syncthreads();
-      }
-      // slot (q+2)%3 == (q-1)%3 was last read in phase q-1: free now
-      if (tid == 0) {
-        const long long qn = q + 2;
-        if (qn < (long long)T * NPH)
-          bulk_load(S.ring[qn % 3], my_blocks + (size_t)(qn % NPH) * phase_stride, BLOCK_BYTES,
-                    &S.mbar[qn % 3]);
+      const int nph = (ph == NPH) ? 1 : ph + 1;
+      const int nt = (ph == NPH) ? t + 1 : t;
+      const bool do_past = (nph <= L) && (nt < T);
+      // history of the next layer (already final: >= 1 step old), fetched early
+      uint4 hraw[4];
+      const unsigned long long* hp2 = nullptr;
+      const unsigned long long* hp1 = nullptr;
+      uint32_t tag2 = 0, tag1 = 0;
+      if (warp < 4 && do_past) {
+        const int d = P.dil[nph];
+        const int R = 2 * d + 1;
+        const unsigned long long* hb = P.hist + P.hist_off[nph];
+        if (nt - 2 * d >= 0) { hp2 = hb + (size_t)((nt - 2 * d) % R) * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
+        if (nt - d >= 0) { hp1 = hb + (size_t)((nt - d) % R) * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
+        hraw[0] = hp2 ? ldv4(hp2) : make_uint4(0, 0, 0, 0);
+        hraw[1] = hp2 ? ldv4(hp2 + 256) : make_uint4(0, 0, 0, 0);
+        hraw[2] = hp1 ? ldv4(hp1) : make_uint4(0, 0, 0, 0);
+        hraw[3] = hp1 ? ldv4(hp1 + 256) : make_uint4(0, 0, 0, 0);
       }
       fg_mbar_wait(&S.mbar[slot], par);
       const float* blk = S.ring[slot];
 
-      // ---- C. critical compute ----
+      // ---- critical compute ----
       if (ph != L + 1) {
         const int r = warp >> 1, half = warp & 1;
-        float a = dot_rows<3>(blk + OFF_D + r * 768 + half * 384, S.v + half * 384, lane);
+        float a = dot_rows<3>(blk + OFF_D + r * 768 + half * 384, v + half * 384, lane);
         float b = 0.f;
-        if (warp < 4 && ph <= L) b = dot_rows<2>(blk + OFF_L + warp * 256, S.v + 512, lane);
+        if (warp < 4 && ph <= L) b = dot_rows<2>(blk + OFF_L + warp * 256, v + 512, lane);
         warp_sum2(a, b);
         if (lane == 0) {
           S.red_d[r][half] = a;
-          if (warp < 4) S.red_l[warp] = b;
+          if (warp < 4 && ph <= L) {
+            // l_{ph-1}[4c+warp] = l_{ph-2}[..] + Wr_{ph-1} g_{ph-1} + br_{ph-1}; doubles as history
+            ls += b + blk[OFF_C + warp];
+            const int R = 2 * P.dil[ph] + 1;
+            publish(P.hist + P.hist_off[ph] + (size_t)(t % R) * FW + 4 * c + warp, ls, tag);
+          }
         }
       } else if (warp < 2) {
-        float a = warp_sum(dot_rows<2>(blk + OFF_S + warp * 512, S.v + 512, lane));
-        if (lane == 0) S.red_s[warp] = a;
+        const float a = warp_sum(dot_rows<2>(blk + OFF_S + warp * 512, v + 512, lane));
+        if (lane == 0) {
+          sk = fmaxf(sk + a + blk[OFF_C + 4 + warp], 0.f);  // relu(s) after the last skip
+          publish(P.xbuf + (size_t)ph * 256 + 2 * c + warp, sk, tag);
+        }
       }
-      __syncthreads();
-      // ---- D. finalize + publish ----
-      if (ph <= L) {
-        if (tid < 2) {
+      __syncthreads();  // S2
+      if (tid < 2) {
+        if (ph <= L) {
           const float ds = S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid] + S.pv[tid];
           const float dt = S.red_d[2 + tid][0] + S.red_d[2 + tid][1] + cnd[ph][2 + tid] + S.pv[2 + tid];
-          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid, sigmoidf_acc(ds) * tanhf(dt), tag);
-        } else if (tid >= 4 && tid < 8) {
-          ls += S.red_l[tid - 4] + blk[OFF_C + tid - 4];
-          const int d = P.dil[ph];
-          const int R = 2 * d + 1;
-          publish(P.hist + P.hist_off[ph] + (size_t)(t % R) * FW + 4 * c + tid - 4, ls, tag);
-        }
-      } else if (ph == L + 1) {
-        if (tid >= 8 && tid < 10) {
-          sk = fmaxf(sk + S.red_s[tid - 8] + blk[OFF_C + 4 + tid - 8], 0.f);
-          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid - 8, sk, tag);
-        }
-      } else {  // ph == L + 2: h = relu(out1 . relu(s) + cond_out1)
-        if (tid < 2) {
-          const float h = fmaxf(S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid], 0.f);
-          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid, h, tag);
+          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid, sigmoid_fast(ds) * tanh_fast(dt), tag);
+        } else if (ph == L + 2) {  // h = relu(out1 . relu(s) + cond_out1)
+          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid,
+                  fmaxf(S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid], 0.f), tag);
         }
       }
 
-      // ---- E. slack work while the exchange is in flight ----
-      // (i) skip accumulation of the previous layer (phase 1: skip_start on l_0)
-      if (ph <= L && warp < 2) {
-        float a = (ph == 1) ? dot_rows<4>(blk + OFF_S + warp * 512, S.v, lane)
-                            : dot_rows<2>(blk + OFF_S + warp * 512, S.v + 512, lane);
-        a = warp_sum(a);
-        if (lane == 0) S.red_s[warp] = a;
+      if (warp < 4) {
+        // ---------------- slack group ----------------
+        if (do_past) {
+          float2 f[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned long long* pp = (i < 2) ? hp2 : hp1;
+            const uint32_t tg = (i < 2) ? tag2 : tag1;
+            if (pp == nullptr) {
+              f[i] = make_float2(0.f, 0.f);
+            } else if (hraw[i].y == tg && hraw[i].w == tg) {
+              f[i] = make_float2(__uint_as_float(hraw[i].x), __uint_as_float(hraw[i].z));
+            } else {
+              f[i] = poll2(pp + ((i & 1) ? 256 : 0), tg);
+            }
+          }
+          S.hv[2 * tid] = f[0].x;         S.hv[2 * tid + 1] = f[0].y;
+          S.hv[256 + 2 * tid] = f[1].x;   S.hv[256 + 2 * tid + 1] = f[1].y;
+          S.hv[512 + 2 * tid] = f[2].x;   S.hv[512 + 2 * tid + 1] = f[2].y;
+          S.hv[768 + 2 * tid] = f[3].x;   S.hv[768 + 2 * tid + 1] = f[3].y;
+        }
+        if (ph == 1 && tid < NPH) {
+          float* dst = S.cnd[(t + 1) & 1][tid + 1];
+          dst[0] = cnext.x; dst[1] = cnext.y; dst[2] = cnext.z; dst[3] = cnext.w;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ph <= L && warp < 2) {
+          // skip accumulation of the previous layer (phase 1: skip_start on l_0)
+          float a = (ph == 1) ? dot_rows<4>(blk + OFF_S + warp * 512, v, lane)
+                              : dot_rows<2>(blk + OFF_S + warp * 512, v + 512, lane);
+          a = warp_sum(a) + blk[OFF_C + 4 + warp];
+          sk = (ph == 1) ? a : sk + a;
+        }
+        if (do_past) {
+          const int nslot = (int)((q + 1) % 3);
+          fg_mbar_wait(&S.mbar[nslot], (uint32_t)(((q + 1) / 3) & 1));
+          const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + warp * 1024, S.hv, lane));
+          if (lane == 0) S.pv[warp] = a;
+        } else if (lane == 0) {
+          S.pv[warp] = 0.f;
+        }
+      } else {
+        // ---------------- poll group ----------------
+        if (tid == 128) {
+          const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
+          if (qn < (long long)T * NPH)
+            bulk_load(S.ring[qn % 3], my_blocks + (size_t)(qn % NPH) * phase_stride, BLOCK_BYTES,
+                      &S.mbar[qn % 3]);
+        }
+        const int k = tid - 128;
+        float* vn = S.v[vb ^ 1];
+        if (ph + 1 <= L) {
+          // next phase needs l_{ph-1} (published into layer ph's history ring) ...
+          const int R = 2 * P.dil[ph] + 1;
+          const unsigned long long* hl = P.hist + P.hist_off[ph] + (size_t)(t % R) * FW;
+          const float2 a0 = poll2(hl + 2 * k, tag);
+          const float2 a1 = poll2(hl + 256 + 2 * k, tag);
+          vn[2 * k] = a0.x; vn[2 * k + 1] = a0.y;
+          vn[256 + 2 * k] = a1.x; vn[256 + 2 * k + 1] = a1.y;
+        }
+        // ... and g_ph / s' / h
+        const float2 g = poll2(P.xbuf + (size_t)ph * 256 + 2 * k, tag);
+        vn[512 + 2 * k] = g.x;
+        vn[512 + 2 * k + 1] = g.y;
       }
-      // (ii) past taps of the next phase's layer
-      const int nph = (ph == NPH) ? 1 : ph + 1;
-      const int nt = (ph == NPH) ? t + 1 : t;
-      const bool do_past = (nph <= L) && (nt < T);
-      if (do_past) {
-        const int d = P.dil[nph];
-        const int R = 2 * d + 1;
-        const unsigned long long* hb = P.hist + P.hist_off[nph];
-        float2 h2 = make_float2(0.f, 0.f), h1 = make_float2(0.f, 0.f);
-        if (nt - 2 * d >= 0) h2 = poll2(hb + (size_t)((nt - 2 * d) % R) * FW + 2 * tid, (uint32_t)(nt - 2 * d) + 1u);
-        if (nt - d >= 0) h1 = poll2(hb + (size_t)((nt - d) % R) * FW + 2 * tid, (uint32_t)(nt - d) + 1u);
-        S.hv[2 * tid] = h2.x;
-        S.hv[2 * tid + 1] = h2.y;
-        S.hv[512 + 2 * tid] = h1.x;
-        S.hv[512 + 2 * tid + 1] = h1.y;
-      }
-      if (ph == 1 && tid < NPH) {
-        float* dst = S.cnd[(t + 1) & 1][tid + 1];
-        dst[0] = cnext.x; dst[1] = cnext.y; dst[2] = cnext.z; dst[3] = cnext.w;
-      }
-      __syncthreads();
-      if (do_past) {
-        const int nslot = (int)((q + 1) % 3);
-        fg_mbar_wait(&S.mbar[nslot], (uint32_t)(((q + 1) / 3) & 1));
-        const float* nblk = S.ring[nslot];
-        const int r = warp >> 1, half = warp & 1;
-        float a = warp_sum(dot_rows<4>(nblk + OFF_P + r * 1024 + half * 512, S.hv + half * 512, lane));
-        if (lane == 0) S.red_p[r][half] = a;
-      }
-      if (ph <= L && tid >= 8 && tid < 10) {
-        const float add = S.red_s[tid - 8] + blk[OFF_C + 4 + tid - 8];
-        sk = (ph == 1) ? add : sk + add;
-      }
-      __syncthreads();
-      if (tid < 4) S.pv[tid] = do_past ? S.red_p[tid][0] + S.red_p[tid][1] : 0.f;
-      // S.pv is read after the next phase's __syncthreads
     }
 
     // ---------------- output head + sampler (every CTA, redundantly) ----------------
-    if (tid < 128) {
-      const float2 h = poll2(P.xbuf + (size_t)NPH * 256 + 2 * tid, tag);
-      S.v[512 + 2 * tid] = h.x;
-      S.v[512 + 2 * tid + 1] = h.y;
-    } else if (tid >= 224 && tid < 236) {
-      // noise for this step (Philox: counter = step, key = seed), off the critical path
+    if (tid >= 224 && tid < 236) {
+      // noise for this step (Philox: counter = step, key = seed)
       const int j = tid - 224;
       const uint4 rr = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)(j >> 2), 0x66617374u, 0u),
                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
@@ -390,11 +412,12 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
     }
     __syncthreads();
     {
+      const float* v = S.v[vb];  // g part holds h
       float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-      if (warp < O) o0 = dot_rows<2>(S.wo2t + warp * FM, S.v + 512, lane);
-      if (warp + 8 < O) o1 = dot_rows<2>(S.wo2t + (warp + 8) * FM, S.v + 512, lane);
-      if (warp + 16 < O) o2 = dot_rows<2>(S.wo2t + (warp + 16) * FM, S.v + 512, lane);
-      if (warp + 24 < O) o3 = dot_rows<2>(S.wo2t + (warp + 24) * FM, S.v + 512, lane);
+      if (warp < O) o0 = dot_rows<2>(S.wo2t + warp * FM, v + 512, lane);
+      if (warp + 8 < O) o1 = dot_rows<2>(S.wo2t + (warp + 8) * FM, v + 512, lane);
+      if (warp + 16 < O) o2 = dot_rows<2>(S.wo2t + (warp + 16) * FM, v + 512, lane);
+      if (warp + 24 < O) o3 = dot_rows<2>(S.wo2t + (warp + 24) * FM, v + 512, lane);
       warp_sum2(o0, o1);
       warp_sum2(o2, o3);
       if (lane == 0) {
