@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace nsw {
 namespace {
@@ -60,6 +61,7 @@ struct FgParams {
   unsigned long long* hist;     // tagged l history rings
   const int* hist_off;          // [L+1] entry offset of layer ph's ring
   const int* dil;               // [L+1]
+  long long* dbg;               // optional [NC][8] cycle counters (NULL = off)
   const float* wcs;             // conv_start W [3][512]
   const float* bcs;             // [512]
   const float* wo2t;            // out2 W transposed [O][256]
@@ -99,7 +101,7 @@ __device__ __forceinline__ float2 poll2(const unsigned long long* p, uint32_t ta
   long long t0 = 0;
   int spins = 0;
   for (;;) {
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
                  : "l"(p)
                  : "memory");
@@ -113,7 +115,7 @@ __device__ __forceinline__ float2 poll2(const unsigned long long* p, uint32_t ta
   return make_float2(__uint_as_float(a), __uint_as_float(c));
 }
 __device__ __forceinline__ void publish(unsigned long long* p, float v, uint32_t tag) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)),
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)),
                "r"(tag)
                : "memory");
 }
@@ -181,7 +183,7 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b) {
 
 __device__ __forceinline__ uint4 ldv4(const unsigned long long* p) {
   uint4 r;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p)
                : "memory");
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   float ls = 0.f, sk = 0.f;
   long long q = 0;           // global phase counter -> weight ring slot / parity
   int vb = 0;                // which S.v buffer the current phase reads
+  long long tEnd = 0;
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
@@ -267,6 +270,11 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
 
     for (int ph = 1; ph <= NPH; ++ph, ++q, vb ^= 1) {
       __syncthreads();  // S1: S.v[vb], S.pv, S.cnd complete; S.hv and S.v[vb^1] free
+      long long tS1 = 0, tS2 = 0, tPub = 0;
+      if (P.dbg) {
+        tS1 = clock64();
+        if (tid == 0 && tEnd) P.dbg[8 * c + 4] += tS1 - tEnd;  // wait at S1 after my slack
+      }
       const float* v = S.v[vb];
       if (ph == 1 && warp < 4 && lane == 0) ls = v[4 * c + warp];
       const int slot = (int)(q % 3);
@@ -316,7 +324,12 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
           publish(P.xbuf + (size_t)ph * 256 + 2 * c + warp, sk, tag);
         }
       }
+      if (P.dbg && tid == 0) P.dbg[8 * c + 0] += clock64() - tS1;  // hist issue + ring wait + critical
       __syncthreads();  // S2
+      if (P.dbg) {
+        tS2 = clock64();
+        if (tid == 0) P.dbg[8 * c + 1] += tS2 - tS1;
+      }
       if (tid < 2) {
         if (ph <= L) {
           const float ds = S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid] + S.pv[tid];
@@ -328,6 +341,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         }
       }
 
+      if (P.dbg && tid == 0) { tPub = clock64(); P.dbg[8 * c + 2] += tPub - tS2; }  // finalize + publish
       if (warp < 4) {
         // ---------------- slack group ----------------
         if (do_past) {
@@ -379,20 +393,42 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         }
         const int k = tid - 128;
         float* vn = S.v[vb ^ 1];
-        if (ph + 1 <= L) {
-          // next phase needs l_{ph-1} (published into layer ph's history ring) ...
+        // next phase needs g_ph / s' / h, and (layers only) l_{ph-1} from layer ph's history
+        // ring; the three 16-byte words are polled together so one L2 round trip covers all
+        const bool need_l = (ph + 1 <= L);
+        const unsigned long long* pg = P.xbuf + (size_t)ph * 256 + 2 * k;
+        const unsigned long long* pl0 = pg;
+        if (need_l) {
           const int R = 2 * P.dil[ph] + 1;
-          const unsigned long long* hl = P.hist + P.hist_off[ph] + (size_t)(t % R) * FW;
-          const float2 a0 = poll2(hl + 2 * k, tag);
-          const float2 a1 = poll2(hl + 256 + 2 * k, tag);
-          vn[2 * k] = a0.x; vn[2 * k + 1] = a0.y;
-          vn[256 + 2 * k] = a1.x; vn[256 + 2 * k + 1] = a1.y;
+          pl0 = P.hist + P.hist_off[ph] + (size_t)(t % R) * FW + 2 * k;
         }
-        // ... and g_ph / s' / h
-        const float2 g = poll2(P.xbuf + (size_t)ph * 256 + 2 * k, tag);
-        vn[512 + 2 * k] = g.x;
-        vn[512 + 2 * k + 1] = g.y;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
+        bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
+        long long w0 = 0;
+        int spins = 0;
+        for (;;) {
+          if (!ok0) r0 = ldv4(pl0);
+          if (!ok1) r1 = ldv4(pl0 + 256);
+          if (!ok2) r2 = ldv4(pg);
+          ok0 = ok0 || (r0.y == tag && r0.w == tag);
+          ok1 = ok1 || (r1.y == tag && r1.w == tag);
+          ok2 = ok2 || (r2.y == tag && r2.w == tag);
+          if (ok0 && ok1 && ok2) break;
+          if (++spins == 4096) {
+            spins = 0;
+            if (w0 == 0) w0 = clock64();
+            else if (clock64() - w0 > FG_WATCHDOG) fg_die("exchange wait");
+          }
+        }
+        if (need_l) {
+          vn[2 * k] = __uint_as_float(r0.x); vn[2 * k + 1] = __uint_as_float(r0.z);
+          vn[256 + 2 * k] = __uint_as_float(r1.x); vn[256 + 2 * k + 1] = __uint_as_float(r1.z);
+        }
+        vn[512 + 2 * k] = __uint_as_float(r2.x);
+        vn[512 + 2 * k + 1] = __uint_as_float(r2.z);
+        if (P.dbg && tid == 128) P.dbg[8 * c + 5] += clock64() - tS2;
       }
+      if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[8 * c + 3] += now - tPub; tEnd = now; }
     }
 
     // ---------------- output head + sampler (every CTA, redundantly) ----------------
@@ -455,6 +491,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
     }
     if (c == 0 && P.out && tid < O) P.out[(size_t)t * O + tid] = S.outv[tid];
     __syncthreads();
+    if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[8 * c + 6] += now - tEnd; tEnd = now; }
   }
 }
 
@@ -480,6 +517,7 @@ struct nsw_fastgen {
   int L = 0, NPH = 0, O = 0, NPL = 0;  // NPL: cond planes of 64 columns
   DeconvStack deconv;
   DevBuf blocks, wcs, bcs, wo2t, bo2, cond_w, cond_wt_hi, cond_wt_lo, cond_b, hist_off, dil;
+  DevBuf dbg;
   DevBuf xbuf, hist, cond, enc_split, scratch, stage_in, stage_tf, stage_audio, stage_out,
       stage_mel, stage_enc;
   size_t hist_entries = 0;
@@ -826,6 +864,13 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     P.hist = h->hist.as<unsigned long long>();
     P.hist_off = h->hist_off.as<int>();
     P.dil = h->dil.as<int>();
+    P.dbg = nullptr;
+    const bool want_dbg = getenv("NSW_FASTGEN_DEBUG") != nullptr;
+    if (want_dbg) {
+      NSW_TRY(h->dbg.ensure(128 * 8 * sizeof(long long)));
+      NSW_CUDA(cudaMemsetAsync(h->dbg.p, 0, 128 * 8 * sizeof(long long), st));
+      P.dbg = h->dbg.as<long long>();
+    }
     P.wcs = h->wcs.as<float>();
     P.bcs = h->bcs.as<float>();
     P.wo2t = h->wo2t.as<float>();
@@ -843,6 +888,19 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     NSW_CUDA(cudaLaunchCooperativeKernel((void*)fastgen_kernel, dim3(NC), dim3(NT), args,
                                          sizeof(FgSmem), st));
     count_launch();
+    if (want_dbg) {
+      std::vector<long long> host(128 * 8);
+      NSW_CUDA(cudaStreamSynchronize(st));
+      NSW_CUDA(cudaMemcpy(host.data(), h->dbg.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      const double phases = (double)T * (h->L + 2);
+      const char* names[7] = {"crit", "crit+S2", "finalize+publish", "slack", "S1 wait", "poll(after S2)", "head"};
+      for (int cta : {0, 1, 64, 127}) {
+        fprintf(stderr, "[nsw fastgen dbg] cta %3d cycles/phase:", cta);
+        for (int i = 0; i < 7; ++i)
+          fprintf(stderr, " %s=%.0f", names[i], (double)host[8 * cta + i] / (i == 6 ? (double)T : phases));
+        fprintf(stderr, "\n");
+      }
+    }
   }
   NSW_CUDA(cudaEventRecord(h->ev1, st));
   return NSW_OK;

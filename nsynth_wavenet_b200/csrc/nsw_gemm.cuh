@@ -55,6 +55,14 @@ bool conv_gemm_tc_supported(const ConvGemm& g);
 // host-side split of fp32 into bf16 hi + bf16 lo (round-to-nearest each)
 void split_bf16(const float* src, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
 
+// ---- tcgen05 fused IAF residual layer (nsw_iaf_layer_tc.cu); maps are 128-byte CUtensorMaps ----
+int layer_tc_make_act_map(void* map_out, const __nv_bfloat16* base, int B, int T);
+int layer_tc_make_weight_map(void* map_out, const __nv_bfloat16* base, int rows, int k);
+int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
+                    const void* map_wrh, const void* map_wrl, const float* cond, const float* l_in,
+                    float* l_out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const float* br, int T,
+                    int rows, int dil, int layer, int num_sms, cudaStream_t stream);
+
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
 struct DeconvLayer {
   DeconvGeom g;

@@ -71,7 +71,7 @@ __global__ void iaf_noise_kernel(float* __restrict__ z, size_t n, uint64_t seed,
 __global__ void __launch_bounds__(256)
 iaf_start_conv_kernel(const float* __restrict__ x, float* __restrict__ l,
                       const float* __restrict__ w /*[3][64]*/, const float* __restrict__ b, int T,
-                      size_t rows) {
+                      size_t rows, __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (row, c4)
   const size_t row = idx >> 4;
   if (row >= rows) return;
@@ -90,6 +90,17 @@ iaf_start_conv_kernel(const float* __restrict__ x, float* __restrict__ l,
   o.z = fmaf(w2.z, x1, fmaf(w1.z, x2, fmaf(w0.z, x3, bb.z)));
   o.w = fmaf(w2.w, x1, fmaf(w1.w, x2, fmaf(w0.w, x3, bb.w)));
   *reinterpret_cast<float4*>(l + row * C + c) = o;
+  if (l_hi) {  // split-bf16 copy for the tcgen05 layer kernel's MMA operand
+    const float f[4] = {o.x, o.y, o.z, o.w};
+    __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hi[i] = __float2bfloat16_rn(f[i]);
+      lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+    }
+    *reinterpret_cast<uint2*>(l_hi + row * C + c) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(l_lo + row * C + c) = *reinterpret_cast<uint2*>(lo);
+  }
 }
 
 // ------------------------------ residual layer ------------------------------
@@ -373,6 +384,11 @@ struct FlowWeights {
   DevBuf Wc, bc;            // cond projection B: fp32 [256][(L+1)*64]; bias [(L+1)*64]
   DevBuf Wct_hi, Wct_lo;    // bf16 [(L+1)*64][256]
   DevBuf W1, wm, ws;        // [64][64], [64], [64]
+  // tcgen05 layer engine: K-major bf16 hi/lo weights + their tensor maps
+  DevBuf WdT_hi, WdT_lo;    // [L][3][64 pos][64 cin]
+  DevBuf WrT_hi, WrT_lo;    // [L][64 c][32 j]
+  DevBuf br_nat;            // [L][64] natural channel order
+  alignas(64) unsigned char map_wdh[128], map_wdl[128], map_wrh[128], map_wrl[128];
   float bm = 0.f, bs = 0.f;
   int deconv_index = 0;     // which DeconvStack feeds this flow
 };
@@ -387,7 +403,9 @@ struct nsw_iaf {
   // workspace
   int ws_B = 0, ws_F = 0;
   DevBuf mel, mel_en, mel_en_split, cond, l0, l1, x, z, mean_tot, scale_tot, log_scale_tot,
-      deconv_scratch;
+      deconv_scratch, ls0, ls1;  // ls*: bf16 hi plane then lo plane of l0 / l1 (tc2 engine)
+  alignas(64) unsigned char map_act[2][2][128];  // [buffer][hi, lo]
+  int map_B = 0, map_T = 0;
   // debug tap
   int tap_flow = -1, tap_layer = -1;
   float* tap_dst = nullptr;
@@ -464,6 +482,36 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
   NSW_TRY(upload(fw.W1, w1, C * C * sizeof(float)));
   NSW_TRY(upload(fw.wm, wm, C * sizeof(float)));
   NSW_TRY(upload(fw.ws, wsc, C * sizeof(float)));
+  if (cfg.engine == NSW_ENGINE_TC2) {
+    std::vector<float> wdt((size_t)L * 3 * C * C), wrt((size_t)L * C * HALF), brn((size_t)L * C);
+    for (int i = 0; i < L; ++i) {
+      const std::string li = std::to_string(i + 1);
+      const float* wd = tm.get(p + "/dilated_conv_" + li + "/W", 3 * C * C);
+      const float* wr = tm.get(p + "/res_" + li + "/W", HALF * C);
+      const float* brr = tm.get(p + "/res_" + li + "/biases", C);
+      for (int tap = 0; tap < 3; ++tap)
+        for (int pos = 0; pos < C; ++pos)
+          for (int k = 0; k < C; ++k)
+            wdt[(((size_t)i * 3 + tap) * C + pos) * C + k] =
+                wd[((size_t)tap * C + k) * C + gate_pos_to_channel(pos)];
+      for (int c = 0; c < C; ++c)
+        for (int j = 0; j < HALF; ++j) wrt[((size_t)i * C + c) * HALF + j] = wr[(size_t)j * C + c];
+      for (int c = 0; c < C; ++c) brn[(size_t)i * C + c] = brr[c];
+    }
+    std::vector<__nv_bfloat16> hi(wdt.size()), lo(wdt.size());
+    split_bf16(wdt.data(), wdt.size(), hi.data(), lo.data());
+    NSW_TRY(upload(fw.WdT_hi, hi.data(), hi.size() * 2));
+    NSW_TRY(upload(fw.WdT_lo, lo.data(), lo.size() * 2));
+    hi.resize(wrt.size()); lo.resize(wrt.size());
+    split_bf16(wrt.data(), wrt.size(), hi.data(), lo.data());
+    NSW_TRY(upload(fw.WrT_hi, hi.data(), hi.size() * 2));
+    NSW_TRY(upload(fw.WrT_lo, lo.data(), lo.size() * 2));
+    NSW_TRY(upload(fw.br_nat, brn.data(), brn.size() * 4));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdh, fw.WdT_hi.as<__nv_bfloat16>(), L * 3 * C, C));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdl, fw.WdT_lo.as<__nv_bfloat16>(), L * 3 * C, C));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wrh, fw.WrT_hi.as<__nv_bfloat16>(), L * C, HALF));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wrl, fw.WrT_lo.as<__nv_bfloat16>(), L * C, HALF));
+  }
   if (want_tc) {
     std::vector<float> bt((size_t)NP * D);
     for (int k = 0; k < D; ++k)
@@ -505,7 +553,7 @@ extern "C" int nsw_iaf_create(const nsw_iaf_config* cfg, const nsw_tensor* tenso
   h->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
-  const bool want_tc = cfg->engine == NSW_ENGINE_TC;
+  const bool want_tc = cfg->engine >= NSW_ENGINE_TC;
   TensorMap tm(tensors, n);
   int rc = NSW_OK;
   const int n_stacks = cfg->share_deconv ? 1 : cfg->num_flows;
@@ -558,13 +606,18 @@ static int ensure_workspace(nsw_iaf* h, int B, int F) {
   const size_t Lc = (size_t)nF * iaf_total_stride(h->cfg);
   const size_t rows = (size_t)nB * T;
   NSW_TRY(h->mel.ensure((size_t)nB * nF * h->cfg.num_mel * sizeof(float)));
-  if (h->cfg.engine == NSW_ENGINE_TC)
+  if (h->cfg.engine >= NSW_ENGINE_TC)
     NSW_TRY(h->mel_en_split.ensure((size_t)nB * Lc * D * 2 * sizeof(__nv_bfloat16)));
   else
     NSW_TRY(h->mel_en.ensure((size_t)nB * Lc * D * sizeof(float)));
   NSW_TRY(h->cond.ensure((size_t)(h->max_layers + 1) * rows * C * sizeof(float)));
   NSW_TRY(h->l0.ensure(rows * C * sizeof(float)));
   NSW_TRY(h->l1.ensure(rows * C * sizeof(float)));
+  if (h->cfg.engine == NSW_ENGINE_TC2) {
+    NSW_TRY(h->ls0.ensure(rows * C * 2 * sizeof(__nv_bfloat16)));
+    NSW_TRY(h->ls1.ensure(rows * C * 2 * sizeof(__nv_bfloat16)));
+    h->map_B = h->map_T = 0;  // buffers may have moved
+  }
   NSW_TRY(h->x.ensure(rows * sizeof(float)));
   NSW_TRY(h->z.ensure(rows * sizeof(float)));
   NSW_TRY(h->mean_tot.ensure(rows * sizeof(float)));
@@ -578,7 +631,7 @@ static int ensure_workspace(nsw_iaf* h, int B, int F) {
 extern "C" size_t nsw_iaf_workspace_bytes(const nsw_iaf* h) {
   if (!h) return 0;
   return h->mel.bytes + h->mel_en.bytes + h->mel_en_split.bytes + h->cond.bytes + h->l0.bytes +
-         h->l1.bytes + h->x.bytes + h->z.bytes + h->mean_tot.bytes + h->scale_tot.bytes +
+         h->l1.bytes + h->ls0.bytes + h->ls1.bytes + h->x.bytes + h->z.bytes + h->mean_tot.bytes + h->scale_tot.bytes +
          h->log_scale_tot.bytes + h->deconv_scratch.bytes;
 }
 
@@ -645,10 +698,25 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     count_launch();
   }
 
-  const bool tc = cfg.engine == NSW_ENGINE_TC;
+  const bool tc = cfg.engine >= NSW_ENGINE_TC;
+  const bool tc_layers = cfg.engine == NSW_ENGINE_TC2;
   __nv_bfloat16* me_hi = tc ? h->mel_en_split.as<__nv_bfloat16>() : nullptr;
   __nv_bfloat16* me_lo = tc ? me_hi + (size_t)B * Lc * D : nullptr;
   float* l_buf[2] = {h->l0.as<float>(), h->l1.as<float>()};
+  __nv_bfloat16* ls_hi[2] = {nullptr, nullptr};
+  __nv_bfloat16* ls_lo[2] = {nullptr, nullptr};
+  if (tc_layers) {
+    ls_hi[0] = h->ls0.as<__nv_bfloat16>(); ls_lo[0] = ls_hi[0] + rows * C;
+    ls_hi[1] = h->ls1.as<__nv_bfloat16>(); ls_lo[1] = ls_hi[1] + rows * C;
+    if (h->map_B != B || h->map_T != T) {
+      for (int b = 0; b < 2; ++b) {
+        NSW_TRY(layer_tc_make_act_map(h->map_act[b][0], ls_hi[b], B, T));
+        NSW_TRY(layer_tc_make_act_map(h->map_act[b][1], ls_lo[b], B, T));
+      }
+      h->map_B = B;
+      h->map_T = T;
+    }
+  }
   const int grid_lk = std::min(n_tiles, 2 * h->num_sms);
 
   for (int f = 0; f < cfg.num_flows; ++f) {
@@ -658,7 +726,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       rec(0);
       NSW_TRY(h->deconvs[fw.deconv_index].forward(h->mel.as<float>(), B, F,
                                                   tc ? nullptr : h->mel_en.as<float>(), me_hi,
-                                                  me_lo, cfg.engine, h->deconv_scratch, st));
+                                                  me_lo, tc ? NSW_ENGINE_TC : NSW_ENGINE_FFMA, h->deconv_scratch, st));
       rec(1);
       lap(0, 0, 1);
     }
@@ -684,7 +752,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     rec(0);
     const float* x_cur = (f == 0) ? h->z.as<float>() : h->x.as<float>();
     iaf_start_conv_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256, 0, st>>>(
-        x_cur, l_buf[0], fw.start_w.as<float>(), fw.start_b.as<float>(), T, rows);
+        x_cur, l_buf[0], fw.start_w.as<float>(), fw.start_b.as<float>(), T, rows, ls_hi[0], ls_lo[0]);
     count_launch();
     rec(1);
     lap(3, 0, 1);
@@ -695,11 +763,19 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
                                cudaMemcpyDeviceToDevice, st));
     for (int i = 0; i < fw.L; ++i) {
       const int dil = 1 << (i % cfg.num_stages);
+      if (tc_layers) {
+        NSW_TRY(layer_tc_launch(h->map_act[cur][0], h->map_act[cur][1], fw.map_wdh, fw.map_wdl,
+                                fw.map_wrh, fw.map_wrl, h->cond.as<float>() + (size_t)i * rows * C,
+                                l_buf[cur], l_buf[cur ^ 1], ls_hi[cur ^ 1], ls_lo[cur ^ 1],
+                                fw.br_nat.as<float>() + (size_t)i * C, T, (int)rows, dil, i,
+                                h->num_sms, st));
+      } else {
       iaf_layer_kernel<<<grid_lk, LK_THREADS, sizeof(LayerSmem), st>>>(
           l_buf[cur], h->cond.as<float>() + (size_t)i * rows * C, l_buf[cur ^ 1],
           fw.Wd.as<float>() + (size_t)i * 3 * C * C, fw.Wr.as<float>() + (size_t)i * HALF * C,
           fw.br.as<float>() + (size_t)i * C, T, dil, n_tiles);
       count_launch();
+      }
       cur ^= 1;
       if (h->tap_flow == f && h->tap_layer == i + 1)
         NSW_CUDA(cudaMemcpyAsync(h->tap_dst, l_buf[cur], rows * C * sizeof(float),

@@ -1,0 +1,486 @@
+// tcgen05 version of the fused IAF residual layer (parallel_wavenet.py:227-254):
+//   D1[128 x 64] = sum_tap L[t-(2-tap)d][128 x 64] . Wd_tap[64 x 64]      (split bf16, fp32 acc)
+//   g = sigmoid(D1[:, even] + cond[:, even]) * tanh(D1[:, odd] + cond[:, odd])   (gate-interleaved)
+//   D2[128 x 64] = g[128 x 32] . Wr[32 x 64]                                (A operand from TMEM)
+//   l_new = l + br + D2  ->  fp32 stream + bf16 hi/lo planes for the next layer's MMA operand
+//
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer: weights once, then per 128-row tile the six [128 x 64] bf16
+//               operand tiles (3 taps x {lo, hi}) through an 8-stage ring (SWIZZLE_128B)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; MMA2 of tile i is queued
+//               behind MMA1 of tile i+1 so the tensor pipe never waits for the gate epilogue
+//   warps 2-5   epilogue warpgroup 0 (even local tiles), warps 6-9 warpgroup 1 (odd tiles):
+//               tcgen05.ld D1 -> gate -> tcgen05.st g (bf16 hi|lo) -> ... -> tcgen05.ld D2 ->
+//               residual add -> global stores
+// TMEM (512 columns): D1[2] 0..127, D2[2] 128..255, G[2] 256..319 (16 cols hi + 16 cols lo each).
+#include "nsw_gemm.cuh"
+
+#include <cuda.h>
+
+namespace nsw {
+
+namespace {
+
+constexpr int C = 64, HALF = 32;
+constexpr int LT_BM = 128;
+constexpr int LT_STAGES = 8;
+constexpr int LT_THREADS = 320;
+constexpr uint32_t A_TILE_BYTES = LT_BM * 64 * 2;   // 16 KB
+constexpr uint32_t WD_TILE_BYTES = 64 * 64 * 2;     // 8 KB per tap per plane
+constexpr uint32_t WR_TILE_BYTES = 64 * 32 * 2;     // 4 KB per plane
+constexpr uint32_t W_BYTES = 6 * WD_TILE_BYTES + 2 * WR_TILE_BYTES;  // 56 KB
+constexpr long long LT_WATCHDOG = 4000000000ll;
+
+struct LtBars {
+  uint64_t wfull;
+  uint64_t full[LT_STAGES];
+  uint64_t empty[LT_STAGES];
+  uint64_t d1_full[2], d1_empty[2], g_full[2], d2_full[2], d2_empty[2];
+  uint32_t tmem_base;
+};
+// smem: [Wd_hi 3x8K][Wd_lo 3x8K][Wr_hi 4K][Wr_lo 4K][A ring 8x16K][bars]
+constexpr uint32_t OFF_WDH = 0, OFF_WDL = 3 * WD_TILE_BYTES, OFF_WRH = 6 * WD_TILE_BYTES,
+                   OFF_WRL = OFF_WRH + WR_TILE_BYTES, OFF_A = OFF_WRL + WR_TILE_BYTES,
+                   OFF_BARS = OFF_A + LT_STAGES * A_TILE_BYTES;
+constexpr size_t LT_SMEM_BYTES = OFF_BARS + sizeof(LtBars) + 1024;
+
+__device__ __forceinline__ void lt_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void lt_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void lt_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lt_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins == 2048) {
+      spins = 0;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > LT_WATCHDOG) {
+        printf("nsw iaf_layer_tc: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void lt_tma_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                          int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void lt_tma_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                          int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major smem matrix descriptors (sm_100 UMMA): 128 B rows / SWIZZLE_128B, 64 B rows / SWIZZLE_64B
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+// D=f32, A=B=bf16, K-major, M=128, N=64
+__device__ __forceinline__ uint32_t lt_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc,
+                                       uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void lt_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float sig_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x (low 16 bits) = a
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct LayerTcParams {
+  const float* cond;   // [rows][64] gate-interleaved, biases folded
+  const float* l_in;   // [rows][64] fp32
+  float* l_out;        // [rows][64] fp32
+  __nv_bfloat16* out_hi;  // [rows][64]
+  __nv_bfloat16* out_lo;
+  const float* br;     // [64] natural order
+  int dil, tiles_per_clip, n_tiles, layer;
+};
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_constant__ CUtensorMap map_ll,
+                    const __grid_constant__ CUtensorMap map_wdh, const __grid_constant__ CUtensorMap map_wdl,
+                    const __grid_constant__ CUtensorMap map_wrh, const __grid_constant__ CUtensorMap map_wrl,
+                    LayerTcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  LtBars* B = reinterpret_cast<LtBars*>(smem + OFF_BARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    lt_mbar_init(&B->wfull, 1);
+    for (int s = 0; s < LT_STAGES; ++s) { lt_mbar_init(&B->full[s], 1); lt_mbar_init(&B->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      lt_mbar_init(&B->d1_full[b], 1);
+      lt_mbar_init(&B->d1_empty[b], 4);
+      lt_mbar_init(&B->g_full[b], 4);
+      lt_mbar_init(&B->d2_full[b], 1);
+      lt_mbar_init(&B->d2_empty[b], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&B->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = B->tmem_base;
+  const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      lt_expect_tx(&B->wfull, W_BYTES);
+      for (int tap = 0; tap < 3; ++tap) {
+        lt_tma_2d(sbase + OFF_WDH + tap * WD_TILE_BYTES, &map_wdh, &B->wfull, 0, (p.layer * 3 + tap) * 64);
+        lt_tma_2d(sbase + OFF_WDL + tap * WD_TILE_BYTES, &map_wdl, &B->wfull, 0, (p.layer * 3 + tap) * 64);
+      }
+      lt_tma_2d(sbase + OFF_WRH, &map_wrh, &B->wfull, 0, p.layer * 64);
+      lt_tma_2d(sbase + OFF_WRL, &map_wrl, &B->wfull, 0, p.layer * 64);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int clip = tile / p.tiles_per_clip;
+        const int t0 = (tile - clip * p.tiles_per_clip) * LT_BM;
+        for (int tap = 0; tap < 3; ++tap) {
+          const int trow = t0 - (2 - tap) * p.dil;  // negative rows: TMA zero fill = causal padding
+          for (int pl = 0; pl < 2; ++pl) {          // lo plane first, then hi
+            lt_wait(&B->empty[stage], phase ^ 1);
+            lt_expect_tx(&B->full[stage], A_TILE_BYTES);
+            lt_tma_3d(sbase + OFF_A + stage * A_TILE_BYTES, pl == 0 ? &map_ll : &map_lh,
+                      &B->full[stage], 0, trow, clip);
+            if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    const uint32_t idesc = lt_idesc();
+    lt_wait(&B->wfull, 0);
+    fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    auto mma2 = [&](int j) {
+      const int b = j & 1;
+      const uint32_t u = (uint32_t)(j >> 1);
+      lt_wait(&B->g_full[b], u & 1);
+      lt_wait(&B->d2_empty[b], (u & 1) ^ 1);
+      fence_after();
+      if (lane == 0) {
+        const uint32_t d2 = tmem + 128 + b * 64;
+        const uint32_t g_hi = tmem + 256 + b * 32, g_lo = g_hi + 16;
+        const uint64_t wrh = desc_sw64(sbase + OFF_WRH), wrl = desc_sw64(sbase + OFF_WRL);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          mma_ts(d2, g_lo + 8 * k, wrh + 2 * k, idesc, k != 0);
+          mma_ts(d2, g_hi + 8 * k, wrl + 2 * k, idesc, 1);
+          mma_ts(d2, g_hi + 8 * k, wrh + 2 * k, idesc, 1);
+        }
+        lt_commit(&B->d2_full[b]);
+      }
+      __syncwarp();
+    };
+    for (int it = 0; it < n_my; ++it) {
+      const int b = it & 1;
+      const uint32_t u = (uint32_t)(it >> 1);
+      lt_wait(&B->d1_empty[b], (u & 1) ^ 1);
+      fence_after();
+      const uint32_t d1 = tmem + b * 64;
+      for (int tap = 0; tap < 3; ++tap) {
+        const uint64_t wh = desc_sw128(sbase + OFF_WDH + tap * WD_TILE_BYTES);
+        const uint64_t wl = desc_sw128(sbase + OFF_WDL + tap * WD_TILE_BYTES);
+        // lo plane of the activations: A_lo . W_hi
+        lt_wait(&B->full[stage], phase);
+        fence_after();
+        if (lane == 0) {
+          const uint64_t a = desc_sw128(sbase + OFF_A + stage * A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, (tap | k) != 0);
+          lt_commit(&B->empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+        // hi plane: A_hi . W_lo + A_hi . W_hi
+        lt_wait(&B->full[stage], phase);
+        fence_after();
+        if (lane == 0) {
+          const uint64_t a = desc_sw128(sbase + OFF_A + stage * A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_ss(d1, a + 2 * k, wl + 2 * k, idesc, 1);
+            mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, 1);
+          }
+          lt_commit(&B->empty[stage]);
+          if (tap == 2) lt_commit(&B->d1_full[b]);
+        }
+        __syncwarp();
+        if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (it >= 1) mma2(it - 1);
+    }
+    if (n_my >= 1) mma2(n_my - 1);
+  } else {
+    // ================================ epilogue warpgroups =========================
+    const int wg = (warp - 2) >> 2;
+    const int qd = warp & 3;  // TMEM lane quarter accessible to this warp
+    const int row = qd * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+    for (int it = wg; it < n_my; it += 2) {
+      const uint32_t u = (uint32_t)(it >> 1);
+      const int tile = blockIdx.x + it * gridDim.x;
+      const size_t grow = (size_t)tile * LT_BM + row;
+      // ---- E1: gate ----
+      float4 cq[16];
+      const float4* cptr = reinterpret_cast<const float4*>(p.cond + grow * C);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cq[i] = __ldg(cptr + i);
+      lt_wait(&B->d1_full[wg], u & 1);
+      fence_after();
+      uint32_t d[64];
+      tmem_ld32(tmem + lane_sel + wg * 64, d);
+      tmem_ld32(tmem + lane_sel + wg * 64 + 32, d + 32);
+      tmem_ld_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) lt_arrive(&B->d1_empty[wg]);
+      uint32_t ghi[16], glo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        // columns 4i..4i+3 = (sig j, tanh j, sig j+1, tanh j+1), j = 2i
+        const float s0 = __uint_as_float(d[4 * i]) + cq[i].x;
+        const float t0 = __uint_as_float(d[4 * i + 1]) + cq[i].y;
+        const float s1 = __uint_as_float(d[4 * i + 2]) + cq[i].z;
+        const float t1 = __uint_as_float(d[4 * i + 3]) + cq[i].w;
+        const float g0 = sig_fast(s0) * (2.0f * sig_fast(2.0f * t0) - 1.0f);
+        const float g1 = sig_fast(s1) * (2.0f * sig_fast(2.0f * t1) - 1.0f);
+        const float h0 = __bfloat162float(__float2bfloat16_rn(g0));
+        const float h1 = __bfloat162float(__float2bfloat16_rn(g1));
+        ghi[i] = pack_bf16(h0, h1);
+        glo[i] = pack_bf16(g0 - h0, g1 - h1);
+      }
+      tmem_st16(tmem + lane_sel + 256 + wg * 32, ghi);
+      tmem_st16(tmem + lane_sel + 256 + wg * 32 + 16, glo);
+      tmem_st_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) lt_arrive(&B->g_full[wg]);
+      // ---- E2: residual ----
+      float4 lq[16];
+      const float4* lptr = reinterpret_cast<const float4*>(p.l_in + grow * C);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) lq[i] = __ldg(lptr + i);
+      lt_wait(&B->d2_full[wg], u & 1);
+      fence_after();
+      tmem_ld32(tmem + lane_sel + 128 + wg * 64, d);
+      tmem_ld32(tmem + lane_sel + 128 + wg * 64 + 32, d + 32);
+      tmem_ld_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) lt_arrive(&B->d2_empty[wg]);
+      float4* optr = reinterpret_cast<float4*>(p.l_out + grow * C);
+      uint4* hptr = reinterpret_cast<uint4*>(p.out_hi + grow * C);
+      uint4* lptr2 = reinterpret_cast<uint4*>(p.out_lo + grow * C);
+      const float4* bptr = reinterpret_cast<const float4*>(p.br);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float o[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 bb = __ldg(bptr + 2 * i + h);
+          const float4 ll = lq[2 * i + h];
+          o[4 * h + 0] = ll.x + bb.x + __uint_as_float(d[8 * i + 4 * h + 0]);
+          o[4 * h + 1] = ll.y + bb.y + __uint_as_float(d[8 * i + 4 * h + 1]);
+          o[4 * h + 2] = ll.z + bb.z + __uint_as_float(d[8 * i + 4 * h + 2]);
+          o[4 * h + 3] = ll.w + bb.w + __uint_as_float(d[8 * i + 4 * h + 3]);
+        }
+        optr[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+        optr[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        uint32_t hh[4], ll2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a0 = __bfloat162float(__float2bfloat16_rn(o[2 * j]));
+          const float a1 = __bfloat162float(__float2bfloat16_rn(o[2 * j + 1]));
+          hh[j] = pack_bf16(a0, a1);
+          ll2[j] = pack_bf16(o[2 * j] - a0, o[2 * j + 1] - a1);
+        }
+        hptr[i] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        lptr2[i] = make_uint4(ll2[0], ll2[1], ll2[2], ll2[3]);
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int lt_encode_fn(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    NSW_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    NSW_CHECK(ptr != nullptr && qres == cudaDriverEntryPointSuccess, NSW_ECUDA,
+              "cuTensorMapEncodeTiled is not available from this driver");
+    cached = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  *fn = cached;
+  return NSW_OK;
+}
+
+}  // namespace
+
+// ---- host API used by nsw_iaf.cu (opaque 128-byte tensor maps) ----
+int layer_tc_make_act_map(void* map_out, const __nv_bfloat16* base, int B, int T) {
+  EncodeTiledFn enc;
+  NSW_TRY(lt_encode_fn(&enc));
+  const cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {128, (cuuint64_t)T * 128};
+  const cuuint32_t box[3] = {64, LT_BM, 1}, es[3] = {1, 1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NSW_CHECK(r == CUDA_SUCCESS, NSW_ECUDA, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
+  return NSW_OK;
+}
+
+int layer_tc_make_weight_map(void* map_out, const __nv_bfloat16* base, int rows, int k) {
+  EncodeTiledFn enc;
+  NSW_TRY(lt_encode_fn(&enc));
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)k, 64}, es[2] = {1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NSW_CHECK(r == CUDA_SUCCESS, NSW_ECUDA, "cuTensorMapEncodeTiled(weight) failed: %d", (int)r);
+  return NSW_OK;
+}
+
+int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
+                    const void* map_wrh, const void* map_wrl, const float* cond, const float* l_in,
+                    float* l_out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const float* br, int T,
+                    int rows, int dil, int layer, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSW_CUDA(cudaFuncSetAttribute(iaf_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)LT_SMEM_BYTES));
+    attr_set = true;
+  }
+  NSW_CHECK(T % LT_BM == 0, NSW_EINVAL, "layer_tc: T=%d must be a multiple of %d", T, LT_BM);
+  LayerTcParams p;
+  p.cond = cond;
+  p.l_in = l_in;
+  p.l_out = l_out;
+  p.out_hi = out_hi;
+  p.out_lo = out_lo;
+  p.br = br;
+  p.dil = dil;
+  p.tiles_per_clip = T / LT_BM;
+  p.n_tiles = rows / LT_BM;
+  p.layer = layer;
+  const int grid = std::min(p.n_tiles, num_sms);
+  iaf_layer_tc_kernel<<<grid, LT_THREADS, LT_SMEM_BYTES, stream>>>(
+      *reinterpret_cast<const CUtensorMap*>(map_lh), *reinterpret_cast<const CUtensorMap*>(map_ll),
+      *reinterpret_cast<const CUtensorMap*>(map_wdh), *reinterpret_cast<const CUtensorMap*>(map_wdl),
+      *reinterpret_cast<const CUtensorMap*>(map_wrh), *reinterpret_cast<const CUtensorMap*>(map_wrl), p);
+  count_launch();
+  NSW_CUDA(cudaGetLastError());
+  return NSW_OK;
+}
+
+}  // namespace nsw

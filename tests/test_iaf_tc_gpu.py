@@ -21,41 +21,49 @@ def make_engine(hp, engine, seed=12345, bias_std=0.02):
     return IAFEngine(hp, w, device=0, engine=engine), w
 
 
-def test_tc_engine_matches_golden_config1(student_hp):
-    eng, _ = make_engine(student_hp, 'tc')
+ENGINES = ['tc', 'tc2']   # tc: conv-GEMMs on tcgen05; tc2: + the residual layers on tcgen05
+
+
+@pytest.mark.parametrize('engine', ENGINES)
+def test_tc_engine_matches_golden_config1(student_hp, engine):
+    eng, _ = make_engine(student_hp, engine)
     g = np.load(os.path.join(GOLDEN_DIR, 'iaf_logistic_1x21.npz'))
     out = eng.forward_host(g['mel'], g['z'], quantize=False, want=('x',) + KEYS)
     errs = {k: float(np.abs(out[k] - g[k]).max()) for k in KEYS}
-    print('tc engine max-abs errors', errs)
+    print(engine, 'engine max-abs errors', errs)
     for k in KEYS:
         assert errs[k] < TOL, errs
 
 
-def test_tc_engine_first_layers_close_to_oracle(student_hp):
+@pytest.mark.parametrize('engine', ENGINES)
+def test_tc_engine_first_layers_close_to_oracle(student_hp, engine):
     hp = student_hp
-    eng, w = make_engine(hp, 'tc')
+    eng, w = make_engine(hp, engine)
     mel, z = synth_inputs(hp, 1, 6)
     taps = {}
     O.student_feed_forward(w, hp, mel, z, np.float64, taps=taps)
     buf = torch.empty((1, eng.length(6), 64), device='cuda')
-    for flow, layer in ((0, 1), (0, 10), (3, 30)):
+    for flow, layer in ((0, 1), (0, 2), (0, 10), (3, 30)):
         eng.set_tap(flow, layer, buf)
         eng.forward_host(mel, z, quantize=False)
         err = np.abs(buf.cpu().numpy() - taps['iaf_{}/l{}'.format(flow + 1, layer)]).max()
+        print(engine, 'flow', flow, 'layer', layer, 'max-abs err', err)
         assert err < TOL, (flow, layer, err)
 
 
-def test_tc_engine_clarinet_matches_golden(clarinet_hp):
-    eng, _ = make_engine(clarinet_hp, 'tc')
+@pytest.mark.parametrize('engine', ENGINES)
+def test_tc_engine_clarinet_matches_golden(clarinet_hp, engine):
+    eng, _ = make_engine(clarinet_hp, engine)
     g = np.load(os.path.join(GOLDEN_DIR, 'iaf_gauss_2x6.npz'))
     out = eng.forward_host(g['mel'], g['z'], quantize=False, want=KEYS)
     for k in KEYS:
         assert np.abs(out[k] - g[k]).max() < TOL, k
 
 
-def test_tc_and_ffma_engines_agree_at_full_size(student_hp):
+@pytest.mark.parametrize('engine', ENGINES)
+def test_tc_and_ffma_engines_agree_at_full_size(student_hp, engine):
     hp = student_hp
-    a, _ = make_engine(hp, 'tc')
+    a, _ = make_engine(hp, engine)
     b, _ = make_engine(hp, 'ffma')
     mel, z = synth_inputs(hp, 8, 39)
     oa = a.forward_host(mel, z, quantize=False, want=KEYS)
@@ -63,3 +71,6 @@ def test_tc_and_ffma_engines_agree_at_full_size(student_hp):
     for k in KEYS:
         assert np.abs(oa[k] - ob[k]).max() < TOL, k
     assert np.all(oa['scale_tot'] > 0)
+    again = a.forward_host(mel, z, quantize=False, want=KEYS)
+    for k in KEYS:
+        assert np.array_equal(again[k], oa[k])  # deterministic
