@@ -61,7 +61,7 @@ struct FgParams {
   unsigned long long* hist;     // tagged l history rings
   const int* hist_off;          // [L+1] entry offset of layer ph's ring
   const int* dil;               // [L+1]
-  long long* dbg;               // optional [NC][8] cycle counters (NULL = off)
+  long long* dbg;               // optional [NC][16] cycle counters (NULL = off)
   const float* wcs;             // conv_start W [3][512]
   const float* bcs;             // [512]
   const float* wo2t;            // out2 W transposed [O][256]
@@ -88,6 +88,9 @@ struct FgSmem {
   float outv[MAX_O];
   float gum[12];
   float xnext;
+  int dil[MAX_PH];       // per layer (1-based), copied from global once
+  int hoff[MAX_PH];      // entry offset of the layer's history ring
+  int pos[MAX_PH];       // t mod (2*dil+1), advanced once per step
   unsigned long long mbar[3];
 };
 
@@ -211,6 +214,11 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   if (tid < O) S.bo2[tid] = P.bo2[tid];
   for (int i = tid; i < 1024; i += NT) { S.v[0][i] = 0.f; S.v[1][i] = 0.f; S.hv[i] = 0.f; }
   if (tid < 4) S.pv[tid] = 0.f;
+  if (tid <= L) {
+    S.dil[tid] = tid >= 1 ? P.dil[tid] : 1;
+    S.hoff[tid] = tid >= 1 ? P.hist_off[tid] : 0;
+    S.pos[tid] = 0;
+  }
   if (tid == 0) {
     for (int s = 0; s < 3; ++s)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[s])));
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
       long long tS1 = 0, tS2 = 0, tPub = 0;
       if (P.dbg) {
         tS1 = clock64();
-        if (tid == 0 && tEnd) P.dbg[8 * c + 4] += tS1 - tEnd;  // wait at S1 after my slack
+        if (tid == 0 && tEnd) P.dbg[16 * c + 4] += tS1 - tEnd;  // wait at S1 after my slack
       }
       const float* v = S.v[vb];
       if (ph == 1 && warp < 4 && lane == 0) ls = v[4 * c + warp];
@@ -288,17 +296,27 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
       const unsigned long long* hp1 = nullptr;
       uint32_t tag2 = 0, tag1 = 0;
       if (warp < 4 && do_past) {
-        const int d = P.dil[nph];
+        const int d = S.dil[nph];
         const int R = 2 * d + 1;
-        const unsigned long long* hb = P.hist + P.hist_off[nph];
-        if (nt - 2 * d >= 0) { hp2 = hb + (size_t)((nt - 2 * d) % R) * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
-        if (nt - d >= 0) { hp1 = hb + (size_t)((nt - d) % R) * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
+        const unsigned long long* hb = P.hist + S.hoff[nph];
+        // ring slot of step nt: S.pos holds t mod R (nt == t, or t + 1 for the wrap to phase 1)
+        int pn = S.pos[nph] + (nt - t);
+        if (pn >= R) pn -= R;
+        int p1 = pn - d;        // (nt - d) mod R
+        if (p1 < 0) p1 += R;
+        int p2 = p1 - d;        // (nt - 2d) mod R
+        if (p2 < 0) p2 += R;
+        if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
+        if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
         hraw[0] = hp2 ? ldv4(hp2) : make_uint4(0, 0, 0, 0);
         hraw[1] = hp2 ? ldv4(hp2 + 256) : make_uint4(0, 0, 0, 0);
         hraw[2] = hp1 ? ldv4(hp1) : make_uint4(0, 0, 0, 0);
         hraw[3] = hp1 ? ldv4(hp1 + 256) : make_uint4(0, 0, 0, 0);
       }
+      long long tH = 0, tR = 0;
+      if (P.dbg && tid == 0) tH = clock64();
       fg_mbar_wait(&S.mbar[slot], par);
+      if (P.dbg && tid == 0) { tR = clock64(); P.dbg[16 * c + 7] += tH - tS1; P.dbg[16 * c + 8] += tR - tH; }
       const float* blk = S.ring[slot];
 
       // ---- critical compute ----
@@ -308,13 +326,13 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         float b = 0.f;
         if (warp < 4 && ph <= L) b = dot_rows<2>(blk + OFF_L + warp * 256, v + 512, lane);
         warp_sum2(a, b);
+        if (P.dbg && tid == 0) P.dbg[16 * c + 9] += clock64() - tR;
         if (lane == 0) {
           S.red_d[r][half] = a;
           if (warp < 4 && ph <= L) {
             // l_{ph-1}[4c+warp] = l_{ph-2}[..] + Wr_{ph-1} g_{ph-1} + br_{ph-1}; doubles as history
             ls += b + blk[OFF_C + warp];
-            const int R = 2 * P.dil[ph] + 1;
-            publish(P.hist + P.hist_off[ph] + (size_t)(t % R) * FW + 4 * c + warp, ls, tag);
+            publish(P.hist + S.hoff[ph] + (size_t)S.pos[ph] * FW + 4 * c + warp, ls, tag);
           }
         }
       } else if (warp < 2) {
@@ -324,11 +342,11 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
           publish(P.xbuf + (size_t)ph * 256 + 2 * c + warp, sk, tag);
         }
       }
-      if (P.dbg && tid == 0) P.dbg[8 * c + 0] += clock64() - tS1;  // hist issue + ring wait + critical
+      if (P.dbg && tid == 0) P.dbg[16 * c + 0] += clock64() - tS1;  // hist issue + ring wait + critical
       __syncthreads();  // S2
       if (P.dbg) {
         tS2 = clock64();
-        if (tid == 0) P.dbg[8 * c + 1] += tS2 - tS1;
+        if (tid == 0) P.dbg[16 * c + 1] += tS2 - tS1;
       }
       if (tid < 2) {
         if (ph <= L) {
@@ -341,7 +359,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         }
       }
 
-      if (P.dbg && tid == 0) { tPub = clock64(); P.dbg[8 * c + 2] += tPub - tS2; }  // finalize + publish
+      if (P.dbg && tid == 0) { tPub = clock64(); P.dbg[16 * c + 2] += tPub - tS2; }  // finalize + publish
       if (warp < 4) {
         // ---------------- slack group ----------------
         if (do_past) {
@@ -398,10 +416,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         const bool need_l = (ph + 1 <= L);
         const unsigned long long* pg = P.xbuf + (size_t)ph * 256 + 2 * k;
         const unsigned long long* pl0 = pg;
-        if (need_l) {
-          const int R = 2 * P.dil[ph] + 1;
-          pl0 = P.hist + P.hist_off[ph] + (size_t)(t % R) * FW + 2 * k;
-        }
+        if (need_l) pl0 = P.hist + S.hoff[ph] + (size_t)S.pos[ph] * FW + 2 * k;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
         bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
         long long w0 = 0;
@@ -426,9 +441,9 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         }
         vn[512 + 2 * k] = __uint_as_float(r2.x);
         vn[512 + 2 * k + 1] = __uint_as_float(r2.z);
-        if (P.dbg && tid == 128) P.dbg[8 * c + 5] += clock64() - tS2;
+        if (P.dbg && tid == 128) P.dbg[16 * c + 5] += clock64() - tS2;
       }
-      if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[8 * c + 3] += now - tPub; tEnd = now; }
+      if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[16 * c + 3] += now - tPub; tEnd = now; }
     }
 
     // ---------------- output head + sampler (every CTA, redundantly) ----------------
@@ -490,8 +505,13 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
       if (c == 0 && P.audio) P.audio[t] = fed;
     }
     if (c == 0 && P.out && tid < O) P.out[(size_t)t * O + tid] = S.outv[tid];
+    if (tid >= 1 && tid <= L) {  // ring slot of step t+1 (all of this step's users are done)
+      const int R = 2 * S.dil[tid] + 1;
+      const int pn = S.pos[tid] + 1;
+      S.pos[tid] = pn >= R ? 0 : pn;
+    }
     __syncthreads();
-    if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[8 * c + 6] += now - tEnd; tEnd = now; }
+    if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[16 * c + 6] += now - tEnd; tEnd = now; }
   }
 }
 
@@ -867,8 +887,8 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     P.dbg = nullptr;
     const bool want_dbg = getenv("NSW_FASTGEN_DEBUG") != nullptr;
     if (want_dbg) {
-      NSW_TRY(h->dbg.ensure(128 * 8 * sizeof(long long)));
-      NSW_CUDA(cudaMemsetAsync(h->dbg.p, 0, 128 * 8 * sizeof(long long), st));
+      NSW_TRY(h->dbg.ensure(128 * 16 * sizeof(long long)));
+      NSW_CUDA(cudaMemsetAsync(h->dbg.p, 0, 128 * 16 * sizeof(long long), st));
       P.dbg = h->dbg.as<long long>();
     }
     P.wcs = h->wcs.as<float>();
@@ -889,15 +909,16 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
                                          sizeof(FgSmem), st));
     count_launch();
     if (want_dbg) {
-      std::vector<long long> host(128 * 8);
+      std::vector<long long> host(128 * 16);
       NSW_CUDA(cudaStreamSynchronize(st));
       NSW_CUDA(cudaMemcpy(host.data(), h->dbg.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       const double phases = (double)T * (h->L + 2);
-      const char* names[7] = {"crit", "crit+S2", "finalize+publish", "slack", "S1 wait", "poll(after S2)", "head"};
+      const char* names[10] = {"crit", "crit+S2", "finalize+publish", "slack", "S1 wait", "poll(after S2)", "head",
+                               "hist issue", "ring wait", "dots+reduce"};
       for (int cta : {0, 1, 64, 127}) {
         fprintf(stderr, "[nsw fastgen dbg] cta %3d cycles/phase:", cta);
-        for (int i = 0; i < 7; ++i)
-          fprintf(stderr, " %s=%.0f", names[i], (double)host[8 * cta + i] / (i == 6 ? (double)T : phases));
+        for (int i = 0; i < 10; ++i)
+          fprintf(stderr, " %s=%.0f", names[i], (double)host[16 * cta + i] / (i == 6 ? (double)T : phases));
         fprintf(stderr, "\n");
       }
     }

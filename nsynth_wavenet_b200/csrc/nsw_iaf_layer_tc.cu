@@ -21,7 +21,7 @@ namespace nsw {
 
 namespace {
 
-constexpr int C = 64, HALF = 32;
+constexpr int C = 64;
 constexpr int LT_BM = 128;
 constexpr int LT_STAGES = 8;
 constexpr int LT_THREADS = 320;
@@ -153,9 +153,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float sig_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid(s) * tanh(t) = (1 - b) / ((1 + a)(1 + b)), a = e^-s, b = e^-2t : 3 MUFU ops.
+// Exponents are clamped at 40 so the product stays finite; both functions are saturated to
+// fp32 precision long before that.
+__device__ __forceinline__ float gate_fast(float s, float t) {
+  const float a = __expf(fminf(-s, 40.0f));
+  const float b = __expf(fminf(-2.0f * t, 40.0f));
+  return __fdividef(1.0f - b, (1.0f + a) * (1.0f + b));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x (low 16 bits) = a
   return *reinterpret_cast<uint32_t*>(&v);
@@ -188,10 +201,10 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     for (int s = 0; s < LT_STAGES; ++s) { lt_mbar_init(&B->full[s], 1); lt_mbar_init(&B->empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       lt_mbar_init(&B->d1_full[b], 1);
-      lt_mbar_init(&B->d1_empty[b], 4);
-      lt_mbar_init(&B->g_full[b], 4);
+      lt_mbar_init(&B->d1_empty[b], 8);
+      lt_mbar_init(&B->g_full[b], 8);
       lt_mbar_init(&B->d2_full[b], 1);
-      lt_mbar_init(&B->d2_empty[b], 4);
+      lt_mbar_init(&B->d2_empty[b], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -218,6 +231,10 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
       }
       lt_tma_2d(sbase + OFF_WRH, &map_wrh, &B->wfull, 0, p.layer * 64);
       lt_tma_2d(sbase + OFF_WRL, &map_wrl, &B->wfull, 0, p.layer * 64);
+      for (int it = 0; it < n_my; ++it) {  // conditioning rows stream from HBM: warm L2 early
+        const float* ct = p.cond + (size_t)(blockIdx.x + it * gridDim.x) * LT_BM * C;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ct), "r"(LT_BM * C * 4) : "memory");
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_my; ++it) {
@@ -303,69 +320,71 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     }
     if (n_my >= 1) mma2(n_my - 1);
   } else {
-    // ================================ epilogue warpgroups =========================
-    const int wg = (warp - 2) >> 2;
+    // ================================ epilogue (8 warps) ===========================
+    // every tile is handled by all 8 warps: warp w and w+4 share a TMEM lane quarter and
+    // split the 64 columns, so each thread owns half a row (32 conv outputs = 16 gates,
+    // then 32 residual channels)
+    const int half = (warp - 2) >> 2;
     const int qd = warp & 3;  // TMEM lane quarter accessible to this warp
     const int row = qd * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
-    for (int it = wg; it < n_my; it += 2) {
+    const float4* bptr = reinterpret_cast<const float4*>(p.br) + half * 8;
+    for (int it = 0; it < n_my; ++it) {
+      const int b = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
       const int tile = blockIdx.x + it * gridDim.x;
       const size_t grow = (size_t)tile * LT_BM + row;
-      // ---- E1: gate ----
-      float4 cq[16];
-      const float4* cptr = reinterpret_cast<const float4*>(p.cond + grow * C);
+      // both operand rows are requested before any waiting so their latency overlaps MMA1
+      float4 cq[8], lq[8];
+      const float4* cptr = reinterpret_cast<const float4*>(p.cond + grow * C) + half * 8;
+      const float4* lptr = reinterpret_cast<const float4*>(p.l_in + grow * C) + half * 8;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) cq[i] = __ldg(cptr + i);
-      lt_wait(&B->d1_full[wg], u & 1);
+      for (int i = 0; i < 8; ++i) cq[i] = __ldg(cptr + i);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lq[i] = __ldg(lptr + i);
+      // ---- E1: gate ----
+      lt_wait(&B->d1_full[b], u & 1);
       fence_after();
-      uint32_t d[64];
-      tmem_ld32(tmem + lane_sel + wg * 64, d);
-      tmem_ld32(tmem + lane_sel + wg * 64 + 32, d + 32);
+      uint32_t d[32];
+      tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
       tmem_ld_wait();
       fence_before();
       __syncwarp();
-      if (lane == 0) lt_arrive(&B->d1_empty[wg]);
-      uint32_t ghi[16], glo[16];
+      if (lane == 0) lt_arrive(&B->d1_empty[b]);
+      uint32_t ghi[8], glo[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        // columns 4i..4i+3 = (sig j, tanh j, sig j+1, tanh j+1), j = 2i
+      for (int i = 0; i < 8; ++i) {
+        // columns 4i..4i+3 of this half = (sig j, tanh j, sig j+1, tanh j+1)
         const float s0 = __uint_as_float(d[4 * i]) + cq[i].x;
         const float t0 = __uint_as_float(d[4 * i + 1]) + cq[i].y;
         const float s1 = __uint_as_float(d[4 * i + 2]) + cq[i].z;
         const float t1 = __uint_as_float(d[4 * i + 3]) + cq[i].w;
-        const float g0 = sig_fast(s0) * (2.0f * sig_fast(2.0f * t0) - 1.0f);
-        const float g1 = sig_fast(s1) * (2.0f * sig_fast(2.0f * t1) - 1.0f);
+        const float g0 = gate_fast(s0, t0);
+        const float g1 = gate_fast(s1, t1);
         const float h0 = __bfloat162float(__float2bfloat16_rn(g0));
         const float h1 = __bfloat162float(__float2bfloat16_rn(g1));
         ghi[i] = pack_bf16(h0, h1);
         glo[i] = pack_bf16(g0 - h0, g1 - h1);
       }
-      tmem_st16(tmem + lane_sel + 256 + wg * 32, ghi);
-      tmem_st16(tmem + lane_sel + 256 + wg * 32 + 16, glo);
+      tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
+      tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
       tmem_st_wait();
       fence_before();
       __syncwarp();
-      if (lane == 0) lt_arrive(&B->g_full[wg]);
+      if (lane == 0) lt_arrive(&B->g_full[b]);
       // ---- E2: residual ----
-      float4 lq[16];
-      const float4* lptr = reinterpret_cast<const float4*>(p.l_in + grow * C);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) lq[i] = __ldg(lptr + i);
-      lt_wait(&B->d2_full[wg], u & 1);
+      lt_wait(&B->d2_full[b], u & 1);
       fence_after();
-      tmem_ld32(tmem + lane_sel + 128 + wg * 64, d);
-      tmem_ld32(tmem + lane_sel + 128 + wg * 64 + 32, d + 32);
+      tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
       tmem_ld_wait();
       fence_before();
       __syncwarp();
-      if (lane == 0) lt_arrive(&B->d2_empty[wg]);
-      float4* optr = reinterpret_cast<float4*>(p.l_out + grow * C);
-      uint4* hptr = reinterpret_cast<uint4*>(p.out_hi + grow * C);
-      uint4* lptr2 = reinterpret_cast<uint4*>(p.out_lo + grow * C);
-      const float4* bptr = reinterpret_cast<const float4*>(p.br);
+      if (lane == 0) lt_arrive(&B->d2_empty[b]);
+      float4* optr = reinterpret_cast<float4*>(p.l_out + grow * C) + half * 8;
+      uint4* hptr = reinterpret_cast<uint4*>(p.out_hi + grow * C) + half * 4;
+      uint4* lptr2 = reinterpret_cast<uint4*>(p.out_lo + grow * C) + half * 4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         float o[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
