@@ -41,6 +41,8 @@ constexpr int NC = 128;   // CTAs
 constexpr int NT = 256;   // threads per CTA
 constexpr int MAX_O = 32;
 constexpr int MAX_PH = 40;
+constexpr int XREP = 8;     // replicas of every exchange slot (CTA c polls replica c % XREP)
+constexpr int XSLOT = 768;  // entries per slot: [l (512) | g / s' / h (256)]
 
 // per-(phase, cta) weight block, in floats
 constexpr int OFF_D = 0;                    // 4 rows x 768: [W2 row (512) | M row (256)]
@@ -57,7 +59,7 @@ constexpr long long FG_WATCHDOG = 6000000000ll;  // ~3 s of SM clocks
 struct FgParams {
   const float* blocks;          // [NPH][NC][BLOCK_FLOATS]
   const float* cond;            // planes [(L*512+256)/64][T][64]
-  unsigned long long* xbuf;     // [NPH+1][256] tagged g / s' / h exchange slots
+  unsigned long long* xbuf;     // [NPH+1][XREP][XSLOT] tagged exchange slots
   unsigned long long* hist;     // tagged l history rings
   const int* hist_off;          // [L+1] entry offset of layer ph's ring
   const int* dil;               // [L+1]
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         if (tid == 0 && tEnd) P.dbg[16 * c + 4] += tS1 - tEnd;  // wait at S1 after my slack
       }
       const float* v = S.v[vb];
-      if (ph == 1 && warp < 4 && lane == 0) ls = v[4 * c + warp];
+      if (ph == 1 && warp < 4) ls = v[4 * c + warp];
       const int slot = (int)(q % 3);
       const uint32_t par = (uint32_t)((q / 3) & 1);
       const int nph = (ph == NPH) ? 1 : ph + 1;
@@ -327,20 +329,20 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         if (warp < 4 && ph <= L) b = dot_rows<2>(blk + OFF_L + warp * 256, v + 512, lane);
         warp_sum2(a, b);
         if (P.dbg && tid == 0) P.dbg[16 * c + 9] += clock64() - tR;
-        if (lane == 0) {
-          S.red_d[r][half] = a;
-          if (warp < 4 && ph <= L) {
-            // l_{ph-1}[4c+warp] = l_{ph-2}[..] + Wr_{ph-1} g_{ph-1} + br_{ph-1}; doubles as history
-            ls += b + blk[OFF_C + warp];
+        if (lane == 0) S.red_d[r][half] = a;
+        if (warp < 4 && ph <= L) {
+          // l_{ph-1}[4c+warp] = l_{ph-2}[..] + Wr_{ph-1} g_{ph-1} + br_{ph-1}  (all lanes agree)
+          ls += b + blk[OFF_C + warp];
+          if (lane < XREP)        // exchange copies, one per replica
+            publish(P.xbuf + ((size_t)ph * XREP + lane) * XSLOT + 4 * c + warp, ls, tag);
+          else if (lane == XREP)  // history ring of layer ph (read again d and 2d steps later)
             publish(P.hist + S.hoff[ph] + (size_t)S.pos[ph] * FW + 4 * c + warp, ls, tag);
-          }
         }
       } else if (warp < 2) {
         const float a = warp_sum(dot_rows<2>(blk + OFF_S + warp * 512, v + 512, lane));
-        if (lane == 0) {
-          sk = fmaxf(sk + a + blk[OFF_C + 4 + warp], 0.f);  // relu(s) after the last skip
-          publish(P.xbuf + (size_t)ph * 256 + 2 * c + warp, sk, tag);
-        }
+        sk = fmaxf(sk + a + blk[OFF_C + 4 + warp], 0.f);  // relu(s) after the last skip
+        if (lane < XREP)
+          publish(P.xbuf + ((size_t)ph * XREP + lane) * XSLOT + 512 + 2 * c + warp, sk, tag);
       }
       if (P.dbg && tid == 0) P.dbg[16 * c + 0] += clock64() - tS1;  // hist issue + ring wait + critical
       __syncthreads();  // S2
@@ -348,14 +350,15 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         tS2 = clock64();
         if (tid == 0) P.dbg[16 * c + 1] += tS2 - tS1;
       }
-      if (tid < 2) {
+      if (tid < 2 * XREP) {  // thread (j, replica): the value is recomputed per replica
+        const int j = tid & 1, rep = tid >> 1;
+        unsigned long long* dst = P.xbuf + ((size_t)ph * XREP + rep) * XSLOT + 512 + 2 * c + j;
         if (ph <= L) {
-          const float ds = S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid] + S.pv[tid];
-          const float dt = S.red_d[2 + tid][0] + S.red_d[2 + tid][1] + cnd[ph][2 + tid] + S.pv[2 + tid];
-          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid, sigmoid_fast(ds) * tanh_fast(dt), tag);
+          const float ds = S.red_d[j][0] + S.red_d[j][1] + cnd[ph][j] + S.pv[j];
+          const float dt = S.red_d[2 + j][0] + S.red_d[2 + j][1] + cnd[ph][2 + j] + S.pv[2 + j];
+          publish(dst, sigmoid_fast(ds) * tanh_fast(dt), tag);
         } else if (ph == L + 2) {  // h = relu(out1 . relu(s) + cond_out1)
-          publish(P.xbuf + (size_t)ph * 256 + 2 * c + tid,
-                  fmaxf(S.red_d[tid][0] + S.red_d[tid][1] + cnd[ph][tid], 0.f), tag);
+          publish(dst, fmaxf(S.red_d[j][0] + S.red_d[j][1] + cnd[ph][j], 0.f), tag);
         }
       }
 
@@ -414,9 +417,9 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         // next phase needs g_ph / s' / h, and (layers only) l_{ph-1} from layer ph's history
         // ring; the three 16-byte words are polled together so one L2 round trip covers all
         const bool need_l = (ph + 1 <= L);
-        const unsigned long long* pg = P.xbuf + (size_t)ph * 256 + 2 * k;
-        const unsigned long long* pl0 = pg;
-        if (need_l) pl0 = P.hist + S.hoff[ph] + (size_t)S.pos[ph] * FW + 2 * k;
+        const unsigned long long* slotp = P.xbuf + ((size_t)ph * XREP + (c & (XREP - 1))) * XSLOT;
+        const unsigned long long* pg = slotp + 512 + 2 * k;
+        const unsigned long long* pl0 = slotp + 2 * k;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
         bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
         long long w0 = 0;
@@ -785,7 +788,7 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
   if (rc == NSW_OK)
     rc = h->deconv.init(tm, "", cfg->num_mel, FD, cfg->num_deconv, cfg->deconv_filter,
                         cfg->deconv_stride, cfg->upsample_act, want_tc);
-  if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * 256 * 8);
+  if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * XREP * XSLOT * 8);
   if (rc == NSW_OK) rc = h->hist.ensure(h->hist_entries * 8);
   if (rc == NSW_OK) {
     cudaError_t e = cudaFuncSetAttribute(fastgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -42,7 +42,10 @@ struct LtBars {
 constexpr uint32_t OFF_WDH = 0, OFF_WDL = 3 * WD_TILE_BYTES, OFF_WRH = 6 * WD_TILE_BYTES,
                    OFF_WRL = OFF_WRH + WR_TILE_BYTES, OFF_A = OFF_WRL + WR_TILE_BYTES,
                    OFF_BARS = OFF_A + LT_STAGES * A_TILE_BYTES;
-constexpr size_t LT_SMEM_BYTES = OFF_BARS + sizeof(LtBars) + 1024;
+constexpr uint32_t OFF_SCR = OFF_BARS + 512;                 // 8 warps x 4 KB transposition scratch
+constexpr uint32_t SCR_BYTES = 8 * 4096;
+static_assert(sizeof(LtBars) <= 512, "barrier block grew");
+constexpr size_t LT_SMEM_BYTES = OFF_SCR + SCR_BYTES + 1024;
 
 __device__ __forceinline__ void lt_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -172,6 +175,53 @@ __device__ __forceinline__ float gate_fast(float s, float t) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x (low 16 bits) = a
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- coalesced global access for row-per-thread data --------------------------------------
+// A warp owns 32 rows x 128 B (its half of the 256 B fp32 rows).  Global memory is touched with
+// fully used 128 B lines (lane -> row 4i + lane/8, 16 B chunk lane%8); a 4 KB per-warp smem
+// scratch with an XOR swizzle (chunk ^ row%8) turns that into one full half-row per thread and
+// back, conflict-free in both directions.  (Row-per-thread LDG/STG costs 32 L1TEX sectors per
+// instruction and made L1TEX the limiter: profiles/r01.)
+__device__ __forceinline__ void rows_load128(const float4* __restrict__ g /*row 0 of this warp, this half*/,
+                                             float4* scr, int lane, float4 (&out)[8]) {
+  float4 t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = __ldg(g + (size_t)(4 * i + (lane >> 3)) * 16 + (lane & 7));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    scr[r * 8 + ((lane & 7) ^ (r & 7))] = t[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) out[j] = scr[lane * 8 + (j ^ (lane & 7))];
+  __syncwarp();
+}
+__device__ __forceinline__ void rows_store128(float4* __restrict__ g, float4* scr, int lane,
+                                              const float4 (&in)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) scr[lane * 8 + (j ^ (lane & 7))] = in[j];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    g[(size_t)r * 16 + (lane & 7)] = scr[r * 8 + ((lane & 7) ^ (r & 7))];
+  }
+  __syncwarp();
+}
+// 32 rows x 64 B (half of a 128 B bf16 row): lane -> row 8i + lane/4, chunk lane%4
+__device__ __forceinline__ void rows_store64(uint4* __restrict__ g /*row pitch 8 uint4*/, uint4* scr,
+                                             int lane, const uint4 (&in)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) scr[lane * 4 + (j ^ ((lane >> 1) & 3))] = in[j];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    g[(size_t)r * 8 + (lane & 3)] = scr[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+  }
+  __syncwarp();
 }
 
 struct LayerTcParams {
@@ -326,22 +376,18 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     // then 32 residual channels)
     const int half = (warp - 2) >> 2;
     const int qd = warp & 3;  // TMEM lane quarter accessible to this warp
-    const int row = qd * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+    float4* scr = reinterpret_cast<float4*>(smem + OFF_SCR + (warp - 2) * 4096);
     const float4* bptr = reinterpret_cast<const float4*>(p.br) + half * 8;
     for (int it = 0; it < n_my; ++it) {
       const int b = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
       const int tile = blockIdx.x + it * gridDim.x;
-      const size_t grow = (size_t)tile * LT_BM + row;
-      // both operand rows are requested before any waiting so their latency overlaps MMA1
+      const size_t wrow = (size_t)tile * LT_BM + qd * 32;  // first of this warp's 32 rows
+      // both operand half-rows are fetched (coalesced) before any waiting: overlaps MMA1
       float4 cq[8], lq[8];
-      const float4* cptr = reinterpret_cast<const float4*>(p.cond + grow * C) + half * 8;
-      const float4* lptr = reinterpret_cast<const float4*>(p.l_in + grow * C) + half * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cq[i] = __ldg(cptr + i);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) lq[i] = __ldg(lptr + i);
+      rows_load128(reinterpret_cast<const float4*>(p.cond + wrow * C) + half * 8, scr, lane, cq);
+      rows_load128(reinterpret_cast<const float4*>(p.l_in + wrow * C) + half * 8, scr, lane, lq);
       // ---- E1: gate ----
       lt_wait(&B->d1_full[b], u & 1);
       fence_after();
@@ -380,34 +426,28 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
       fence_before();
       __syncwarp();
       if (lane == 0) lt_arrive(&B->d2_empty[b]);
-      float4* optr = reinterpret_cast<float4*>(p.l_out + grow * C) + half * 8;
-      uint4* hptr = reinterpret_cast<uint4*>(p.out_hi + grow * C) + half * 4;
-      uint4* lptr2 = reinterpret_cast<uint4*>(p.out_lo + grow * C) + half * 4;
+      uint4 hh[4], ll2[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float o[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 bb = __ldg(bptr + 2 * i + h);
-          const float4 ll = lq[2 * i + h];
-          o[4 * h + 0] = ll.x + bb.x + __uint_as_float(d[8 * i + 4 * h + 0]);
-          o[4 * h + 1] = ll.y + bb.y + __uint_as_float(d[8 * i + 4 * h + 1]);
-          o[4 * h + 2] = ll.z + bb.z + __uint_as_float(d[8 * i + 4 * h + 2]);
-          o[4 * h + 3] = ll.w + bb.w + __uint_as_float(d[8 * i + 4 * h + 3]);
-        }
-        optr[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
-        optr[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
-        uint32_t hh[4], ll2[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a0 = __bfloat162float(__float2bfloat16_rn(o[2 * j]));
-          const float a1 = __bfloat162float(__float2bfloat16_rn(o[2 * j + 1]));
-          hh[j] = pack_bf16(a0, a1);
-          ll2[j] = pack_bf16(o[2 * j] - a0, o[2 * j + 1] - a1);
-        }
-        hptr[i] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-        lptr2[i] = make_uint4(ll2[0], ll2[1], ll2[2], ll2[3]);
+      for (int i = 0; i < 8; ++i) {
+        const float4 bb = __ldg(bptr + i);
+        float4 o;
+        o.x = lq[i].x + bb.x + __uint_as_float(d[4 * i + 0]);
+        o.y = lq[i].y + bb.y + __uint_as_float(d[4 * i + 1]);
+        o.z = lq[i].z + bb.z + __uint_as_float(d[4 * i + 2]);
+        o.w = lq[i].w + bb.w + __uint_as_float(d[4 * i + 3]);
+        lq[i] = o;
+        const float a0 = __bfloat162float(__float2bfloat16_rn(o.x));
+        const float a1 = __bfloat162float(__float2bfloat16_rn(o.y));
+        const float a2 = __bfloat162float(__float2bfloat16_rn(o.z));
+        const float a3 = __bfloat162float(__float2bfloat16_rn(o.w));
+        const uint32_t h01 = pack_bf16(a0, a1), h23 = pack_bf16(a2, a3);
+        const uint32_t l01 = pack_bf16(o.x - a0, o.y - a1), l23 = pack_bf16(o.z - a2, o.w - a3);
+        if (i & 1) { hh[i >> 1].z = h01; hh[i >> 1].w = h23; ll2[i >> 1].z = l01; ll2[i >> 1].w = l23; }
+        else       { hh[i >> 1].x = h01; hh[i >> 1].y = h23; ll2[i >> 1].x = l01; ll2[i >> 1].y = l23; }
       }
+      rows_store128(reinterpret_cast<float4*>(p.l_out + wrow * C) + half * 8, scr, lane, lq);
+      rows_store64(reinterpret_cast<uint4*>(p.out_hi + wrow * C) + half * 4, reinterpret_cast<uint4*>(scr), lane, hh);
+      rows_store64(reinterpret_cast<uint4*>(p.out_lo + wrow * C) + half * 4, reinterpret_cast<uint4*>(scr), lane, ll2);
     }
   }
 
