@@ -72,6 +72,7 @@ struct FgParams {
   float* audio;                 // [T] or NULL
   float* out;                   // [T][O] or NULL
   int T, L, O, loss_type;
+  int flags;                    // experiment switches: 1 = sequential polls, 2 = volatile ld/st, 4 = one replica
   unsigned long long seed;
   float quant;                  // quant_chann
 };
@@ -118,6 +119,18 @@ __device__ __forceinline__ float2 poll2(const unsigned long long* p, uint32_t ta
     }
   }
   return make_float2(__uint_as_float(a), __uint_as_float(c));
+}
+__device__ __forceinline__ uint4 ldv4_vol(const unsigned long long* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void publish_vol(unsigned long long* p, float v, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
+               : "memory");
 }
 __device__ __forceinline__ void publish(unsigned long long* p, float v, uint32_t tag) {
   asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)),
@@ -254,11 +267,17 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
     S.cnd[0][tid + 1][2] = cc.z; S.cnd[0][tid + 1][3] = cc.w;
   }
 
+  const bool f_seq = (P.flags & 1) != 0, f_vol = (P.flags & 2) != 0;
+  const int nrep = (P.flags & 4) ? 1 : XREP;
+  auto PUB = [&](unsigned long long* p, float v, uint32_t tg) { if (f_vol) publish_vol(p, v, tg); else publish(p, v, tg); };
+  auto LDX = [&](const unsigned long long* p) -> uint4 { return f_vol ? ldv4_vol(p) : ldv4(p); };
   float x1 = 0.f, x2 = 0.f;  // inputs of the two previous steps (conv_start queues, rate 1)
-  float ls = 0.f, sk = 0.f;
+  float ls0 = 0.f, ls1 = 0.f, sk = 0.f;  // warps 2,3: two residual channels; warps 0,1: one skip channel
   long long q = 0;           // global phase counter -> weight ring slot / parity
   int vb = 0;                // which S.v buffer the current phase reads
   long long tEnd = 0;
+  const long long total_q = (long long)T * NPH;
+  fg_mbar_wait(&S.mbar[0], 0);  // weights of the very first phase
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
@@ -279,92 +298,130 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
     const float(*cnd)[4] = S.cnd[t & 1];
 
     for (int ph = 1; ph <= NPH; ++ph, ++q, vb ^= 1) {
-      __syncthreads();  // S1: S.v[vb], S.pv, S.cnd complete; S.hv and S.v[vb^1] free
-      long long tS1 = 0, tS2 = 0, tPub = 0;
+      __syncthreads();  // S1 (the only CTA-wide barrier of a phase): S.v[vb], S.pv, S.cnd complete
+      long long tS1 = 0;
       if (P.dbg) {
         tS1 = clock64();
         if (tid == 0 && tEnd) P.dbg[16 * c + 4] += tS1 - tEnd;  // wait at S1 after my slack
       }
       const float* v = S.v[vb];
-      if (ph == 1 && warp < 4) ls = v[4 * c + warp];
       const int slot = (int)(q % 3);
-      const uint32_t par = (uint32_t)((q / 3) & 1);
-      const int nph = (ph == NPH) ? 1 : ph + 1;
-      const int nt = (ph == NPH) ? t + 1 : t;
-      const bool do_past = (nph <= L) && (nt < T);
-      // history of the next layer (already final: >= 1 step old), fetched early
-      uint4 hraw[4];
-      const unsigned long long* hp2 = nullptr;
-      const unsigned long long* hp1 = nullptr;
-      uint32_t tag2 = 0, tag1 = 0;
-      if (warp < 4 && do_past) {
-        const int d = S.dil[nph];
-        const int R = 2 * d + 1;
-        const unsigned long long* hb = P.hist + S.hoff[nph];
-        // ring slot of step nt: S.pos holds t mod R (nt == t, or t + 1 for the wrap to phase 1)
-        int pn = S.pos[nph] + (nt - t);
-        if (pn >= R) pn -= R;
-        int p1 = pn - d;        // (nt - d) mod R
-        if (p1 < 0) p1 += R;
-        int p2 = p1 - d;        // (nt - 2d) mod R
-        if (p2 < 0) p2 += R;
-        if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
-        if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
-        hraw[0] = hp2 ? ldv4(hp2) : make_uint4(0, 0, 0, 0);
-        hraw[1] = hp2 ? ldv4(hp2 + 256) : make_uint4(0, 0, 0, 0);
-        hraw[2] = hp1 ? ldv4(hp1) : make_uint4(0, 0, 0, 0);
-        hraw[3] = hp1 ? ldv4(hp1 + 256) : make_uint4(0, 0, 0, 0);
-      }
-      long long tH = 0, tR = 0;
-      if (P.dbg && tid == 0) tH = clock64();
-      fg_mbar_wait(&S.mbar[slot], par);
-      if (P.dbg && tid == 0) { tR = clock64(); P.dbg[16 * c + 7] += tH - tS1; P.dbg[16 * c + 8] += tR - tH; }
-      const float* blk = S.ring[slot];
-
-      // ---- critical compute ----
-      if (ph != L + 1) {
-        const int r = warp >> 1, half = warp & 1;
-        float a = dot_rows<3>(blk + OFF_D + r * 768 + half * 384, v + half * 384, lane);
-        float b = 0.f;
-        if (warp < 4 && ph <= L) b = dot_rows<2>(blk + OFF_L + warp * 256, v + 512, lane);
-        warp_sum2(a, b);
-        if (P.dbg && tid == 0) P.dbg[16 * c + 9] += clock64() - tR;
-        if (lane == 0) S.red_d[r][half] = a;
-        if (warp < 4 && ph <= L) {
-          // l_{ph-1}[4c+warp] = l_{ph-2}[..] + Wr_{ph-1} g_{ph-1} + br_{ph-1}  (all lanes agree)
-          ls += b + blk[OFF_C + warp];
-          if (lane < XREP)        // exchange copies, one per replica
-            publish(P.xbuf + ((size_t)ph * XREP + lane) * XSLOT + 4 * c + warp, ls, tag);
-          else if (lane == XREP)  // history ring of layer ph (read again d and 2d steps later)
-            publish(P.hist + S.hoff[ph] + (size_t)S.pos[ph] * FW + 4 * c + warp, ls, tag);
+      if (warp >= 4) {
+        // ======================= poll group (warps 4-7) =======================
+        // receives THIS phase's exchange (what the compute groups of all CTAs publish below)
+        // into S.v[vb^1] for the next phase; it never waits for this CTA's own compute
+        if (tid == 128) {
+          const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
+          if (qn < total_q)
+            bulk_load(S.ring[qn % 3], my_blocks + (size_t)(qn % NPH) * phase_stride, BLOCK_BYTES,
+                      &S.mbar[qn % 3]);
         }
-      } else if (warp < 2) {
-        const float a = warp_sum(dot_rows<2>(blk + OFF_S + warp * 512, v + 512, lane));
-        sk = fmaxf(sk + a + blk[OFF_C + 4 + warp], 0.f);  // relu(s) after the last skip
-        if (lane < XREP)
-          publish(P.xbuf + ((size_t)ph * XREP + lane) * XSLOT + 512 + 2 * c + warp, sk, tag);
-      }
-      if (P.dbg && tid == 0) P.dbg[16 * c + 0] += clock64() - tS1;  // hist issue + ring wait + critical
-      __syncthreads();  // S2
-      if (P.dbg) {
-        tS2 = clock64();
-        if (tid == 0) P.dbg[16 * c + 1] += tS2 - tS1;
-      }
-      if (tid < 2 * XREP) {  // thread (j, replica): the value is recomputed per replica
-        const int j = tid & 1, rep = tid >> 1;
-        unsigned long long* dst = P.xbuf + ((size_t)ph * XREP + rep) * XSLOT + 512 + 2 * c + j;
-        if (ph <= L) {
-          const float ds = S.red_d[j][0] + S.red_d[j][1] + cnd[ph][j] + S.pv[j];
-          const float dt = S.red_d[2 + j][0] + S.red_d[2 + j][1] + cnd[ph][2 + j] + S.pv[2 + j];
-          publish(dst, sigmoid_fast(ds) * tanh_fast(dt), tag);
-        } else if (ph == L + 2) {  // h = relu(out1 . relu(s) + cond_out1)
-          publish(dst, fmaxf(S.red_d[j][0] + S.red_d[j][1] + cnd[ph][j], 0.f), tag);
+        const int k = tid - 128;
+        float* vn = S.v[vb ^ 1];
+        const bool need_l = (ph + 1 <= L);
+        const unsigned long long* slotp = P.xbuf + ((size_t)ph * XREP + (c & (nrep - 1))) * XSLOT;
+        const unsigned long long* pg = slotp + 512 + 2 * k;
+        const unsigned long long* pl0 = slotp + 2 * k;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
+        bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
+        long long w0 = 0;
+        int spins = 0;
+        for (;;) {
+          if (!ok0) r0 = LDX(pl0);
+          if (!ok1 && (!f_seq || ok0)) r1 = LDX(pl0 + 256);
+          if (!ok2 && (!f_seq || (ok0 && ok1))) r2 = LDX(pg);
+          ok0 = ok0 || (r0.y == tag && r0.w == tag);
+          ok1 = ok1 || (r1.y == tag && r1.w == tag);
+          ok2 = ok2 || (r2.y == tag && r2.w == tag);
+          if (ok0 && ok1 && ok2) break;
+          if (++spins == 4096) {
+            spins = 0;
+            if (w0 == 0) w0 = clock64();
+            else if (clock64() - w0 > FG_WATCHDOG) fg_die("exchange wait");
+          }
         }
-      }
+        if (need_l) {
+          vn[2 * k] = __uint_as_float(r0.x); vn[2 * k + 1] = __uint_as_float(r0.z);
+          vn[256 + 2 * k] = __uint_as_float(r1.x); vn[256 + 2 * k + 1] = __uint_as_float(r1.z);
+        }
+        vn[512 + 2 * k] = __uint_as_float(r2.x);
+        vn[512 + 2 * k + 1] = __uint_as_float(r2.z);
+        if (P.dbg && tid == 128) P.dbg[16 * c + 5] += clock64() - tS1;
+      } else {
+        // ======================= compute group (warps 0-3) =======================
+        if (ph == 1) {
+          if (warp >= 2) { ls0 = v[4 * c + 2 * (warp - 2)]; ls1 = v[4 * c + 2 * (warp - 2) + 1]; }
+        }
+        const int nph = (ph == NPH) ? 1 : ph + 1;
+        const int nt = (ph == NPH) ? t + 1 : t;
+        const bool do_past = (nph <= L) && (nt < T);
+        // history of the next layer (>= 1 step old, so already final), requested early
+        uint4 hraw[4];
+        const unsigned long long* hp2 = nullptr;
+        const unsigned long long* hp1 = nullptr;
+        uint32_t tag2 = 0, tag1 = 0;
+        if (do_past) {
+          const int d = S.dil[nph];
+          const int R = 2 * d + 1;
+          const unsigned long long* hb = P.hist + S.hoff[nph];
+          int pn = S.pos[nph] + (nt - t);
+          if (pn >= R) pn -= R;
+          int p1 = pn - d;
+          if (p1 < 0) p1 += R;
+          int p2 = p1 - d;
+          if (p2 < 0) p2 += R;
+          if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
+          if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
+          hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
+          hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
+          hraw[2] = hp1 ? LDX(hp1) : make_uint4(0, 0, 0, 0);
+          hraw[3] = hp1 ? LDX(hp1 + 256) : make_uint4(0, 0, 0, 0);
+        }
+        const float* blk = S.ring[slot];  // arrival was checked in the previous phase's slack
+        unsigned long long* xs = P.xbuf + ((size_t)ph * XREP + lane) * XSLOT;  // my replica (lane < nrep)
 
-      if (P.dbg && tid == 0) { tPub = clock64(); P.dbg[16 * c + 2] += tPub - tS2; }  // finalize + publish
-      if (warp < 4) {
-        // ---------------- slack group ----------------
+        // ---- critical section: no CTA barrier, every warp publishes its own results ----
+        if (ph == L + 1) {
+          if (warp < 2) {
+            const float a = warp_sum(dot_rows<2>(blk + OFF_S + warp * 512, v + 512, lane));
+            sk = fmaxf(sk + a + blk[OFF_C + 4 + warp], 0.f);  // relu(s) after the last skip
+            if (lane < nrep) PUB(xs + 512 + 2 * c + warp, sk, tag);
+          }
+        } else if (warp < 2) {
+          // gate pair `warp`: rows (sig, tanh) of the dilated conv [W2 | M] . [l_{ph-2} | g_{ph-1}]
+          float a = dot_rows<6>(blk + OFF_D + warp * 768, v, lane);
+          float b = (ph <= L) ? dot_rows<6>(blk + OFF_D + (2 + warp) * 768, v, lane) : 0.f;
+          warp_sum2(a, b);
+          if (lane < nrep) {
+            float val;
+            if (ph <= L)
+              val = sigmoid_fast(a + cnd[ph][warp] + S.pv[warp]) *
+                    tanh_fast(b + cnd[ph][2 + warp] + S.pv[2 + warp]);
+            else  // ph == L + 2: h = relu(out1 . relu(s) + cond_out1)
+              val = fmaxf(a + cnd[ph][warp], 0.f);
+            PUB(xs + 512 + 2 * c + warp, val, tag);
+          }
+        } else if (ph <= L) {
+          // residual channels 4c + r0, 4c + r0 + 1:  l_{ph-1} = l_{ph-2} + Wr_{ph-1} g_{ph-1} + br_{ph-1}
+          const int r0 = 2 * (warp - 2);
+          float a = dot_rows<2>(blk + OFF_L + r0 * 256, v + 512, lane);
+          float b = dot_rows<2>(blk + OFF_L + (r0 + 1) * 256, v + 512, lane);
+          warp_sum2(a, b);
+          ls0 += a + blk[OFF_C + r0];
+          ls1 += b + blk[OFF_C + r0 + 1];
+          if (lane < nrep) {
+            PUB(xs + 4 * c + r0, ls0, tag);
+            PUB(xs + 4 * c + r0 + 1, ls1, tag);
+          } else if (lane == XREP) {  // history ring of layer ph (read again d and 2d steps later)
+            unsigned long long* hq = P.hist + S.hoff[ph] + (size_t)S.pos[ph] * FW + 4 * c + r0;
+            PUB(hq, ls0, tag);
+            PUB(hq + 1, ls1, tag);
+          }
+        }
+        long long tPub = 0;
+        if (P.dbg && tid == 0) { tPub = clock64(); P.dbg[16 * c + 0] += tPub - tS1; }
+
+        // ---- slack: overlaps the exchange latency ----
         if (do_past) {
           float2 f[4];
 #pragma unroll
@@ -396,57 +453,18 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
           a = warp_sum(a) + blk[OFF_C + 4 + warp];
           sk = (ph == 1) ? a : sk + a;
         }
-        if (do_past) {
+        if (q + 1 < total_q) {
+          // next phase's weights: verified here so the next critical section starts at once
           const int nslot = (int)((q + 1) % 3);
           fg_mbar_wait(&S.mbar[nslot], (uint32_t)(((q + 1) / 3) & 1));
-          const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + warp * 1024, S.hv, lane));
-          if (lane == 0) S.pv[warp] = a;
-        } else if (lane == 0) {
-          S.pv[warp] = 0.f;
-        }
-      } else {
-        // ---------------- poll group ----------------
-        if (tid == 128) {
-          const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
-          if (qn < (long long)T * NPH)
-            bulk_load(S.ring[qn % 3], my_blocks + (size_t)(qn % NPH) * phase_stride, BLOCK_BYTES,
-                      &S.mbar[qn % 3]);
-        }
-        const int k = tid - 128;
-        float* vn = S.v[vb ^ 1];
-        // next phase needs g_ph / s' / h, and (layers only) l_{ph-1} from layer ph's history
-        // ring; the three 16-byte words are polled together so one L2 round trip covers all
-        const bool need_l = (ph + 1 <= L);
-        const unsigned long long* slotp = P.xbuf + ((size_t)ph * XREP + (c & (XREP - 1))) * XSLOT;
-        const unsigned long long* pg = slotp + 512 + 2 * k;
-        const unsigned long long* pl0 = slotp + 2 * k;
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
-        bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
-        long long w0 = 0;
-        int spins = 0;
-        for (;;) {
-          if (!ok0) r0 = ldv4(pl0);
-          if (!ok1) r1 = ldv4(pl0 + 256);
-          if (!ok2) r2 = ldv4(pg);
-          ok0 = ok0 || (r0.y == tag && r0.w == tag);
-          ok1 = ok1 || (r1.y == tag && r1.w == tag);
-          ok2 = ok2 || (r2.y == tag && r2.w == tag);
-          if (ok0 && ok1 && ok2) break;
-          if (++spins == 4096) {
-            spins = 0;
-            if (w0 == 0) w0 = clock64();
-            else if (clock64() - w0 > FG_WATCHDOG) fg_die("exchange wait");
+          if (do_past) {
+            const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + warp * 1024, S.hv, lane));
+            if (lane == 0) S.pv[warp] = a;
           }
         }
-        if (need_l) {
-          vn[2 * k] = __uint_as_float(r0.x); vn[2 * k + 1] = __uint_as_float(r0.z);
-          vn[256 + 2 * k] = __uint_as_float(r1.x); vn[256 + 2 * k + 1] = __uint_as_float(r1.z);
-        }
-        vn[512 + 2 * k] = __uint_as_float(r2.x);
-        vn[512 + 2 * k + 1] = __uint_as_float(r2.z);
-        if (P.dbg && tid == 128) P.dbg[16 * c + 5] += clock64() - tS2;
+        if (!do_past && lane == 0) S.pv[warp] = 0.f;
+        if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[16 * c + 3] += now - tPub; tEnd = now; }
       }
-      if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[16 * c + 3] += now - tPub; tEnd = now; }
     }
 
     // ---------------- output head + sampler (every CTA, redundantly) ----------------
@@ -906,6 +924,7 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     P.O = h->O;
     P.loss_type = h->cfg.loss_type;
     P.seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)b;
+    P.flags = getenv("NSW_FASTGEN_FLAGS") ? atoi(getenv("NSW_FASTGEN_FLAGS")) : 0;
     P.quant = 65536.0f;
     void* args[] = {&P};
     NSW_CUDA(cudaLaunchCooperativeKernel((void*)fastgen_kernel, dim3(NC), dim3(NT), args,

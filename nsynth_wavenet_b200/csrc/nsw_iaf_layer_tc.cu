@@ -183,43 +183,63 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // scratch with an XOR swizzle (chunk ^ row%8) turns that into one full half-row per thread and
 // back, conflict-free in both directions.  (Row-per-thread LDG/STG costs 32 L1TEX sectors per
 // instruction and made L1TEX the limiter: profiles/r01.)
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
+}
+// scr: 32-bit shared-space address of this warp's 4 KB scratch
 __device__ __forceinline__ void rows_load128(const float4* __restrict__ g /*row 0 of this warp, this half*/,
-                                             float4* scr, int lane, float4 (&out)[8]) {
+                                             uint32_t scr, int lane, float4 (&out)[8]) {
   float4 t[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) t[i] = __ldg(g + (size_t)(4 * i + (lane >> 3)) * 16 + (lane & 7));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + (lane >> 3);
-    scr[r * 8 + ((lane & 7) ^ (r & 7))] = t[i];
+    sts128(scr + (uint32_t)(r * 8 + ((lane & 7) ^ (r & 7))) * 16u, t[i]);
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) out[j] = scr[lane * 8 + (j ^ (lane & 7))];
+  for (int j = 0; j < 8; ++j) out[j] = lds128(scr + (uint32_t)(lane * 8 + (j ^ (lane & 7))) * 16u);
   __syncwarp();
 }
-__device__ __forceinline__ void rows_store128(float4* __restrict__ g, float4* scr, int lane,
+__device__ __forceinline__ void rows_store128(float4* __restrict__ g, uint32_t scr, int lane,
                                               const float4 (&in)[8]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) scr[lane * 8 + (j ^ (lane & 7))] = in[j];
+  for (int j = 0; j < 8; ++j) sts128(scr + (uint32_t)(lane * 8 + (j ^ (lane & 7))) * 16u, in[j]);
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + (lane >> 3);
-    g[(size_t)r * 16 + (lane & 7)] = scr[r * 8 + ((lane & 7) ^ (r & 7))];
+    g[(size_t)r * 16 + (lane & 7)] = lds128(scr + (uint32_t)(r * 8 + ((lane & 7) ^ (r & 7))) * 16u);
   }
   __syncwarp();
 }
 // 32 rows x 64 B (half of a 128 B bf16 row): lane -> row 8i + lane/4, chunk lane%4
-__device__ __forceinline__ void rows_store64(uint4* __restrict__ g /*row pitch 8 uint4*/, uint4* scr,
+__device__ __forceinline__ void rows_store64(uint4* __restrict__ g /*row pitch 8 uint4*/, uint32_t scr,
                                              int lane, const uint4 (&in)[4]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) scr[lane * 4 + (j ^ ((lane >> 1) & 3))] = in[j];
+  for (int j = 0; j < 4; ++j) {
+    const uint4 v = in[j];
+    sts128(scr + (uint32_t)(lane * 4 + (j ^ ((lane >> 1) & 3))) * 16u,
+           make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)));
+  }
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = 8 * i + (lane >> 2);
-    g[(size_t)r * 8 + (lane & 3)] = scr[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+    const float4 v = lds128(scr + (uint32_t)(r * 4 + ((lane & 3) ^ ((r >> 1) & 3))) * 16u);
+    g[(size_t)r * 8 + (lane & 3)] =
+        make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
   }
   __syncwarp();
 }
@@ -377,7 +397,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     const int half = (warp - 2) >> 2;
     const int qd = warp & 3;  // TMEM lane quarter accessible to this warp
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
-    float4* scr = reinterpret_cast<float4*>(smem + OFF_SCR + (warp - 2) * 4096);
+    const uint32_t scr = sbase + OFF_SCR + (uint32_t)(warp - 2) * 4096u;
     const float4* bptr = reinterpret_cast<const float4*>(p.br) + half * 8;
     for (int it = 0; it < n_my; ++it) {
       const int b = it & 1;
@@ -446,8 +466,8 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
         else       { hh[i >> 1].x = h01; hh[i >> 1].y = h23; ll2[i >> 1].x = l01; ll2[i >> 1].y = l23; }
       }
       rows_store128(reinterpret_cast<float4*>(p.l_out + wrow * C) + half * 8, scr, lane, lq);
-      rows_store64(reinterpret_cast<uint4*>(p.out_hi + wrow * C) + half * 4, reinterpret_cast<uint4*>(scr), lane, hh);
-      rows_store64(reinterpret_cast<uint4*>(p.out_lo + wrow * C) + half * 4, reinterpret_cast<uint4*>(scr), lane, ll2);
+      rows_store64(reinterpret_cast<uint4*>(p.out_hi + wrow * C) + half * 4, scr, lane, hh);
+      rows_store64(reinterpret_cast<uint4*>(p.out_lo + wrow * C) + half * 4, scr, lane, ll2);
     }
   }
 
