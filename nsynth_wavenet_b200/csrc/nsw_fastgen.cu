@@ -128,6 +128,18 @@ __device__ __forceinline__ uint4 ldv4_vol(const unsigned long long* p) {
                : "memory");
   return r;
 }
+__device__ __forceinline__ uint4 ldv4_cg(const unsigned long long* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void publish_cg(unsigned long long* p, float v, uint32_t tag) {
+  asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
+               : "memory");
+}
 __device__ __forceinline__ void publish_vol(unsigned long long* p, float v, uint32_t tag) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
                : "memory");
@@ -269,8 +281,10 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
 
   const bool f_seq = (P.flags & 1) != 0, f_vol = (P.flags & 2) != 0;
   const int nrep = (P.flags & 4) ? 1 : XREP;
-  auto PUB = [&](unsigned long long* p, float v, uint32_t tg) { if (f_vol) publish_vol(p, v, tg); else publish(p, v, tg); };
-  auto LDX = [&](const unsigned long long* p) -> uint4 { return f_vol ? ldv4_vol(p) : ldv4(p); };
+  const bool f_nostream = (P.flags & 8) != 0;  // TIMING EXPERIMENT ONLY: reuse stale weights, results are wrong
+  const bool f_cgld = (P.flags & 16) != 0, f_cgst = (P.flags & 32) != 0;
+  auto PUB = [&](unsigned long long* p, float v, uint32_t tg) { if (f_cgst) publish_cg(p, v, tg); else if (f_vol) publish_vol(p, v, tg); else publish(p, v, tg); };
+  auto LDX = [&](const unsigned long long* p) -> uint4 { return f_cgld ? ldv4_cg(p) : (f_vol ? ldv4_vol(p) : ldv4(p)); };
   float x1 = 0.f, x2 = 0.f;  // inputs of the two previous steps (conv_start queues, rate 1)
   float ls0 = 0.f, ls1 = 0.f, sk = 0.f;  // warps 2,3: two residual channels; warps 0,1: one skip channel
   long long q = 0;           // global phase counter -> weight ring slot / parity
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         // into S.v[vb^1] for the next phase; it never waits for this CTA's own compute
         if (tid == 128) {
           const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
-          if (qn < total_q)
+          if (qn < total_q && !(f_nostream && qn >= 3))
             bulk_load(S.ring[qn % 3], my_blocks + (size_t)(qn % NPH) * phase_stride, BLOCK_BYTES,
                       &S.mbar[qn % 3]);
         }
@@ -456,7 +470,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         if (q + 1 < total_q) {
           // next phase's weights: verified here so the next critical section starts at once
           const int nslot = (int)((q + 1) % 3);
-          fg_mbar_wait(&S.mbar[nslot], (uint32_t)(((q + 1) / 3) & 1));
+          if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (uint32_t)(((q + 1) / 3) & 1));
           if (do_past) {
             const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + warp * 1024, S.hv, lane));
             if (lane == 0) S.pv[warp] = a;
