@@ -32,7 +32,9 @@ struct TcSmemTail {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
-constexpr size_t TC_SMEM_BYTES = STAGES * STAGE_BYTES + sizeof(TcSmemTail) + 1024;
+constexpr uint32_t TC_OFF_SCR = STAGES * STAGE_BYTES + 512;  // 4 epilogue warps x 4 KB
+static_assert(sizeof(TcSmemTail) <= 512, "barrier block grew");
+constexpr size_t TC_SMEM_BYTES = TC_OFF_SCR + 4 * 4096 + 1024;
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -138,28 +140,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// one output row, 32 consecutive columns starting at n (n % 32 == 0)
-__device__ __forceinline__ void store_row32(const ConvGemm& g, const EpiParams& e, int clip, int m,
-                                            int n, const float* v) {
-  if (m >= g.mclip || n >= g.N) return;
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
+}
+
+// Epilogue of one warp for 32 rows x 32 consecutive columns (n % 32 == 0).  Thread `lane` holds
+// row m0 + lane in v[32].  Values go through a swizzled 4 KB smem scratch so that global memory
+// is written with full 128 B lines (8 lanes per row) instead of 32 scattered 16 B pieces per
+// instruction (row-per-thread stores made L1TEX the limiter; profiles/r01).
+__device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams& e, int clip, int m0,
+                                             int n, const float* v, uint32_t scr, int lane) {
+  if (n >= g.N) return;  // warp-uniform
+  float f[32];
+  int rr = 0, co = n;
   if (e.mode == EPI_PLANES) {
-    const size_t M = (size_t)g.nclips * g.mclip;
-    const size_t grow = (size_t)clip * g.mclip + m;
-    float* dst = e.out_f32 + ((size_t)(n >> 6) * M + grow) * 64 + (n & 63);
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 b = __ldg(b4 + j);
-      reinterpret_cast<float4*>(dst)[j] =
-          make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+      f[4 * j] = v[4 * j] + b.x; f[4 * j + 1] = v[4 * j + 1] + b.y;
+      f[4 * j + 2] = v[4 * j + 2] + b.z; f[4 * j + 3] = v[4 * j + 3] + b.w;
     }
   } else {
-    const int rr = n / e.cout, co = n - rr * e.cout;
-    const int o = m * e.s + rr - e.p;
-    if (o < 0 || o >= e.Lout) return;
-    const size_t off = ((size_t)clip * e.Lout + o) * e.cout + co;
+    rr = n / e.cout;
+    co = n - rr * e.cout;
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + co);
-    float f[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 b = __ldg(b4 + j);
@@ -168,24 +183,64 @@ __device__ __forceinline__ void store_row32(const ConvGemm& g, const EpiParams& 
       f[4 * j + 2] = apply_act(v[4 * j + 2] + b.z, e.act);
       f[4 * j + 3] = apply_act(v[4 * j + 3] + b.w, e.act);
     }
-    if (e.out_f32) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(e.out_f32 + off)[j] =
-            make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  }
+  // destination of row r (0..31) of this warp: pointer to its 32-float chunk, or NULL
+  auto row_f32 = [&](int r) -> float4* {
+    const int m = m0 + r;
+    if (m >= g.mclip || e.out_f32 == nullptr) return nullptr;
+    if (e.mode == EPI_PLANES) {
+      const size_t M = (size_t)g.nclips * g.mclip;
+      return reinterpret_cast<float4*>(e.out_f32 + ((size_t)(n >> 6) * M + (size_t)clip * g.mclip + m) * 64 + (n & 63));
     }
-    if (e.out_hi) {
+    const int o = m * e.s + rr - e.p;
+    if (o < 0 || o >= e.Lout) return nullptr;
+    return reinterpret_cast<float4*>(e.out_f32 + ((size_t)clip * e.Lout + o) * e.cout + co);
+  };
+  if (e.out_f32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts128(scr + (uint32_t)(lane * 8 + (j ^ (lane & 7))) * 16u,
+             make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3);
+      float4* dst = row_f32(r);
+      const float4 val = lds128(scr + (uint32_t)(r * 8 + ((lane & 7) ^ (r & 7))) * 16u);
+      if (dst) dst[lane & 7] = val;
+    }
+    __syncwarp();
+  }
+  if (e.mode == EPI_DECONV && e.out_hi) {
+    // bf16 split planes: 32 values = 64 B per row per plane; both planes share one pass
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        __align__(16) __nv_bfloat16 hi[8], lo[8];
+        uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          hi[i] = __float2bfloat16_rn(f[8 * j + i]);
-          lo[i] = __float2bfloat16_rn(f[8 * j + i] - __bfloat162float(hi[i]));
+        for (int k = 0; k < 4; ++k) {
+          const float a = f[8 * j + 2 * k], b = f[8 * j + 2 * k + 1];
+          const float ah = __bfloat162float(__float2bfloat16_rn(a));
+          const float bh = __bfloat162float(__float2bfloat16_rn(b));
+          __nv_bfloat162 pk = pl == 0 ? __floats2bfloat162_rn(ah, bh) : __floats2bfloat162_rn(a - ah, b - bh);
+          w[k] = *reinterpret_cast<uint32_t*>(&pk);
         }
-        reinterpret_cast<uint4*>(e.out_hi + off)[j] = *reinterpret_cast<uint4*>(hi);
-        reinterpret_cast<uint4*>(e.out_lo + off)[j] = *reinterpret_cast<uint4*>(lo);
+        sts128(scr + (uint32_t)(lane * 4 + (j ^ ((lane >> 1) & 3))) * 16u,
+               make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3])));
       }
+      __syncwarp();
+      __nv_bfloat16* base = pl == 0 ? e.out_hi : e.out_lo;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + (lane >> 2);
+        const int m = m0 + r;
+        const int o = m * e.s + rr - e.p;
+        const float4 val = lds128(scr + (uint32_t)(r * 4 + ((lane & 3) ^ ((r >> 1) & 3))) * 16u);
+        if (m < g.mclip && o >= 0 && o < e.Lout)
+          reinterpret_cast<float4*>(base + ((size_t)clip * e.Lout + o) * e.cout + co)[lane & 3] = val;
+      }
+      __syncwarp();
     }
   }
 }
@@ -290,11 +345,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh,
   } else {
     // ------------------------------- epilogue ---------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t scr = smem_u32(smem) + TC_OFF_SCR + (uint32_t)(warp - 2) * 4096u;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int clip = mt / tiles_per_clip;
-      const int m = (mt - clip * tiles_per_clip) * TBM + q * 32 + lane;
+      const int m0 = (mt - clip * tiles_per_clip) * TBM + q * 32;  // first of this warp's 32 rows
       const int n0 = nt * TBN;
       const int as = it & 1;
       mbar_wait(&tail->tmem_full[as], (it >> 1) & 1);
@@ -303,7 +359,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh,
       for (int c0 = 0; c0 < TBN; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TBN + c0), v);
-        store_row32(g, e, clip, m, n0 + c0, v);
+        store_tile32(g, e, clip, m0, n0 + c0, v, scr, lane);
       }
       tc_fence_before();
       __syncwarp();

@@ -17,6 +17,8 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
+
 namespace nsw {
 
 namespace {
@@ -197,11 +199,13 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 // scr: 32-bit shared-space address of this warp's 4 KB scratch
-__device__ __forceinline__ void rows_load128(const float4* __restrict__ g /*row 0 of this warp, this half*/,
-                                             uint32_t scr, int lane, float4 (&out)[8]) {
-  float4 t[8];
+__device__ __forceinline__ void rows_issue128(const float4* __restrict__ g /*row 0 of this warp, this half*/,
+                                              int lane, float4 (&t)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) t[i] = __ldg(g + (size_t)(4 * i + (lane >> 3)) * 16 + (lane & 7));
+}
+__device__ __forceinline__ void rows_transpose128(uint32_t scr, int lane, const float4 (&t)[8],
+                                                  float4 (&out)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + (lane >> 3);
@@ -252,6 +256,7 @@ struct LayerTcParams {
   __nv_bfloat16* out_lo;
   const float* br;     // [64] natural order
   int dil, tiles_per_clip, n_tiles, layer;
+  long long* dbg;  // optional timeline of CTA 0 (NULL = off): [0..31] MMA warp, [32..95] epilogue warp 2
 };
 
 __global__ void __launch_bounds__(LT_THREADS, 1)
@@ -289,6 +294,8 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem = B->tmem_base;
+  const long long tk0 = clock64();
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
@@ -328,6 +335,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     const uint32_t idesc = lt_idesc();
     lt_wait(&B->wfull, 0);
     fence_after();
+    if (dbg && lane == 0) p.dbg[0] = clock64() - tk0;  // weights landed
     int stage = 0;
     uint32_t phase = 0;
     auto mma2 = [&](int j) {
@@ -347,6 +355,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
           mma_ts(d2, g_hi + 8 * k, wrh + 2 * k, idesc, 1);
         }
         lt_commit(&B->d2_full[b]);
+        if (dbg && j < 6) p.dbg[8 + j] = clock64() - tk0;  // MMA2(j) issued
       }
       __syncwarp();
     };
@@ -381,7 +390,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
             mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, 1);
           }
           lt_commit(&B->empty[stage]);
-          if (tap == 2) lt_commit(&B->d1_full[b]);
+          if (tap == 2) { lt_commit(&B->d1_full[b]); if (dbg && it < 6) p.dbg[1 + it] = clock64() - tk0; }  // MMA1(it) issued
         }
         __syncwarp();
         if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
@@ -399,18 +408,30 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     const uint32_t scr = sbase + OFF_SCR + (uint32_t)(warp - 2) * 4096u;
     const float4* bptr = reinterpret_cast<const float4*>(p.br) + half * 8;
+    // operand half-rows (cond, l) are requested one tile ahead and sit in registers (tc, tl)
+    // while the previous tile's epilogue runs, so their DRAM/L2 latency is never exposed
+    float4 tc[8];
+    if (n_my > 0) {
+      const size_t w0 = (size_t)blockIdx.x * LT_BM + qd * 32;
+      rows_issue128(reinterpret_cast<const float4*>(p.cond + w0 * C) + half * 8, lane, tc);
+    }
     for (int it = 0; it < n_my; ++it) {
       const int b = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
       const int tile = blockIdx.x + it * gridDim.x;
       const size_t wrow = (size_t)tile * LT_BM + qd * 32;  // first of this warp's 32 rows
-      // both operand half-rows are fetched (coalesced) before any waiting: overlaps MMA1
-      float4 cq[8], lq[8];
-      rows_load128(reinterpret_cast<const float4*>(p.cond + wrow * C) + half * 8, scr, lane, cq);
-      rows_load128(reinterpret_cast<const float4*>(p.l_in + wrow * C) + half * 8, scr, lane, lq);
+      float4 cq[8];
+      rows_transpose128(scr, lane, tc, cq);
+      if (it + 1 < n_my) {  // cond streams from HBM: request the next tile's rows now
+        const size_t wn = (size_t)(tile + gridDim.x) * LT_BM + qd * 32;
+        rows_issue128(reinterpret_cast<const float4*>(p.cond + wn * C) + half * 8, lane, tc);
+      }
+      const bool ed = dbg && warp == 2 && lane == 0 && it < 6;
+      if (ed) p.dbg[32 + it * 8 + 0] = clock64() - tk0;  // operands loaded
       // ---- E1: gate ----
       lt_wait(&B->d1_full[b], u & 1);
       fence_after();
+      if (ed) p.dbg[32 + it * 8 + 1] = clock64() - tk0;  // D1 ready
       uint32_t d[32];
       tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
       tmem_ld_wait();
@@ -438,9 +459,15 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
       fence_before();
       __syncwarp();
       if (lane == 0) lt_arrive(&B->g_full[b]);
+      // residual input rows (L2-resident): requested now, their latency hides behind MMA2
+      float4 tl[8], lq[8];
+      rows_issue128(reinterpret_cast<const float4*>(p.l_in + wrow * C) + half * 8, lane, tl);
+      if (ed) p.dbg[32 + it * 8 + 2] = clock64() - tk0;  // g stored
       // ---- E2: residual ----
       lt_wait(&B->d2_full[b], u & 1);
       fence_after();
+      if (ed) p.dbg[32 + it * 8 + 3] = clock64() - tk0;  // D2 ready
+      rows_transpose128(scr, lane, tl, lq);
       tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
       tmem_ld_wait();
       fence_before();
@@ -468,11 +495,13 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
       rows_store128(reinterpret_cast<float4*>(p.l_out + wrow * C) + half * 8, scr, lane, lq);
       rows_store64(reinterpret_cast<uint4*>(p.out_hi + wrow * C) + half * 4, scr, lane, hh);
       rows_store64(reinterpret_cast<uint4*>(p.out_lo + wrow * C) + half * 4, scr, lane, ll2);
+      if (ed) p.dbg[32 + it * 8 + 4] = clock64() - tk0;  // tile stored
     }
   }
 
   fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[30] = clock64() - tk0;
   if (warp == 1) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -552,6 +581,14 @@ int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh,
   p.tiles_per_clip = T / LT_BM;
   p.n_tiles = rows / LT_BM;
   p.layer = layer;
+  p.dbg = nullptr;
+  static long long* dbg_buf = nullptr;
+  const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr && layer == 3;
+  if (want_dbg) {
+    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 128 * sizeof(long long)));
+    NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * sizeof(long long), stream));
+    p.dbg = dbg_buf;
+  }
   const int grid = std::min(p.n_tiles, num_sms);
   iaf_layer_tc_kernel<<<grid, LT_THREADS, LT_SMEM_BYTES, stream>>>(
       *reinterpret_cast<const CUtensorMap*>(map_lh), *reinterpret_cast<const CUtensorMap*>(map_ll),
@@ -559,6 +596,19 @@ int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh,
       *reinterpret_cast<const CUtensorMap*>(map_wrh), *reinterpret_cast<const CUtensorMap*>(map_wrl), p);
   count_launch();
   NSW_CUDA(cudaGetLastError());
+  if (want_dbg) {
+    long long hbuf[128];
+    NSW_CUDA(cudaStreamSynchronize(stream));
+    NSW_CUDA(cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[layer_tc dbg dil=%d] weights %lld | MMA1 issued:", dil, hbuf[0]);
+    for (int i = 0; i < 5; ++i) fprintf(stderr, " %lld", hbuf[1 + i]);
+    fprintf(stderr, " | MMA2 issued:");
+    for (int i = 0; i < 5; ++i) fprintf(stderr, " %lld", hbuf[8 + i]);
+    fprintf(stderr, " | end %lld\n", hbuf[30]);
+    for (int i = 0; i < 5; ++i)
+      fprintf(stderr, "   tile %d: loaded %lld  D1 %lld  g %lld  D2 %lld  stored %lld\n", i, hbuf[32 + 8 * i],
+              hbuf[33 + 8 * i], hbuf[34 + 8 * i], hbuf[35 + 8 * i], hbuf[36 + 8 * i]);
+  }
   return NSW_OK;
 }
 
