@@ -224,21 +224,11 @@ def main():
 
     hp = load_hparams(args.config)
     # ---- weights: rank 0 initialises, NCCL broadcasts one flat blob (the only collective) ----
+    from nsynth_wavenet_b200 import parallel
     w0 = O.init_student_weights(hp, seed=12345)
-    names = list(w0)
-    if world > 1:
-        flat = torch.from_numpy(np.concatenate([w0[n].ravel() for n in names])).to(dev)
-        if rank != 0:
-            flat.zero_()
-        dist.broadcast(flat, src=0)
-        host = flat.cpu().numpy()
-        weights, off = {}, 0
-        for n in names:
-            sz = w0[n].size
-            weights[n] = host[off:off + sz].reshape(w0[n].shape)
-            off += sz
-    else:
-        weights = w0
+    if rank != 0:  # only rank 0's values survive: proves the broadcast carries the weights
+        w0 = {k: np.zeros_like(v) for k, v in w0.items()}
+    weights = parallel.broadcast_weights(w0, device=dev)
     eng = IAFEngine(hp, weights, device=local_rank, engine=args.engine)
 
     B, F = args.batch, args.frames
@@ -279,10 +269,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     gpu_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([gpu_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = parallel.max_over_ranks(gpu_ms, device=dev)
     ms_per_step = total_ms / args.steps
     value = world * B * T * args.steps / (total_ms * 1e-3)
 
@@ -299,10 +286,7 @@ def main():
         _lib.check(lib.nsw_iaf_forward_host(eng._h, mel_h.data_ptr(), None, 2000 + i, B, F, 1,
                                             x_pin.data_ptr(), None, None, None, None))
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T * args.steps / float(te.item())
+    e2e_value = world * B * T * args.steps / parallel.max_over_ranks(e2e_s, device=dev)
 
     # ---- roofline of the dominant kernel (iaf_layer_kernel), measured live with CUDA events
     #      on the launch stream inside the library (separate profiled passes) ----
