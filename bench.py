@@ -159,7 +159,7 @@ def fastgen_bench(device, steps, hbm_peak):
             'note': 'includes the hoisted cond GEMM; weights stream L2/HBM -> smem every step'}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's own CPU path restated (TF 1.x is not installable
     here), bounded sample, rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
@@ -182,7 +182,7 @@ def run_reference(args):
         'note': 'TensorFlow 1.x is absent: this is the fp32 torch-CPU restatement of the '
                 'reference graph (oracle/torch_port.py), all host threads',
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -202,9 +202,19 @@ def main():
     ap.add_argument('--fastgen-steps', type=int, default=32000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # the contract is ONE JSON line on stdout: anything libraries print (e.g. NCCL's version
+    # banner) goes to stderr until the result line is emitted
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
 
     if args.impl == 'reference':
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import torch
@@ -354,7 +364,7 @@ def main():
     elif rank == 0:
         line['cpu_baseline'] = None
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

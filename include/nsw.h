@@ -197,6 +197,29 @@ int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tenso
                           int32_t n_tensors, float* blocks, int64_t blocks_cap, float* cond_w,
                           float* cond_b, int64_t* sizes);
 
+/* ---- teacher full-sequence forward + distillation cross-entropy (BASELINE config 5) --------
+ * replaces: Wavenet.feed_forward (wavenet.py:180-291) as called by
+ * ParallelWavenet.kl_loss_logistic (parallel_wavenet.py:382) — every contraction on tcgen05. */
+typedef struct nsw_teacher nsw_teacher;
+int nsw_teacher_create(const nsw_wavenet_config* cfg, const nsw_tensor* tensors, int32_t n_tensors,
+                       int32_t device, nsw_teacher** out);
+void nsw_teacher_destroy(nsw_teacher* h);
+/* wav_scaled [B,T] (T % 128 == 0), mel [B,F,num_mel] with F*prod(strides) >= T (centre-trimmed,
+ * wavenet.py:76-85) -> out_params [B,T,out_width] */
+int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, const float* d_mel, int32_t B,
+                               int32_t T, int32_t F, float* d_out_params, void* stream);
+int nsw_teacher_forward_host(nsw_teacher* h, const float* wav, const float* mel, int32_t B, int32_t T,
+                             int32_t F, float* out_params);
+int nsw_teacher_last_timing(nsw_teacher* h, float* ms);
+/* replaces: loss_func.mol_log_probs (loss_func.py:22-63) on num_samples logistic draws per
+ * (b,t) from the student's (mean_tot, scale_tot) without materialising the xS tile
+ * (parallel_wavenet.py:373-398).  d_eps [S,B,T] logistic noise or NULL (Philox from seed).
+ * result[0] = H_Ps, result[1] = H_Ps_Pt, result[2] = kl_loss (host doubles; synchronises). */
+int nsw_mol_score_device(nsw_teacher* h, const float* d_te_out_params, const float* d_mean_tot,
+                         const float* d_scale_tot, const float* d_log_scale_tot, const float* d_eps,
+                         uint64_t seed, int32_t num_samples, int32_t B, int32_t T, double* result,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

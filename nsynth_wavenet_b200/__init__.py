@@ -2,6 +2,6 @@
 bfs18/nsynth_wavenet: hand-written sm_100a CUDA behind a C ABI (include/nsw.h) and
 the reference's own Python entry points (wavenet.parallelgen / wavenet.fastgen)."""
 from . import _lib  # noqa: F401
-from .engine import IAFEngine, FastgenEngine, iaf_config, wavenet_config  # noqa: F401
+from .engine import IAFEngine, FastgenEngine, TeacherEngine, iaf_config, wavenet_config  # noqa: F401
 
-__all__ = ['IAFEngine', 'FastgenEngine', 'iaf_config', 'wavenet_config']
+__all__ = ['IAFEngine', 'FastgenEngine', 'TeacherEngine', 'iaf_config', 'wavenet_config']

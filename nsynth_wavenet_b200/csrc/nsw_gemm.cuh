@@ -27,9 +27,16 @@ struct ConvGemm {
   int a_off;
   int mclip;  // GEMM rows per clip
   int N;      // GEMM columns (multiple of 64)
+  int tap_stride = 1;  // frame = m + a_off + tap * tap_stride (dilated causal conv: stride = d)
+  int x_pitch = 0;     // elements between consecutive frames of X (0 = cin)
 };
 
-enum EpiMode { EPI_PLANES = 0, EPI_DECONV = 1 };
+// EPI_ROWS : out[row * ld_out + n] (+)= D + bias[n] (+ addend[row * ld_add + n]); optional relu;
+//            optional bf16 hi/lo copy of the result (relu'd for n >= relu_split_from)
+// EPI_GATE : columns are gate-interleaved (2j = sigmoid half, 2j+1 = tanh half of gate j);
+//            g[row * ld_split + n/2 + j] = sigmoid(D[2j] + c[2j]) * tanh(D[2j+1] + c[2j+1]),
+//            c = addend[row * ld_add + n + ...]; g is written as bf16 hi/lo only
+enum EpiMode { EPI_PLANES = 0, EPI_DECONV = 1, EPI_ROWS = 2, EPI_GATE = 3 };
 
 struct EpiParams {
   int mode;
@@ -40,6 +47,10 @@ struct EpiParams {
   __nv_bfloat16* out_hi;  // optional bf16 split of the same values (hi + lo ~ fp32)
   __nv_bfloat16* out_lo;
   int s, p, cout, act, Lout;
+  // EPI_ROWS / EPI_GATE
+  const float* addend = nullptr;
+  int ld_out = 0, ld_add = 0, ld_split = 0;
+  int accumulate = 0, relu_out = 0, relu_split_from = 1 << 30;
 };
 
 // fp32 X [nclips, L, cin], fp32 Bw [ntaps*cin, N]

@@ -154,6 +154,139 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
+// coalesced read of a [32 rows x 32 floats] block (row pitch `ld` floats) into one row per thread
+__device__ __forceinline__ void load_rows32(const float* base, size_t row0, int ld, int col, int rows_valid,
+                                            uint32_t scr, int lane, float (&out)[32]) {
+  float4 t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    t[i] = r < rows_valid
+               ? __ldg(reinterpret_cast<const float4*>(base + (row0 + r) * (size_t)ld + col) + (lane & 7))
+               : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    sts128(scr + (uint32_t)(r * 8 + ((lane & 7) ^ (r & 7))) * 16u, t[i]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 q = lds128(scr + (uint32_t)(lane * 8 + (j ^ (lane & 7))) * 16u);
+    out[4 * j] = q.x; out[4 * j + 1] = q.y; out[4 * j + 2] = q.z; out[4 * j + 3] = q.w;
+  }
+  __syncwarp();
+}
+// coalesced write of one row per thread: nchunks 16-byte chunks per row (8 = 32 floats, 4 = 32 bf16,
+// 2 = 16 bf16), destination row pitch given in bytes
+template <int NCH>
+__device__ __forceinline__ void store_rows(unsigned char* base, size_t row0, size_t pitch_bytes,
+                                           int rows_valid, uint32_t scr, int lane, const uint4 (&in)[NCH]) {
+  constexpr int RPI = 32 / NCH;  // rows per instruction
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+    sts128(scr + (uint32_t)(lane * NCH + (j ^ ((lane * NCH / 8) & (NCH - 1)))) * 16u,
+           make_float4(__uint_as_float(in[j].x), __uint_as_float(in[j].y), __uint_as_float(in[j].z),
+                       __uint_as_float(in[j].w)));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int r = RPI * i + lane / NCH;
+    const int c = lane % NCH;
+    const float4 q = lds128(scr + (uint32_t)(r * NCH + (c ^ ((r * NCH / 8) & (NCH - 1)))) * 16u);
+    if (r < rows_valid)
+      reinterpret_cast<float4*>(base + (row0 + r) * pitch_bytes)[c] = q;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* a) {
+  uint4 r;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(a[4], a[5]), p3 = __floats2bfloat162_rn(a[6], a[7]);
+  r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+  r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+  return r;
+}
+
+// EPI_ROWS / EPI_GATE (see nsw_gemm.cuh) for 32 rows x 32 columns
+__device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiParams& e, int clip, int m0,
+                                                  int n, const float* v, uint32_t scr, int lane) {
+  const int rows_valid = min(32, g.mclip - m0);
+  if (rows_valid <= 0) return;
+  const size_t row0 = (size_t)clip * g.mclip + m0;
+  float f[32];
+  if (e.mode == EPI_GATE) {
+    float c[32];
+    load_rows32(e.addend, row0, e.ld_add, n, rows_valid, scr, lane, c);
+    float gh[16], gl[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float sg = 1.0f / (1.0f + expf(-(v[2 * j] + c[2 * j])));
+      const float gv = sg * tanhf(v[2 * j + 1] + c[2 * j + 1]);
+      gh[j] = __bfloat162float(__float2bfloat16_rn(gv));
+      gl[j] = gv - gh[j];
+    }
+    const uint4 hi[2] = {pack8_bf16(gh), pack8_bf16(gh + 8)};
+    const uint4 lo[2] = {pack8_bf16(gl), pack8_bf16(gl + 8)};
+    const size_t pb = (size_t)e.ld_split * 2;
+    store_rows<2>(reinterpret_cast<unsigned char*>(e.out_hi + (n >> 1)), row0, pb, rows_valid, scr, lane, hi);
+    store_rows<2>(reinterpret_cast<unsigned char*>(e.out_lo + (n >> 1)), row0, pb, rows_valid, scr, lane, lo);
+    return;
+  }
+  // EPI_ROWS
+  const float4* b4 = reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(b4 + j);
+    f[4 * j] = v[4 * j] + b.x; f[4 * j + 1] = v[4 * j + 1] + b.y;
+    f[4 * j + 2] = v[4 * j + 2] + b.z; f[4 * j + 3] = v[4 * j + 3] + b.w;
+  }
+  if (e.addend) {
+    float c[32];
+    load_rows32(e.addend, row0, e.ld_add, n, rows_valid, scr, lane, c);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += c[j];
+  }
+  if (e.accumulate) {
+    float c[32];
+    load_rows32(e.out_f32, row0, e.ld_out, n, rows_valid, scr, lane, c);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += c[j];
+  }
+  if (e.relu_out) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (e.out_f32) {
+    uint4 w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      w[j] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                        __float_as_uint(f[4 * j + 3]));
+    store_rows<8>(reinterpret_cast<unsigned char*>(e.out_f32 + n), row0, (size_t)e.ld_out * 4, rows_valid, scr,
+                  lane, w);
+  }
+  if (e.out_hi) {
+    if (n >= e.relu_split_from) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    float h[32], l[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+      l[j] = f[j] - h[j];
+    }
+    const uint4 hi[4] = {pack8_bf16(h), pack8_bf16(h + 8), pack8_bf16(h + 16), pack8_bf16(h + 24)};
+    const uint4 lo[4] = {pack8_bf16(l), pack8_bf16(l + 8), pack8_bf16(l + 16), pack8_bf16(l + 24)};
+    const size_t pb = (size_t)e.ld_split * 2;
+    store_rows<4>(reinterpret_cast<unsigned char*>(e.out_hi + n), row0, pb, rows_valid, scr, lane, hi);
+    store_rows<4>(reinterpret_cast<unsigned char*>(e.out_lo + n), row0, pb, rows_valid, scr, lane, lo);
+  }
+}
+
 // Epilogue of one warp for 32 rows x 32 consecutive columns (n % 32 == 0).  Thread `lane` holds
 // row m0 + lane in v[32].  Values go through a swizzled 4 KB smem scratch so that global memory
 // is written with full 128 B lines (8 lanes per row) instead of 32 scattered 16 B pieces per
@@ -161,6 +294,10 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams& e, int clip, int m0,
                                              int n, const float* v, uint32_t scr, int lane) {
   if (n >= g.N) return;  // warp-uniform
+  if (e.mode == EPI_ROWS || e.mode == EPI_GATE) {
+    store_tile32_rows(g, e, clip, m0, n, v, scr, lane);
+    return;
+  }
   float f[32];
   int rr = 0, co = n;
   if (e.mode == EPI_PLANES) {
@@ -297,7 +434,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh,
           mbar_wait(&tail->empty[stage], phase ^ 1);
           const int tap = kb / kb_per_tap;
           const int c0 = (kb - tap * kb_per_tap) * TBK;
-          const int frame0 = m0 + g.a_off + tap;  // may be negative: TMA zero-fills
+          const int frame0 = m0 + g.a_off + tap * g.tap_stride;  // may be negative: TMA zero-fills
           const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
           mbar_expect_tx(&tail->full[stage], STAGE_BYTES);
           tma_load_3d(sbase, &map_xh, &tail->full[stage], c0, frame0, clip);
@@ -423,13 +560,20 @@ int conv_gemm_tc(const ConvGemm& g, const __nv_bfloat16* X_hi, const __nv_bfloat
   NSW_CHECK(X_hi && X_lo && Bt_hi && Bt_lo, NSW_EINVAL, "conv_gemm_tc: null operand");
   if (e.mode == EPI_DECONV)
     NSW_CHECK(e.cout % 32 == 0, NSW_EINVAL, "conv_gemm_tc: cout %d must be a multiple of 32", e.cout);
+  if (e.mode == EPI_ROWS)
+    NSW_CHECK(e.ld_out % 4 == 0 && e.ld_add % 4 == 0 && e.ld_split % 8 == 0 && e.bias, NSW_EINVAL,
+              "conv_gemm_tc: EPI_ROWS leading dimensions must keep 16-byte alignment");
+  if (e.mode == EPI_GATE)
+    NSW_CHECK(e.addend && e.out_hi && e.out_lo && e.ld_add % 4 == 0 && e.ld_split % 8 == 0, NSW_EINVAL,
+              "conv_gemm_tc: EPI_GATE needs cond rows and split outputs");
   EncodeTiledFn enc;
   NSW_TRY(get_encode_fn(&enc));
   const int K = g.ntaps * g.cin;
   CUtensorMap mxh, mxl, mwh, mwl;
   {
     const uint64_t dims[3] = {(uint64_t)g.cin, (uint64_t)g.L, (uint64_t)g.nclips};
-    const uint64_t strides[2] = {(uint64_t)g.cin * 2, (uint64_t)g.L * g.cin * 2};
+    const uint64_t pitch = (uint64_t)(g.x_pitch > 0 ? g.x_pitch : g.cin);
+    const uint64_t strides[2] = {pitch * 2, (uint64_t)g.L * pitch * 2};
     const uint32_t box[3] = {TBK, TBM, 1};
     NSW_TRY(make_map(enc, &mxh, X_hi, 3, dims, strides, box));
     NSW_TRY(make_map(enc, &mxl, X_lo, 3, dims, strides, box));

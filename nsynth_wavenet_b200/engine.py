@@ -260,3 +260,65 @@ class FastgenEngine:
         ms = C.c_float()
         L.check(self.lib.nsw_fastgen_last_timing(self._h, C.byref(ms)))
         return float(ms.value)
+
+
+class TeacherEngine:
+    """Teacher WaveNet full-sequence forward + student->teacher cross-entropy (distillation
+    scoring, BASELINE config 5), all contractions on tcgen05."""
+
+    def __init__(self, hparams, weights, device=0, num_mel=80):
+        self.lib = L.load()
+        self.hparams = hparams
+        cfg = wavenet_config(hparams, num_mel, 'tc')
+        self.out_width = cfg.out_width
+        tensors, keep = L.make_tensors(fold_weight_norm(weights))
+        h = C.c_void_p()
+        L.check(self.lib.nsw_teacher_create(C.byref(cfg), tensors, len(tensors), device, C.byref(h)))
+        del keep
+        self._h = h
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.nsw_teacher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward_host(self, wav_scaled, mel):
+        wav = np.ascontiguousarray(wav_scaled, np.float32)
+        mel = np.ascontiguousarray(mel, np.float32)
+        B, T = wav.shape
+        F = mel.shape[1]
+        out = np.empty((B, T, self.out_width), np.float32)
+        L.check(self.lib.nsw_teacher_forward_host(self._h, L.ptr(wav), L.ptr(mel), B, T, F, L.ptr(out)))
+        return out
+
+    def forward_device(self, wav_scaled, mel):
+        import torch
+        B, T = wav_scaled.shape
+        F = mel.shape[1]
+        out = torch.empty((B, T, self.out_width), dtype=torch.float32, device=wav_scaled.device)
+        st = torch.cuda.current_stream(wav_scaled.device).cuda_stream
+        L.check(self.lib.nsw_teacher_forward_device(self._h, L.ptr(wav_scaled), L.ptr(mel), B, T, F,
+                                                    L.ptr(out), st))
+        return out
+
+    def mol_score(self, te_out, mean_tot, scale_tot, log_scale_tot, num_samples=100, eps=None, seed=0):
+        """-> dict(H_Ps, H_Ps_Pt, kl_loss) like ParallelWavenet.kl_loss_logistic (torch CUDA inputs)."""
+        import torch
+        B, T = mean_tot.shape
+        res = (C.c_double * 3)()
+        st = torch.cuda.current_stream(mean_tot.device).cuda_stream
+        L.check(self.lib.nsw_mol_score_device(self._h, L.ptr(te_out), L.ptr(mean_tot), L.ptr(scale_tot),
+                                              L.ptr(log_scale_tot), L.ptr(eps), seed, num_samples, B, T,
+                                              C.byref(res), st))
+        return {'H_Ps': res[0], 'H_Ps_Pt': res[1], 'kl_loss': res[2]}
+
+    def last_timing(self):
+        ms = C.c_float()
+        L.check(self.lib.nsw_teacher_last_timing(self._h, C.byref(ms)))
+        return float(ms.value)

@@ -626,3 +626,21 @@ def load_hparams(path):
     import json
     with open(path, 'rt') as f:
         return Namespace(**json.load(f))
+
+
+# --------------------------------------------------------------------------
+# Distillation cross-entropy (wavenet/parallel_wavenet.py:361-402)
+# --------------------------------------------------------------------------
+def kl_loss_logistic(te_out, mean_tot, scale_tot, log_scale_tot, eps, quant_chann):
+    """ParallelWavenet.kl_loss_logistic with the teacher output `te_out` [B,T,3*nr] and the
+    logistic draws `eps` [S,B,T] given (the reference tiles with tf_repeat along the batch axis,
+    utils.py:175-195, which is np.repeat; averaging over the S copies is order-independent).
+    CLIP=False (parallel_wavenet.py:15), so x_xp is not clipped."""
+    S = eps.shape[0]
+    x_xp = eps * scale_tot[None] + mean_tot[None]                       # :373-377
+    te = np.broadcast_to(te_out[None], (S,) + te_out.shape)
+    B, T = mean_tot.shape
+    lp = mol_log_probs(te.reshape(S * B, T, -1), x_xp.reshape(S * B, T), quant_chann)   # :385-390
+    H_Ps_Pt = float(-lp.mean())                                         # :392-396
+    H_Ps = float(log_scale_tot.mean() + 2.0)                            # :395
+    return {'H_Ps': H_Ps, 'H_Ps_Pt': H_Ps_Pt, 'kl_loss': H_Ps_Pt - H_Ps}

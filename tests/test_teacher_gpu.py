@@ -1,0 +1,94 @@
+"""GPU parity of the teacher full-sequence forward (a14) and the distillation cross-entropy
+(a15) against the CPU oracle.  Tolerance 1e-4 on out_params (split-bf16 tensor cores)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def make_teacher(hp, seed=12345):
+    from nsynth_wavenet_b200 import TeacherEngine
+    w = O.init_teacher_weights(hp, seed=seed, bias_std=0.02)
+    return TeacherEngine(hp, w, device=0), w
+
+
+@pytest.mark.timeout(600)
+def test_teacher_forward_matches_oracle_small(teacher_hp):
+    hp = teacher_hp
+    eng, w = make_teacher(hp)
+    rng = np.random.default_rng(31)
+    mel = rng.uniform(0, 1, (1, 3, 80)).astype(np.float32)       # 600 cond steps, trimmed to 512
+    wav = rng.uniform(-0.5, 0.5, (1, 512)).astype(np.float32)
+    out = eng.forward_host(wav, mel)
+    ref = O.teacher_feed_forward(w, hp, wav, mel, np.float64)['out_params']
+    err = np.abs(out - ref).max()
+    print('teacher forward max-abs err', err, 'ms', eng.last_timing())
+    assert out.shape == (1, 512, 30) and err < TOL, err
+
+
+@pytest.mark.timeout(900)
+def test_teacher_forward_batch_and_deep_dilations(teacher_hp):
+    hp = teacher_hp
+    eng, w = make_teacher(hp, seed=7)
+    rng = np.random.default_rng(32)
+    mel = rng.uniform(0, 1, (2, 8, 80)).astype(np.float32)       # 1600 -> 1536 samples (d up to 512 twice)
+    wav = rng.uniform(-0.5, 0.5, (2, 1536)).astype(np.float32)
+    out = eng.forward_host(wav, mel)
+    ref = O.teacher_feed_forward(w, hp, wav, mel, np.float32)['out_params']
+    err = np.abs(out - ref).max()
+    print('teacher forward 2x1536 max-abs err', err)
+    assert err < TOL, err
+    # batch rows are independent
+    single = eng.forward_host(wav[1:2], mel[1:2])
+    assert np.abs(single[0] - out[1]).max() < 1e-6
+
+
+@pytest.mark.timeout(600)
+def test_mol_score_matches_oracle_with_shared_noise(teacher_hp):
+    hp = teacher_hp
+    eng, _ = make_teacher(hp)
+    rng = np.random.default_rng(33)
+    B, T, S = 2, 256, 7
+    te = rng.normal(0, 1.0, (B, T, 30)).astype(np.float32)
+    te[..., 20:] = rng.uniform(-9, -2, (B, T, 10))                # log-scales incl. values below the -7 floor
+    mean = rng.uniform(-1.2, 1.2, (B, T)).astype(np.float32)      # some targets hit the +-1 edge branches
+    scale = rng.uniform(0.01, 0.2, (B, T)).astype(np.float32)
+    ls = np.log(scale)
+    u = rng.uniform(1e-5, 1 - 1e-5, (S, B, T))
+    eps = O.logistic_from_uniform(u).astype(np.float32)
+    ref = O.kl_loss_logistic(te.astype(np.float64), mean.astype(np.float64), scale.astype(np.float64),
+                             ls.astype(np.float64), eps.astype(np.float64), 65536)
+    got = eng.mol_score(torch.from_numpy(te).cuda(), torch.from_numpy(mean).cuda(), torch.from_numpy(scale).cuda(),
+                        torch.from_numpy(ls).cuda(), num_samples=S, eps=torch.from_numpy(eps).cuda())
+    print('mol score', got, ref)
+    for k in ('H_Ps', 'H_Ps_Pt', 'kl_loss'):
+        assert abs(got[k] - ref[k]) < 1e-4 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
+
+
+@pytest.mark.timeout(900)
+def test_distillation_forward_pipeline(student_hp, teacher_hp):
+    # BASELINE config 5 (reduced batch): student forward -> teacher forward on x -> 100-sample scoring
+    from nsynth_wavenet_b200 import IAFEngine
+    st_w = O.init_student_weights(student_hp, seed=12345)
+    st = IAFEngine(student_hp, st_w, device=0)
+    te, te_w = make_teacher(teacher_hp)
+    rng = np.random.default_rng(34)
+    mel = torch.from_numpy(rng.uniform(0, 1, (2, 6, 80)).astype(np.float32)).cuda()
+    out = st.forward_device(mel, None, seed=5, quantize=False)
+    te_out = te.forward_device(out['x'], mel)
+    torch.cuda.synchronize()
+    ref_te = O.teacher_feed_forward(te_w, teacher_hp, out['x'].cpu().numpy(), mel.cpu().numpy(), np.float32)['out_params']
+    assert np.abs(te_out.cpu().numpy() - ref_te).max() < TOL
+    got = te.mol_score(te_out, out['mean_tot'], out['scale_tot'], out['log_scale_tot'], num_samples=100, seed=9)
+    S = 100
+    eps = O.logistic_from_uniform(rng.uniform(1e-5, 1 - 1e-5, (S, 2, 1024)))
+    ref = O.kl_loss_logistic(ref_te.astype(np.float64), out['mean_tot'].cpu().numpy().astype(np.float64),
+                             out['scale_tot'].cpu().numpy().astype(np.float64),
+                             out['log_scale_tot'].cpu().numpy().astype(np.float64), eps, 65536)
+    print('distillation losses', got, ref)
+    assert abs(got['H_Ps'] - ref['H_Ps']) < 1e-4
+    assert abs(got['H_Ps_Pt'] - ref['H_Ps_Pt']) < 0.02 * abs(ref['H_Ps_Pt'])   # different noise draws
