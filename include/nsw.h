@@ -55,7 +55,7 @@ extern "C" {
 
 /* engine selection for the dense contractions (cond projection, deconv) */
 #define NSW_ENGINE_FFMA 0 /* fp32 CUDA-core path, bit-for-bit fp32 products   */
-#define NSW_ENGINE_TC 1   /* tcgen05 split-bf16 (hi*hi + hi*lo + lo*hi)       */
+#define NSW_ENGINE_TC 1   /* tcgen05 split-fp16 (hi*hi + hi*lo + lo*hi)       */
 #define NSW_ENGINE_TC2 2  /* NSW_ENGINE_TC + the IAF residual layers on tcgen05  */
 
 typedef struct nsw_tensor {

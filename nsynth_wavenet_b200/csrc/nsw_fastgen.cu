@@ -550,14 +550,14 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   }
 }
 
-__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, size_t n) {
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                  __half* __restrict__ lo, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i];
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __half h = __float2half_rn(v);
   hi[i] = h;
-  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  lo[i] = __float2half_rn(v - __half2float(h));
 }
 
 }  // namespace
@@ -810,8 +810,8 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
     std::vector<float> bt((size_t)N * FD);
     for (int k = 0; k < FD; ++k)
       for (int nn = 0; nn < N; ++nn) bt[(size_t)nn * FD + k] = pk.cond_w[(size_t)k * N + nn];
-    std::vector<__nv_bfloat16> hi(bt.size()), lo(bt.size());
-    split_bf16(bt.data(), bt.size(), hi.data(), lo.data());
+    std::vector<__half> hi(bt.size()), lo(bt.size());
+    split_f16(bt.data(), bt.size(), hi.data(), lo.data());
     up(h->cond_wt_hi, hi.data(), hi.size() * 2);
     up(h->cond_wt_lo, lo.data(), lo.size() * 2);
   } else {
@@ -886,7 +886,7 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
   const int N = h->NPL * 64;
   NSW_TRY(h->cond.ensure((size_t)h->NPL * T * 64 * sizeof(float)));
   const bool tc = h->cfg.engine == NSW_ENGINE_TC;
-  if (tc) NSW_TRY(h->enc_split.ensure((size_t)T * FD * 2 * sizeof(__nv_bfloat16)));
+  if (tc) NSW_TRY(h->enc_split.ensure((size_t)T * FD * 2 * sizeof(__half)));
   NSW_CUDA(cudaEventRecord(h->ev0, st));
   for (int b = 0; b < B; ++b) {
     const float* enc = d_encoding + (size_t)b * T * FD;
@@ -899,13 +899,13 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     e.bias = h->cond_b.as<float>();
     e.out_f32 = h->cond.as<float>();
     if (tc) {
-      __nv_bfloat16* hi = h->enc_split.as<__nv_bfloat16>();
-      __nv_bfloat16* lo = hi + (size_t)T * FD;
+      __half* hi = h->enc_split.as<__half>();
+      __half* lo = hi + (size_t)T * FD;
       const size_t ne = (size_t)T * FD;
-      split_bf16_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(enc, hi, lo, ne);
+      split_f16_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(enc, hi, lo, ne);
       count_launch();
-      NSW_TRY(conv_gemm_tc(g, hi, lo, h->cond_wt_hi.as<__nv_bfloat16>(),
-                           h->cond_wt_lo.as<__nv_bfloat16>(), e, st));
+      NSW_TRY(conv_gemm_tc(g, hi, lo, h->cond_wt_hi.as<__half>(),
+                           h->cond_wt_lo.as<__half>(), e, st));
     } else {
       NSW_TRY(conv_gemm_ffma(g, enc, h->cond_w.as<float>(), e, st));
     }

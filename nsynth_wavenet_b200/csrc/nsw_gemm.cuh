@@ -13,7 +13,7 @@
 //   n = r*cout + co.
 //
 // Two engines implement it: fp32 CUDA cores (nsw_gemm_ffma.cu) and tcgen05
-// split-bf16 tensor cores (nsw_gemm_tc.cu).
+// split-fp16 tensor cores (nsw_gemm_tc.cu).
 #pragma once
 #include "nsw_common.cuh"
 
@@ -32,10 +32,10 @@ struct ConvGemm {
 };
 
 // EPI_ROWS : out[row * ld_out + n] (+)= D + bias[n] (+ addend[row * ld_add + n]); optional relu;
-//            optional bf16 hi/lo copy of the result (relu'd for n >= relu_split_from)
+//            optional fp16 hi/lo copy of the result (relu'd for n >= relu_split_from)
 // EPI_GATE : columns are gate-interleaved (2j = sigmoid half, 2j+1 = tanh half of gate j);
 //            g[row * ld_split + n/2 + j] = sigmoid(D[2j] + c[2j]) * tanh(D[2j+1] + c[2j+1]),
-//            c = addend[row * ld_add + n + ...]; g is written as bf16 hi/lo only
+//            c = addend[row * ld_add + n + ...]; g is written as fp16 hi/lo only
 enum EpiMode { EPI_PLANES = 0, EPI_DECONV = 1, EPI_ROWS = 2, EPI_GATE = 3 };
 
 struct EpiParams {
@@ -44,8 +44,8 @@ struct EpiParams {
   // EPI_PLANES: out_f32[n/64][clip*mclip + m][n%64]
   // EPI_DECONV: out_*[clip][o][co], o = m*s + n/cout - p in [0, Lout)
   float* out_f32;
-  __nv_bfloat16* out_hi;  // optional bf16 split of the same values (hi + lo ~ fp32)
-  __nv_bfloat16* out_lo;
+  __half* out_hi;  // optional fp16 split of the same values (hi + lo ~ fp32)
+  __half* out_lo;
   int s, p, cout, act, Lout;
   // EPI_ROWS / EPI_GATE
   const float* addend = nullptr;
@@ -57,28 +57,28 @@ struct EpiParams {
 int conv_gemm_ffma(const ConvGemm& g, const float* X, const float* Bw, const EpiParams& e,
                    cudaStream_t stream);
 
-// bf16 split operands: X_hi/X_lo [nclips, L, cin], Bt_hi/Bt_lo [N, ntaps*cin] (K-major)
-int conv_gemm_tc(const ConvGemm& g, const __nv_bfloat16* X_hi, const __nv_bfloat16* X_lo,
-                 const __nv_bfloat16* Bt_hi, const __nv_bfloat16* Bt_lo, const EpiParams& e,
+// fp16 split operands: X_hi/X_lo [nclips, L, cin], Bt_hi/Bt_lo [N, ntaps*cin] (K-major)
+int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
+                 const __half* Bt_hi, const __half* Bt_lo, const EpiParams& e,
                  cudaStream_t stream);
 bool conv_gemm_tc_supported(const ConvGemm& g);
 
-// host-side split of fp32 into bf16 hi + bf16 lo (round-to-nearest each)
-void split_bf16(const float* src, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
+// host-side split of fp32 into fp16 hi + fp16 lo (round-to-nearest each)
+void split_f16(const float* src, size_t n, __half* hi, __half* lo);
 
 // ---- tcgen05 fused IAF residual layer (nsw_iaf_layer_tc.cu); maps are 128-byte CUtensorMaps ----
-int layer_tc_make_act_map(void* map_out, const __nv_bfloat16* base, int B, int T);
-int layer_tc_make_weight_map(void* map_out, const __nv_bfloat16* base, int rows, int k);
+int layer_tc_make_act_map(void* map_out, const __half* base, int B, int T);
+int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k);
 int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
                     const void* map_wrh, const void* map_wrl, const float* cond, const float* l_in,
-                    float* l_out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const float* br, int T,
+                    float* l_out, __half* out_hi, __half* out_lo, const float* br, int T,
                     int rows, int dil, int layer, int num_sms, cudaStream_t stream);
 
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
 struct DeconvLayer {
   DeconvGeom g;
   DevBuf Bw;              // fp32 [ntaps*cin][s*cout]
-  DevBuf Bt_hi, Bt_lo;    // bf16 [s*cout][ntaps*cin] (tensor-core engine)
+  DevBuf Bt_hi, Bt_lo;    // fp16 [s*cout][ntaps*cin] (tensor-core engine)
   DevBuf bias;            // [cout]
 };
 
@@ -92,8 +92,8 @@ struct DeconvStack {
   // mel [B,F,num_mel] -> out [B, F*total_stride, width]; intermediates live in `scratch`.
   // engine FFMA: writes out_f32 (required).  engine TC: the last layer runs on tensor
   // cores when supported and writes out_hi/out_lo (and out_f32 if non-NULL).
-  int forward(const float* d_mel, int B, int F, float* out_f32, __nv_bfloat16* out_hi,
-              __nv_bfloat16* out_lo, int engine, DevBuf& scratch, cudaStream_t stream) const;
+  int forward(const float* d_mel, int B, int F, float* out_f32, __half* out_hi,
+              __half* out_lo, int engine, DevBuf& scratch, cudaStream_t stream) const;
 };
 
 }  // namespace nsw

@@ -33,11 +33,11 @@ __device__ __forceinline__ void store_epi(const ConvGemm& g, const EpiParams& e,
     if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + off) = v;
     if (e.out_hi) {
       float f[4] = {v.x, v.y, v.z, v.w};
-      __nv_bfloat16 hi[4], lo[4];
+      __half hi[4], lo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        hi[i] = __float2bfloat16_rn(f[i]);
-        lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+        hi[i] = __float2half_rn(f[i]);
+        lo[i] = __float2half_rn(f[i] - __half2float(hi[i]));
       }
       *reinterpret_cast<uint2*>(e.out_hi + off) = *reinterpret_cast<uint2*>(hi);
       *reinterpret_cast<uint2*>(e.out_lo + off) = *reinterpret_cast<uint2*>(lo);
@@ -115,10 +115,10 @@ int conv_gemm_ffma(const ConvGemm& g, const float* X, const float* Bw, const Epi
   return NSW_OK;
 }
 
-void split_bf16(const float* src, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+void split_f16(const float* src, size_t n, __half* hi, __half* lo) {
   for (size_t i = 0; i < n; ++i) {
-    hi[i] = __float2bfloat16_rn(src[i]);
-    lo[i] = __float2bfloat16_rn(src[i] - __bfloat162float(hi[i]));
+    hi[i] = __float2half_rn(src[i]);
+    lo[i] = __float2half_rn(src[i] - __half2float(hi[i]));
   }
 }
 
@@ -167,18 +167,18 @@ int DeconvStack::init(const TensorMap& tm, const std::string& prefix, int num_me
       std::vector<float> bt((size_t)N * K);
       for (int kk = 0; kk < K; ++kk)
         for (int nn = 0; nn < N; ++nn) bt[(size_t)nn * K + kk] = bw[(size_t)kk * N + nn];
-      std::vector<__nv_bfloat16> hi(bt.size()), lo(bt.size());
-      split_bf16(bt.data(), bt.size(), hi.data(), lo.data());
-      NSW_TRY(upload(L.Bt_hi, hi.data(), hi.size() * sizeof(__nv_bfloat16)));
-      NSW_TRY(upload(L.Bt_lo, lo.data(), lo.size() * sizeof(__nv_bfloat16)));
+      std::vector<__half> hi(bt.size()), lo(bt.size());
+      split_f16(bt.data(), bt.size(), hi.data(), lo.data());
+      NSW_TRY(upload(L.Bt_hi, hi.data(), hi.size() * sizeof(__half)));
+      NSW_TRY(upload(L.Bt_lo, lo.data(), lo.size() * sizeof(__half)));
     }
     cin = width;
   }
   return NSW_OK;
 }
 
-int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __nv_bfloat16* out_hi,
-                         __nv_bfloat16* out_lo, int engine, DevBuf& scratch,
+int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __half* out_hi,
+                         __half* out_lo, int engine, DevBuf& scratch,
                          cudaStream_t stream) const {
   const int n = (int)layers.size();
   NSW_CHECK(n >= 1, NSW_EINVAL, "deconv stack is empty");
@@ -191,12 +191,12 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __nv_
       max_elems = std::max(max_elems, (size_t)B * L * layers[i].g.cout);
     }
   }
-  // two ping-pong slots, each big enough for fp32 or (bf16 hi + bf16 lo)
+  // two ping-pong slots, each big enough for fp32 or (fp16 hi + fp16 lo)
   NSW_TRY(scratch.ensure(2 * max_elems * sizeof(float) + 256));
   float* slot[2] = {scratch.as<float>(), scratch.as<float>() + max_elems};
 
   const float* x_f32 = d_mel;
-  const __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr;
+  const __half *x_hi = nullptr, *x_lo = nullptr;
   int L = F;
   for (int i = 0; i < n; ++i) {
     const DeconvLayer& ly = layers[i];
@@ -219,7 +219,7 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __nv_
     e.act = act;
     e.Lout = L * dg.s;
     const bool this_tc = (engine == NSW_ENGINE_TC) && x_hi != nullptr && conv_gemm_tc_supported(g);
-    // does the NEXT consumer want split-bf16 input?
+    // does the NEXT consumer want split-fp16 input?
     bool next_wants_split = false;
     if (engine == NSW_ENGINE_TC) {
       if (last) {
@@ -234,14 +234,14 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __nv_
       }
     }
     float* o_f32 = nullptr;
-    __nv_bfloat16 *o_hi = nullptr, *o_lo = nullptr;
+    __half *o_hi = nullptr, *o_lo = nullptr;
     if (last) {
       o_f32 = out_f32;
       if (next_wants_split) { o_hi = out_hi; o_lo = out_lo; }
     } else {
       float* s = slot[i & 1];
       if (next_wants_split) {
-        o_hi = reinterpret_cast<__nv_bfloat16*>(s);
+        o_hi = reinterpret_cast<__half*>(s);
         o_lo = o_hi + (size_t)B * e.Lout * dg.cout;
       } else {
         o_f32 = s;
@@ -252,8 +252,8 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __nv_
     e.out_hi = o_hi;
     e.out_lo = o_lo;
     if (this_tc) {
-      NSW_TRY(conv_gemm_tc(g, x_hi, x_lo, ly.Bt_hi.as<__nv_bfloat16>(),
-                           ly.Bt_lo.as<__nv_bfloat16>(), e, stream));
+      NSW_TRY(conv_gemm_tc(g, x_hi, x_lo, ly.Bt_hi.as<__half>(),
+                           ly.Bt_lo.as<__half>(), e, stream));
     } else {
       NSW_CHECK(x_f32 != nullptr, NSW_EINVAL, "deconv layer %d: fp32 input unavailable", i + 1);
       NSW_TRY(conv_gemm_ffma(g, x_f32, ly.Bw.as<float>(), e, stream));

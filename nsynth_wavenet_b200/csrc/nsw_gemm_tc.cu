@@ -1,12 +1,12 @@
-// tcgen05 engine of the conv-GEMM (see nsw_gemm.cuh): split-bf16 operands
-// (x = hi + lo, both bf16), fp32 accumulation in TMEM, three tensor-core products
+// tcgen05 engine of the conv-GEMM (see nsw_gemm.cuh): split-fp16 operands
+// (x = hi + lo, both fp16), fp32 accumulation in TMEM, three tensor-core products
 // per k-block (lo*hi + hi*lo + hi*hi; lo*lo ~ 2^-18 relative is dropped).
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor 3D for X, 2D for W; SWIZZLE_128B)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
 //   warps 2..5  epilogue: tcgen05.ld (32x32b.x32) -> bias/activation -> global stores
-// smem ring: 3 stages x {X_hi, X_lo [128 x 64], W_hi, W_lo [128 x 64]} bf16 = 64 KB/stage.
+// smem ring: 3 stages x {X_hi, X_lo [128 x 64], W_hi, W_lo [128 x 64]} fp16 = 64 KB/stage.
 // TMEM: two accumulator stages of 128 fp32 columns each, so the epilogue of tile i
 // overlaps the main loop of tile i+1.
 #include "nsw_gemm.cuh"
@@ -87,7 +87,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (64 bf16 = 128 B per row,
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (64 fp16 = 128 B per row,
 // 8-row groups 1024 B apart); field layout per the sm_100 UMMA descriptor.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
@@ -98,12 +98,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=TBN
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=TBN
 __device__ __forceinline__ uint32_t umma_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) |
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TBN >> 3) << 17) |
          ((uint32_t)(TBM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -178,8 +178,8 @@ __device__ __forceinline__ void load_rows32(const float* base, size_t row0, int 
   }
   __syncwarp();
 }
-// coalesced write of one row per thread: nchunks 16-byte chunks per row (8 = 32 floats, 4 = 32 bf16,
-// 2 = 16 bf16), destination row pitch given in bytes
+// coalesced write of one row per thread: nchunks 16-byte chunks per row (8 = 32 floats, 4 = 32 halves,
+// 2 = 16 halves), destination row pitch given in bytes
 template <int NCH>
 __device__ __forceinline__ void store_rows(unsigned char* base, size_t row0, size_t pitch_bytes,
                                            int rows_valid, uint32_t scr, int lane, const uint4 (&in)[NCH]) {
@@ -201,10 +201,10 @@ __device__ __forceinline__ void store_rows(unsigned char* base, size_t row0, siz
   __syncwarp();
 }
 
-__device__ __forceinline__ uint4 pack8_bf16(const float* a) {
+__device__ __forceinline__ uint4 pack8_f16(const float* a) {
   uint4 r;
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
-  __nv_bfloat162 p2 = __floats2bfloat162_rn(a[4], a[5]), p3 = __floats2bfloat162_rn(a[6], a[7]);
+  __half2 p0 = __floats2half2_rn(a[0], a[1]), p1 = __floats2half2_rn(a[2], a[3]);
+  __half2 p2 = __floats2half2_rn(a[4], a[5]), p3 = __floats2half2_rn(a[6], a[7]);
   r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
   r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
   return r;
@@ -225,11 +225,11 @@ __device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiPa
     for (int j = 0; j < 16; ++j) {
       const float sg = 1.0f / (1.0f + expf(-(v[2 * j] + c[2 * j])));
       const float gv = sg * tanhf(v[2 * j + 1] + c[2 * j + 1]);
-      gh[j] = __bfloat162float(__float2bfloat16_rn(gv));
+      gh[j] = __half2float(__float2half_rn(gv));
       gl[j] = gv - gh[j];
     }
-    const uint4 hi[2] = {pack8_bf16(gh), pack8_bf16(gh + 8)};
-    const uint4 lo[2] = {pack8_bf16(gl), pack8_bf16(gl + 8)};
+    const uint4 hi[2] = {pack8_f16(gh), pack8_f16(gh + 8)};
+    const uint4 lo[2] = {pack8_f16(gl), pack8_f16(gl + 8)};
     const size_t pb = (size_t)e.ld_split * 2;
     store_rows<2>(reinterpret_cast<unsigned char*>(e.out_hi + (n >> 1)), row0, pb, rows_valid, scr, lane, hi);
     store_rows<2>(reinterpret_cast<unsigned char*>(e.out_lo + (n >> 1)), row0, pb, rows_valid, scr, lane, lo);
@@ -276,11 +276,11 @@ __device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiPa
     float h[32], l[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      h[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+      h[j] = __half2float(__float2half_rn(f[j]));
       l[j] = f[j] - h[j];
     }
-    const uint4 hi[4] = {pack8_bf16(h), pack8_bf16(h + 8), pack8_bf16(h + 16), pack8_bf16(h + 24)};
-    const uint4 lo[4] = {pack8_bf16(l), pack8_bf16(l + 8), pack8_bf16(l + 16), pack8_bf16(l + 24)};
+    const uint4 hi[4] = {pack8_f16(h), pack8_f16(h + 8), pack8_f16(h + 16), pack8_f16(h + 24)};
+    const uint4 lo[4] = {pack8_f16(l), pack8_f16(l + 8), pack8_f16(l + 16), pack8_f16(l + 24)};
     const size_t pb = (size_t)e.ld_split * 2;
     store_rows<4>(reinterpret_cast<unsigned char*>(e.out_hi + n), row0, pb, rows_valid, scr, lane, hi);
     store_rows<4>(reinterpret_cast<unsigned char*>(e.out_lo + n), row0, pb, rows_valid, scr, lane, lo);
@@ -349,7 +349,7 @@ __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams&
     __syncwarp();
   }
   if (e.mode == EPI_DECONV && e.out_hi) {
-    // bf16 split planes: 32 values = 64 B per row per plane; both planes share one pass
+    // fp16 split planes: 32 values = 64 B per row per plane; both planes share one pass
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
@@ -358,16 +358,16 @@ __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams&
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float a = f[8 * j + 2 * k], b = f[8 * j + 2 * k + 1];
-          const float ah = __bfloat162float(__float2bfloat16_rn(a));
-          const float bh = __bfloat162float(__float2bfloat16_rn(b));
-          __nv_bfloat162 pk = pl == 0 ? __floats2bfloat162_rn(ah, bh) : __floats2bfloat162_rn(a - ah, b - bh);
+          const float ah = __half2float(__float2half_rn(a));
+          const float bh = __half2float(__float2half_rn(b));
+          __half2 pk = pl == 0 ? __floats2half2_rn(ah, bh) : __floats2half2_rn(a - ah, b - bh);
           w[k] = *reinterpret_cast<uint32_t*>(&pk);
         }
         sts128(scr + (uint32_t)(lane * 4 + (j ^ ((lane >> 1) & 3))) * 16u,
                make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3])));
       }
       __syncwarp();
-      __nv_bfloat16* base = pl == 0 ? e.out_hi : e.out_lo;
+      __half* base = pl == 0 ? e.out_hi : e.out_lo;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = 8 * i + (lane >> 2);
@@ -468,9 +468,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh,
 #pragma unroll
           for (int k = 0; k < TBK / 16; ++k) {
             const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 B per UMMA_K step
-            umma_bf16(d_tmem, xl + adv, wh + adv, idesc, (kb | k) != 0);
-            umma_bf16(d_tmem, xh + adv, wl + adv, idesc, 1);
-            umma_bf16(d_tmem, xh + adv, wh + adv, idesc, 1);
+            umma_f16(d_tmem, xl + adv, wh + adv, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, xh + adv, wl + adv, idesc, 1);
+            umma_f16(d_tmem, xh + adv, wh + adv, idesc, 1);
           }
           umma_commit(&tail->empty[stage]);  // frees the smem stage when these MMAs retire
           if (kb == num_kb - 1) umma_commit(&tail->tmem_full[as]);
@@ -539,7 +539,7 @@ int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int rank, co
   cuuint32_t bx[3], es[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                    gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NSW_CHECK(r == CUDA_SUCCESS, NSW_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -552,8 +552,8 @@ bool conv_gemm_tc_supported(const ConvGemm& g) {
   return g.cin % TBK == 0 && g.N % 64 == 0 && g.ntaps >= 1;
 }
 
-int conv_gemm_tc(const ConvGemm& g, const __nv_bfloat16* X_hi, const __nv_bfloat16* X_lo,
-                 const __nv_bfloat16* Bt_hi, const __nv_bfloat16* Bt_lo, const EpiParams& e,
+int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
+                 const __half* Bt_hi, const __half* Bt_lo, const EpiParams& e,
                  cudaStream_t stream) {
   NSW_CHECK(conv_gemm_tc_supported(g), NSW_EINVAL, "conv_gemm_tc: unsupported shape cin=%d N=%d",
             g.cin, g.N);

@@ -11,7 +11,7 @@
 //                                  layer planes are stored gate-interleaved:
 //                                  position 2j <- channel j (sigmoid half),
 //                                  position 2j+1 <- channel j+32 (tanh half)
-//   mel_en    [B, 200F, 256]       fp32 (FFMA engine) or bf16 hi + bf16 lo (tcgen05 engine)
+//   mel_en    [B, 200F, 256]       fp32 (FFMA engine) or fp16 hi + fp16 lo (tcgen05 engine)
 //   x, z, mean_tot, scale_tot, log_scale_tot   [B*T]
 //
 // Kernels (one launch each):
@@ -71,7 +71,7 @@ __global__ void iaf_noise_kernel(float* __restrict__ z, size_t n, uint64_t seed,
 __global__ void __launch_bounds__(256)
 iaf_start_conv_kernel(const float* __restrict__ x, float* __restrict__ l,
                       const float* __restrict__ w /*[3][64]*/, const float* __restrict__ b, int T,
-                      size_t rows, __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo) {
+                      size_t rows, __half* __restrict__ l_hi, __half* __restrict__ l_lo) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (row, c4)
   const size_t row = idx >> 4;
   if (row >= rows) return;
@@ -90,13 +90,13 @@ iaf_start_conv_kernel(const float* __restrict__ x, float* __restrict__ l,
   o.z = fmaf(w2.z, x1, fmaf(w1.z, x2, fmaf(w0.z, x3, bb.z)));
   o.w = fmaf(w2.w, x1, fmaf(w1.w, x2, fmaf(w0.w, x3, bb.w)));
   *reinterpret_cast<float4*>(l + row * C + c) = o;
-  if (l_hi) {  // split-bf16 copy for the tcgen05 layer kernel's MMA operand
+  if (l_hi) {  // split-fp16 copy for the tcgen05 layer kernel's MMA operand
     const float f[4] = {o.x, o.y, o.z, o.w};
-    __align__(8) __nv_bfloat16 hi[4], lo[4];
+    __align__(8) __half hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      hi[i] = __float2bfloat16_rn(f[i]);
-      lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+      hi[i] = __float2half_rn(f[i]);
+      lo[i] = __float2half_rn(f[i] - __half2float(hi[i]));
     }
     *reinterpret_cast<uint2*>(l_hi + row * C + c) = *reinterpret_cast<uint2*>(hi);
     *reinterpret_cast<uint2*>(l_lo + row * C + c) = *reinterpret_cast<uint2*>(lo);
@@ -382,9 +382,9 @@ struct FlowWeights {
   DevBuf start_w, start_b;  // [3][64], [64]
   DevBuf Wd, Wr, br;        // [L][192][64], [L][32][64], [L][64]  (gate-interleaved columns)
   DevBuf Wc, bc;            // cond projection B: fp32 [256][(L+1)*64]; bias [(L+1)*64]
-  DevBuf Wct_hi, Wct_lo;    // bf16 [(L+1)*64][256]
+  DevBuf Wct_hi, Wct_lo;    // fp16 [(L+1)*64][256]
   DevBuf W1, wm, ws;        // [64][64], [64], [64]
-  // tcgen05 layer engine: K-major bf16 hi/lo weights + their tensor maps
+  // tcgen05 layer engine: K-major fp16 hi/lo weights + their tensor maps
   DevBuf WdT_hi, WdT_lo;    // [L][3][64 pos][64 cin]
   DevBuf WrT_hi, WrT_lo;    // [L][64 c][32 j]
   DevBuf br_nat;            // [L][64] natural channel order
@@ -403,7 +403,7 @@ struct nsw_iaf {
   // workspace
   int ws_B = 0, ws_F = 0;
   DevBuf mel, mel_en, mel_en_split, cond, l0, l1, x, z, mean_tot, scale_tot, log_scale_tot,
-      deconv_scratch, ls0, ls1;  // ls*: bf16 hi plane then lo plane of l0 / l1 (tc2 engine)
+      deconv_scratch, ls0, ls1;  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
   alignas(64) unsigned char map_act[2][2][128];  // [buffer][hi, lo]
   int map_B = 0, map_T = 0;
   // debug tap
@@ -498,28 +498,28 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
         for (int j = 0; j < HALF; ++j) wrt[((size_t)i * C + c) * HALF + j] = wr[(size_t)j * C + c];
       for (int c = 0; c < C; ++c) brn[(size_t)i * C + c] = brr[c];
     }
-    std::vector<__nv_bfloat16> hi(wdt.size()), lo(wdt.size());
-    split_bf16(wdt.data(), wdt.size(), hi.data(), lo.data());
+    std::vector<__half> hi(wdt.size()), lo(wdt.size());
+    split_f16(wdt.data(), wdt.size(), hi.data(), lo.data());
     NSW_TRY(upload(fw.WdT_hi, hi.data(), hi.size() * 2));
     NSW_TRY(upload(fw.WdT_lo, lo.data(), lo.size() * 2));
     hi.resize(wrt.size()); lo.resize(wrt.size());
-    split_bf16(wrt.data(), wrt.size(), hi.data(), lo.data());
+    split_f16(wrt.data(), wrt.size(), hi.data(), lo.data());
     NSW_TRY(upload(fw.WrT_hi, hi.data(), hi.size() * 2));
     NSW_TRY(upload(fw.WrT_lo, lo.data(), lo.size() * 2));
     NSW_TRY(upload(fw.br_nat, brn.data(), brn.size() * 4));
-    NSW_TRY(layer_tc_make_weight_map(fw.map_wdh, fw.WdT_hi.as<__nv_bfloat16>(), L * 3 * C, C));
-    NSW_TRY(layer_tc_make_weight_map(fw.map_wdl, fw.WdT_lo.as<__nv_bfloat16>(), L * 3 * C, C));
-    NSW_TRY(layer_tc_make_weight_map(fw.map_wrh, fw.WrT_hi.as<__nv_bfloat16>(), L * C, HALF));
-    NSW_TRY(layer_tc_make_weight_map(fw.map_wrl, fw.WrT_lo.as<__nv_bfloat16>(), L * C, HALF));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdh, fw.WdT_hi.as<__half>(), L * 3 * C, C));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdl, fw.WdT_lo.as<__half>(), L * 3 * C, C));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wrh, fw.WrT_hi.as<__half>(), L * C, HALF));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wrl, fw.WrT_lo.as<__half>(), L * C, HALF));
   }
   if (want_tc) {
     std::vector<float> bt((size_t)NP * D);
     for (int k = 0; k < D; ++k)
       for (int n = 0; n < NP; ++n) bt[(size_t)n * D + k] = Wc[(size_t)k * NP + n];
-    std::vector<__nv_bfloat16> hi(bt.size()), lo(bt.size());
-    split_bf16(bt.data(), bt.size(), hi.data(), lo.data());
-    NSW_TRY(upload(fw.Wct_hi, hi.data(), hi.size() * sizeof(__nv_bfloat16)));
-    NSW_TRY(upload(fw.Wct_lo, lo.data(), lo.size() * sizeof(__nv_bfloat16)));
+    std::vector<__half> hi(bt.size()), lo(bt.size());
+    split_f16(bt.data(), bt.size(), hi.data(), lo.data());
+    NSW_TRY(upload(fw.Wct_hi, hi.data(), hi.size() * sizeof(__half)));
+    NSW_TRY(upload(fw.Wct_lo, lo.data(), lo.size() * sizeof(__half)));
   }
   return NSW_OK;
 }
@@ -607,15 +607,15 @@ static int ensure_workspace(nsw_iaf* h, int B, int F) {
   const size_t rows = (size_t)nB * T;
   NSW_TRY(h->mel.ensure((size_t)nB * nF * h->cfg.num_mel * sizeof(float)));
   if (h->cfg.engine >= NSW_ENGINE_TC)
-    NSW_TRY(h->mel_en_split.ensure((size_t)nB * Lc * D * 2 * sizeof(__nv_bfloat16)));
+    NSW_TRY(h->mel_en_split.ensure((size_t)nB * Lc * D * 2 * sizeof(__half)));
   else
     NSW_TRY(h->mel_en.ensure((size_t)nB * Lc * D * sizeof(float)));
   NSW_TRY(h->cond.ensure((size_t)(h->max_layers + 1) * rows * C * sizeof(float)));
   NSW_TRY(h->l0.ensure(rows * C * sizeof(float)));
   NSW_TRY(h->l1.ensure(rows * C * sizeof(float)));
   if (h->cfg.engine == NSW_ENGINE_TC2) {
-    NSW_TRY(h->ls0.ensure(rows * C * 2 * sizeof(__nv_bfloat16)));
-    NSW_TRY(h->ls1.ensure(rows * C * 2 * sizeof(__nv_bfloat16)));
+    NSW_TRY(h->ls0.ensure(rows * C * 2 * sizeof(__half)));
+    NSW_TRY(h->ls1.ensure(rows * C * 2 * sizeof(__half)));
     h->map_B = h->map_T = 0;  // buffers may have moved
   }
   NSW_TRY(h->x.ensure(rows * sizeof(float)));
@@ -700,14 +700,14 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
 
   const bool tc = cfg.engine >= NSW_ENGINE_TC;
   const bool tc_layers = cfg.engine == NSW_ENGINE_TC2;
-  __nv_bfloat16* me_hi = tc ? h->mel_en_split.as<__nv_bfloat16>() : nullptr;
-  __nv_bfloat16* me_lo = tc ? me_hi + (size_t)B * Lc * D : nullptr;
+  __half* me_hi = tc ? h->mel_en_split.as<__half>() : nullptr;
+  __half* me_lo = tc ? me_hi + (size_t)B * Lc * D : nullptr;
   float* l_buf[2] = {h->l0.as<float>(), h->l1.as<float>()};
-  __nv_bfloat16* ls_hi[2] = {nullptr, nullptr};
-  __nv_bfloat16* ls_lo[2] = {nullptr, nullptr};
+  __half* ls_hi[2] = {nullptr, nullptr};
+  __half* ls_lo[2] = {nullptr, nullptr};
   if (tc_layers) {
-    ls_hi[0] = h->ls0.as<__nv_bfloat16>(); ls_lo[0] = ls_hi[0] + rows * C;
-    ls_hi[1] = h->ls1.as<__nv_bfloat16>(); ls_lo[1] = ls_hi[1] + rows * C;
+    ls_hi[0] = h->ls0.as<__half>(); ls_lo[0] = ls_hi[0] + rows * C;
+    ls_hi[1] = h->ls1.as<__half>(); ls_lo[1] = ls_hi[1] + rows * C;
     if (h->map_B != B || h->map_T != T) {
       for (int b = 0; b < 2; ++b) {
         NSW_TRY(layer_tc_make_act_map(h->map_act[b][0], ls_hi[b], B, T));
@@ -741,8 +741,8 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       e.bias = fw.bc.as<float>();
       e.out_f32 = h->cond.as<float>();
       if (tc)
-        NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, fw.Wct_hi.as<__nv_bfloat16>(),
-                             fw.Wct_lo.as<__nv_bfloat16>(), e, st));
+        NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, fw.Wct_hi.as<__half>(),
+                             fw.Wct_lo.as<__half>(), e, st));
       else
         NSW_TRY(conv_gemm_ffma(g, h->mel_en.as<float>(), fw.Wc.as<float>(), e, st));
       rec(1);

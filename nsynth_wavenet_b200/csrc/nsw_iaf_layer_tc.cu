@@ -1,16 +1,16 @@
 // tcgen05 version of the fused IAF residual layer (parallel_wavenet.py:227-254):
-//   D1[128 x 64] = sum_tap L[t-(2-tap)d][128 x 64] . Wd_tap[64 x 64]      (split bf16, fp32 acc)
+//   D1[128 x 64] = sum_tap L[t-(2-tap)d][128 x 64] . Wd_tap[64 x 64]      (split fp16, fp32 acc)
 //   g = sigmoid(D1[:, even] + cond[:, even]) * tanh(D1[:, odd] + cond[:, odd])   (gate-interleaved)
 //   D2[128 x 64] = g[128 x 32] . Wr[32 x 64]                                (A operand from TMEM)
-//   l_new = l + br + D2  ->  fp32 stream + bf16 hi/lo planes for the next layer's MMA operand
+//   l_new = l + br + D2  ->  fp32 stream + fp16 hi/lo planes for the next layer's MMA operand
 //
 // One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer: weights once, then per 128-row tile the six [128 x 64] bf16
+//   warp 0      TMA producer: weights once, then per 128-row tile the six [128 x 64] fp16
 //               operand tiles (3 taps x {lo, hi}) through an 8-stage ring (SWIZZLE_128B)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; MMA2 of tile i is queued
 //               behind MMA1 of tile i+1 so the tensor pipe never waits for the gate epilogue
 //   warps 2-5   epilogue warpgroup 0 (even local tiles), warps 6-9 warpgroup 1 (odd tiles):
-//               tcgen05.ld D1 -> gate -> tcgen05.st g (bf16 hi|lo) -> ... -> tcgen05.ld D2 ->
+//               tcgen05.ld D1 -> gate -> tcgen05.st g (fp16 hi|lo) -> ... -> tcgen05.ld D2 ->
 //               residual add -> global stores
 // TMEM (512 columns): D1[2] 0..127, D2[2] 128..255, G[2] 256..319 (16 cols hi + 16 cols lo each).
 #include "nsw_gemm.cuh"
@@ -108,9 +108,9 @@ __device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
-// D=f32, A=B=bf16, K-major, M=128, N=64
+// D=f32, A=B=f16, K-major, M=128, N=64
 __device__ __forceinline__ uint32_t lt_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -174,8 +174,8 @@ __device__ __forceinline__ float gate_fast(float s, float t) {
   const float b = __expf(fminf(-2.0f * t, 40.0f));
   return __fdividef(1.0f - b, (1.0f + a) * (1.0f + b));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x (low 16 bits) = a
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);  // .x (low 16 bits) = a
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -228,7 +228,7 @@ __device__ __forceinline__ void rows_store128(float4* __restrict__ g, uint32_t s
   }
   __syncwarp();
 }
-// 32 rows x 64 B (half of a 128 B bf16 row): lane -> row 8i + lane/4, chunk lane%4
+// 32 rows x 64 B (half of a 128 B fp16 row): lane -> row 8i + lane/4, chunk lane%4
 __device__ __forceinline__ void rows_store64(uint4* __restrict__ g /*row pitch 8 uint4*/, uint32_t scr,
                                              int lane, const uint4 (&in)[4]) {
 #pragma unroll
@@ -252,8 +252,8 @@ struct LayerTcParams {
   const float* cond;   // [rows][64] gate-interleaved, biases folded
   const float* l_in;   // [rows][64] fp32
   float* l_out;        // [rows][64] fp32
-  __nv_bfloat16* out_hi;  // [rows][64]
-  __nv_bfloat16* out_lo;
+  __half* out_hi;  // [rows][64]
+  __half* out_lo;
   const float* br;     // [64] natural order
   int dil, tiles_per_clip, n_tiles, layer;
   long long* dbg;  // optional timeline of CTA 0 (NULL = off): [0..31] MMA warp, [32..95] epilogue warp 2
@@ -448,10 +448,10 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
         const float t1 = __uint_as_float(d[4 * i + 3]) + cq[i].w;
         const float g0 = gate_fast(s0, t0);
         const float g1 = gate_fast(s1, t1);
-        const float h0 = __bfloat162float(__float2bfloat16_rn(g0));
-        const float h1 = __bfloat162float(__float2bfloat16_rn(g1));
-        ghi[i] = pack_bf16(h0, h1);
-        glo[i] = pack_bf16(g0 - h0, g1 - h1);
+        const float h0 = __half2float(__float2half_rn(g0));
+        const float h1 = __half2float(__float2half_rn(g1));
+        ghi[i] = pack_f16(h0, h1);
+        glo[i] = pack_f16(g0 - h0, g1 - h1);
       }
       tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
       tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
@@ -483,12 +483,12 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
         o.z = lq[i].z + bb.z + __uint_as_float(d[4 * i + 2]);
         o.w = lq[i].w + bb.w + __uint_as_float(d[4 * i + 3]);
         lq[i] = o;
-        const float a0 = __bfloat162float(__float2bfloat16_rn(o.x));
-        const float a1 = __bfloat162float(__float2bfloat16_rn(o.y));
-        const float a2 = __bfloat162float(__float2bfloat16_rn(o.z));
-        const float a3 = __bfloat162float(__float2bfloat16_rn(o.w));
-        const uint32_t h01 = pack_bf16(a0, a1), h23 = pack_bf16(a2, a3);
-        const uint32_t l01 = pack_bf16(o.x - a0, o.y - a1), l23 = pack_bf16(o.z - a2, o.w - a3);
+        const float a0 = __half2float(__float2half_rn(o.x));
+        const float a1 = __half2float(__float2half_rn(o.y));
+        const float a2 = __half2float(__float2half_rn(o.z));
+        const float a3 = __half2float(__float2half_rn(o.w));
+        const uint32_t h01 = pack_f16(a0, a1), h23 = pack_f16(a2, a3);
+        const uint32_t l01 = pack_f16(o.x - a0, o.y - a1), l23 = pack_f16(o.z - a2, o.w - a3);
         if (i & 1) { hh[i >> 1].z = h01; hh[i >> 1].w = h23; ll2[i >> 1].z = l01; ll2[i >> 1].w = l23; }
         else       { hh[i >> 1].x = h01; hh[i >> 1].y = h23; ll2[i >> 1].x = l01; ll2[i >> 1].y = l23; }
       }
@@ -530,28 +530,28 @@ int lt_encode_fn(EncodeTiledFn* fn) {
 }  // namespace
 
 // ---- host API used by nsw_iaf.cu (opaque 128-byte tensor maps) ----
-int layer_tc_make_act_map(void* map_out, const __nv_bfloat16* base, int B, int T) {
+int layer_tc_make_act_map(void* map_out, const __half* base, int B, int T) {
   EncodeTiledFn enc;
   NSW_TRY(lt_encode_fn(&enc));
   const cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)B};
   const cuuint64_t strides[2] = {128, (cuuint64_t)T * 128};
   const cuuint32_t box[3] = {64, LT_BM, 1}, es[3] = {1, 1, 1};
-  CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                   const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<__half*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NSW_CHECK(r == CUDA_SUCCESS, NSW_ECUDA, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
   return NSW_OK;
 }
 
-int layer_tc_make_weight_map(void* map_out, const __nv_bfloat16* base, int rows, int k) {
+int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k) {
   EncodeTiledFn enc;
   NSW_TRY(lt_encode_fn(&enc));
   const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
   const cuuint32_t box[2] = {(cuuint32_t)k, 64}, es[2] = {1, 1};
-  CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<__half*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -561,7 +561,7 @@ int layer_tc_make_weight_map(void* map_out, const __nv_bfloat16* base, int rows,
 
 int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
                     const void* map_wrh, const void* map_wrl, const float* cond, const float* l_in,
-                    float* l_out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const float* br, int T,
+                    float* l_out, __half* out_hi, __half* out_lo, const float* br, int T,
                     int rows, int dil, int layer, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {

@@ -3,12 +3,12 @@
 // loss_func.py:22-63 inside ParallelWavenet.kl_loss_logistic parallel_wavenet.py:361-402).
 //
 // Every contraction of the teacher is a real GEMM (K = 1536 / 256 / 512, N = 512 / 768 / 256), so
-// the whole forward is a sequence of tcgen05 conv-GEMM launches (nsw_gemm_tc.cu, split bf16):
+// the whole forward is a sequence of tcgen05 conv-GEMM launches (nsw_gemm_tc.cu, split fp16):
 //   cond_all  = mel_en . [Wc_1 .. Wc_L | Wc_out1]                 (centre trim = row offset)
 //   per layer : g  = gate( dilated3tap(l) + cond_i )               EPI_GATE, tap stride = dilation
 //               [l | s] += g . [Wr_i | Ws_i] + [br_i | bs_i]       EPI_ROWS accumulate, one GEMM
 //   head      : h = relu(out1 . relu(s) + cond_out1);  out = out2 . h
-// Activations live as fp32 master rows [B*T, 768] = [l (512) | s (256)] plus a bf16 hi/lo copy that
+// Activations live as fp32 master rows [B*T, 768] = [l (512) | s (256)] plus a fp16 hi/lo copy that
 // feeds the next GEMM's A operand through TMA.
 #include "nsw_gemm.cuh"
 
@@ -23,8 +23,8 @@ constexpr int TW = 512, TM = 256, TS = 256, TD = 256, TLS = TW + TS;
 // l0 = conv_start(shift_right(x)) : l0[t,c] = b[c] + W0[c] x[t-3] + W1[c] x[t-2] + W2[c] x[t-1]
 __global__ void __launch_bounds__(256)
 teacher_start_kernel(const float* __restrict__ x, const float* __restrict__ w /*[3][512]*/,
-                     const float* __restrict__ b, float* __restrict__ ls, __nv_bfloat16* __restrict__ hi,
-                     __nv_bfloat16* __restrict__ lo, int T, size_t rows) {
+                     const float* __restrict__ b, float* __restrict__ ls, __half* __restrict__ hi,
+                     __half* __restrict__ lo, int T, size_t rows) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (row, c4)
   const size_t row = idx >> 7;
   if (row >= rows) return;
@@ -41,11 +41,11 @@ teacher_start_kernel(const float* __restrict__ x, const float* __restrict__ w /*
   f[2] = fmaf(w2.z, x1, fmaf(w1.z, x2, fmaf(w0.z, x3, bb.z)));
   f[3] = fmaf(w2.w, x1, fmaf(w1.w, x2, fmaf(w0.w, x3, bb.w)));
   *reinterpret_cast<float4*>(ls + row * TLS + c) = make_float4(f[0], f[1], f[2], f[3]);
-  __align__(8) __nv_bfloat16 h[4], l[4];
+  __align__(8) __half h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    h[i] = __float2bfloat16_rn(f[i]);
-    l[i] = __float2bfloat16_rn(f[i] - __bfloat162float(h[i]));
+    h[i] = __float2half_rn(f[i]);
+    l[i] = __float2half_rn(f[i] - __half2float(h[i]));
   }
   *reinterpret_cast<uint2*>(hi + row * TLS + c) = *reinterpret_cast<uint2*>(h);
   *reinterpret_cast<uint2*>(lo + row * TLS + c) = *reinterpret_cast<uint2*>(l);
@@ -152,8 +152,8 @@ namespace nsw_teacher_host {
 static inline int gate_ch(int pos) { return (pos & 1) ? (pos >> 1) + TM : (pos >> 1); }
 
 static int upload_split(DevBuf& hi, DevBuf& lo, const std::vector<float>& w) {
-  std::vector<__nv_bfloat16> h(w.size()), l(w.size());
-  split_bf16(w.data(), w.size(), h.data(), l.data());
+  std::vector<__half> h(w.size()), l(w.size());
+  split_f16(w.data(), w.size(), h.data(), l.data());
   NSW_TRY(upload(hi, h.data(), h.size() * 2));
   NSW_TRY(upload(lo, l.data(), l.size() * 2));
   return NSW_OK;
@@ -283,21 +283,21 @@ extern "C" int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, co
   const int left = (Lc - T) / 2;  // wavenet._condition (wavenet.py:76-85)
   const size_t rows = (size_t)B * T;
   const int L = h->L, NC = h->NC, G = 2 * TM;
-  NSW_TRY(h->mel_en.ensure((size_t)B * Lc * TD * 2 * sizeof(__nv_bfloat16)));
+  NSW_TRY(h->mel_en.ensure((size_t)B * Lc * TD * 2 * sizeof(__half)));
   NSW_TRY(h->cond_all.ensure(rows * NC * sizeof(float)));
   NSW_TRY(h->ls.ensure(rows * TLS * sizeof(float)));
-  NSW_TRY(h->ls_split.ensure(rows * TLS * 2 * sizeof(__nv_bfloat16)));
-  NSW_TRY(h->g_split.ensure(rows * TM * 2 * sizeof(__nv_bfloat16)));
-  NSW_TRY(h->h_split.ensure(rows * TS * 2 * sizeof(__nv_bfloat16)));
+  NSW_TRY(h->ls_split.ensure(rows * TLS * 2 * sizeof(__half)));
+  NSW_TRY(h->g_split.ensure(rows * TM * 2 * sizeof(__half)));
+  NSW_TRY(h->h_split.ensure(rows * TS * 2 * sizeof(__half)));
   NSW_TRY(h->out_pad.ensure(rows * 64 * sizeof(float)));
-  __nv_bfloat16* me_hi = h->mel_en.as<__nv_bfloat16>();
-  __nv_bfloat16* me_lo = me_hi + (size_t)B * Lc * TD;
-  __nv_bfloat16* ls_hi = h->ls_split.as<__nv_bfloat16>();
-  __nv_bfloat16* ls_lo = ls_hi + rows * TLS;
-  __nv_bfloat16* g_hi = h->g_split.as<__nv_bfloat16>();
-  __nv_bfloat16* g_lo = g_hi + rows * TM;
-  __nv_bfloat16* h_hi = h->h_split.as<__nv_bfloat16>();
-  __nv_bfloat16* h_lo = h_hi + rows * TS;
+  __half* me_hi = h->mel_en.as<__half>();
+  __half* me_lo = me_hi + (size_t)B * Lc * TD;
+  __half* ls_hi = h->ls_split.as<__half>();
+  __half* ls_lo = ls_hi + rows * TLS;
+  __half* g_hi = h->g_split.as<__half>();
+  __half* g_lo = g_hi + rows * TM;
+  __half* h_hi = h->h_split.as<__half>();
+  __half* h_lo = h_hi + rows * TS;
   float* ls = h->ls.as<float>();
   float* cond = h->cond_all.as<float>();
   NSW_CUDA(cudaEventRecord(h->ev0, st));
@@ -305,7 +305,7 @@ extern "C" int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, co
   {  // all conditioning projections at once; the centre trim is the row offset
     ConvGemm g; g.nclips = B; g.L = Lc; g.cin = TD; g.ntaps = 1; g.a_off = left; g.mclip = T; g.N = NC;
     EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->bc.as<float>(); e.out_f32 = cond; e.ld_out = NC;
-    NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, h->wc_hi.as<__nv_bfloat16>(), h->wc_lo.as<__nv_bfloat16>(), e, st));
+    NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, h->wc_hi.as<__half>(), h->wc_lo.as<__half>(), e, st));
   }
   teacher_start_kernel<<<(unsigned)((rows * 128 + 255) / 256), 256, 0, st>>>(
       d_wav, h->wcs.as<float>(), h->bcs.as<float>(), ls, ls_hi, ls_lo, T, rows);
@@ -314,7 +314,7 @@ extern "C" int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, co
     ConvGemm g; g.nclips = B; g.L = T; g.cin = TW; g.x_pitch = TLS; g.ntaps = 1; g.a_off = 0; g.mclip = T; g.N = TS;
     EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->bss.as<float>(); e.out_f32 = ls + TW; e.ld_out = TLS;
     e.out_hi = ls_hi + TW; e.out_lo = ls_lo + TW; e.ld_split = TLS;
-    NSW_TRY(conv_gemm_tc(g, ls_hi, ls_lo, h->wss_hi.as<__nv_bfloat16>(), h->wss_lo.as<__nv_bfloat16>(), e, st));
+    NSW_TRY(conv_gemm_tc(g, ls_hi, ls_lo, h->wss_hi.as<__half>(), h->wss_lo.as<__half>(), e, st));
   }
   for (int i = 0; i < L; ++i) {
     const int d = 1 << (i % h->cfg.num_stages);
@@ -324,26 +324,26 @@ extern "C" int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, co
       g.a_off = -2 * d; g.mclip = T; g.N = G;
       EpiParams e{}; e.mode = EPI_GATE; e.addend = cond + (size_t)i * G; e.ld_add = NC;
       e.out_hi = g_hi; e.out_lo = g_lo; e.ld_split = TM;
-      NSW_TRY(conv_gemm_tc(g, ls_hi, ls_lo, ly.wd_hi.as<__nv_bfloat16>(), ly.wd_lo.as<__nv_bfloat16>(), e, st));
+      NSW_TRY(conv_gemm_tc(g, ls_hi, ls_lo, ly.wd_hi.as<__half>(), ly.wd_lo.as<__half>(), e, st));
     }
     {  // l += res(g), s += skip(g) in one GEMM  (wavenet.py:269-274)
       ConvGemm g; g.nclips = B; g.L = T; g.cin = TM; g.ntaps = 1; g.a_off = 0; g.mclip = T; g.N = TLS;
       EpiParams e{}; e.mode = EPI_ROWS; e.bias = ly.brs.as<float>(); e.out_f32 = ls; e.ld_out = TLS; e.accumulate = 1;
       e.out_hi = ls_hi; e.out_lo = ls_lo; e.ld_split = TLS;
       if (i == L - 1) e.relu_split_from = TW;  // the head consumes relu(s) (wavenet.py:281)
-      NSW_TRY(conv_gemm_tc(g, g_hi, g_lo, ly.wrs_hi.as<__nv_bfloat16>(), ly.wrs_lo.as<__nv_bfloat16>(), e, st));
+      NSW_TRY(conv_gemm_tc(g, g_hi, g_lo, ly.wrs_hi.as<__half>(), ly.wrs_lo.as<__half>(), e, st));
     }
   }
   {  // h = relu(out1 . relu(s) + cond_out1)  (wavenet.py:281-286)
     ConvGemm g; g.nclips = B; g.L = T; g.cin = TS; g.x_pitch = TLS; g.ntaps = 1; g.a_off = 0; g.mclip = T; g.N = TS;
     EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->zeros.as<float>(); e.addend = cond + (size_t)L * G; e.ld_add = NC;
     e.relu_out = 1; e.out_hi = h_hi; e.out_lo = h_lo; e.ld_split = TS;
-    NSW_TRY(conv_gemm_tc(g, ls_hi + TW, ls_lo + TW, h->wo1_hi.as<__nv_bfloat16>(), h->wo1_lo.as<__nv_bfloat16>(), e, st));
+    NSW_TRY(conv_gemm_tc(g, ls_hi + TW, ls_lo + TW, h->wo1_hi.as<__half>(), h->wo1_lo.as<__half>(), e, st));
   }
   {  // out = out2 . h  (wavenet.py:287-288), padded to 64 columns
     ConvGemm g; g.nclips = B; g.L = T; g.cin = TS; g.ntaps = 1; g.a_off = 0; g.mclip = T; g.N = 64;
     EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->bo2.as<float>(); e.out_f32 = h->out_pad.as<float>(); e.ld_out = 64;
-    NSW_TRY(conv_gemm_tc(g, h_hi, h_lo, h->wo2_hi.as<__nv_bfloat16>(), h->wo2_lo.as<__nv_bfloat16>(), e, st));
+    NSW_TRY(conv_gemm_tc(g, h_hi, h_lo, h->wo2_hi.as<__half>(), h->wo2_lo.as<__half>(), e, st));
   }
   NSW_CUDA(cudaMemcpy2DAsync(d_out, (size_t)h->O * 4, h->out_pad.p, 64 * 4, (size_t)h->O * 4, rows,
                              cudaMemcpyDeviceToDevice, st));
