@@ -159,6 +159,40 @@ def fastgen_bench(device, steps, hbm_peak):
             'note': 'includes the hoisted cond GEMM; weights stream L2/HBM -> smem every step'}
 
 
+def distill_bench(device, hbm_peak):
+    """BASELINE configs[4] forward pieces on one GPU at the author's per-GPU batch (7 x 7680):
+    student forward + teacher full-sequence forward on the student's output + 100-sample MoL
+    cross-entropy (parallel_wavenet.py:361-402).  Secondary metric, reported not optimised."""
+    import torch
+    from argparse import Namespace
+    from nsynth_wavenet_b200 import IAFEngine, TeacherEngine
+    from oracle import wavenet_oracle as O
+    cfgdir = os.path.join(ROOT, 'nsynth_wavenet_b200', 'config_jsons')
+    with open(os.path.join(cfgdir, 'wavenet_mol.json')) as f:
+        thp = Namespace(**json.load(f))
+    shp = load_hparams('student')
+    st = IAFEngine(shp, O.init_student_weights(shp, seed=12345), device=device)
+    te = TeacherEngine(thp, O.init_teacher_weights(thp, seed=12345), device=device)
+    dev = 'cuda:%d' % device
+    mel = torch.rand((7, 39, 80), device=dev)
+    res = None
+    evs = []
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = st.forward_device(mel, None, seed=i, quantize=False)
+        te_out = te.forward_device(out['x'], mel)
+        res = te.mol_score(te_out, out['mean_tot'], out['scale_tot'], out['log_scale_tot'],
+                           num_samples=100, seed=i)
+        e1.record()
+        torch.cuda.synchronize()
+        evs.append(e0.elapsed_time(e1))
+    ms = float(np.median(evs[1:]))
+    return {'metric': 'distillation forward (student + teacher + 100-sample MoL CE), 7x7680 per GPU',
+            'ms': ms, 'teacher_forward_ms': te.last_timing(), 'clips_per_s': 7 / (ms * 1e-3),
+            'losses': res}
+
+
 def run_reference(args, emit):
     """--impl reference: the reference's own CPU path restated (TF 1.x is not installable
     here), bounded sample, rank 0 only."""
@@ -199,6 +233,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fastgen', action='store_true')
+    ap.add_argument('--no-distill', action='store_true')
     ap.add_argument('--fastgen-steps', type=int, default=32000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -353,6 +388,12 @@ def main():
             line['fastgen'] = fastgen_bench(local_rank, args.fastgen_steps, hbm_peak)
         except Exception as ex:  # reported, never silently dropped
             line['fastgen'] = {'error': str(ex)[:300]}
+
+    if rank == 0 and not args.no_distill:
+        try:
+            line['distill'] = distill_bench(local_rank, hbm_peak)
+        except Exception as ex:
+            line['distill'] = {'error': str(ex)[:300]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample (about cpu-seconds of work): single-clip forwards
