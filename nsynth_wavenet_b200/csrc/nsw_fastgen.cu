@@ -369,28 +369,6 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         const int nph = (ph == NPH) ? 1 : ph + 1;
         const int nt = (ph == NPH) ? t + 1 : t;
         const bool do_past = (nph <= L) && (nt < T);
-        // history of the next layer (>= 1 step old, so already final), requested early
-        uint4 hraw[4];
-        const unsigned long long* hp2 = nullptr;
-        const unsigned long long* hp1 = nullptr;
-        uint32_t tag2 = 0, tag1 = 0;
-        if (do_past) {
-          const int d = S.dil[nph];
-          const int R = 2 * d + 1;
-          const unsigned long long* hb = P.hist + S.hoff[nph];
-          int pn = S.pos[nph] + (nt - t);
-          if (pn >= R) pn -= R;
-          int p1 = pn - d;
-          if (p1 < 0) p1 += R;
-          int p2 = p1 - d;
-          if (p2 < 0) p2 += R;
-          if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
-          if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
-          hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
-          hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
-          hraw[2] = hp1 ? LDX(hp1) : make_uint4(0, 0, 0, 0);
-          hraw[3] = hp1 ? LDX(hp1 + 256) : make_uint4(0, 0, 0, 0);
-        }
         const float* blk = S.ring[slot];  // arrival was checked in the previous phase's slack
         unsigned long long* xs = P.xbuf + ((size_t)ph * XREP + lane) * XSLOT;  // my replica (lane < nrep)
 
@@ -434,6 +412,30 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         }
         long long tPub = 0;
         if (P.dbg && tid == 0) { tPub = clock64(); P.dbg[16 * c + 0] += tPub - tS1; }
+
+        // history of the next layer (>= 1 step old, so already final), requested right after this
+        // phase's publish so the strong loads never sit in front of the publishing stores
+        uint4 hraw[4];
+        const unsigned long long* hp2 = nullptr;
+        const unsigned long long* hp1 = nullptr;
+        uint32_t tag2 = 0, tag1 = 0;
+        if (do_past) {
+          const int d = S.dil[nph];
+          const int R = 2 * d + 1;
+          const unsigned long long* hb = P.hist + S.hoff[nph];
+          int pn = S.pos[nph] + (nt - t);
+          if (pn >= R) pn -= R;
+          int p1 = pn - d;
+          if (p1 < 0) p1 += R;
+          int p2 = p1 - d;
+          if (p2 < 0) p2 += R;
+          if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
+          if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
+          hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
+          hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
+          hraw[2] = hp1 ? LDX(hp1) : make_uint4(0, 0, 0, 0);
+          hraw[3] = hp1 ? LDX(hp1 + 256) : make_uint4(0, 0, 0, 0);
+        }
 
         // ---- slack: overlaps the exchange latency ----
         if (do_past) {
