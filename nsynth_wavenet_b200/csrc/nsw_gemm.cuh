@@ -70,8 +70,8 @@ void split_f16(const float* src, size_t n, __half* hi, __half* lo);
 int layer_tc_make_act_map(void* map_out, const __half* base, int B, int T);
 int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k);
 int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
-                    const void* map_wrh, const void* map_wrl, const float* cond, const float* l_in,
-                    float* l_out, __half* out_hi, __half* out_lo, const float* br, int T,
+                    const void* map_wrh, const void* map_wrl, const float* cond,
+                    __half* out_hi, __half* out_lo, const float* br, int T,
                     int rows, int dil, int layer, int num_sms, cudaStream_t stream);
 
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----

@@ -103,6 +103,27 @@ iaf_start_conv_kernel(const float* __restrict__ x, float* __restrict__ l,
   }
 }
 
+// fp32 view of a split (fp16 hi + fp16 lo) residual stream: the tcgen05 layer engine keeps l only
+// as the split pair; the head kernel and the debug tap read this merged copy
+__global__ void __launch_bounds__(256)
+iaf_merge_split_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                       float* __restrict__ out, size_t n8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 h = reinterpret_cast<const uint4*>(hi)[i], l = reinterpret_cast<const uint4*>(lo)[i];
+  const __half2* hp = reinterpret_cast<const __half2*>(&h);
+  const __half2* lp = reinterpret_cast<const __half2*>(&l);
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 a = __half22float2(hp[e]), b = __half22float2(lp[e]);
+    o[2 * e] = a.x + b.x;
+    o[2 * e + 1] = a.y + b.y;
+  }
+  reinterpret_cast<float4*>(out)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
 // ------------------------------ residual layer ------------------------------
 // One warp owns RT consecutive time steps; lane j owns the output-channel pair
 // (j, j+32), i.e. both gate halves of gate channel j, so the gate is lane-local.
@@ -766,7 +787,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       if (tc_layers) {
         NSW_TRY(layer_tc_launch(h->map_act[cur][0], h->map_act[cur][1], fw.map_wdh, fw.map_wdl,
                                 fw.map_wrh, fw.map_wrl, h->cond.as<float>() + (size_t)i * rows * C,
-                                l_buf[cur], l_buf[cur ^ 1], ls_hi[cur ^ 1], ls_lo[cur ^ 1],
+                                ls_hi[cur ^ 1], ls_lo[cur ^ 1],
                                 fw.br_nat.as<float>() + (size_t)i * C, T, (int)rows, dil, i,
                                 h->num_sms, st));
       } else {
@@ -777,9 +798,21 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       count_launch();
       }
       cur ^= 1;
-      if (h->tap_flow == f && h->tap_layer == i + 1)
-        NSW_CUDA(cudaMemcpyAsync(h->tap_dst, l_buf[cur], rows * C * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, st));
+      if (h->tap_flow == f && h->tap_layer == i + 1) {
+        if (tc_layers) {
+          iaf_merge_split_kernel<<<(unsigned)((rows * C / 8 + 255) / 256), 256, 0, st>>>(
+              ls_hi[cur], ls_lo[cur], h->tap_dst, rows * C / 8);
+          count_launch();
+        } else {
+          NSW_CUDA(cudaMemcpyAsync(h->tap_dst, l_buf[cur], rows * C * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, st));
+        }
+      }
+    }
+    if (tc_layers && fw.L > 0) {  // the head consumes fp32 rows
+      iaf_merge_split_kernel<<<(unsigned)((rows * C / 8 + 255) / 256), 256, 0, st>>>(
+          ls_hi[cur], ls_lo[cur], l_buf[cur], rows * C / 8);
+      count_launch();
     }
     rec(1);
     lap(2, 0, 1);

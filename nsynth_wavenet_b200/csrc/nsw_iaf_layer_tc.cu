@@ -25,7 +25,7 @@ namespace {
 
 constexpr int C = 64;
 constexpr int LT_BM = 128;
-constexpr int LT_STAGES = 8;
+constexpr int LT_STAGES = 4;   // ring for the two PAST taps (t-2d, t-d): 2 planes x 2 taps per tile
 constexpr int LT_THREADS = 320;
 constexpr uint32_t A_TILE_BYTES = LT_BM * 64 * 2;   // 16 KB
 constexpr uint32_t WD_TILE_BYTES = 64 * 64 * 2;     // 8 KB per tap per plane
@@ -37,13 +37,17 @@ struct LtBars {
   uint64_t wfull;
   uint64_t full[LT_STAGES];
   uint64_t empty[LT_STAGES];
+  uint64_t cur_full[2], cur_free[2];
   uint64_t d1_full[2], d1_empty[2], g_full[2], d2_full[2], d2_empty[2];
   uint32_t tmem_base;
 };
-// smem: [Wd_hi 3x8K][Wd_lo 3x8K][Wr_hi 4K][Wr_lo 4K][A ring 8x16K][bars]
+// smem: [Wd_hi 3x8K][Wd_lo 3x8K][Wr_hi 4K][Wr_lo 4K][past-tap ring 4x16K][current-tap tiles 2x2x16K][bars][scratch]
+// The current-tap (t) operand tiles live in their own double buffer because they are read twice:
+// by the MMA and, as the residual input l[t] = hi + lo, by the epilogue.
 constexpr uint32_t OFF_WDH = 0, OFF_WDL = 3 * WD_TILE_BYTES, OFF_WRH = 6 * WD_TILE_BYTES,
                    OFF_WRL = OFF_WRH + WR_TILE_BYTES, OFF_A = OFF_WRL + WR_TILE_BYTES,
-                   OFF_BARS = OFF_A + LT_STAGES * A_TILE_BYTES;
+                   OFF_CUR = OFF_A + LT_STAGES * A_TILE_BYTES,
+                   OFF_BARS = OFF_CUR + 4 * A_TILE_BYTES;
 constexpr uint32_t OFF_SCR = OFF_BARS + 512;                 // 8 warps x 4 KB transposition scratch
 constexpr uint32_t SCR_BYTES = 8 * 4096;
 static_assert(sizeof(LtBars) <= 512, "barrier block grew");
@@ -250,9 +254,7 @@ __device__ __forceinline__ void rows_store64(uint4* __restrict__ g /*row pitch 8
 
 struct LayerTcParams {
   const float* cond;   // [rows][64] gate-interleaved, biases folded
-  const float* l_in;   // [rows][64] fp32
-  float* l_out;        // [rows][64] fp32
-  __half* out_hi;  // [rows][64]
+  __half* out_hi;  // [rows][64]  (the residual stream IS the fp16 hi + lo pair: 22 mantissa bits)
   __half* out_lo;
   const float* br;     // [64] natural order
   int dil, tiles_per_clip, n_tiles, layer;
@@ -275,6 +277,8 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     lt_mbar_init(&B->wfull, 1);
     for (int s = 0; s < LT_STAGES; ++s) { lt_mbar_init(&B->full[s], 1); lt_mbar_init(&B->empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
+      lt_mbar_init(&B->cur_full[b], 1);
+      lt_mbar_init(&B->cur_free[b], 9);  // MMA commit + 8 epilogue warps
       lt_mbar_init(&B->d1_full[b], 1);
       lt_mbar_init(&B->d1_empty[b], 8);
       lt_mbar_init(&B->g_full[b], 8);
@@ -318,7 +322,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
         const int tile = blockIdx.x + it * gridDim.x;
         const int clip = tile / p.tiles_per_clip;
         const int t0 = (tile - clip * p.tiles_per_clip) * LT_BM;
-        for (int tap = 0; tap < 3; ++tap) {
+        for (int tap = 0; tap < 2; ++tap) {
           const int trow = t0 - (2 - tap) * p.dil;  // negative rows: TMA zero fill = causal padding
           for (int pl = 0; pl < 2; ++pl) {          // lo plane first, then hi
             lt_wait(&B->empty[stage], phase ^ 1);
@@ -327,6 +331,13 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
                       &B->full[stage], 0, trow, clip);
             if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
           }
+        }
+        {  // current tap: both planes into the double buffer shared with the epilogue
+          const int b = it & 1;
+          lt_wait(&B->cur_free[b], (uint32_t)(((it >> 1) & 1) ^ 1));
+          lt_expect_tx(&B->cur_full[b], 2 * A_TILE_BYTES);
+          lt_tma_3d(sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES, &map_ll, &B->cur_full[b], 0, t0, clip);
+          lt_tma_3d(sbase + OFF_CUR + (b * 2 + 1) * A_TILE_BYTES, &map_lh, &B->cur_full[b], 0, t0, clip);
         }
       }
     }
@@ -365,7 +376,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
       lt_wait(&B->d1_empty[b], (u & 1) ^ 1);
       fence_after();
       const uint32_t d1 = tmem + b * 64;
-      for (int tap = 0; tap < 3; ++tap) {
+      for (int tap = 0; tap < 2; ++tap) {
         const uint64_t wh = desc_sw128(sbase + OFF_WDH + tap * WD_TILE_BYTES);
         const uint64_t wl = desc_sw128(sbase + OFF_WDL + tap * WD_TILE_BYTES);
         // lo plane of the activations: A_lo . W_hi
@@ -390,10 +401,30 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
             mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, 1);
           }
           lt_commit(&B->empty[stage]);
-          if (tap == 2) { lt_commit(&B->d1_full[b]); if (dbg && it < 6) p.dbg[1 + it] = clock64() - tk0; }  // MMA1(it) issued
         }
         __syncwarp();
         if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+      }
+      {  // current tap from the shared double buffer
+        const uint64_t wh = desc_sw128(sbase + OFF_WDH + 2 * WD_TILE_BYTES);
+        const uint64_t wl = desc_sw128(sbase + OFF_WDL + 2 * WD_TILE_BYTES);
+        lt_wait(&B->cur_full[b], u & 1);
+        fence_after();
+        if (lane == 0) {
+          const uint64_t alo = desc_sw128(sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES);
+          const uint64_t ahi = desc_sw128(sbase + OFF_CUR + (b * 2 + 1) * A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(d1, alo + 2 * k, wh + 2 * k, idesc, 1);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_ss(d1, ahi + 2 * k, wl + 2 * k, idesc, 1);
+            mma_ss(d1, ahi + 2 * k, wh + 2 * k, idesc, 1);
+          }
+          lt_commit(&B->cur_free[b]);
+          lt_commit(&B->d1_full[b]);
+          if (dbg && it < 6) p.dbg[1 + it] = clock64() - tk0;  // MMA1(it) issued
+        }
+        __syncwarp();
       }
       if (it >= 1) mma2(it - 1);
     }
@@ -459,40 +490,51 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
       fence_before();
       __syncwarp();
       if (lane == 0) lt_arrive(&B->g_full[b]);
-      // residual input rows (L2-resident): requested now, their latency hides behind MMA2
-      float4 tl[8], lq[8];
-      rows_issue128(reinterpret_cast<const float4*>(p.l_in + wrow * C) + half * 8, lane, tl);
       if (ed) p.dbg[32 + it * 8 + 2] = clock64() - tk0;  // g stored
       // ---- E2: residual ----
       lt_wait(&B->d2_full[b], u & 1);
       fence_after();
       if (ed) p.dbg[32 + it * 8 + 3] = clock64() - tk0;  // D2 ready
-      rows_transpose128(scr, lane, tl, lq);
       tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
       tmem_ld_wait();
       fence_before();
       __syncwarp();
       if (lane == 0) lt_arrive(&B->d2_empty[b]);
+      // l[t] = hi + lo straight from the current-tap operand tiles (SWIZZLE_128B: 16-byte chunk c of
+      // row r sits at chunk c ^ (r & 7)); they were loaded for the MMA anyway
+      lt_wait(&B->cur_full[b], u & 1);
+      const int row = qd * 32 + lane;
+      const uint32_t cur_lo = sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES + (uint32_t)row * 128u;
+      const uint32_t cur_hi = cur_lo + A_TILE_BYTES;
       uint4 hh[4], ll2[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 bb = __ldg(bptr + i);
-        float4 o;
-        o.x = lq[i].x + bb.x + __uint_as_float(d[4 * i + 0]);
-        o.y = lq[i].y + bb.y + __uint_as_float(d[4 * i + 1]);
-        o.z = lq[i].z + bb.z + __uint_as_float(d[4 * i + 2]);
-        o.w = lq[i].w + bb.w + __uint_as_float(d[4 * i + 3]);
-        lq[i] = o;
-        const float a0 = __half2float(__float2half_rn(o.x));
-        const float a1 = __half2float(__float2half_rn(o.y));
-        const float a2 = __half2float(__float2half_rn(o.z));
-        const float a3 = __half2float(__float2half_rn(o.w));
-        const uint32_t h01 = pack_f16(a0, a1), h23 = pack_f16(a2, a3);
-        const uint32_t l01 = pack_f16(o.x - a0, o.y - a1), l23 = pack_f16(o.z - a2, o.w - a3);
-        if (i & 1) { hh[i >> 1].z = h01; hh[i >> 1].w = h23; ll2[i >> 1].z = l01; ll2[i >> 1].w = l23; }
-        else       { hh[i >> 1].x = h01; hh[i >> 1].y = h23; ll2[i >> 1].x = l01; ll2[i >> 1].y = l23; }
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t coff = (uint32_t)(((4 * half + j) ^ (row & 7)) * 16);
+        const float4 hraw = lds128(cur_hi + coff), lraw = lds128(cur_lo + coff);
+        const __half2* hp = reinterpret_cast<const __half2*>(&hraw);
+        const __half2* lp = reinterpret_cast<const __half2*>(&lraw);
+        const float4 b0 = __ldg(bptr + 2 * j), b1 = __ldg(bptr + 2 * j + 1);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hv = __half22float2(hp[e]), lv = __half22float2(lp[e]);
+          o[2 * e] = (hv.x + lv.x) + bb[2 * e] + __uint_as_float(d[8 * j + 2 * e]);
+          o[2 * e + 1] = (hv.y + lv.y) + bb[2 * e + 1] + __uint_as_float(d[8 * j + 2 * e + 1]);
+        }
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a0 = __half2float(__float2half_rn(o[2 * e]));
+          const float a1 = __half2float(__float2half_rn(o[2 * e + 1]));
+          hw[e] = pack_f16(a0, a1);
+          lw[e] = pack_f16(o[2 * e] - a0, o[2 * e + 1] - a1);
+        }
+        hh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        ll2[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
-      rows_store128(reinterpret_cast<float4*>(p.l_out + wrow * C) + half * 8, scr, lane, lq);
+      __syncwarp();
+      if (lane == 0) lt_arrive(&B->cur_free[b]);
       rows_store64(reinterpret_cast<uint4*>(p.out_hi + wrow * C) + half * 4, scr, lane, hh);
       rows_store64(reinterpret_cast<uint4*>(p.out_lo + wrow * C) + half * 4, scr, lane, ll2);
       if (ed) p.dbg[32 + it * 8 + 4] = clock64() - tk0;  // tile stored
@@ -560,8 +602,8 @@ int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k)
 }
 
 int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
-                    const void* map_wrh, const void* map_wrl, const float* cond, const float* l_in,
-                    float* l_out, __half* out_hi, __half* out_lo, const float* br, int T,
+                    const void* map_wrh, const void* map_wrl, const float* cond,
+                    __half* out_hi, __half* out_lo, const float* br, int T,
                     int rows, int dil, int layer, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -572,8 +614,6 @@ int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh,
   NSW_CHECK(T % LT_BM == 0, NSW_EINVAL, "layer_tc: T=%d must be a multiple of %d", T, LT_BM);
   LayerTcParams p;
   p.cond = cond;
-  p.l_in = l_in;
-  p.l_out = l_out;
   p.out_hi = out_hi;
   p.out_lo = out_lo;
   p.br = br;
