@@ -69,10 +69,11 @@ void split_f16(const float* src, size_t n, __half* hi, __half* lo);
 // ---- tcgen05 fused IAF residual layer (nsw_iaf_layer_tc.cu); maps are 128-byte CUtensorMaps ----
 int layer_tc_make_act_map(void* map_out, const __half* base, int B, int T);
 int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k);
-int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
-                    const void* map_wrh, const void* map_wrl, const float* cond,
-                    __half* out_hi, __half* out_lo, const float* br, int T,
-                    int rows, int dil, int layer, int num_sms, cudaStream_t stream);
+int layer_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
+                    const void* map_wrh, const void* map_wrl, const float* cond, size_t cond_plane,
+                    __half* const hi[2], __half* const lo[2], const float* br, int T, int rows, int buf0,
+                    int l0, int l1, int num_stages, unsigned int* grid_counter, int num_sms,
+                    cudaStream_t stream);
 
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
 struct DeconvLayer {

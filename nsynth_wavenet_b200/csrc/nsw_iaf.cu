@@ -424,7 +424,7 @@ struct nsw_iaf {
   // workspace
   int ws_B = 0, ws_F = 0;
   DevBuf mel, mel_en, mel_en_split, cond, l0, l1, x, z, mean_tot, scale_tot, log_scale_tot,
-      deconv_scratch, ls0, ls1;  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
+      deconv_scratch, ls0, ls1, grid_counter;  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
   alignas(64) unsigned char map_act[2][2][128];  // [buffer][hi, lo]
   int map_B = 0, map_T = 0;
   // debug tap
@@ -782,32 +782,40 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     if (h->tap_flow == f && h->tap_layer == 0)
       NSW_CUDA(cudaMemcpyAsync(h->tap_dst, l_buf[cur], rows * C * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
+    if (tc_layers) {
+      // one persistent cooperative launch for all layers of the flow (two when a debug tap
+      // asks for the residual stream after an inner layer)
+      NSW_TRY(h->grid_counter.ensure(sizeof(unsigned int)));
+      const void* const maps[2][2] = {{h->map_act[0][0], h->map_act[0][1]}, {h->map_act[1][0], h->map_act[1][1]}};
+      int split_at = (h->tap_flow == f && h->tap_layer >= 1 && h->tap_layer <= fw.L) ? h->tap_layer : fw.L;
+      int l0 = 0;
+      while (l0 < fw.L) {
+        const int l1 = (l0 < split_at) ? split_at : fw.L;
+        NSW_TRY(layer_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
+                                h->cond.as<float>() + (size_t)l0 * rows * C, rows * C, ls_hi, ls_lo,
+                                fw.br_nat.as<float>(), T, (int)rows, cur, l0, l1, cfg.num_stages,
+                                h->grid_counter.as<unsigned int>(), h->num_sms, st));
+        cur = (cur + (l1 - l0)) & 1;
+        if (l1 == split_at && split_at < fw.L + 1 && h->tap_flow == f && h->tap_layer == l1) {
+          iaf_merge_split_kernel<<<(unsigned)((rows * C / 8 + 255) / 256), 256, 0, st>>>(
+              ls_hi[cur], ls_lo[cur], h->tap_dst, rows * C / 8);
+          count_launch();
+        }
+        l0 = l1;
+      }
+    } else {
     for (int i = 0; i < fw.L; ++i) {
       const int dil = 1 << (i % cfg.num_stages);
-      if (tc_layers) {
-        NSW_TRY(layer_tc_launch(h->map_act[cur][0], h->map_act[cur][1], fw.map_wdh, fw.map_wdl,
-                                fw.map_wrh, fw.map_wrl, h->cond.as<float>() + (size_t)i * rows * C,
-                                ls_hi[cur ^ 1], ls_lo[cur ^ 1],
-                                fw.br_nat.as<float>() + (size_t)i * C, T, (int)rows, dil, i,
-                                h->num_sms, st));
-      } else {
       iaf_layer_kernel<<<grid_lk, LK_THREADS, sizeof(LayerSmem), st>>>(
           l_buf[cur], h->cond.as<float>() + (size_t)i * rows * C, l_buf[cur ^ 1],
           fw.Wd.as<float>() + (size_t)i * 3 * C * C, fw.Wr.as<float>() + (size_t)i * HALF * C,
           fw.br.as<float>() + (size_t)i * C, T, dil, n_tiles);
       count_launch();
-      }
       cur ^= 1;
-      if (h->tap_flow == f && h->tap_layer == i + 1) {
-        if (tc_layers) {
-          iaf_merge_split_kernel<<<(unsigned)((rows * C / 8 + 255) / 256), 256, 0, st>>>(
-              ls_hi[cur], ls_lo[cur], h->tap_dst, rows * C / 8);
-          count_launch();
-        } else {
-          NSW_CUDA(cudaMemcpyAsync(h->tap_dst, l_buf[cur], rows * C * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, st));
-        }
-      }
+      if (h->tap_flow == f && h->tap_layer == i + 1)
+        NSW_CUDA(cudaMemcpyAsync(h->tap_dst, l_buf[cur], rows * C * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+    }
     }
     if (tc_layers && fw.L > 0) {  // the head consumes fp32 rows
       iaf_merge_split_kernel<<<(unsigned)((rows * C / 8 + 255) / 256), 256, 0, st>>>(

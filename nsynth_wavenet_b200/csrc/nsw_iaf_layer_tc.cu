@@ -34,7 +34,7 @@ constexpr uint32_t W_BYTES = 6 * WD_TILE_BYTES + 2 * WR_TILE_BYTES;  // 56 KB
 constexpr long long LT_WATCHDOG = 4000000000ll;
 
 struct LtBars {
-  uint64_t wfull;
+  uint64_t wfull, wfree;
   uint64_t full[LT_STAGES];
   uint64_t empty[LT_STAGES];
   uint64_t cur_full[2], cur_free[2];
@@ -253,16 +253,26 @@ __device__ __forceinline__ void rows_store64(uint4* __restrict__ g /*row pitch 8
 }
 
 struct LayerTcParams {
-  const float* cond;   // [rows][64] gate-interleaved, biases folded
-  __half* out_hi;  // [rows][64]  (the residual stream IS the fp16 hi + lo pair: 22 mantissa bits)
-  __half* out_lo;
-  const float* br;     // [64] natural order
-  int dil, tiles_per_clip, n_tiles, layer;
+  const float* cond;       // plane of layer 0 of this flow: [rows][64] gate-interleaved, biases folded
+  size_t cond_plane;       // floats between consecutive layers' planes
+  __half* hi[2];           // ping-pong residual stream (fp16 hi / lo planes, [rows][64] each);
+  __half* lo[2];           //   layer l0 reads buffer `buf0`, writes the other, and so on
+  const float* br;         // [L][64] natural order
+  int buf0, l0, l1, num_stages;
+  int tiles_per_clip, n_tiles;
+  unsigned int* grid_counter;  // arrival counter of the inter-layer grid barrier (zeroed per launch)
+  unsigned int grid_base;
   long long* dbg;  // optional timeline of CTA 0 (NULL = off): [0..31] MMA warp, [32..95] epilogue warp 2
 };
 
+// Persistent over the layers [l0, l1) of one flow: a layer needs rows t-d, t-2d written by OTHER
+// CTAs in the previous layer, so layers are separated by a grid-wide barrier (one arrival per CTA
+// on a global counter, polled by each CTA's TMA producer).  Barrier state, TMEM and the smem
+// pipelines simply keep running across layers; the next layer's weights are fetched as soon as
+// the MMA warp has retired the current layer, i.e. while the last epilogues and the barrier run.
 __global__ void __launch_bounds__(LT_THREADS, 1)
-iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_constant__ CUtensorMap map_ll,
+iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_constant__ CUtensorMap map_l0,
+                    const __grid_constant__ CUtensorMap map_h1, const __grid_constant__ CUtensorMap map_l1,
                     const __grid_constant__ CUtensorMap map_wdh, const __grid_constant__ CUtensorMap map_wdl,
                     const __grid_constant__ CUtensorMap map_wrh, const __grid_constant__ CUtensorMap map_wrl,
                     LayerTcParams p) {
@@ -275,6 +285,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
 
   if (threadIdx.x == 0) {
     lt_mbar_init(&B->wfull, 1);
+    lt_mbar_init(&B->wfree, 1);
     for (int s = 0; s < LT_STAGES; ++s) { lt_mbar_init(&B->full[s], 1); lt_mbar_init(&B->empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       lt_mbar_init(&B->cur_full[b], 1);
@@ -301,55 +312,80 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
   const long long tk0 = clock64();
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_layers = p.l1 - p.l0;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      lt_expect_tx(&B->wfull, W_BYTES);
-      for (int tap = 0; tap < 3; ++tap) {
-        lt_tma_2d(sbase + OFF_WDH + tap * WD_TILE_BYTES, &map_wdh, &B->wfull, 0, (p.layer * 3 + tap) * 64);
-        lt_tma_2d(sbase + OFF_WDL + tap * WD_TILE_BYTES, &map_wdl, &B->wfull, 0, (p.layer * 3 + tap) * 64);
-      }
-      lt_tma_2d(sbase + OFF_WRH, &map_wrh, &B->wfull, 0, p.layer * 64);
-      lt_tma_2d(sbase + OFF_WRL, &map_wrl, &B->wfull, 0, p.layer * 64);
-      for (int it = 0; it < n_my; ++it) {  // conditioning rows stream from HBM: warm L2 early
-        const float* ct = p.cond + (size_t)(blockIdx.x + it * gridDim.x) * LT_BM * C;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ct), "r"(LT_BM * C * 4) : "memory");
-      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < n_my; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int clip = tile / p.tiles_per_clip;
-        const int t0 = (tile - clip * p.tiles_per_clip) * LT_BM;
-        for (int tap = 0; tap < 2; ++tap) {
-          const int trow = t0 - (2 - tap) * p.dil;  // negative rows: TMA zero fill = causal padding
-          for (int pl = 0; pl < 2; ++pl) {          // lo plane first, then hi
-            lt_wait(&B->empty[stage], phase ^ 1);
-            lt_expect_tx(&B->full[stage], A_TILE_BYTES);
-            lt_tma_3d(sbase + OFF_A + stage * A_TILE_BYTES, pl == 0 ? &map_ll : &map_lh,
-                      &B->full[stage], 0, trow, clip);
-            if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
-          }
+      int itg = 0;  // running tile counter across layers (buffer parity / barrier phases)
+      for (int li = 0; li < n_layers; ++li) {
+        const int layer = p.l0 + li;
+        const int dil = 1 << (layer % p.num_stages);
+        const int rb = (p.buf0 + li) & 1;  // buffer this layer reads
+        const CUtensorMap* mh = rb ? &map_h1 : &map_h0;
+        const CUtensorMap* ml = rb ? &map_l1 : &map_l0;
+        // weights of this layer (after the MMA warp retired the previous layer's)
+        if (li > 0) lt_wait(&B->wfree, (uint32_t)((li - 1) & 1));
+        lt_expect_tx(&B->wfull, W_BYTES);
+        for (int tap = 0; tap < 3; ++tap) {
+          lt_tma_2d(sbase + OFF_WDH + tap * WD_TILE_BYTES, &map_wdh, &B->wfull, 0, (layer * 3 + tap) * 64);
+          lt_tma_2d(sbase + OFF_WDL + tap * WD_TILE_BYTES, &map_wdl, &B->wfull, 0, (layer * 3 + tap) * 64);
         }
-        {  // current tap: both planes into the double buffer shared with the epilogue
-          const int b = it & 1;
-          lt_wait(&B->cur_free[b], (uint32_t)(((it >> 1) & 1) ^ 1));
-          lt_expect_tx(&B->cur_full[b], 2 * A_TILE_BYTES);
-          lt_tma_3d(sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES, &map_ll, &B->cur_full[b], 0, t0, clip);
-          lt_tma_3d(sbase + OFF_CUR + (b * 2 + 1) * A_TILE_BYTES, &map_lh, &B->cur_full[b], 0, t0, clip);
+        lt_tma_2d(sbase + OFF_WRH, &map_wrh, &B->wfull, 0, layer * 64);
+        lt_tma_2d(sbase + OFF_WRL, &map_wrl, &B->wfull, 0, layer * 64);
+        const float* cond = p.cond + (size_t)li * p.cond_plane;
+        for (int it = 0; it < n_my; ++it) {  // conditioning rows stream from HBM: warm L2 early
+          const float* ct = cond + (size_t)(blockIdx.x + it * gridDim.x) * LT_BM * C;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ct), "r"(LT_BM * C * 4) : "memory");
+        }
+        if (li > 0) {
+          // grid barrier: every CTA has stored (and fenced) its rows of the previous layer
+          const unsigned int target = p.grid_base + (unsigned int)li * gridDim.x;
+          long long w0 = 0;
+          int spins = 0;
+          for (;;) {
+            unsigned int seen;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.grid_counter) : "memory");
+            if ((int)(seen - target) >= 0) break;
+            if (++spins == 1024) {
+              spins = 0;
+              if (w0 == 0) w0 = clock64();
+              else if (clock64() - w0 > LT_WATCHDOG) { printf("nsw iaf_layer_tc: grid barrier watchdog\n"); __trap(); }
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> TMA reads
+        }
+        for (int it = 0; it < n_my; ++it, ++itg) {
+          const int tile = blockIdx.x + it * gridDim.x;
+          const int clip = tile / p.tiles_per_clip;
+          const int t0 = (tile - clip * p.tiles_per_clip) * LT_BM;
+          for (int tap = 0; tap < 2; ++tap) {
+            const int trow = t0 - (2 - tap) * dil;  // negative rows: TMA zero fill = causal padding
+            for (int pl = 0; pl < 2; ++pl) {        // lo plane first, then hi
+              lt_wait(&B->empty[stage], phase ^ 1);
+              lt_expect_tx(&B->full[stage], A_TILE_BYTES);
+              lt_tma_3d(sbase + OFF_A + stage * A_TILE_BYTES, pl == 0 ? ml : mh, &B->full[stage], 0, trow, clip);
+              if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          {  // current tap: both planes into the double buffer shared with the epilogue
+            const int b = itg & 1;
+            lt_wait(&B->cur_free[b], (uint32_t)(((itg >> 1) & 1) ^ 1));
+            lt_expect_tx(&B->cur_full[b], 2 * A_TILE_BYTES);
+            lt_tma_3d(sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES, ml, &B->cur_full[b], 0, t0, clip);
+            lt_tma_3d(sbase + OFF_CUR + (b * 2 + 1) * A_TILE_BYTES, mh, &B->cur_full[b], 0, t0, clip);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     const uint32_t idesc = lt_idesc();
-    lt_wait(&B->wfull, 0);
-    fence_after();
-    if (dbg && lane == 0) p.dbg[0] = clock64() - tk0;  // weights landed
     int stage = 0;
     uint32_t phase = 0;
-    auto mma2 = [&](int j) {
+    auto mma2 = [&](int j) {  // j: running tile index
       const int b = j & 1;
       const uint32_t u = (uint32_t)(j >> 1);
       lt_wait(&B->g_full[b], u & 1);
@@ -370,65 +406,74 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
       }
       __syncwarp();
     };
-    for (int it = 0; it < n_my; ++it) {
-      const int b = it & 1;
-      const uint32_t u = (uint32_t)(it >> 1);
-      lt_wait(&B->d1_empty[b], (u & 1) ^ 1);
+    int itg = 0;
+    for (int li = 0; li < n_layers; ++li) {
+      lt_wait(&B->wfull, (uint32_t)(li & 1));
       fence_after();
-      const uint32_t d1 = tmem + b * 64;
-      for (int tap = 0; tap < 2; ++tap) {
-        const uint64_t wh = desc_sw128(sbase + OFF_WDH + tap * WD_TILE_BYTES);
-        const uint64_t wl = desc_sw128(sbase + OFF_WDL + tap * WD_TILE_BYTES);
-        // lo plane of the activations: A_lo . W_hi
-        lt_wait(&B->full[stage], phase);
+      if (dbg && lane == 0 && li == 0) p.dbg[0] = clock64() - tk0;  // weights landed
+      for (int it = 0; it < n_my; ++it, ++itg) {
+        const int b = itg & 1;
+        const uint32_t u = (uint32_t)(itg >> 1);
+        lt_wait(&B->d1_empty[b], (u & 1) ^ 1);
         fence_after();
-        if (lane == 0) {
-          const uint64_t a = desc_sw128(sbase + OFF_A + stage * A_TILE_BYTES);
+        const uint32_t d1 = tmem + b * 64;
+        for (int tap = 0; tap < 2; ++tap) {
+          const uint64_t wh = desc_sw128(sbase + OFF_WDH + tap * WD_TILE_BYTES);
+          const uint64_t wl = desc_sw128(sbase + OFF_WDL + tap * WD_TILE_BYTES);
+          // lo plane of the activations: A_lo . W_hi
+          lt_wait(&B->full[stage], phase);
+          fence_after();
+          if (lane == 0) {
+            const uint64_t a = desc_sw128(sbase + OFF_A + stage * A_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, (tap | k) != 0);
-          lt_commit(&B->empty[stage]);
-        }
-        __syncwarp();
-        if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
-        // hi plane: A_hi . W_lo + A_hi . W_hi
-        lt_wait(&B->full[stage], phase);
-        fence_after();
-        if (lane == 0) {
-          const uint64_t a = desc_sw128(sbase + OFF_A + stage * A_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            mma_ss(d1, a + 2 * k, wl + 2 * k, idesc, 1);
-            mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, 1);
+            for (int k = 0; k < 4; ++k) mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, (tap | k) != 0);
+            lt_commit(&B->empty[stage]);
           }
-          lt_commit(&B->empty[stage]);
-        }
-        __syncwarp();
-        if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
-      }
-      {  // current tap from the shared double buffer
-        const uint64_t wh = desc_sw128(sbase + OFF_WDH + 2 * WD_TILE_BYTES);
-        const uint64_t wl = desc_sw128(sbase + OFF_WDL + 2 * WD_TILE_BYTES);
-        lt_wait(&B->cur_full[b], u & 1);
-        fence_after();
-        if (lane == 0) {
-          const uint64_t alo = desc_sw128(sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES);
-          const uint64_t ahi = desc_sw128(sbase + OFF_CUR + (b * 2 + 1) * A_TILE_BYTES);
+          __syncwarp();
+          if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+          // hi plane: A_hi . W_lo + A_hi . W_hi
+          lt_wait(&B->full[stage], phase);
+          fence_after();
+          if (lane == 0) {
+            const uint64_t a = desc_sw128(sbase + OFF_A + stage * A_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(d1, alo + 2 * k, wh + 2 * k, idesc, 1);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            mma_ss(d1, ahi + 2 * k, wl + 2 * k, idesc, 1);
-            mma_ss(d1, ahi + 2 * k, wh + 2 * k, idesc, 1);
+            for (int k = 0; k < 4; ++k) {
+              mma_ss(d1, a + 2 * k, wl + 2 * k, idesc, 1);
+              mma_ss(d1, a + 2 * k, wh + 2 * k, idesc, 1);
+            }
+            lt_commit(&B->empty[stage]);
           }
-          lt_commit(&B->cur_free[b]);
-          lt_commit(&B->d1_full[b]);
-          if (dbg && it < 6) p.dbg[1 + it] = clock64() - tk0;  // MMA1(it) issued
+          __syncwarp();
+          if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
+        {  // current tap from the shared double buffer
+          const uint64_t wh = desc_sw128(sbase + OFF_WDH + 2 * WD_TILE_BYTES);
+          const uint64_t wl = desc_sw128(sbase + OFF_WDL + 2 * WD_TILE_BYTES);
+          lt_wait(&B->cur_full[b], u & 1);
+          fence_after();
+          if (lane == 0) {
+            const uint64_t alo = desc_sw128(sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES);
+            const uint64_t ahi = desc_sw128(sbase + OFF_CUR + (b * 2 + 1) * A_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(d1, alo + 2 * k, wh + 2 * k, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_ss(d1, ahi + 2 * k, wl + 2 * k, idesc, 1);
+              mma_ss(d1, ahi + 2 * k, wh + 2 * k, idesc, 1);
+            }
+            lt_commit(&B->cur_free[b]);
+            lt_commit(&B->d1_full[b]);
+            if (dbg && itg < 6) p.dbg[1 + itg] = clock64() - tk0;  // MMA1 issued
+          }
+          __syncwarp();
+        }
+        if (it >= 1) mma2(itg - 1);
       }
-      if (it >= 1) mma2(it - 1);
+      if (n_my >= 1) mma2(itg - 1);
+      // every MMA of this layer is issued: when they retire, the weight tiles may be replaced
+      if (lane == 0) lt_commit(&B->wfree);
+      __syncwarp();
     }
-    if (n_my >= 1) mma2(n_my - 1);
   } else {
     // ================================ epilogue (8 warps) ===========================
     // every tile is handled by all 8 warps: warp w and w+4 share a TMEM lane quarter and
@@ -438,106 +483,122 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_lh, const __grid_con
     const int qd = warp & 3;  // TMEM lane quarter accessible to this warp
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     const uint32_t scr = sbase + OFF_SCR + (uint32_t)(warp - 2) * 4096u;
-    const float4* bptr = reinterpret_cast<const float4*>(p.br) + half * 8;
-    // operand half-rows (cond, l) are requested one tile ahead and sit in registers (tc, tl)
-    // while the previous tile's epilogue runs, so their DRAM/L2 latency is never exposed
-    float4 tc[8];
-    if (n_my > 0) {
-      const size_t w0 = (size_t)blockIdx.x * LT_BM + qd * 32;
-      rows_issue128(reinterpret_cast<const float4*>(p.cond + w0 * C) + half * 8, lane, tc);
-    }
-    for (int it = 0; it < n_my; ++it) {
-      const int b = it & 1;
-      const uint32_t u = (uint32_t)(it >> 1);
-      const int tile = blockIdx.x + it * gridDim.x;
-      const size_t wrow = (size_t)tile * LT_BM + qd * 32;  // first of this warp's 32 rows
-      float4 cq[8];
-      rows_transpose128(scr, lane, tc, cq);
-      if (it + 1 < n_my) {  // cond streams from HBM: request the next tile's rows now
-        const size_t wn = (size_t)(tile + gridDim.x) * LT_BM + qd * 32;
-        rows_issue128(reinterpret_cast<const float4*>(p.cond + wn * C) + half * 8, lane, tc);
+    int itg = 0;
+    for (int li = 0; li < n_layers; ++li) {
+      const int layer = p.l0 + li;
+      const int wb = ((p.buf0 + li) & 1) ^ 1;  // buffer this layer writes
+      __half* out_hi = p.hi[wb];
+      __half* out_lo = p.lo[wb];
+      const float* cond = p.cond + (size_t)li * p.cond_plane;
+      const float4* bptr = reinterpret_cast<const float4*>(p.br + (size_t)layer * C) + half * 8;
+      // conditioning half-rows are requested one tile ahead and sit in registers (tc) while the
+      // previous tile's epilogue runs, so their HBM latency is never exposed
+      float4 tc[8];
+      if (n_my > 0) {
+        const size_t w0 = (size_t)blockIdx.x * LT_BM + qd * 32;
+        rows_issue128(reinterpret_cast<const float4*>(cond + w0 * C) + half * 8, lane, tc);
       }
-      const bool ed = dbg && warp == 2 && lane == 0 && it < 6;
-      if (ed) p.dbg[32 + it * 8 + 0] = clock64() - tk0;  // operands loaded
-      // ---- E1: gate ----
-      lt_wait(&B->d1_full[b], u & 1);
-      fence_after();
-      if (ed) p.dbg[32 + it * 8 + 1] = clock64() - tk0;  // D1 ready
-      uint32_t d[32];
-      tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
-      tmem_ld_wait();
-      fence_before();
-      __syncwarp();
-      if (lane == 0) lt_arrive(&B->d1_empty[b]);
-      uint32_t ghi[8], glo[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // columns 4i..4i+3 of this half = (sig j, tanh j, sig j+1, tanh j+1)
-        const float s0 = __uint_as_float(d[4 * i]) + cq[i].x;
-        const float t0 = __uint_as_float(d[4 * i + 1]) + cq[i].y;
-        const float s1 = __uint_as_float(d[4 * i + 2]) + cq[i].z;
-        const float t1 = __uint_as_float(d[4 * i + 3]) + cq[i].w;
-        const float g0 = gate_fast(s0, t0);
-        const float g1 = gate_fast(s1, t1);
-        const float h0 = __half2float(__float2half_rn(g0));
-        const float h1 = __half2float(__float2half_rn(g1));
-        ghi[i] = pack_f16(h0, h1);
-        glo[i] = pack_f16(g0 - h0, g1 - h1);
-      }
-      tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
-      tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
-      tmem_st_wait();
-      fence_before();
-      __syncwarp();
-      if (lane == 0) lt_arrive(&B->g_full[b]);
-      if (ed) p.dbg[32 + it * 8 + 2] = clock64() - tk0;  // g stored
-      // ---- E2: residual ----
-      lt_wait(&B->d2_full[b], u & 1);
-      fence_after();
-      if (ed) p.dbg[32 + it * 8 + 3] = clock64() - tk0;  // D2 ready
-      tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
-      tmem_ld_wait();
-      fence_before();
-      __syncwarp();
-      if (lane == 0) lt_arrive(&B->d2_empty[b]);
-      // l[t] = hi + lo straight from the current-tap operand tiles (SWIZZLE_128B: 16-byte chunk c of
-      // row r sits at chunk c ^ (r & 7)); they were loaded for the MMA anyway
-      lt_wait(&B->cur_full[b], u & 1);
-      const int row = qd * 32 + lane;
-      const uint32_t cur_lo = sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES + (uint32_t)row * 128u;
-      const uint32_t cur_hi = cur_lo + A_TILE_BYTES;
-      uint4 hh[4], ll2[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t coff = (uint32_t)(((4 * half + j) ^ (row & 7)) * 16);
-        const float4 hraw = lds128(cur_hi + coff), lraw = lds128(cur_lo + coff);
-        const __half2* hp = reinterpret_cast<const __half2*>(&hraw);
-        const __half2* lp = reinterpret_cast<const __half2*>(&lraw);
-        const float4 b0 = __ldg(bptr + 2 * j), b1 = __ldg(bptr + 2 * j + 1);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 hv = __half22float2(hp[e]), lv = __half22float2(lp[e]);
-          o[2 * e] = (hv.x + lv.x) + bb[2 * e] + __uint_as_float(d[8 * j + 2 * e]);
-          o[2 * e + 1] = (hv.y + lv.y) + bb[2 * e + 1] + __uint_as_float(d[8 * j + 2 * e + 1]);
+      for (int it = 0; it < n_my; ++it, ++itg) {
+        const int b = itg & 1;
+        const uint32_t u = (uint32_t)(itg >> 1);
+        const int tile = blockIdx.x + it * gridDim.x;
+        const size_t wrow = (size_t)tile * LT_BM + qd * 32;  // first of this warp's 32 rows
+        float4 cq[8];
+        rows_transpose128(scr, lane, tc, cq);
+        if (it + 1 < n_my) {
+          const size_t wn = (size_t)(tile + gridDim.x) * LT_BM + qd * 32;
+          rows_issue128(reinterpret_cast<const float4*>(cond + wn * C) + half * 8, lane, tc);
         }
-        uint32_t hw[4], lw[4];
+        const bool ed = dbg && warp == 2 && lane == 0 && itg < 6;
+        if (ed) p.dbg[32 + itg * 8 + 0] = clock64() - tk0;  // operands loaded
+        // ---- E1: gate ----
+        lt_wait(&B->d1_full[b], u & 1);
+        fence_after();
+        if (ed) p.dbg[32 + itg * 8 + 1] = clock64() - tk0;  // D1 ready
+        uint32_t d[32];
+        tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
+        tmem_ld_wait();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) lt_arrive(&B->d1_empty[b]);
+        uint32_t ghi[8], glo[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float a0 = __half2float(__float2half_rn(o[2 * e]));
-          const float a1 = __half2float(__float2half_rn(o[2 * e + 1]));
-          hw[e] = pack_f16(a0, a1);
-          lw[e] = pack_f16(o[2 * e] - a0, o[2 * e + 1] - a1);
+        for (int i = 0; i < 8; ++i) {
+          // columns 4i..4i+3 of this half = (sig j, tanh j, sig j+1, tanh j+1)
+          const float s0 = __uint_as_float(d[4 * i]) + cq[i].x;
+          const float t0 = __uint_as_float(d[4 * i + 1]) + cq[i].y;
+          const float s1 = __uint_as_float(d[4 * i + 2]) + cq[i].z;
+          const float t1 = __uint_as_float(d[4 * i + 3]) + cq[i].w;
+          const float g0 = gate_fast(s0, t0);
+          const float g1 = gate_fast(s1, t1);
+          const float h0 = __half2float(__float2half_rn(g0));
+          const float h1 = __half2float(__float2half_rn(g1));
+          ghi[i] = pack_f16(h0, h1);
+          glo[i] = pack_f16(g0 - h0, g1 - h1);
         }
-        hh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        ll2[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
+        tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
+        tmem_st_wait();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) lt_arrive(&B->g_full[b]);
+        if (ed) p.dbg[32 + itg * 8 + 2] = clock64() - tk0;  // g stored
+        // ---- E2: residual ----
+        lt_wait(&B->d2_full[b], u & 1);
+        fence_after();
+        if (ed) p.dbg[32 + itg * 8 + 3] = clock64() - tk0;  // D2 ready
+        tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
+        tmem_ld_wait();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) lt_arrive(&B->d2_empty[b]);
+        // l[t] = hi + lo straight from the current-tap operand tiles (SWIZZLE_128B: 16-byte chunk c of
+        // row r sits at chunk c ^ (r & 7)); they were loaded for the MMA anyway
+        lt_wait(&B->cur_full[b], u & 1);
+        const int row = qd * 32 + lane;
+        const uint32_t cur_lo = sbase + OFF_CUR + (b * 2 + 0) * A_TILE_BYTES + (uint32_t)row * 128u;
+        const uint32_t cur_hi = cur_lo + A_TILE_BYTES;
+        uint4 hh[4], ll2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t coff = (uint32_t)(((4 * half + j) ^ (row & 7)) * 16);
+          const float4 hraw = lds128(cur_hi + coff), lraw = lds128(cur_lo + coff);
+          const __half2* hp = reinterpret_cast<const __half2*>(&hraw);
+          const __half2* lp = reinterpret_cast<const __half2*>(&lraw);
+          const float4 b0 = __ldg(bptr + 2 * j), b1 = __ldg(bptr + 2 * j + 1);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 hv = __half22float2(hp[e]), lv = __half22float2(lp[e]);
+            o[2 * e] = (hv.x + lv.x) + bb[2 * e] + __uint_as_float(d[8 * j + 2 * e]);
+            o[2 * e + 1] = (hv.y + lv.y) + bb[2 * e + 1] + __uint_as_float(d[8 * j + 2 * e + 1]);
+          }
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = __half2float(__float2half_rn(o[2 * e]));
+            const float a1 = __half2float(__float2half_rn(o[2 * e + 1]));
+            hw[e] = pack_f16(a0, a1);
+            lw[e] = pack_f16(o[2 * e] - a0, o[2 * e + 1] - a1);
+          }
+          hh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          ll2[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        __syncwarp();
+        if (lane == 0) lt_arrive(&B->cur_free[b]);
+        rows_store64(reinterpret_cast<uint4*>(out_hi + wrow * C) + half * 4, scr, lane, hh);
+        rows_store64(reinterpret_cast<uint4*>(out_lo + wrow * C) + half * 4, scr, lane, ll2);
+        if (ed) p.dbg[32 + itg * 8 + 4] = clock64() - tk0;  // tile stored
       }
-      __syncwarp();
-      if (lane == 0) lt_arrive(&B->cur_free[b]);
-      rows_store64(reinterpret_cast<uint4*>(p.out_hi + wrow * C) + half * 4, scr, lane, hh);
-      rows_store64(reinterpret_cast<uint4*>(p.out_lo + wrow * C) + half * 4, scr, lane, ll2);
-      if (ed) p.dbg[32 + it * 8 + 4] = clock64() - tk0;  // tile stored
+      if (li + 1 < n_layers) {
+        // grid barrier arrival: this CTA's rows of the layer are stored and visible device-wide
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.grid_counter) : "memory");
+      }
     }
   }
 
@@ -601,10 +662,11 @@ int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k)
   return NSW_OK;
 }
 
-int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh, const void* map_wdl,
-                    const void* map_wrh, const void* map_wrl, const float* cond,
-                    __half* out_hi, __half* out_lo, const float* br, int T,
-                    int rows, int dil, int layer, int num_sms, cudaStream_t stream) {
+int layer_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
+                    const void* map_wrh, const void* map_wrl, const float* cond, size_t cond_plane,
+                    __half* const hi[2], __half* const lo[2], const float* br, int T, int rows, int buf0,
+                    int l0, int l1, int num_stages, unsigned int* grid_counter, int num_sms,
+                    cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     NSW_CUDA(cudaFuncSetAttribute(iaf_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -612,40 +674,50 @@ int layer_tc_launch(const void* map_lh, const void* map_ll, const void* map_wdh,
     attr_set = true;
   }
   NSW_CHECK(T % LT_BM == 0, NSW_EINVAL, "layer_tc: T=%d must be a multiple of %d", T, LT_BM);
+  NSW_CHECK(l1 > l0, NSW_EINVAL, "layer_tc: empty layer range");
   LayerTcParams p;
   p.cond = cond;
-  p.out_hi = out_hi;
-  p.out_lo = out_lo;
+  p.cond_plane = cond_plane;
+  p.hi[0] = hi[0]; p.hi[1] = hi[1];
+  p.lo[0] = lo[0]; p.lo[1] = lo[1];
   p.br = br;
-  p.dil = dil;
+  p.buf0 = buf0;
+  p.l0 = l0;
+  p.l1 = l1;
+  p.num_stages = num_stages;
   p.tiles_per_clip = T / LT_BM;
   p.n_tiles = rows / LT_BM;
-  p.layer = layer;
+  p.grid_counter = grid_counter;
+  p.grid_base = 0;
+  NSW_CUDA(cudaMemsetAsync(grid_counter, 0, sizeof(unsigned int), stream));
   p.dbg = nullptr;
   static long long* dbg_buf = nullptr;
-  const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr && layer == 3;
+  const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr;
   if (want_dbg) {
     if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 128 * sizeof(long long)));
     NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * sizeof(long long), stream));
     p.dbg = dbg_buf;
   }
   const int grid = std::min(p.n_tiles, num_sms);
-  iaf_layer_tc_kernel<<<grid, LT_THREADS, LT_SMEM_BYTES, stream>>>(
-      *reinterpret_cast<const CUtensorMap*>(map_lh), *reinterpret_cast<const CUtensorMap*>(map_ll),
-      *reinterpret_cast<const CUtensorMap*>(map_wdh), *reinterpret_cast<const CUtensorMap*>(map_wdl),
-      *reinterpret_cast<const CUtensorMap*>(map_wrh), *reinterpret_cast<const CUtensorMap*>(map_wrl), p);
+  void* args[] = {const_cast<void*>(map_act[0][0]), const_cast<void*>(map_act[0][1]),
+                  const_cast<void*>(map_act[1][0]), const_cast<void*>(map_act[1][1]),
+                  const_cast<void*>(map_wdh), const_cast<void*>(map_wdl), const_cast<void*>(map_wrh),
+                  const_cast<void*>(map_wrl), &p};
+  // cooperative launch: every CTA must be co-resident for the inter-layer grid barrier
+  NSW_CUDA(cudaLaunchCooperativeKernel((void*)iaf_layer_tc_kernel, dim3(grid), dim3(LT_THREADS), args,
+                                       LT_SMEM_BYTES, stream));
   count_launch();
   NSW_CUDA(cudaGetLastError());
   if (want_dbg) {
     long long hbuf[128];
     NSW_CUDA(cudaStreamSynchronize(stream));
     NSW_CUDA(cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[layer_tc dbg dil=%d] weights %lld | MMA1 issued:", dil, hbuf[0]);
-    for (int i = 0; i < 5; ++i) fprintf(stderr, " %lld", hbuf[1 + i]);
+    fprintf(stderr, "[layer_tc dbg layers %d..%d] weights %lld | MMA1 issued:", l0, l1, hbuf[0]);
+    for (int i = 0; i < 6; ++i) fprintf(stderr, " %lld", hbuf[1 + i]);
     fprintf(stderr, " | MMA2 issued:");
-    for (int i = 0; i < 5; ++i) fprintf(stderr, " %lld", hbuf[8 + i]);
+    for (int i = 0; i < 6; ++i) fprintf(stderr, " %lld", hbuf[8 + i]);
     fprintf(stderr, " | end %lld\n", hbuf[30]);
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 6; ++i)
       fprintf(stderr, "   tile %d: loaded %lld  D1 %lld  g %lld  D2 %lld  stored %lld\n", i, hbuf[32 + 8 * i],
               hbuf[33 + 8 * i], hbuf[34 + 8 * i], hbuf[35 + 8 * i], hbuf[36 + 8 * i]);
   }
