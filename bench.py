@@ -228,7 +228,7 @@ def main():
     ap.add_argument('--config', default='student', choices=list(CONFIGS))
     ap.add_argument('--batch', type=int, default=8, help='clips per GPU')
     ap.add_argument('--frames', type=int, default=39, help='mel frames per clip (39 -> 7680 samples)')
-    ap.add_argument('--engine', default=None, choices=[None, 'ffma', 'tc', 'tc2'])
+    ap.add_argument('--engine', default=None, choices=[None, 'ffma', 'tc', 'tc2', 'tc3'])
     ap.add_argument('--ref-batch', type=int, default=1)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -368,7 +368,7 @@ def main():
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
         'roofline': {
-            'kernel': 'iaf_layer_tc_kernel' if eng.engine == 'tc2' else 'iaf_layer_kernel', 'bound': 'hbm', 'achieved': layer_gbs, 'peak': hbm_peak,
+            'kernel': {'tc3': 'iaf_flow_tc_kernel', 'tc2': 'iaf_layer_tc_kernel'}.get(eng.engine, 'iaf_layer_kernel'), 'bound': 'hbm', 'achieved': layer_gbs, 'peak': hbm_peak,
             'unit': 'GB/s', 'frac': layer_gbs / hbm_peak, 'traffic': None,
             'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
             'bytes_per_launch': LAYER_BYTES_PER_SAMPLE * B * T, 'launch_ms': layer_launch_ms,

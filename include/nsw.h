@@ -57,6 +57,9 @@ extern "C" {
 #define NSW_ENGINE_FFMA 0 /* fp32 CUDA-core path, bit-for-bit fp32 products   */
 #define NSW_ENGINE_TC 1   /* tcgen05 split-fp16 (hi*hi + hi*lo + lo*hi)       */
 #define NSW_ENGINE_TC2 2  /* NSW_ENGINE_TC + the IAF residual layers on tcgen05  */
+#define NSW_ENGINE_TC3 3  /* NSW_ENGINE_TC2 with the residual stream resident in shared memory for a
+                             whole flow (one persistent launch per flow, no grid barrier); shapes it
+                             cannot take (a clip longer than 4 * 128 * #SMs samples) run as TC2 */
 
 typedef struct nsw_tensor {
   const char* name;    /* TF variable name, without ":0" and without EMA suffix */

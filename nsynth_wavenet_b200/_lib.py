@@ -17,7 +17,7 @@ NSW_MAX_DECONV = 4
 
 LOSS = {'logistic': 0, 'gauss': 1, 'mol': 2, 'ce': 3}
 ACT = {'tanh': 0, 'relu': 1, 'leaky_relu': 2}
-ENGINE = {'ffma': 0, 'tc': 1, 'tc2': 2}
+ENGINE = {'ffma': 0, 'tc': 1, 'tc2': 2, 'tc3': 3}
 
 ERRORS = {-1: 'NSW_EINVAL', -2: 'NSW_ECUDA', -3: 'NSW_EMISSING', -4: 'NSW_ETIMEOUT'}
 

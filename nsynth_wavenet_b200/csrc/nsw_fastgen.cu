@@ -796,7 +796,7 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
   h->NPL = N / 64;
   h->hist_entries = pk.hist_entries;
   int rc = NSW_OK;
-  const bool want_tc = cfg->engine == NSW_ENGINE_TC;
+  const bool want_tc = cfg->engine >= NSW_ENGINE_TC;
   auto up = [&](DevBuf& b, const void* p, size_t bytes) {
     if (rc == NSW_OK) rc = upload(b, p, bytes);
   };
@@ -887,7 +887,7 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
   cudaStream_t st = (cudaStream_t)stream;
   const int N = h->NPL * 64;
   NSW_TRY(h->cond.ensure((size_t)h->NPL * T * 64 * sizeof(float)));
-  const bool tc = h->cfg.engine == NSW_ENGINE_TC;
+  const bool tc = h->cfg.engine >= NSW_ENGINE_TC;
   if (tc) NSW_TRY(h->enc_split.ensure((size_t)T * FD * 2 * sizeof(__half)));
   NSW_CUDA(cudaEventRecord(h->ev0, st));
   for (int b = 0; b < B; ++b) {

@@ -51,6 +51,10 @@ struct EpiParams {
   const float* addend = nullptr;
   int ld_out = 0, ld_add = 0, ld_split = 0;
   int accumulate = 0, relu_out = 0, relu_split_from = 1 << 30;
+  // EPI_PLANES: planes [0, tiled_planes) are written row-interleaved for the tc3 layer kernel:
+  //   plane[((row/128)*8 + (row%128)/32*2 + (n%64)/32) * 1024 + ((n%32)/4)*128 + (row%32)*4 + n%4]
+  // (a warp-level 16-byte access of one column group is 512 contiguous bytes); needs mclip % 128 == 0
+  int tiled_planes = 0;
 };
 
 // fp32 X [nclips, L, cin], fp32 Bw [ntaps*cin, N]
@@ -74,6 +78,13 @@ int layer_tc_launch(const void* const map_act[2][2], const void* map_wdh, const 
                     __half* const hi[2], __half* const lo[2], const float* br, int T, int rows, int buf0,
                     int l0, int l1, int num_stages, unsigned int* grid_counter, int num_sms,
                     cudaStream_t stream);
+
+// ---- tcgen05 fused IAF flow, residual stream resident in shared memory (nsw_iaf_flow_tc.cu) ----
+int flow_tc_clips_per_launch(int T, int num_sms);  // 0 = shape not supported
+int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
+                   const void* map_wrh, const void* map_wrl, const float* cond_tiled, size_t cond_plane,
+                   const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
+                   unsigned int* sync_words, int num_sms, cudaStream_t stream);
 
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
 struct DeconvLayer {

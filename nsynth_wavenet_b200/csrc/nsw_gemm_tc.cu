@@ -333,6 +333,19 @@ __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams&
     if (o < 0 || o >= e.Lout) return nullptr;
     return reinterpret_cast<float4*>(e.out_f32 + ((size_t)clip * e.Lout + o) * e.cout + co);
   };
+  if (e.mode == EPI_PLANES && (n >> 6) < e.tiled_planes) {
+    // row-interleaved plane (tc3 layer kernel): lane's row, float4 j -> [j][lane]; 512 B per store
+    const size_t M = (size_t)g.nclips * g.mclip;
+    const size_t grow0 = (size_t)clip * g.mclip + m0;  // m0 % 32 == 0, mclip % 128 == 0
+    float4* dst = reinterpret_cast<float4*>(e.out_f32 + (size_t)(n >> 6) * M * 64 +
+                                            ((grow0 >> 7) * 8 + ((grow0 & 127) >> 5) * 2 + ((n & 63) >> 5)) * 1024);
+    if (m0 + lane < g.mclip) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        dst[j * 32 + lane] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    }
+    return;
+  }
   if (e.out_f32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -558,6 +571,8 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
   NSW_CHECK(conv_gemm_tc_supported(g), NSW_EINVAL, "conv_gemm_tc: unsupported shape cin=%d N=%d",
             g.cin, g.N);
   NSW_CHECK(X_hi && X_lo && Bt_hi && Bt_lo, NSW_EINVAL, "conv_gemm_tc: null operand");
+  if (e.mode == EPI_PLANES && e.tiled_planes > 0)
+    NSW_CHECK(g.mclip % 128 == 0 && e.out_f32, NSW_EINVAL, "conv_gemm_tc: tiled planes need mclip %% 128 == 0");
   if (e.mode == EPI_DECONV)
     NSW_CHECK(e.cout % 32 == 0, NSW_EINVAL, "conv_gemm_tc: cout %d must be a multiple of 32", e.cout);
   if (e.mode == EPI_ROWS)

@@ -424,7 +424,7 @@ struct nsw_iaf {
   // workspace
   int ws_B = 0, ws_F = 0;
   DevBuf mel, mel_en, mel_en_split, cond, l0, l1, x, z, mean_tot, scale_tot, log_scale_tot,
-      deconv_scratch, ls0, ls1, grid_counter;  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
+      deconv_scratch, ls0, ls1, grid_counter, sync_words;  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
   alignas(64) unsigned char map_act[2][2][128];  // [buffer][hi, lo]
   int map_B = 0, map_T = 0;
   // debug tap
@@ -503,7 +503,7 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
   NSW_TRY(upload(fw.W1, w1, C * C * sizeof(float)));
   NSW_TRY(upload(fw.wm, wm, C * sizeof(float)));
   NSW_TRY(upload(fw.ws, wsc, C * sizeof(float)));
-  if (cfg.engine == NSW_ENGINE_TC2) {
+  if (cfg.engine >= NSW_ENGINE_TC2) {
     std::vector<float> wdt((size_t)L * 3 * C * C), wrt((size_t)L * C * HALF), brn((size_t)L * C);
     for (int i = 0; i < L; ++i) {
       const std::string li = std::to_string(i + 1);
@@ -634,7 +634,8 @@ static int ensure_workspace(nsw_iaf* h, int B, int F) {
   NSW_TRY(h->cond.ensure((size_t)(h->max_layers + 1) * rows * C * sizeof(float)));
   NSW_TRY(h->l0.ensure(rows * C * sizeof(float)));
   NSW_TRY(h->l1.ensure(rows * C * sizeof(float)));
-  if (h->cfg.engine == NSW_ENGINE_TC2) {
+  if (h->cfg.engine >= NSW_ENGINE_TC2) {
+    NSW_TRY(h->sync_words.ensure((rows / 128 + 1 + (size_t)h->num_sms) * sizeof(unsigned int)));
     NSW_TRY(h->ls0.ensure(rows * C * 2 * sizeof(__half)));
     NSW_TRY(h->ls1.ensure(rows * C * 2 * sizeof(__half)));
     h->map_B = h->map_T = 0;  // buffers may have moved
@@ -720,7 +721,10 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
   }
 
   const bool tc = cfg.engine >= NSW_ENGINE_TC;
-  const bool tc_layers = cfg.engine == NSW_ENGINE_TC2;
+  const bool tc_layers = cfg.engine >= NSW_ENGINE_TC2;
+  // tc3: residual stream resident in shared memory; needs every clip to fit 4 tiles x its share of SMs
+  const int tc3_clips = (cfg.engine == NSW_ENGINE_TC3 && T % 128 == 0) ? flow_tc_clips_per_launch(T, h->num_sms) : 0;
+  const bool tc3 = tc3_clips > 0;
   __half* me_hi = tc ? h->mel_en_split.as<__half>() : nullptr;
   __half* me_lo = tc ? me_hi + (size_t)B * Lc * D : nullptr;
   float* l_buf[2] = {h->l0.as<float>(), h->l1.as<float>()};
@@ -761,6 +765,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       e.mode = EPI_PLANES;
       e.bias = fw.bc.as<float>();
       e.out_f32 = h->cond.as<float>();
+      e.tiled_planes = tc3 ? fw.L : 0;
       if (tc)
         NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, fw.Wct_hi.as<__half>(),
                              fw.Wct_lo.as<__half>(), e, st));
@@ -791,10 +796,18 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       int l0 = 0;
       while (l0 < fw.L) {
         const int l1 = (l0 < split_at) ? split_at : fw.L;
-        NSW_TRY(layer_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
-                                h->cond.as<float>() + (size_t)l0 * rows * C, rows * C, ls_hi, ls_lo,
-                                fw.br_nat.as<float>(), T, (int)rows, cur, l0, l1, cfg.num_stages,
-                                h->grid_counter.as<unsigned int>(), h->num_sms, st));
+        if (tc3) {
+          for (int c0 = 0; c0 < B; c0 += tc3_clips)
+            NSW_TRY(flow_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
+                                   h->cond.as<float>() + (size_t)l0 * rows * C, rows * C,
+                                   fw.br_nat.as<float>(), T, c0, std::min(tc3_clips, B - c0), cur, l0, l1,
+                                   cfg.num_stages, h->sync_words.as<unsigned int>(), h->num_sms, st));
+        } else {
+          NSW_TRY(layer_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
+                                  h->cond.as<float>() + (size_t)l0 * rows * C, rows * C, ls_hi, ls_lo,
+                                  fw.br_nat.as<float>(), T, (int)rows, cur, l0, l1, cfg.num_stages,
+                                  h->grid_counter.as<unsigned int>(), h->num_sms, st));
+        }
         cur = (cur + (l1 - l0)) & 1;
         if (l1 == split_at && split_at < fw.L + 1 && h->tap_flow == f && h->tap_layer == l1) {
           iaf_merge_split_kernel<<<(unsigned)((rows * C / 8 + 255) / 256), 256, 0, st>>>(

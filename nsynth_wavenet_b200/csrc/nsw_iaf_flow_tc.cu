@@ -1,0 +1,782 @@
+// Engine "tc3": all residual layers of one IAF flow (parallel_wavenet.py:227-254) in ONE persistent
+// kernel whose residual stream never leaves the SM.
+//
+// Work split.  Every clip's time axis is cut into 128-row tiles; consecutive tiles of ONE clip are
+// owned by one CTA (<= 4 tiles, one CTA per SM, ranges never straddle clips).  The CTA keeps its
+// rows resident in shared memory as the split pair (fp16 hi plane, fp16 lo plane, 22 mantissa bits)
+// in the K-major SWIZZLE_128B layout tcgen05.mma reads, for all layers of the flow:
+//
+//   plane = [halo tile 16 KB][own tile 0][own tile 1][own tile 2][own tile 3]      (x2: hi, lo)
+//
+// A causal tap t-o of tile k is just a matrix descriptor whose start address is o rows earlier
+// (the swizzle is a function of absolute smem address bits, so any row offset is legal - probed in
+// scripts/probes/umma_rowshift_probe.cu).  For dilations d <= 64 every tap of every own tile lies in
+// [halo | own]; the halo (last tile of the previous CTA, or zeros at the start of a clip) is the
+// only thing fetched per layer.  For d >= 128 taps are whole tiles: own ones are read in place,
+// foreign ones stream through the halo slot.
+//
+// A layer updates the rows IN PLACE.  Tiles are processed latest-first, so a tile's old values are
+// still there for the later tiles' past taps (their MMAs were issued earlier and tcgen05.mma
+// retires in order), and layer i+1 can start on the latest tile while layer i is still working on
+// earlier ones: there is no grid-wide barrier.  Cross-CTA dependencies are per-tile "published
+// layer" counters in global memory (written after the tile's TMA store has completed) plus one
+// "consumed layer" counter per CTA that protects the ping-pong global buffers from being
+// overwritten before the neighbours have read them.
+//
+// Per tile and layer (as in engine tc2):
+//   D1[128x64] = sum_tap A_tap . Wd_tap (split fp16: lo.hi + hi.lo + hi.hi, fp32 accumulate in TMEM)
+//   g = sigmoid(D1[:, even] + cond[:, even]) * tanh(D1[:, odd] + cond[:, odd])   -> TMEM (fp16 hi|lo)
+//   D2[128x64] = g . Wr (A operand from TMEM);   l += br + D2   (in place, re-split)
+//
+// Warps: 0 loader (TMA: weights, own tiles, halo / foreign tiles; polls the flags), 1 tcgen05.mma
+// issuer (dependency-driven scheduler over MMA1 / MMA2), 2-9 epilogue, 10 publisher (TMA stores +
+// flags).  The conditioning planes come from the conv-GEMM in a row-interleaved layout
+// ([tile][quarter][half][j][row][4 floats]) so each warp-level LDG.128 reads 512 contiguous bytes
+// and needs no shared memory.
+#include "nsw_gemm.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace nsw {
+
+namespace {
+
+constexpr int C = 64;
+constexpr int BM = 128;
+constexpr int KMAX = 4;
+constexpr int FT_THREADS = 352;
+constexpr uint32_t TILE_B = BM * 128;                  // one plane of one tile: 16 KB
+constexpr uint32_t PLANE_B = (1 + KMAX) * TILE_B;      // halo + own tiles: 80 KB
+constexpr uint32_t WD_TILE = 64 * 64 * 2;              // 8 KB per tap per plane
+constexpr uint32_t WR_TILE = 64 * 32 * 2;              // 4 KB per plane
+constexpr uint32_t OFF_HI = 0, OFF_LO = PLANE_B;
+constexpr uint32_t OFF_WDH = 2 * PLANE_B, OFF_WDL = OFF_WDH + 3 * WD_TILE;
+constexpr uint32_t OFF_WR = OFF_WDL + 3 * WD_TILE;     // 2 buffers x [hi 4 KB][lo 4 KB]
+constexpr uint32_t OFF_BARS = OFF_WR + 4 * WR_TILE;
+constexpr size_t FT_SMEM_BYTES = OFF_BARS + 1024 + 1024;
+constexpr long long FT_WATCHDOG = 4000000000ll;
+
+struct FtBars {
+  uint64_t own_loaded[KMAX];
+  uint64_t tile_ready[KMAX];
+  uint64_t pub_done[KMAX];
+  uint64_t ring_full, ring_free;
+  uint64_t wd_full, wd_free;
+  uint64_t wr_full[2], wr_free[2];
+  uint64_t d1_full[2], d1_empty[2], g_full[2], d2_full[2], d2_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(FtBars) <= 1024, "barrier block grew");
+
+// ---------------------------------- PTX wrappers ----------------------------------
+__device__ __forceinline__ void ft_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ft_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void ft_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool ft_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void ft_die(const char* what) {
+  printf("nsw iaf_flow_tc: watchdog in %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void ft_wait(uint64_t* bar, uint32_t parity, const char* what) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins == 1024) {
+      spins = 0;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > FT_WATCHDOG) ft_die(what);
+    }
+  }
+}
+__device__ __forceinline__ void ft_poll_ge(const unsigned int* p, unsigned int target, const char* what) {
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    unsigned int seen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p) : "memory");
+    if ((int)(seen - target) >= 0) return;
+    if (++spins == 256) {
+      spins = 0;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > FT_WATCHDOG) ft_die(what);
+    }
+  }
+}
+__device__ __forceinline__ void ft_tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                               int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void ft_tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                               int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void ft_tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t ft_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t ft_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+// D = f32, A = B = f16, K-major, M = 128, N = 64
+__device__ __forceinline__ uint32_t ft_idesc() {
+  return (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void ft_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void ft_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void ft_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void ft_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ft_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ft_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void ft_tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void ft_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ft_tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void ft_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void ft_sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ft_lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
+}
+
+// sigmoid(s) * tanh(t) = (1 - b) / ((1 + a)(1 + b)), a = e^-s, b = e^-2t : 3 MUFU ops
+__device__ __forceinline__ float ft_gate(float s, float t) {
+  const float a = __expf(fminf(-s, 40.0f));
+  const float b = __expf(fminf(-2.0f * t, 40.0f));
+  return __fdividef(1.0f - b, (1.0f + a) * (1.0f + b));
+}
+__device__ __forceinline__ uint32_t ft_pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct FlowTcParams {
+  const float* cond;      // tiled conditioning plane of layer l0 (see file header)
+  size_t cond_plane;      // floats between consecutive layers' planes
+  const float* br;        // [L][64] residual bias, natural channel order
+  unsigned int* flags;    // [clips * tiles_per_clip] layers published per tile   (zeroed per launch)
+  unsigned int* cons;     // [grid] layers whose foreign loads a CTA has finished (zeroed per launch)
+  int buf0, l0, l1, num_stages;
+  int tiles_per_clip, clip0, nclips;
+  int cta_base, cta_rem;  // clip c (0-based within the launch) is split over cta_base + (c < cta_rem) CTAs
+  int reach_tiles;        // 2 * max dilation / 128 (how far ahead a published tile is read)
+  long long* dbg;
+};
+
+struct Range {  // the tiles a CTA owns
+  int clip, tk0, K, idx, n_c;
+};
+__device__ __forceinline__ Range ft_range(const FlowTcParams& p, int b) {
+  Range r;
+  const int big = p.cta_rem * (p.cta_base + 1);
+  int c;
+  if (b < big) {
+    c = b / (p.cta_base + 1);
+    r.idx = b - c * (p.cta_base + 1);
+    r.n_c = p.cta_base + 1;
+  } else {
+    const int bb = b - big;
+    c = p.cta_rem + bb / p.cta_base;
+    r.idx = bb - (c - p.cta_rem) * p.cta_base;
+    r.n_c = p.cta_base;
+  }
+  r.clip = c;
+  const int bt = p.tiles_per_clip / r.n_c, rt = p.tiles_per_clip - bt * r.n_c;
+  r.K = bt + (r.idx < rt ? 1 : 0);
+  r.tk0 = r.idx * bt + min(r.idx, rt);
+  return r;
+}
+// index (within its clip's CTA group) of the CTA that owns tile tk of a clip split over n_c CTAs
+__device__ __forceinline__ int ft_owner(int tiles_per_clip, int n_c, int tk) {
+  const int bt = tiles_per_clip / n_c, rt = tiles_per_clip - bt * n_c;
+  const int big = rt * (bt + 1);
+  return tk < big ? tk / (bt + 1) : rt + (tk - big) / bt;
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_constant__ CUtensorMap map_l0,
+                   const __grid_constant__ CUtensorMap map_h1, const __grid_constant__ CUtensorMap map_l1,
+                   const __grid_constant__ CUtensorMap map_wdh, const __grid_constant__ CUtensorMap map_wdl,
+                   const __grid_constant__ CUtensorMap map_wrh, const __grid_constant__ CUtensorMap map_wrl,
+                   FlowTcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  FtBars* B = reinterpret_cast<FtBars*>(smem + OFF_BARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < KMAX; ++k) {
+      ft_mbar_init(&B->own_loaded[k], 1);
+      ft_mbar_init(&B->tile_ready[k], 8);
+      ft_mbar_init(&B->pub_done[k], 1);
+    }
+    ft_mbar_init(&B->ring_full, 1);
+    ft_mbar_init(&B->ring_free, 1);
+    ft_mbar_init(&B->wd_full, 1);
+    ft_mbar_init(&B->wd_free, 1);
+    for (int b = 0; b < 2; ++b) {
+      ft_mbar_init(&B->wr_full[b], 1);
+      ft_mbar_init(&B->wr_free[b], 1);
+      ft_mbar_init(&B->d1_full[b], 1);
+      ft_mbar_init(&B->d1_empty[b], 8);
+      ft_mbar_init(&B->g_full[b], 8);
+      ft_mbar_init(&B->d2_full[b], 1);
+      ft_mbar_init(&B->d2_empty[b], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ft_fence_before();
+  __syncthreads();
+  ft_fence_after();
+  const uint32_t tmem = B->tmem_base;
+
+  const Range R = ft_range(p, (int)blockIdx.x);
+  const int K = R.K;
+  const int nl = p.l1 - p.l0;
+  const int total = nl * K;
+  const int gclip = p.clip0 + R.clip;                 // clip coordinate in the tensor maps
+  const int gt0 = gclip * p.tiles_per_clip + R.tk0;   // global tile id of own tile 0
+  const long long tk_start = clock64();
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+
+  // does the output of (own tile k, layer li) have a reader outside this CTA?
+  auto published = [&](int k, int li) -> bool {
+    if (li == nl - 1) return true;                                // the head reads every row
+    if ((1 << ((p.l0 + li + 1) % p.num_stages)) >= BM) return true;  // next layer reads whole foreign tiles
+    return k == K - 1;                                            // next CTA's halo
+  };
+
+  if (warp == 0) {
+    // =================================== loader ===================================
+    if (lane == 0) {
+      auto load_wd = [&](int layer) {
+        ft_expect_tx(&B->wd_full, 6 * WD_TILE);
+        for (int tap = 0; tap < 3; ++tap) {
+          ft_tma_load_2d(sbase + OFF_WDH + tap * WD_TILE, &map_wdh, &B->wd_full, 0, (layer * 3 + tap) * 64);
+          ft_tma_load_2d(sbase + OFF_WDL + tap * WD_TILE, &map_wdl, &B->wd_full, 0, (layer * 3 + tap) * 64);
+        }
+      };
+      auto load_wr = [&](int layer, int b) {
+        ft_expect_tx(&B->wr_full[b], 2 * WR_TILE);
+        ft_tma_load_2d(sbase + OFF_WR + (2 * b) * WR_TILE, &map_wrh, &B->wr_full[b], 0, layer * 64);
+        ft_tma_load_2d(sbase + OFF_WR + (2 * b + 1) * WR_TILE, &map_wrl, &B->wr_full[b], 0, layer * 64);
+      };
+      auto prefetch_cond = [&](int li) {
+        if (li >= nl) return;
+        const float* c = p.cond + (size_t)li * p.cond_plane + (size_t)gt0 * (BM * C);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c), "r"((uint32_t)(K * BM * C * 4)) : "memory");
+      };
+      load_wd(p.l0);
+      load_wr(p.l0, 0);
+      if (nl > 1) load_wr(p.l0 + 1, 1);
+      {
+        const CUtensorMap* mh = (p.buf0 & 1) ? &map_h1 : &map_h0;
+        const CUtensorMap* ml = (p.buf0 & 1) ? &map_l1 : &map_l0;
+        for (int k = K - 1; k >= 0; --k) {
+          ft_expect_tx(&B->own_loaded[k], 2 * TILE_B);
+          ft_tma_load_3d(sbase + OFF_LO + (1 + k) * TILE_B, ml, &B->own_loaded[k], 0, (R.tk0 + k) * BM, gclip);
+          ft_tma_load_3d(sbase + OFF_HI + (1 + k) * TILE_B, mh, &B->own_loaded[k], 0, (R.tk0 + k) * BM, gclip);
+        }
+      }
+      prefetch_cond(0);
+      prefetch_cond(1);
+      int n_ring = 0;
+      auto foreign = [&](int li, int src_tk, const CUtensorMap* mh, const CUtensorMap* ml) {
+        // src_tk may be -1 (halo before the clip start): TMA zero-fills the out-of-range rows
+        if (li > 0 && src_tk >= 0)
+          ft_poll_ge(p.flags + (size_t)gclip * p.tiles_per_clip + src_tk, (unsigned int)li, "flag poll");
+        if (n_ring > 0) ft_wait(&B->ring_free, (uint32_t)((n_ring - 1) & 1), "ring_free");
+        ft_fence_async();
+        ft_expect_tx(&B->ring_full, 2 * TILE_B);
+        ft_tma_load_3d(sbase + OFF_LO, ml, &B->ring_full, 0, src_tk * BM, gclip);
+        ft_tma_load_3d(sbase + OFF_HI, mh, &B->ring_full, 0, src_tk * BM, gclip);
+        ++n_ring;
+      };
+      for (int li = 0; li < nl; ++li) {
+        const int layer = p.l0 + li;
+        const int d = 1 << (layer % p.num_stages);
+        if (li > 0) {
+          ft_wait(&B->wd_free, (uint32_t)((li - 1) & 1), "wd_free");
+          load_wd(layer);
+          if (li >= 2) {
+            ft_wait(&B->wr_free[li & 1], (uint32_t)(((li >> 1) - 1) & 1), "wr_free");
+            load_wr(layer, li & 1);
+          }
+          prefetch_cond(li + 1);
+        }
+        const int rb = (p.buf0 + li) & 1;  // global buffer holding the previous layer's output
+        const CUtensorMap* mh = rb ? &map_h1 : &map_h0;
+        const CUtensorMap* ml = rb ? &map_l1 : &map_l0;
+        if (2 * d <= BM) {
+          foreign(li, R.tk0 - 1, mh, ml);  // halo for own tile 0 (the last task of the layer)
+        } else {
+          const int dt = d / BM;
+          for (int k = K - 1; k >= 0; --k)
+            for (int tap = 1; tap >= 0; --tap) {  // same order as the MMA issuer: t-d, then t-2d
+              const int src = R.tk0 + k - (2 - tap) * dt;
+              if (src < 0 || src >= R.tk0) continue;  // causal zeros / own tile
+              foreign(li, src, mh, ml);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const uint32_t idesc = ft_idesc();
+      int j1 = 0, j2 = 0;   // next MMA1 / MMA2 task
+      int seg = -1;         // progress inside MMA1(j1): -1 not started, 0..2 next segment
+      int n_ring = 0;       // foreign loads consumed
+      long long idle0 = 0;
+      int idle = 0;
+      // is own tile x's output of layer li-1 in shared memory (and visible to the async proxy)?
+      auto own_ready = [&](int x, int li) -> bool {
+        return li == 0 ? ft_test(&B->own_loaded[x], 0) : ft_test(&B->tile_ready[x], (uint32_t)((li - 1) & 1));
+      };
+      auto issue_tap = [&](uint32_t d1, uint32_t a_row_bytes, int tap, bool first) {
+        const uint64_t alo = ft_desc_sw128(sbase + OFF_LO + a_row_bytes);
+        const uint64_t ahi = ft_desc_sw128(sbase + OFF_HI + a_row_bytes);
+        const uint64_t wh = ft_desc_sw128(sbase + OFF_WDH + tap * WD_TILE);
+        const uint64_t wl = ft_desc_sw128(sbase + OFF_WDL + tap * WD_TILE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ft_mma_ss(d1, alo + 2 * k, wh + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ft_mma_ss(d1, ahi + 2 * k, wl + 2 * k, idesc, 1);
+          ft_mma_ss(d1, ahi + 2 * k, wh + 2 * k, idesc, 1);
+        }
+      };
+      while (j2 < total) {
+        bool did = false;
+        // ---------------- MMA1(j1): D1 = sum_tap A_tap . Wd_tap ----------------
+        if (j1 < total && j1 - j2 < 2) {
+          const int li = j1 / K, kk = j1 - li * K, k = K - 1 - kk;
+          const int d = 1 << ((p.l0 + li) % p.num_stages);
+          const int b = j1 & 1;
+          const uint32_t d1 = tmem + b * 64;
+          if (seg < 0) {
+            if (ft_test(&B->d1_empty[b], (uint32_t)(((j1 >> 1) & 1) ^ 1)) &&
+                (kk != 0 || ft_test(&B->wd_full, (uint32_t)(li & 1)))) {
+              ft_fence_after();
+              seg = 0;
+            }
+          }
+          while (seg >= 0 && seg < 3) {
+            // segment order: current tap (always own, never skipped), t-d, t-2d
+            const int tap = 2 - seg;
+            const int o = (2 - tap) * d;
+            bool ok = true, skip = false, uses_ring = false;
+            uint32_t a_bytes = 0;
+            if (o == 0) {
+              ok = own_ready(k, li);
+              a_bytes = (uint32_t)(1 + k) * TILE_B;
+            } else if (2 * d <= BM) {
+              // window [128k - o, 128k - o + 128) of [halo | own]
+              if (o < BM) ok = own_ready(k, li);
+              if (k >= 1) ok = ok && own_ready(k - 1, li);
+              else { uses_ring = true; ok = ok && ft_test(&B->ring_full, (uint32_t)(n_ring & 1)); }
+              a_bytes = (uint32_t)((1 + k) * BM - o) * 128u;
+            } else {
+              const int src = R.tk0 + k - o / BM;
+              if (src < 0) skip = true;
+              else if (src >= R.tk0) { ok = own_ready(src - R.tk0, li); a_bytes = (uint32_t)(1 + src - R.tk0) * TILE_B; }
+              else { uses_ring = true; ok = ft_test(&B->ring_full, (uint32_t)(n_ring & 1)); a_bytes = 0; }
+            }
+            if (!ok) break;
+            if (!skip) {
+              ft_fence_after();
+              issue_tap(d1, a_bytes, tap, seg == 0);
+              // the halo serves both past taps of own tile 0; a foreign tile serves one tap
+              if (uses_ring && (2 * d > BM || seg == 2)) { ft_commit(&B->ring_free); ++n_ring; }
+            }
+            ++seg;
+            did = true;
+          }
+          if (seg == 3) {
+            ft_commit(&B->d1_full[b]);
+            if (kk == K - 1) {
+              ft_commit(&B->wd_free);
+              // every foreign tile of this layer has landed in shared memory: the global buffer it
+              // came from may be overwritten (two layers from now) as far as this CTA is concerned
+              asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.cons + blockIdx.x), "r"((unsigned int)(li + 1))
+                           : "memory");
+            }
+            if (dbg && j1 < 8) p.dbg[j1] = clock64() - tk_start;
+            ++j1;
+            seg = -1;
+          }
+        }
+        // ---------------- MMA2(j2): D2 = g . Wr ----------------
+        if (j2 < j1) {
+          const int li = j2 / K, kk = j2 - li * K;
+          const int b = j2 & 1;
+          const uint32_t u = (uint32_t)(j2 >> 1);
+          if (ft_test(&B->g_full[b], u & 1) && ft_test(&B->d2_empty[b], (u & 1) ^ 1) &&
+              (kk != 0 || ft_test(&B->wr_full[li & 1], (uint32_t)((li >> 1) & 1)))) {
+            ft_fence_after();
+            const uint32_t d2 = tmem + 128 + b * 64;
+            const uint32_t g_hi = tmem + 256 + b * 32, g_lo = g_hi + 16;
+            const uint64_t wrh = ft_desc_sw64(sbase + OFF_WR + (2 * (li & 1)) * WR_TILE);
+            const uint64_t wrl = ft_desc_sw64(sbase + OFF_WR + (2 * (li & 1) + 1) * WR_TILE);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              ft_mma_ts(d2, g_lo + 8 * k, wrh + 2 * k, idesc, k != 0);
+              ft_mma_ts(d2, g_hi + 8 * k, wrl + 2 * k, idesc, 1);
+              ft_mma_ts(d2, g_hi + 8 * k, wrh + 2 * k, idesc, 1);
+            }
+            ft_commit(&B->d2_full[b]);
+            if (kk == K - 1) ft_commit(&B->wr_free[li & 1]);
+            if (dbg && j2 < 8) p.dbg[8 + j2] = clock64() - tk_start;
+            ++j2;
+            did = true;
+          }
+        }
+        if (did) {
+          idle = 0;
+          idle0 = 0;
+        } else if (++idle == 4096) {
+          idle = 0;
+          if (idle0 == 0) idle0 = clock64();
+          else if (clock64() - idle0 > FT_WATCHDOG) ft_die("mma scheduler");
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // =================================== epilogue (8 warps) ===================================
+    // warps w and w+4 share a TMEM lane quarter and split the 64 columns: a thread owns half a row
+    // (32 conv outputs = 16 gates, then 32 residual channels)
+    const int half = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+    const int row = qd * 32 + lane;  // row inside a tile
+    int je1 = 0, je2 = 0;
+    uint32_t npub = 0;  // publishes so far per own tile (8 bits each)
+    float4 tc[8];       // conditioning half-row of the NEXT E1 task, requested one task ahead
+    auto cond_issue = [&](int j) {
+      const int li = j / K, k = K - 1 - (j - li * K);
+      const float4* src = reinterpret_cast<const float4*>(
+          p.cond + (size_t)li * p.cond_plane + ((size_t)(gt0 + k) * 8 + qd * 2 + half) * 1024);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc[i] = __ldg(src + i * 32 + lane);
+    };
+    if (total > 0) cond_issue(0);
+    long long idle0 = 0;
+    int idle = 0;
+    while (je2 < total) {
+      int choice = 0;
+      if (lane == 0) {
+        if (je1 < total && je1 - je2 < 2 && ft_test(&B->d1_full[je1 & 1], (uint32_t)((je1 >> 1) & 1))) choice = 1;
+        else if (je2 < je1 && ft_test(&B->d2_full[je2 & 1], (uint32_t)((je2 >> 1) & 1))) choice = 2;
+      }
+      choice = __shfl_sync(0xffffffffu, choice, 0);
+      if (choice == 1) {
+        // ---------------- E1: gate ----------------
+        const int b = je1 & 1;
+        float4 cq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cq[i] = tc[i];
+        if (je1 + 1 < total) cond_issue(je1 + 1);
+        ft_fence_after();
+        uint32_t d[32];
+        ft_tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
+        ft_tmem_ld_wait();
+        ft_fence_before();
+        __syncwarp();
+        if (lane == 0) ft_arrive(&B->d1_empty[b]);
+        uint32_t ghi[8], glo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float s0 = __uint_as_float(d[4 * i]) + cq[i].x;
+          const float t0 = __uint_as_float(d[4 * i + 1]) + cq[i].y;
+          const float s1 = __uint_as_float(d[4 * i + 2]) + cq[i].z;
+          const float t1 = __uint_as_float(d[4 * i + 3]) + cq[i].w;
+          const float g0 = ft_gate(s0, t0);
+          const float g1 = ft_gate(s1, t1);
+          const float h0 = __half2float(__float2half_rn(g0));
+          const float h1 = __half2float(__float2half_rn(g1));
+          ghi[i] = ft_pack_f16(h0, h1);
+          glo[i] = ft_pack_f16(g0 - h0, g1 - h1);
+        }
+        ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
+        ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
+        ft_tmem_st_wait();
+        ft_fence_before();
+        __syncwarp();
+        if (lane == 0) ft_arrive(&B->g_full[b]);
+        if (dbg && warp == 2 && lane == 0 && je1 < 8) p.dbg[16 + je1] = clock64() - tk_start;
+        ++je1;
+      } else if (choice == 2) {
+        // ---------------- E2: residual, in place ----------------
+        const int b = je2 & 1;
+        const int li = je2 / K, k = K - 1 - (je2 - li * K);
+        ft_fence_after();
+        uint32_t d[32];
+        ft_tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
+        ft_tmem_ld_wait();
+        ft_fence_before();
+        __syncwarp();
+        if (lane == 0) ft_arrive(&B->d2_empty[b]);
+        // the TMA store of this tile's previous published value must have finished reading it
+        const uint32_t np = (npub >> (8 * k)) & 0xffu;
+        if (np > 0) ft_wait(&B->pub_done[k], (np - 1) & 1, "pub_done");
+        const float4* bptr = reinterpret_cast<const float4*>(p.br + (size_t)(p.l0 + li) * C) + half * 8;
+        const uint32_t cur_lo = sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+        const uint32_t cur_hi = sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t coff = (uint32_t)(((4 * half + j) ^ (row & 7)) * 16);
+          const uint4 hraw = ft_lds128(cur_hi + coff), lraw = ft_lds128(cur_lo + coff);
+          const __half2* hp = reinterpret_cast<const __half2*>(&hraw);
+          const __half2* lp = reinterpret_cast<const __half2*>(&lraw);
+          const float4 b0 = __ldg(bptr + 2 * j), b1 = __ldg(bptr + 2 * j + 1);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 hv = __half22float2(hp[e]), lv = __half22float2(lp[e]);
+            const float o0 = (hv.x + lv.x) + bb[2 * e] + __uint_as_float(d[8 * j + 2 * e]);
+            const float o1 = (hv.y + lv.y) + bb[2 * e + 1] + __uint_as_float(d[8 * j + 2 * e + 1]);
+            const float a0 = __half2float(__float2half_rn(o0));
+            const float a1 = __half2float(__float2half_rn(o1));
+            hw[e] = ft_pack_f16(a0, a1);
+            lw[e] = ft_pack_f16(o0 - a0, o1 - a1);
+          }
+          ft_sts128(cur_hi + coff, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          ft_sts128(cur_lo + coff, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+        }
+        ft_fence_async();  // generic-proxy writes -> tcgen05.mma / TMA store reads
+        __syncwarp();
+        if (lane == 0) ft_arrive(&B->tile_ready[k]);
+        if (published(k, li)) npub += 1u << (8 * k);
+        if (dbg && warp == 2 && lane == 0 && je2 < 8) p.dbg[24 + je2] = clock64() - tk_start;
+        ++je2;
+      } else {
+        if (++idle == 4096) {
+          idle = 0;
+          if (idle0 == 0) idle0 = clock64();
+          else if (clock64() - idle0 > FT_WATCHDOG) ft_die("epilogue scheduler");
+        }
+        continue;
+      }
+      idle = 0;
+      idle0 = 0;
+    }
+  } else {
+    // =================================== publisher ===================================
+    if (lane == 0) {
+      // CTAs of this clip that may read what this CTA publishes: those owning the next reach_tiles tiles
+      const int last_tk = R.tk0 + K - 1;
+      const int far_tk = min(last_tk + p.reach_tiles, p.tiles_per_clip - 1);
+      const int far_idx = ft_owner(p.tiles_per_clip, R.n_c, far_tk);
+      const int cta0 = (int)blockIdx.x - R.idx;  // first CTA of this clip
+      for (int li = 0; li < nl; ++li) {
+        bool checked = false;
+        const int wb = (p.buf0 + li + 1) & 1;
+        const CUtensorMap* mh = wb ? &map_h1 : &map_h0;
+        const CUtensorMap* ml = wb ? &map_l1 : &map_l0;
+        for (int k = K - 1; k >= 0; --k) {
+          if (!published(k, li)) continue;
+          ft_wait(&B->tile_ready[k], (uint32_t)(li & 1), "tile_ready (publisher)");
+          if (!checked && li >= 1) {
+            // the buffer written now holds layer li-2's output, read by the neighbours during layer li-1
+            for (int i = R.idx + 1; i <= far_idx; ++i) ft_poll_ge(p.cons + cta0 + i, (unsigned int)li, "cons poll");
+            checked = true;
+          }
+          ft_tma_store_3d(mh, sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B, 0, (R.tk0 + k) * BM, gclip);
+          ft_tma_store_3d(ml, sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B, 0, (R.tk0 + k) * BM, gclip);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          ft_arrive(&B->pub_done[k]);  // shared memory may be overwritten by the next layer
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          ft_fence_async();
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + gt0 + k), "r"((unsigned int)(li + 1))
+                       : "memory");
+        }
+      }
+    }
+  }
+
+  ft_fence_before();
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[63] = clock64() - tk_start;
+  if (warp == 1) {
+    ft_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+// how many clips one launch can take: every clip needs ceil(tiles / KMAX) CTAs of its own
+int flow_tc_clips_per_launch(int T, int num_sms) {
+  if (T % BM != 0 || T <= 0) return 0;
+  const int tiles = T / BM;
+  const int need = (tiles + KMAX - 1) / KMAX;
+  return num_sms / need;
+}
+
+int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
+                   const void* map_wrh, const void* map_wrl, const float* cond_tiled, size_t cond_plane,
+                   const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
+                   unsigned int* sync_words /* >= nclips*T/128 + num_sms */, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSW_CUDA(cudaFuncSetAttribute(iaf_flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)FT_SMEM_BYTES));
+    attr_set = true;
+  }
+  NSW_CHECK(T % BM == 0, NSW_EINVAL, "flow_tc: T=%d must be a multiple of %d", T, BM);
+  NSW_CHECK(l1 > l0 && nclips >= 1, NSW_EINVAL, "flow_tc: empty layer or clip range");
+  const int tiles = T / BM;
+  NSW_CHECK(nclips <= flow_tc_clips_per_launch(T, num_sms), NSW_EINVAL,
+            "flow_tc: %d clips of %d tiles do not fit %d SMs", nclips, tiles, num_sms);
+  FlowTcParams p;
+  p.cond = cond_tiled;
+  p.cond_plane = cond_plane;
+  p.br = br;
+  p.buf0 = buf0;
+  p.l0 = l0;
+  p.l1 = l1;
+  p.num_stages = num_stages;
+  p.tiles_per_clip = tiles;
+  p.clip0 = clip0;
+  p.nclips = nclips;
+  int per_clip = std::min(num_sms / nclips, tiles);
+  p.cta_base = per_clip;
+  p.cta_rem = per_clip < tiles ? std::min(num_sms - per_clip * nclips, nclips) : 0;
+  // the remainder CTAs only help if they lower some clip's tiles per CTA; harmless otherwise
+  const int grid = p.cta_base * nclips + p.cta_rem;
+  p.reach_tiles = std::max(1, 2 * (1 << (num_stages - 1)) / BM);
+  // flags are indexed by global tile id (clip coordinate of the tensor map), cons by CTA
+  const size_t n_flags = (size_t)(clip0 + nclips) * tiles;
+  p.flags = sync_words;
+  p.cons = sync_words + n_flags;
+  NSW_CUDA(cudaMemsetAsync(sync_words, 0, (n_flags + grid) * sizeof(unsigned int), stream));
+  p.dbg = nullptr;
+  static long long* dbg_buf = nullptr;
+  const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr;
+  if (want_dbg) {
+    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 64 * sizeof(long long)));
+    NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream));
+    p.dbg = dbg_buf;
+  }
+  void* args[] = {const_cast<void*>(map_act[0][0]), const_cast<void*>(map_act[0][1]),
+                  const_cast<void*>(map_act[1][0]), const_cast<void*>(map_act[1][1]),
+                  const_cast<void*>(map_wdh), const_cast<void*>(map_wdl), const_cast<void*>(map_wrh),
+                  const_cast<void*>(map_wrl), &p};
+  // cooperative launch: the per-tile flags need every CTA to be co-resident
+  NSW_CUDA(cudaLaunchCooperativeKernel((void*)iaf_flow_tc_kernel, dim3(grid), dim3(FT_THREADS), args,
+                                       FT_SMEM_BYTES, stream));
+  count_launch();
+  NSW_CUDA(cudaGetLastError());
+  if (want_dbg) {
+    long long h[64];
+    NSW_CUDA(cudaStreamSynchronize(stream));
+    NSW_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[flow_tc dbg layers %d..%d grid %d] end %lld\n  MMA1:", l0, l1, grid, h[63]);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[i]);
+    fprintf(stderr, "\n  MMA2:");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[8 + i]);
+    fprintf(stderr, "\n  E1  :");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[16 + i]);
+    fprintf(stderr, "\n  E2  :");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[24 + i]);
+    fprintf(stderr, "\n");
+  }
+  return NSW_OK;
+}
+
+}  // namespace nsw

@@ -21,7 +21,7 @@ def _get(hp, name, default):
 
 def default_engine():
     # tc2 = conv-GEMMs and the IAF residual layers on tcgen05 (fp32-grade via split bf16)
-    return os.environ.get('NSW_ENGINE', 'tc2')
+    return os.environ.get('NSW_ENGINE', 'tc3')
 
 
 def iaf_config(hp, num_mel=80, engine=None):

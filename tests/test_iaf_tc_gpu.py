@@ -21,7 +21,8 @@ def make_engine(hp, engine, seed=12345, bias_std=0.02):
     return IAFEngine(hp, w, device=0, engine=engine), w
 
 
-ENGINES = ['tc', 'tc2']   # tc: conv-GEMMs on tcgen05; tc2: + the residual layers on tcgen05
+ENGINES = ['tc', 'tc2', 'tc3']   # tc: conv-GEMMs on tcgen05; tc2: + the residual layers on tcgen05;
+# tc3: + residual stream resident in shared memory for a whole flow (one persistent launch per flow)
 
 
 @pytest.mark.parametrize('engine', ENGINES)
