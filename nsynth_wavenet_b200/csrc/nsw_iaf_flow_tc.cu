@@ -28,9 +28,9 @@
 //   g = sigmoid(D1[:, even] + cond[:, even]) * tanh(D1[:, odd] + cond[:, odd])   -> TMEM (fp16 hi|lo)
 //   D2[128x64] = g . Wr (A operand from TMEM);   l += br + D2   (in place, re-split)
 //
-// Warps: 0 loader (TMA: weights, own tiles, halo / foreign tiles; polls the flags), 1 tcgen05.mma
-// issuer (dependency-driven scheduler over MMA1 / MMA2), 2-9 epilogue, 10 publisher (TMA stores +
-// flags).  The conditioning planes come from the conv-GEMM in a row-interleaved layout
+// Warps: 0 loader (TMA: weights, own tiles, halo / foreign tiles; polls the flags), 1 MMA1 issuer,
+// 2-9 gate epilogue (E1), 10-17 residual epilogue (E2), 18 publisher (TMA stores + flags), 19 MMA2
+// issuer.  Every role walks the same task sequence (layer-major, latest tile first) in order.  The conditioning planes come from the conv-GEMM in a row-interleaved layout
 // ([tile][quarter][half][j][row][4 floats]) so each warp-level LDG.128 reads 512 contiguous bytes
 // and needs no shared memory.
 #include "nsw_gemm.cuh"
@@ -47,7 +47,7 @@ namespace {
 constexpr int C = 64;
 constexpr int BM = 128;
 constexpr int KMAX = 4;
-constexpr int FT_THREADS = 352;
+constexpr int FT_THREADS = 640;  // loader, MMA1, 8 gate warps, 8 residual warps, publisher, MMA2
 constexpr uint32_t TILE_B = BM * 128;                  // one plane of one tile: 16 KB
 constexpr uint32_t PLANE_B = (1 + KMAX) * TILE_B;      // halo + own tiles: 80 KB
 constexpr uint32_t WD_TILE = 64 * 64 * 2;              // 8 KB per tap per plane
@@ -185,6 +185,15 @@ __device__ __forceinline__ void ft_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ bool ft_elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void ft_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ft_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ft_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -206,6 +215,17 @@ __device__ __forceinline__ void ft_tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void ft_tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 __device__ __forceinline__ void ft_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -413,78 +433,84 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // =================================== MMA issuer ===================================
-    if (lane == 0) {
+    // =================================== MMA1 issuer ===================================
+    // D1 = cond (preloaded by the gate warps) + sum_tap A_tap . Wd_tap.  All 32 lanes run the loop
+    // with warp-uniform control flow so ptxas keeps the descriptors in uniform registers; one elected
+    // lane issues.  (A scheduler run by a single divergent lane cost ~16 instructions per
+    // tcgen05.mma, and a combined MMA1/MMA2 polling scheduler ~500 instructions per task: the scalar
+    // instruction stream of this warp, not the tensor pipe, was the limiter.)
+    {
       const uint32_t idesc = ft_idesc();
-      int j1 = 0, j2 = 0;   // next MMA1 / MMA2 task
-      int seg = -1;         // progress inside MMA1(j1): -1 not started, 0..2 next segment
-      int n_ring = 0;       // foreign loads consumed
-      long long idle0 = 0;
-      int idle = 0;
-      // is own tile x's output of layer li-1 in shared memory (and visible to the async proxy)?
-      auto own_ready = [&](int x, int li) -> bool {
-        return li == 0 ? ft_test(&B->own_loaded[x], 0) : ft_test(&B->tile_ready[x], (uint32_t)((li - 1) & 1));
+      const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+      const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase);
+      auto wait_ready = [&](int x, int li) {  // own tile x holds layer li-1's output, visible to the async proxy
+        if (li == 0) ft_wait(&B->own_loaded[x], 0, "own_loaded");
+        else ft_wait(&B->tile_ready[x], (uint32_t)((li - 1) & 1), "tile_ready (mma)");
       };
-      auto issue_tap = [&](uint32_t d1, uint32_t a_row_bytes, int tap, bool first) {
-        const uint64_t alo = ft_desc_sw128(sbase + OFF_LO + a_row_bytes);
-        const uint64_t ahi = ft_desc_sw128(sbase + OFF_HI + a_row_bytes);
-        const uint64_t wh = ft_desc_sw128(sbase + OFF_WDH + tap * WD_TILE);
-        const uint64_t wl = ft_desc_sw128(sbase + OFF_WDL + tap * WD_TILE);
+      auto issue_tap = [&](uint32_t d1, uint32_t a_row_bytes, int tap) {
+        const uint64_t alo = ft_desc_sw128(sbase_u + OFF_LO + a_row_bytes);
+        const uint64_t ahi = ft_desc_sw128(sbase_u + OFF_HI + a_row_bytes);
+        const uint64_t wh = ft_desc_sw128(sbase_u + OFF_WDH + tap * WD_TILE);
+        const uint64_t wl = ft_desc_sw128(sbase_u + OFF_WDL + tap * WD_TILE);
+        if (ft_elect()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ft_mma_ss(d1, alo + 2 * k, wh + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+          for (int k = 0; k < 4; ++k) ft_mma_ss(d1, alo + 2 * k, wh + 2 * k, idesc, 1u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          ft_mma_ss(d1, ahi + 2 * k, wl + 2 * k, idesc, 1);
-          ft_mma_ss(d1, ahi + 2 * k, wh + 2 * k, idesc, 1);
+          for (int k = 0; k < 4; ++k) {
+            ft_mma_ss(d1, ahi + 2 * k, wl + 2 * k, idesc, 1);
+            ft_mma_ss(d1, ahi + 2 * k, wh + 2 * k, idesc, 1);
+          }
         }
+        __syncwarp();
       };
-      while (j2 < total) {
-        bool did = false;
-        // ---------------- MMA1(j1): D1 = sum_tap A_tap . Wd_tap ----------------
-        if (j1 < total && j1 - j2 < 2) {
-          const int li = j1 / K, kk = j1 - li * K, k = K - 1 - kk;
-          const int d = 1 << ((p.l0 + li) % p.num_stages);
-          const int b = j1 & 1;
-          const uint32_t d1 = tmem + b * 64;
-          if (seg < 0) {
-            if (ft_test(&B->d1_empty[b], (uint32_t)(((j1 >> 1) & 1) ^ 1)) &&
-                (kk != 0 || ft_test(&B->wd_full, (uint32_t)(li & 1)))) {
-              ft_fence_after();
-              seg = 0;
+      int stage_mod = p.l0 % p.num_stages;
+      int n_ring = 0, j = 0;
+      for (int li = 0; li < nl; ++li) {
+        const int d = 1 << stage_mod;
+        if (++stage_mod == p.num_stages) stage_mod = 0;
+        const bool small = 2 * d <= BM;
+        ft_wait(&B->wd_full, (uint32_t)(li & 1), "wd_full");
+        for (int kk = 0; kk < K; ++kk, ++j) {
+          const int k = K - 1 - kk;
+          const int b = j & 1;
+          const uint32_t d1 = tmem_u + b * 64;
+          // D1[b] holds the conditioning rows of this task (written by the gate warps)
+          ft_wait(&B->d1_empty[b], (uint32_t)((j >> 1) & 1), "d1_empty");
+          wait_ready(k, li);
+          ft_fence_after();
+          issue_tap(d1, (uint32_t)(1 + k) * TILE_B, 2);
+          if (small) {
+            // windows [128k - o, 128k - o + 128) of [halo | own], o = d, 2d
+            if (k >= 1) wait_ready(k - 1, li);
+            else ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full (halo)");
+            ft_fence_after();
+            issue_tap(d1, (uint32_t)((1 + k) * BM - d) * 128u, 1);
+            issue_tap(d1, (uint32_t)((1 + k) * BM - 2 * d) * 128u, 0);
+            if (k == 0) {
+              if (ft_elect()) ft_commit(&B->ring_free);
+              __syncwarp();
+              ++n_ring;
+            }
+          } else {
+            const int dt = d / BM;
+            for (int tap = 1; tap >= 0; --tap) {
+              const int src = R.tk0 + k - (2 - tap) * dt;
+              if (src < 0) continue;  // causal zeros
+              if (src >= R.tk0) {
+                wait_ready(src - R.tk0, li);
+                ft_fence_after();
+                issue_tap(d1, (uint32_t)(1 + src - R.tk0) * TILE_B, tap);
+              } else {
+                ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full");
+                ft_fence_after();
+                issue_tap(d1, 0u, tap);
+                if (ft_elect()) ft_commit(&B->ring_free);
+                __syncwarp();
+                ++n_ring;
+              }
             }
           }
-          while (seg >= 0 && seg < 3) {
-            // segment order: current tap (always own, never skipped), t-d, t-2d
-            const int tap = 2 - seg;
-            const int o = (2 - tap) * d;
-            bool ok = true, skip = false, uses_ring = false;
-            uint32_t a_bytes = 0;
-            if (o == 0) {
-              ok = own_ready(k, li);
-              a_bytes = (uint32_t)(1 + k) * TILE_B;
-            } else if (2 * d <= BM) {
-              // window [128k - o, 128k - o + 128) of [halo | own]
-              if (o < BM) ok = own_ready(k, li);
-              if (k >= 1) ok = ok && own_ready(k - 1, li);
-              else { uses_ring = true; ok = ok && ft_test(&B->ring_full, (uint32_t)(n_ring & 1)); }
-              a_bytes = (uint32_t)((1 + k) * BM - o) * 128u;
-            } else {
-              const int src = R.tk0 + k - o / BM;
-              if (src < 0) skip = true;
-              else if (src >= R.tk0) { ok = own_ready(src - R.tk0, li); a_bytes = (uint32_t)(1 + src - R.tk0) * TILE_B; }
-              else { uses_ring = true; ok = ft_test(&B->ring_full, (uint32_t)(n_ring & 1)); a_bytes = 0; }
-            }
-            if (!ok) break;
-            if (!skip) {
-              ft_fence_after();
-              issue_tap(d1, a_bytes, tap, seg == 0);
-              // the halo serves both past taps of own tile 0; a foreign tile serves one tap
-              if (uses_ring && (2 * d > BM || seg == 2)) { ft_commit(&B->ring_free); ++n_ring; }
-            }
-            ++seg;
-            did = true;
-          }
-          if (seg == 3) {
+          if (ft_elect()) {
             ft_commit(&B->d1_full[b]);
             if (kk == K - 1) {
               ft_commit(&B->wd_free);
@@ -493,23 +519,33 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
               asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.cons + blockIdx.x), "r"((unsigned int)(li + 1))
                            : "memory");
             }
-            if (dbg && j1 < 8) p.dbg[j1] = clock64() - tk_start;
-            ++j1;
-            seg = -1;
+            if (dbg && j < 8) p.dbg[j] = clock64() - tk_start;
           }
+          __syncwarp();
         }
-        // ---------------- MMA2(j2): D2 = g . Wr ----------------
-        if (j2 < j1) {
-          const int li = j2 / K, kk = j2 - li * K;
-          const int b = j2 & 1;
-          const uint32_t u = (uint32_t)(j2 >> 1);
-          if (ft_test(&B->g_full[b], u & 1) && ft_test(&B->d2_empty[b], (u & 1) ^ 1) &&
-              (kk != 0 || ft_test(&B->wr_full[li & 1], (uint32_t)((li >> 1) & 1)))) {
-            ft_fence_after();
-            const uint32_t d2 = tmem + 128 + b * 64;
-            const uint32_t g_hi = tmem + 256 + b * 32, g_lo = g_hi + 16;
-            const uint64_t wrh = ft_desc_sw64(sbase + OFF_WR + (2 * (li & 1)) * WR_TILE);
-            const uint64_t wrl = ft_desc_sw64(sbase + OFF_WR + (2 * (li & 1) + 1) * WR_TILE);
+      }
+    }
+  } else if (warp == 19) {
+    // =================================== MMA2 issuer ===================================
+    // D2 = g . Wr with the A operand (g, fp16 hi | lo) read from TMEM
+    {
+      const uint32_t idesc = ft_idesc();
+      const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+      const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase);
+      int j = 0;
+      for (int li = 0; li < nl; ++li) {
+        ft_wait(&B->wr_full[li & 1], (uint32_t)((li >> 1) & 1), "wr_full");
+        const uint64_t wrh = ft_desc_sw64(sbase_u + OFF_WR + (2 * (li & 1)) * WR_TILE);
+        const uint64_t wrl = ft_desc_sw64(sbase_u + OFF_WR + (2 * (li & 1) + 1) * WR_TILE);
+        for (int kk = 0; kk < K; ++kk, ++j) {
+          const int b = j & 1;
+          const uint32_t u = (uint32_t)(j >> 1);
+          ft_wait(&B->g_full[b], u & 1, "g_full");
+          ft_wait(&B->d2_empty[b], (u & 1) ^ 1, "d2_empty");
+          ft_fence_after();
+          const uint32_t d2 = tmem_u + 128 + b * 64;
+          const uint32_t g_hi = tmem_u + 256 + b * 32, g_lo = g_hi + 16;
+          if (ft_elect()) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               ft_mma_ts(d2, g_lo + 8 * k, wrh + 2 * k, idesc, k != 0);
@@ -518,142 +554,132 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
             }
             ft_commit(&B->d2_full[b]);
             if (kk == K - 1) ft_commit(&B->wr_free[li & 1]);
-            if (dbg && j2 < 8) p.dbg[8 + j2] = clock64() - tk_start;
-            ++j2;
-            did = true;
+            if (dbg && j < 8) p.dbg[8 + j] = clock64() - tk_start;
           }
-        }
-        if (did) {
-          idle = 0;
-          idle0 = 0;
-        } else if (++idle == 4096) {
-          idle = 0;
-          if (idle0 == 0) idle0 = clock64();
-          else if (clock64() - idle0 > FT_WATCHDOG) ft_die("mma scheduler");
+          __syncwarp();
         }
       }
     }
   } else if (warp < 10) {
-    // =================================== epilogue (8 warps) ===================================
+    // =================================== E1: gate (8 warps) ===================================
     // warps w and w+4 share a TMEM lane quarter and split the 64 columns: a thread owns half a row
-    // (32 conv outputs = 16 gates, then 32 residual channels)
+    // (32 conv outputs = 16 gates).  The conditioning half-row of task j+2 is written into the D1
+    // accumulator as soon as task j's values have been read out of it, so the MMAs accumulate on top
+    // of it and the gate needs no separate add.
     const int half = (warp - 2) >> 2;
     const int qd = warp & 3;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
-    const int row = qd * 32 + lane;  // row inside a tile
-    int je1 = 0, je2 = 0;
-    uint32_t npub = 0;  // publishes so far per own tile (8 bits each)
-    float4 tc[8];       // conditioning half-row of the NEXT E1 task, requested one task ahead
-    auto cond_issue = [&](int j) {
+    auto cond_ptr = [&](int j) -> const float4* {
       const int li = j / K, k = K - 1 - (j - li * K);
-      const float4* src = reinterpret_cast<const float4*>(
-          p.cond + (size_t)li * p.cond_plane + ((size_t)(gt0 + k) * 8 + qd * 2 + half) * 1024);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tc[i] = __ldg(src + i * 32 + lane);
+      return reinterpret_cast<const float4*>(p.cond + (size_t)li * p.cond_plane +
+                                             ((size_t)(gt0 + k) * 8 + qd * 2 + half) * 1024) + lane;
     };
-    if (total > 0) cond_issue(0);
-    long long idle0 = 0;
-    int idle = 0;
-    while (je2 < total) {
-      int choice = 0;
-      if (lane == 0) {
-        if (je1 < total && je1 - je2 < 2 && ft_test(&B->d1_full[je1 & 1], (uint32_t)((je1 >> 1) & 1))) choice = 1;
-        else if (je2 < je1 && ft_test(&B->d2_full[je2 & 1], (uint32_t)((je2 >> 1) & 1))) choice = 2;
-      }
-      choice = __shfl_sync(0xffffffffu, choice, 0);
-      if (choice == 1) {
-        // ---------------- E1: gate ----------------
-        const int b = je1 & 1;
-        float4 cq[8];
+    auto preload = [&](int j, const float4 (&cn)[8]) {  // cond(j) -> D1[j & 1], then release the buffer
+      const int b = j & 1;
+      ft_tmem_st32(tmem + lane_sel + b * 64 + half * 32, reinterpret_cast<const uint32_t*>(cn));
+      ft_tmem_st_wait();
+      ft_fence_before();
+      __syncwarp();
+      if (lane == 0) ft_arrive(&B->d1_empty[b]);
+    };
+    for (int j = 0; j < 2 && j < total; ++j) {
+      float4 cn[8];
+      const float4* src = cond_ptr(j);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cq[i] = tc[i];
-        if (je1 + 1 < total) cond_issue(je1 + 1);
-        ft_fence_after();
-        uint32_t d[32];
-        ft_tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
-        ft_tmem_ld_wait();
-        ft_fence_before();
-        __syncwarp();
-        if (lane == 0) ft_arrive(&B->d1_empty[b]);
-        uint32_t ghi[8], glo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float s0 = __uint_as_float(d[4 * i]) + cq[i].x;
-          const float t0 = __uint_as_float(d[4 * i + 1]) + cq[i].y;
-          const float s1 = __uint_as_float(d[4 * i + 2]) + cq[i].z;
-          const float t1 = __uint_as_float(d[4 * i + 3]) + cq[i].w;
-          const float g0 = ft_gate(s0, t0);
-          const float g1 = ft_gate(s1, t1);
-          const float h0 = __half2float(__float2half_rn(g0));
-          const float h1 = __half2float(__float2half_rn(g1));
-          ghi[i] = ft_pack_f16(h0, h1);
-          glo[i] = ft_pack_f16(g0 - h0, g1 - h1);
-        }
-        ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
-        ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
-        ft_tmem_st_wait();
-        ft_fence_before();
-        __syncwarp();
-        if (lane == 0) ft_arrive(&B->g_full[b]);
-        if (dbg && warp == 2 && lane == 0 && je1 < 8) p.dbg[16 + je1] = clock64() - tk_start;
-        ++je1;
-      } else if (choice == 2) {
-        // ---------------- E2: residual, in place ----------------
-        const int b = je2 & 1;
-        const int li = je2 / K, k = K - 1 - (je2 - li * K);
-        ft_fence_after();
-        uint32_t d[32];
-        ft_tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
-        ft_tmem_ld_wait();
-        ft_fence_before();
-        __syncwarp();
-        if (lane == 0) ft_arrive(&B->d2_empty[b]);
-        // the TMA store of this tile's previous published value must have finished reading it
-        const uint32_t np = (npub >> (8 * k)) & 0xffu;
-        if (np > 0) ft_wait(&B->pub_done[k], (np - 1) & 1, "pub_done");
-        const float4* bptr = reinterpret_cast<const float4*>(p.br + (size_t)(p.l0 + li) * C) + half * 8;
-        const uint32_t cur_lo = sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
-        const uint32_t cur_hi = sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t coff = (uint32_t)(((4 * half + j) ^ (row & 7)) * 16);
-          const uint4 hraw = ft_lds128(cur_hi + coff), lraw = ft_lds128(cur_lo + coff);
-          const __half2* hp = reinterpret_cast<const __half2*>(&hraw);
-          const __half2* lp = reinterpret_cast<const __half2*>(&lraw);
-          const float4 b0 = __ldg(bptr + 2 * j), b1 = __ldg(bptr + 2 * j + 1);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 hv = __half22float2(hp[e]), lv = __half22float2(lp[e]);
-            const float o0 = (hv.x + lv.x) + bb[2 * e] + __uint_as_float(d[8 * j + 2 * e]);
-            const float o1 = (hv.y + lv.y) + bb[2 * e + 1] + __uint_as_float(d[8 * j + 2 * e + 1]);
-            const float a0 = __half2float(__float2half_rn(o0));
-            const float a1 = __half2float(__float2half_rn(o1));
-            hw[e] = ft_pack_f16(a0, a1);
-            lw[e] = ft_pack_f16(o0 - a0, o1 - a1);
-          }
-          ft_sts128(cur_hi + coff, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-          ft_sts128(cur_lo + coff, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-        }
-        ft_fence_async();  // generic-proxy writes -> tcgen05.mma / TMA store reads
-        __syncwarp();
-        if (lane == 0) ft_arrive(&B->tile_ready[k]);
-        if (published(k, li)) npub += 1u << (8 * k);
-        if (dbg && warp == 2 && lane == 0 && je2 < 8) p.dbg[24 + je2] = clock64() - tk_start;
-        ++je2;
-      } else {
-        if (++idle == 4096) {
-          idle = 0;
-          if (idle0 == 0) idle0 = clock64();
-          else if (clock64() - idle0 > FT_WATCHDOG) ft_die("epilogue scheduler");
-        }
-        continue;
-      }
-      idle = 0;
-      idle0 = 0;
+      for (int i = 0; i < 8; ++i) cn[i] = __ldg(src + i * 32);
+      preload(j, cn);
     }
-  } else {
+    for (int j = 0; j < total; ++j) {
+      const int b = j & 1;
+      float4 cn[8];
+      if (j + 2 < total) {
+        const float4* src = cond_ptr(j + 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cn[i] = __ldg(src + i * 32);
+      }
+      ft_wait(&B->d1_full[b], (uint32_t)((j >> 1) & 1), "d1_full");
+      ft_fence_after();
+      uint32_t d[32];
+      ft_tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
+      ft_tmem_ld_wait();
+      if (j + 2 < total) preload(j + 2, cn);
+      // G[b] was last read by MMA2 of task j-2 (issued by another warp): wait until it has retired
+      if (j >= 2) ft_wait(&B->d2_full[b], (uint32_t)((((j - 2) >> 1)) & 1), "d2_full (G free)");
+      uint32_t ghi[8], glo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // columns 4i..4i+3 of this half = (sig jj, tanh jj, sig jj+1, tanh jj+1), cond already added
+        const float g0 = ft_gate(__uint_as_float(d[4 * i]), __uint_as_float(d[4 * i + 1]));
+        const float g1 = ft_gate(__uint_as_float(d[4 * i + 2]), __uint_as_float(d[4 * i + 3]));
+        const float h0 = __half2float(__float2half_rn(g0));
+        const float h1 = __half2float(__float2half_rn(g1));
+        ghi[i] = ft_pack_f16(h0, h1);
+        glo[i] = ft_pack_f16(g0 - h0, g1 - h1);
+      }
+      ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
+      ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
+      ft_tmem_st_wait();
+      ft_fence_before();
+      __syncwarp();
+      if (lane == 0) ft_arrive(&B->g_full[b]);
+      if (dbg && warp == 2 && lane == 0 && j < 8) p.dbg[16 + j] = clock64() - tk_start;
+    }
+  } else if (warp < 18) {
+    // =================================== E2: residual, in place (8 warps) ===================================
+    const int half = (warp - 10) >> 2;
+    const int qd = warp & 3;
+    const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+    const int row = qd * 32 + lane;  // row inside a tile
+    uint32_t npub = 0;               // publishes so far per own tile (8 bits each)
+    int li = 0, kk = 0;
+    for (int j = 0; j < total; ++j) {
+      const int b = j & 1;
+      const int k = K - 1 - kk;
+      ft_wait(&B->d2_full[b], (uint32_t)((j >> 1) & 1), "d2_full");
+      ft_fence_after();
+      uint32_t d[32];
+      ft_tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
+      ft_tmem_ld_wait();
+      ft_fence_before();
+      __syncwarp();
+      if (lane == 0) ft_arrive(&B->d2_empty[b]);
+      // the TMA store of this tile's previous published value must have finished reading it
+      const uint32_t np = (npub >> (8 * k)) & 0xffu;
+      if (np > 0) ft_wait(&B->pub_done[k], (np - 1) & 1, "pub_done");
+      const float4* bptr = reinterpret_cast<const float4*>(p.br + (size_t)(p.l0 + li) * C) + half * 8;
+      const uint32_t cur_lo = sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+      const uint32_t cur_hi = sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint32_t coff = (uint32_t)(((4 * half + jj) ^ (row & 7)) * 16);
+        const uint4 hraw = ft_lds128(cur_hi + coff), lraw = ft_lds128(cur_lo + coff);
+        const __half2* hp = reinterpret_cast<const __half2*>(&hraw);
+        const __half2* lp = reinterpret_cast<const __half2*>(&lraw);
+        const float4 b0 = __ldg(bptr + 2 * jj), b1 = __ldg(bptr + 2 * jj + 1);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hv = __half22float2(hp[e]), lv = __half22float2(lp[e]);
+          const float o0 = (hv.x + lv.x) + bb[2 * e] + __uint_as_float(d[8 * jj + 2 * e]);
+          const float o1 = (hv.y + lv.y) + bb[2 * e + 1] + __uint_as_float(d[8 * jj + 2 * e + 1]);
+          const float a0 = __half2float(__float2half_rn(o0));
+          const float a1 = __half2float(__float2half_rn(o1));
+          hw[e] = ft_pack_f16(a0, a1);
+          lw[e] = ft_pack_f16(o0 - a0, o1 - a1);
+        }
+        ft_sts128(cur_hi + coff, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        ft_sts128(cur_lo + coff, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+      }
+      // generic-proxy writes to shared memory -> tcgen05.mma / TMA store reads (async proxy)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) ft_arrive(&B->tile_ready[k]);
+      if (published(k, li)) npub += 1u << (8 * k);
+      if (dbg && warp == 10 && lane == 0 && j < 8) p.dbg[24 + j] = clock64() - tk_start;
+      if (++kk == K) { kk = 0; ++li; }
+    }
+  } else if (warp == 18) {
     // =================================== publisher ===================================
     if (lane == 0) {
       // CTAs of this clip that may read what this CTA publishes: those owning the next reach_tiles tiles

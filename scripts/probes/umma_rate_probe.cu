@@ -1,0 +1,149 @@
+// Hardware probe (not product code): tcgen05.mma kind::f16 M=128 K=16 issue/execute rate as a function of N
+// and of how many independent TMEM accumulators the instruction stream rotates over.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_rate umma_rate_probe.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int N, int NACC, int ROWSHIFT, int TS, int NOISE>
+__global__ void __launch_bounds__(128 + 256, 1) rate_kernel(long long* out, int iters) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_s;
+  __shared__ volatile int stop_flag;
+  if (threadIdx.x == 0) stop_flag = 0;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero the operand area (values irrelevant)
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) {
+    const uint32_t tmem = __reduce_or_sync(0xffffffffu, tmem_s);
+    const uint32_t sb = __reduce_or_sync(0xffffffffu, smem_u32(smem));
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc = (uint64_t)(((sb + ROWSHIFT * 128) >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+                           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint64_t bdesc = (uint64_t)(((sb + 32768) >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+                           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    long long t0 = clock64();
+    if (elect()) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) {
+            if (TS)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem + a * N),
+                           "r"(tmem + 448), "l"(bdesc + 2 * k), "r"(idesc), "r"(1u) : "memory");
+            else
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + a * N),
+                           "l"(adesc + 2 * k), "l"(bdesc + 2 * k), "r"(idesc), "r"(1u) : "memory");
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    __syncwarp();
+    long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; stop_flag = 1; }
+  }
+  if (warp >= 4 && NOISE == 1) {
+    // LDS.128 + STS.128 traffic on a private 64 KB region (rows swizzled like the epilogue)
+    uint32_t base = smem_u32(smem) + 65536 + (threadIdx.x - 128) * 128;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    while (!stop_flag) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + ((c ^ (threadIdx.x & 7)) * 16)));
+        acc.x += v.x; acc.y ^= v.y;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((c ^ (threadIdx.x & 7)) * 16)), "r"(acc.x), "r"(acc.y), "r"(acc.z), "r"(acc.w) : "memory");
+      }
+    }
+    if (acc.x == 0x12345) out[3] = acc.y;
+  }
+  if (warp >= 4 && NOISE == 2) {
+    // tcgen05.ld traffic on columns 256.. (not touched by the MMAs)
+    uint32_t acc = 0;
+    while (!stop_flag) {
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+            "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+            "=r"(r[30]), "=r"(r[31])
+          : "r"(tmem_s + ((uint32_t)((warp & 3) * 32) << 16) + 256 + ((warp >> 2) & 1) * 32));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int i = 0; i < 32; ++i) acc += r[i];
+    }
+    if (acc == 0x12345) out[3] = acc;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(512u) : "memory");
+}
+
+template <int N, int NACC, int ROWSHIFT, int TS, int NOISE = 0>
+void run(const char* name, long long* d) {
+  const int iters = 64;
+  const size_t smem = 64 * 1024 + 1024 + 1024 + (NOISE == 1 ? 65536 : 0);
+  cudaFuncSetAttribute(rate_kernel<N, NACC, ROWSHIFT, TS, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long h[2];
+  for (int rep = 0; rep < 2; ++rep) {
+    rate_kernel<N, NACC, ROWSHIFT, TS, NOISE><<<1, NOISE ? 384 : 128, smem>>>(d, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  const int n = iters * 4 * NACC;
+  printf("%-34s N=%3d acc=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (%d MMAs)\n", name, N, NACC, (double)h[0] / n, (double)h[1] / n, n);
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 16);
+  run<64, 1, 0, 0>("SS same accumulator", d);
+  run<64, 2, 0, 0>("SS 2 accumulators", d);
+  run<64, 4, 0, 0>("SS 4 accumulators", d);
+  run<64, 1, 3, 0>("SS row-shifted A (3 rows)", d);
+  run<128, 1, 0, 0>("SS same accumulator", d);
+  run<128, 2, 0, 0>("SS 2 accumulators", d);
+  run<256, 1, 0, 0>("SS same accumulator", d);
+  run<32, 1, 0, 0>("SS same accumulator", d);
+  run<64, 1, 0, 0, 1>("SS + 8 warps LDS/STS noise", d);
+  run<64, 1, 0, 0, 2>("SS + 8 warps tcgen05.ld noise", d);
+  run<64, 1, 0, 1>("TS (A from TMEM) same acc", d);
+  run<64, 2, 0, 1>("TS (A from TMEM) 2 acc", d);
+  run<128, 1, 0, 1>("TS (A from TMEM) same acc", d);
+  return 0;
+}
