@@ -26,7 +26,8 @@
 // Per tile and layer (as in engine tc2):
 //   D1[128x64] = sum_tap A_tap . Wd_tap (split fp16: lo.hi + hi.lo + hi.hi, fp32 accumulate in TMEM)
 //   g = sigmoid(D1[:, even] + cond[:, even]) * tanh(D1[:, odd] + cond[:, odd])   -> TMEM (fp16 hi|lo)
-//   D2[128x64] = g . Wr (A operand from TMEM);   l += br + D2   (in place, re-split)
+//   L[128x64] += g . Wr (A operand from TMEM; L = the tile's fp32 residual rows, resident in TMEM)
+//   l = L + br  ->  written back to TMEM and re-split into the fp16 hi / lo planes in shared memory
 //
 // Warps: 0 loader (TMA: weights, own tiles, halo / foreign tiles; polls the flags), 1 MMA1 issuer,
 // 2-9 gate epilogue (E1), 10-17 residual epilogue (E2), 18 publisher (TMA stores + flags), 19 MMA2
@@ -58,6 +59,9 @@ constexpr uint32_t OFF_WR = OFF_WDL + 3 * WD_TILE;     // 2 buffers x [hi 4 KB][
 constexpr uint32_t OFF_BARS = OFF_WR + 4 * WR_TILE;
 constexpr size_t FT_SMEM_BYTES = OFF_BARS + 1024 + 1024;
 constexpr long long FT_WATCHDOG = 4000000000ll;
+// TMEM columns: D1[2] (conv accumulators, preloaded with cond) 0..127, G[2] (gate, fp16 hi 16 | lo 16) 128..191,
+// L[4] (the fp32 residual rows of the own tiles; MMA2 accumulates g.Wr straight into them) 192..447
+constexpr uint32_t TM_G = 128, TM_L = 192;
 
 struct FtBars {
   uint64_t own_loaded[KMAX];
@@ -66,7 +70,9 @@ struct FtBars {
   uint64_t ring_full, ring_free;
   uint64_t wd_full, wd_free;
   uint64_t wr_full[2], wr_free[2];
-  uint64_t d1_full[2], d1_empty[2], g_full[2], d2_full[2], d2_empty[2];
+  uint64_t d1_full[2], d1_empty[2], g_full[2], g_free[2];
+  uint64_t d2_full[KMAX];  // per own tile: MMA2 of the current layer has retired
+  uint64_t l_init;
   uint32_t tmem_base;
 };
 static_assert(sizeof(FtBars) <= 1024, "barrier block grew");
@@ -315,19 +321,20 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       ft_mbar_init(&B->own_loaded[k], 1);
       ft_mbar_init(&B->tile_ready[k], 8);
       ft_mbar_init(&B->pub_done[k], 1);
+      ft_mbar_init(&B->d2_full[k], 1);
     }
     ft_mbar_init(&B->ring_full, 1);
     ft_mbar_init(&B->ring_free, 1);
     ft_mbar_init(&B->wd_full, 1);
     ft_mbar_init(&B->wd_free, 1);
+    ft_mbar_init(&B->l_init, 8);
     for (int b = 0; b < 2; ++b) {
       ft_mbar_init(&B->wr_full[b], 1);
       ft_mbar_init(&B->wr_free[b], 1);
       ft_mbar_init(&B->d1_full[b], 1);
       ft_mbar_init(&B->d1_empty[b], 8);
       ft_mbar_init(&B->g_full[b], 8);
-      ft_mbar_init(&B->d2_full[b], 1);
-      ft_mbar_init(&B->d2_empty[b], 8);
+      ft_mbar_init(&B->g_free[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -476,7 +483,9 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
           const uint32_t d1 = tmem_u + b * 64;
           // D1[b] holds the conditioning rows of this task (written by the gate warps)
           ft_wait(&B->d1_empty[b], (uint32_t)((j >> 1) & 1), "d1_empty");
+          if (dbg && j < 8 && lane == 0) p.dbg[64 + 2 * j] = clock64() - tk_start;
           wait_ready(k, li);
+          if (dbg && j < 8 && lane == 0) p.dbg[2 * j] = clock64() - tk_start;
           ft_fence_after();
           issue_tap(d1, (uint32_t)(1 + k) * TILE_B, 2);
           if (small) {
@@ -519,7 +528,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
               asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.cons + blockIdx.x), "r"((unsigned int)(li + 1))
                            : "memory");
             }
-            if (dbg && j < 8) p.dbg[j] = clock64() - tk_start;
+            if (dbg && j < 8) p.dbg[2 * j + 1] = clock64() - tk_start;
           }
           __syncwarp();
         }
@@ -533,6 +542,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
       const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase);
       int j = 0;
+      ft_wait(&B->l_init, 0, "l_init");  // the residual warps have written l into TMEM
       for (int li = 0; li < nl; ++li) {
         ft_wait(&B->wr_full[li & 1], (uint32_t)((li >> 1) & 1), "wr_full");
         const uint64_t wrh = ft_desc_sw64(sbase_u + OFF_WR + (2 * (li & 1)) * WR_TILE);
@@ -541,20 +551,21 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
           const int b = j & 1;
           const uint32_t u = (uint32_t)(j >> 1);
           ft_wait(&B->g_full[b], u & 1, "g_full");
-          ft_wait(&B->d2_empty[b], (u & 1) ^ 1, "d2_empty");
+          if (dbg && j < 8 && lane == 0) p.dbg[16 + 2 * j] = clock64() - tk_start;
           ft_fence_after();
-          const uint32_t d2 = tmem_u + 128 + b * 64;
-          const uint32_t g_hi = tmem_u + 256 + b * 32, g_lo = g_hi + 16;
+          const uint32_t d2 = tmem_u + TM_L + (K - 1 - kk) * 64;  // the tile's fp32 residual rows
+          const uint32_t g_hi = tmem_u + TM_G + b * 32, g_lo = g_hi + 16;
           if (ft_elect()) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              ft_mma_ts(d2, g_lo + 8 * k, wrh + 2 * k, idesc, k != 0);
+              ft_mma_ts(d2, g_lo + 8 * k, wrh + 2 * k, idesc, 1);
               ft_mma_ts(d2, g_hi + 8 * k, wrl + 2 * k, idesc, 1);
               ft_mma_ts(d2, g_hi + 8 * k, wrh + 2 * k, idesc, 1);
             }
-            ft_commit(&B->d2_full[b]);
+            ft_commit(&B->d2_full[K - 1 - kk]);
+            ft_commit(&B->g_free[b]);
             if (kk == K - 1) ft_commit(&B->wr_free[li & 1]);
-            if (dbg && j < 8) p.dbg[8 + j] = clock64() - tk_start;
+            if (dbg && j < 8) p.dbg[16 + 2 * j + 1] = clock64() - tk_start;
           }
           __syncwarp();
         }
@@ -598,13 +609,14 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         for (int i = 0; i < 8; ++i) cn[i] = __ldg(src + i * 32);
       }
       ft_wait(&B->d1_full[b], (uint32_t)((j >> 1) & 1), "d1_full");
+      if (dbg && warp == 2 && lane == 0 && j < 8) p.dbg[32 + 2 * j] = clock64() - tk_start;
       ft_fence_after();
       uint32_t d[32];
       ft_tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
       ft_tmem_ld_wait();
       if (j + 2 < total) preload(j + 2, cn);
       // G[b] was last read by MMA2 of task j-2 (issued by another warp): wait until it has retired
-      if (j >= 2) ft_wait(&B->d2_full[b], (uint32_t)((((j - 2) >> 1)) & 1), "d2_full (G free)");
+      if (j >= 2) ft_wait(&B->g_free[b], (uint32_t)((((j - 2) >> 1)) & 1), "g_free");
       uint32_t ghi[8], glo[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -616,53 +628,83 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         ghi[i] = ft_pack_f16(h0, h1);
         glo[i] = ft_pack_f16(g0 - h0, g1 - h1);
       }
-      ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + half * 8, ghi);
-      ft_tmem_st8(tmem + lane_sel + 256 + b * 32 + 16 + half * 8, glo);
+      ft_tmem_st8(tmem + lane_sel + TM_G + b * 32 + half * 8, ghi);
+      ft_tmem_st8(tmem + lane_sel + TM_G + b * 32 + 16 + half * 8, glo);
       ft_tmem_st_wait();
       ft_fence_before();
       __syncwarp();
       if (lane == 0) ft_arrive(&B->g_full[b]);
-      if (dbg && warp == 2 && lane == 0 && j < 8) p.dbg[16 + j] = clock64() - tk_start;
+      if (dbg && warp == 2 && lane == 0 && j < 8) p.dbg[32 + 2 * j + 1] = clock64() - tk_start;
     }
   } else if (warp < 18) {
-    // =================================== E2: residual, in place (8 warps) ===================================
+    // =================================== E2: residual (8 warps) ===================================
+    // The fp32 residual rows of the own tiles live in TMEM (L[k]); MMA2 accumulates g.Wr into them.
+    // E2 adds the bias, writes the sum back, and refreshes the tile's fp16 hi / lo planes in shared
+    // memory (the next layer's MMA operand, and what the publisher stores).
     const int half = (warp - 10) >> 2;
     const int qd = warp & 3;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     const int row = qd * 32 + lane;  // row inside a tile
-    uint32_t npub = 0;               // publishes so far per own tile (8 bits each)
-    int li = 0, kk = 0;
-    for (int j = 0; j < total; ++j) {
-      const int b = j & 1;
-      const int k = K - 1 - kk;
-      ft_wait(&B->d2_full[b], (uint32_t)((j >> 1) & 1), "d2_full");
-      ft_fence_after();
-      uint32_t d[32];
-      ft_tmem_ld32(tmem + lane_sel + 128 + b * 64 + half * 32, d);
-      ft_tmem_ld_wait();
-      ft_fence_before();
-      __syncwarp();
-      if (lane == 0) ft_arrive(&B->d2_empty[b]);
-      // the TMA store of this tile's previous published value must have finished reading it
-      const uint32_t np = (npub >> (8 * k)) & 0xffu;
-      if (np > 0) ft_wait(&B->pub_done[k], (np - 1) & 1, "pub_done");
-      const float4* bptr = reinterpret_cast<const float4*>(p.br + (size_t)(p.l0 + li) * C) + half * 8;
+    // init: L[k] = hi + lo of the start-conv output the loader fetched
+    for (int k = K - 1; k >= 0; --k) {
+      ft_wait(&B->own_loaded[k], 0, "own_loaded (E2)");
       const uint32_t cur_lo = sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
       const uint32_t cur_hi = sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+      uint32_t v[32];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const uint32_t coff = (uint32_t)(((4 * half + jj) ^ (row & 7)) * 16);
         const uint4 hraw = ft_lds128(cur_hi + coff), lraw = ft_lds128(cur_lo + coff);
         const __half2* hp = reinterpret_cast<const __half2*>(&hraw);
         const __half2* lp = reinterpret_cast<const __half2*>(&lraw);
-        const float4 b0 = __ldg(bptr + 2 * jj), b1 = __ldg(bptr + 2 * jj + 1);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t hw[4], lw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 hv = __half22float2(hp[e]), lv = __half22float2(lp[e]);
-          const float o0 = (hv.x + lv.x) + bb[2 * e] + __uint_as_float(d[8 * jj + 2 * e]);
-          const float o1 = (hv.y + lv.y) + bb[2 * e + 1] + __uint_as_float(d[8 * jj + 2 * e + 1]);
+          v[8 * jj + 2 * e] = __float_as_uint(hv.x + lv.x);
+          v[8 * jj + 2 * e + 1] = __float_as_uint(hv.y + lv.y);
+        }
+      }
+      ft_tmem_st32(tmem + lane_sel + TM_L + k * 64 + half * 32, v);
+    }
+    ft_tmem_st_wait();
+    ft_fence_before();
+    __syncwarp();
+    if (lane == 0) ft_arrive(&B->l_init);
+    uint32_t npub = 0;  // publishes so far per own tile (8 bits each)
+    int li = 0, kk = 0;
+    for (int j = 0; j < total; ++j) {
+      const int b = j & 1;
+      const int k = K - 1 - kk;
+      const float4* bptr = reinterpret_cast<const float4*>(p.br + (size_t)(p.l0 + li) * C) + half * 8;
+      float4 bb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bb[i] = __ldg(bptr + i);
+      ft_wait(&B->d2_full[k], (uint32_t)(li & 1), "d2_full");
+      if (dbg && warp == 10 && lane == 0 && j < 8) p.dbg[48 + 2 * j] = clock64() - tk_start;
+      ft_fence_after();
+      uint32_t d[32];
+      ft_tmem_ld32(tmem + lane_sel + TM_L + k * 64 + half * 32, d);
+      ft_tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        d[4 * i] = __float_as_uint(__uint_as_float(d[4 * i]) + bb[i].x);
+        d[4 * i + 1] = __float_as_uint(__uint_as_float(d[4 * i + 1]) + bb[i].y);
+        d[4 * i + 2] = __float_as_uint(__uint_as_float(d[4 * i + 2]) + bb[i].z);
+        d[4 * i + 3] = __float_as_uint(__uint_as_float(d[4 * i + 3]) + bb[i].w);
+      }
+      ft_tmem_st32(tmem + lane_sel + TM_L + k * 64 + half * 32, d);
+      // the TMA store of this tile's previous published value must have finished reading it
+      const uint32_t np = (npub >> (8 * k)) & 0xffu;
+      if (np > 0) ft_wait(&B->pub_done[k], (np - 1) & 1, "pub_done");
+      const uint32_t cur_lo = sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+      const uint32_t cur_hi = sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint32_t coff = (uint32_t)(((4 * half + jj) ^ (row & 7)) * 16);
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float o0 = __uint_as_float(d[8 * jj + 2 * e]), o1 = __uint_as_float(d[8 * jj + 2 * e + 1]);
           const float a0 = __half2float(__float2half_rn(o0));
           const float a1 = __half2float(__float2half_rn(o1));
           hw[e] = ft_pack_f16(a0, a1);
@@ -671,12 +713,14 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         ft_sts128(cur_hi + coff, make_uint4(hw[0], hw[1], hw[2], hw[3]));
         ft_sts128(cur_lo + coff, make_uint4(lw[0], lw[1], lw[2], lw[3]));
       }
+      ft_tmem_st_wait();
+      ft_fence_before();
       // generic-proxy writes to shared memory -> tcgen05.mma / TMA store reads (async proxy)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) ft_arrive(&B->tile_ready[k]);
       if (published(k, li)) npub += 1u << (8 * k);
-      if (dbg && warp == 10 && lane == 0 && j < 8) p.dbg[24 + j] = clock64() - tk_start;
+      if (dbg && warp == 10 && lane == 0 && j < 8) p.dbg[48 + 2 * j + 1] = clock64() - tk_start;
       if (++kk == K) { kk = 0; ++li; }
     }
   } else if (warp == 18) {
@@ -717,7 +761,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 
   ft_fence_before();
   __syncthreads();
-  if (dbg && threadIdx.x == 0) p.dbg[63] = clock64() - tk_start;
+  if (dbg && threadIdx.x == 0) p.dbg[127] = clock64() - tk_start;
   if (warp == 1) {
     ft_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -775,8 +819,8 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
   static long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr;
   if (want_dbg) {
-    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 64 * sizeof(long long)));
-    NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream));
+    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 128 * sizeof(long long)));
+    NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * sizeof(long long), stream));
     p.dbg = dbg_buf;
   }
   void* args[] = {const_cast<void*>(map_act[0][0]), const_cast<void*>(map_act[0][1]),
@@ -789,17 +833,19 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
   count_launch();
   NSW_CUDA(cudaGetLastError());
   if (want_dbg) {
-    long long h[64];
+    long long h[128];
     NSW_CUDA(cudaStreamSynchronize(stream));
     NSW_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[flow_tc dbg layers %d..%d grid %d] end %lld\n  MMA1:", l0, l1, grid, h[63]);
-    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[i]);
-    fprintf(stderr, "\n  MMA2:");
-    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[8 + i]);
-    fprintf(stderr, "\n  E1  :");
-    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[16 + i]);
-    fprintf(stderr, "\n  E2  :");
-    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[24 + i]);
+    fprintf(stderr, "[flow_tc dbg layers %d..%d grid %d] end %lld\n", l0, l1, grid, h[127]);
+    const char* names[4] = {"MMA1 (operands ready, issued)", "MMA2 (g ready, issued)", "E1   (D1 ready, g stored)",
+                            "E2   (D2 ready, tile stored)"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "  %-30s:", names[r]);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld-%lld", h[16 * r + 2 * i], h[16 * r + 2 * i + 1]);
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "  %-30s:", "MMA1 D1 buffer free at");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[64 + 2 * i]);
     fprintf(stderr, "\n");
   }
   return NSW_OK;

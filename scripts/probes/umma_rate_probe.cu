@@ -19,7 +19,7 @@ __device__ __forceinline__ bool elect() {
 }
 
 template <int N, int NACC, int ROWSHIFT, int TS, int NOISE>
-__global__ void __launch_bounds__(128 + 256, 1) rate_kernel(long long* out, int iters) {
+__global__ void __launch_bounds__(128 + 512, 1) rate_kernel(long long* out, int iters) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -88,6 +88,20 @@ __global__ void __launch_bounds__(128 + 256, 1) rate_kernel(long long* out, int 
     }
     if (acc.x == 0x12345) out[3] = acc.y;
   }
+  if (warp >= 4 && NOISE == 3) {
+    // ALU/MUFU-heavy loop (like the gate epilogue): competes for issue slots with the MMA warp
+    float a = threadIdx.x * 0.001f, b2 = 1.0f, c = 0.5f, e = 0.25f;
+    while (!stop_flag) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        a = __expf(fminf(a, 4.0f)) * 0.01f + c;
+        b2 = fmaf(b2, 0.999f, a);
+        c = fmaf(c, 0.5f, e);
+        e = __fdividef(e + 1.0f, b2 + 2.0f);
+      }
+    }
+    if (a + b2 + c + e == 0.12345f) out[3] = 1;
+  }
   if (warp >= 4 && NOISE == 2) {
     // tcgen05.ld traffic on columns 256.. (not touched by the MMAs)
     uint32_t acc = 0;
@@ -113,6 +127,86 @@ __global__ void __launch_bounds__(128 + 256, 1) rate_kernel(long long* out, int 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(512u) : "memory");
 }
 
+// the exact MMA1 operand pattern of iaf_flow_tc_kernel: hi / lo activation planes 80 KB apart, row-shifted
+// windows, 3 taps x (lo.Wh, hi.Wl, hi.Wh) x 4 k-steps = 36 MMAs per task, one commit per task
+template <int VARIANT>
+__global__ void __launch_bounds__(128, 1) pattern_kernel(long long* out, int tasks) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_s;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < (208 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) {
+    const uint32_t tmem = __reduce_or_sync(0xffffffffu, tmem_s);
+    const uint32_t sb = __reduce_or_sync(0xffffffffu, smem_u32(smem));
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto desc = [](uint32_t a) -> uint64_t {
+      return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    };
+    const uint32_t OFF_LO = 81920, OFF_WDH = 163840, OFF_WDL = OFF_WDH + 24576;
+    long long t0 = clock64();
+    for (int t = 0; t < tasks; ++t) {
+      const int k = 3 - (t & 3);
+      const int d = 4;
+      if (elect()) {
+#pragma unroll
+        for (int seg = 0; seg < 3; ++seg) {
+          const int tap = 2 - seg;
+          const uint32_t arow = (uint32_t)((1 + k) * 128 - seg * d) * 128u;
+          const uint64_t alo = desc(sb + (VARIANT == 1 ? 0 : OFF_LO) + arow), ahi = desc(sb + arow);
+          const uint64_t wh = desc(sb + OFF_WDH + tap * 8192), wl = desc(sb + (VARIANT == 2 ? OFF_WDH : OFF_WDL) + tap * 8192);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (t & 1) * 64),
+                         "l"(alo + 2 * kk), "l"(wh + 2 * kk), "r"(idesc), "r"(1u) : "memory");
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (t & 1) * 64),
+                         "l"(ahi + 2 * kk), "l"(wl + 2 * kk), "r"(idesc), "r"(1u) : "memory");
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (t & 1) * 64),
+                         "l"(ahi + 2 * kk), "l"(wh + 2 * kk), "r"(idesc), "r"(1u) : "memory");
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (elect()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t2 - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(512u) : "memory");
+}
+template <int VARIANT>
+void run_pattern(const char* name, long long* d) {
+  const size_t smem = 208 * 1024 + 2048;
+  cudaFuncSetAttribute(pattern_kernel<VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long h[2];
+  for (int rep = 0; rep < 2; ++rep) {
+    pattern_kernel<VARIANT><<<1, 128, smem>>>(d, 64);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("%-50s: %.1f cyc per 36-MMA task = %.1f cyc/MMA\n", name, (double)h[0] / 64, (double)h[0] / 64 / 36);
+}
+
 template <int N, int NACC, int ROWSHIFT, int TS, int NOISE = 0>
 void run(const char* name, long long* d) {
   const int iters = 64;
@@ -120,7 +214,7 @@ void run(const char* name, long long* d) {
   cudaFuncSetAttribute(rate_kernel<N, NACC, ROWSHIFT, TS, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long h[2];
   for (int rep = 0; rep < 2; ++rep) {
-    rate_kernel<N, NACC, ROWSHIFT, TS, NOISE><<<1, NOISE ? 384 : 128, smem>>>(d, iters);
+    rate_kernel<N, NACC, ROWSHIFT, TS, NOISE><<<1, NOISE == 3 ? 640 : (NOISE ? 384 : 128), smem>>>(d, iters);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
   }
@@ -132,6 +226,9 @@ void run(const char* name, long long* d) {
 int main() {
   long long* d;
   cudaMalloc(&d, 16);
+  run_pattern<0>("flow kernel MMA1 pattern", d);
+  run_pattern<1>("pattern, lo plane aliased onto hi plane", d);
+  run_pattern<2>("pattern, Wl aliased onto Wh", d);
   run<64, 1, 0, 0>("SS same accumulator", d);
   run<64, 2, 0, 0>("SS 2 accumulators", d);
   run<64, 4, 0, 0>("SS 4 accumulators", d);
@@ -142,6 +239,8 @@ int main() {
   run<32, 1, 0, 0>("SS same accumulator", d);
   run<64, 1, 0, 0, 1>("SS + 8 warps LDS/STS noise", d);
   run<64, 1, 0, 0, 2>("SS + 8 warps tcgen05.ld noise", d);
+  run<64, 1, 0, 0, 3>("SS + 16 warps ALU/MUFU noise", d);
+  run<64, 1, 0, 1, 3>("TS + 16 warps ALU/MUFU noise", d);
   run<64, 1, 0, 1>("TS (A from TMEM) same acc", d);
   run<64, 2, 0, 1>("TS (A from TMEM) 2 acc", d);
   run<128, 1, 0, 1>("TS (A from TMEM) same acc", d);
