@@ -66,6 +66,10 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
                  const __half* Bt_hi, const __half* Bt_lo, const EpiParams& e,
                  cudaStream_t stream);
 bool conv_gemm_tc_supported(const ConvGemm& g);
+// X-resident projection of [nclips, L, 256] activations; ALL output planes row-interleaved (tc3 engine)
+int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X_hi, const __half* X_lo,
+                 const __half* Bt_hi, const __half* Bt_lo, const float* bias, float* out_tiled,
+                 cudaStream_t stream);
 
 // host-side split of fp32 into fp16 hi + fp16 lo (round-to-nearest each)
 void split_f16(const float* src, size_t n, __half* hi, __half* lo);

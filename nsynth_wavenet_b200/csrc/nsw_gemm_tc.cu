@@ -559,6 +559,197 @@ int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int rank, co
   return NSW_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Mel-conditioning projection with the activation tile RESIDENT in shared memory.
+//
+// conv_gemm_tc_kernel re-fetches the [128 x 256] activation tile (hi + lo = 128 KB) for every
+// 128-column block of the output, so per output tile it pulls 256 KB through L2 for ~3100 cycles
+// of tensor work: it ran at the chip's L2 -> SM limit (~6300 B/clk), not at the tensor limit.  Here
+// a CTA loads the activation tile once and streams only the weights (128 KB per 128 columns)
+// through a 3-stage ring.  Output: row-interleaved planes (EpiParams::tiled_planes layout) for ALL
+// planes, written straight from registers (512 contiguous bytes per warp store).
+//   warp 0 TMA producer, warp 1 MMA issuer (uniform control flow, elected lane), warps 2..9 epilogue
+// ---------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 320;
+constexpr int CP_WSTAGES = 3;
+constexpr uint32_t CP_X_BYTES = 8 * TILE_BYTES;       // hi/lo x 4 k-blocks = 128 KB
+constexpr uint32_t CP_W_STAGE = 2 * TILE_BYTES;       // W hi + lo [128 n x 64 k] = 32 KB
+constexpr uint32_t CP_OFF_W = CP_X_BYTES;
+constexpr uint32_t CP_OFF_BARS = CP_OFF_W + CP_WSTAGES * CP_W_STAGE;
+constexpr size_t CP_SMEM_BYTES = CP_OFF_BARS + 1024 + 1024;
+
+struct CpBars {
+  uint64_t x_full, x_free;
+  uint64_t w_full[CP_WSTAGES], w_empty[CP_WSTAGES];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+struct CondProj {
+  int nclips, mclip, a_off, N;
+  int tiles_per_clip, n_tiles;  // n-tiles of 128 columns
+  const float* bias;
+  float* out;  // [N/64] planes of nclips*mclip rows, row-interleaved
+};
+
+__device__ __forceinline__ bool tc_elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                    const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                    CondProj g) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  CpBars* B = reinterpret_cast<CpBars*>(smem + CP_OFF_BARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  if (threadIdx.x == 0) {
+    mbar_init(&B->x_full, 1);
+    mbar_init(&B->x_free, 1);
+    for (int s = 0; s < CP_WSTAGES; ++s) { mbar_init(&B->w_full[s], 1); mbar_init(&B->w_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&B->tmem_full[a], 1); mbar_init(&B->tmem_empty[a], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = B->tmem_base;
+  // work items = (m-tile, n-tile) pairs in m-major order; every CTA takes an equal contiguous share and
+  // (re)loads the activation tile whenever its share crosses into a new m-tile
+  const long long items = (long long)g.nclips * g.tiles_per_clip * g.n_tiles;
+  const int i0 = (int)(items * blockIdx.x / gridDim.x), i1 = (int)(items * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      int xit = 0, cur_mt = -1;
+      for (int i = i0; i < i1; ++i) {
+        const int mt = i / g.n_tiles, nt = i - mt * g.n_tiles;
+        if (mt != cur_mt) {
+          cur_mt = mt;
+          const int clip = mt / g.tiles_per_clip;
+          const int m0 = (mt - clip * g.tiles_per_clip) * TBM;
+          if (xit > 0) mbar_wait(&B->x_free, (uint32_t)((xit - 1) & 1));
+          ++xit;
+          mbar_expect_tx(&B->x_full, CP_X_BYTES);
+          for (int kb = 0; kb < 4; ++kb) {
+            tma_load_3d(sbase + (2 * kb) * TILE_BYTES, &map_xh, &B->x_full, kb * TBK, m0 + g.a_off, clip);
+            tma_load_3d(sbase + (2 * kb + 1) * TILE_BYTES, &map_xl, &B->x_full, kb * TBK, m0 + g.a_off, clip);
+          }
+        }
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&B->w_empty[ws], wphase ^ 1);
+          const uint32_t dst = sbase + CP_OFF_W + ws * CP_W_STAGE;
+          mbar_expect_tx(&B->w_full[ws], CP_W_STAGE);
+          tma_load_2d(dst, &map_wh, &B->w_full[ws], kb * TBK, nt * TBN);
+          tma_load_2d(dst + TILE_BYTES, &map_wl, &B->w_full[ws], kb * TBK, nt * TBN);
+          if (++ws == CP_WSTAGES) { ws = 0; wphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc();
+    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+    const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase);
+    int ws = 0;
+    uint32_t wphase = 0;
+    int xit = 0, cur_mt = -1, acc_it = 0;
+    for (int i = i0; i < i1; ++i, ++acc_it) {
+      const int mt = i / g.n_tiles;
+      if (mt != cur_mt) {
+        cur_mt = mt;
+        mbar_wait(&B->x_full, (uint32_t)(xit & 1));
+        ++xit;
+      }
+      const bool last_of_x = (i + 1 == i1) || ((i + 1) / g.n_tiles != mt);
+      const int as = acc_it & 1;
+      mbar_wait(&B->tmem_empty[as], (uint32_t)(((acc_it >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + (uint32_t)(as * TBN);
+      for (int kb = 0; kb < 4; ++kb) {
+        mbar_wait(&B->w_full[ws], wphase);
+        tc_fence_after();
+        const uint64_t xh = umma_desc_sw128(sbase_u + (2 * kb) * TILE_BYTES);
+        const uint64_t xl = umma_desc_sw128(sbase_u + (2 * kb + 1) * TILE_BYTES);
+        const uint64_t wh = umma_desc_sw128(sbase_u + CP_OFF_W + ws * CP_W_STAGE);
+        const uint64_t wl = umma_desc_sw128(sbase_u + CP_OFF_W + ws * CP_W_STAGE + TILE_BYTES);
+        if (tc_elect()) {
+#pragma unroll
+          for (int k = 0; k < TBK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+            umma_f16(d_tmem, xl + adv, wh + adv, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, xh + adv, wl + adv, idesc, 1);
+            umma_f16(d_tmem, xh + adv, wh + adv, idesc, 1);
+          }
+          umma_commit(&B->w_empty[ws]);
+          if (kb == 3) {
+            umma_commit(&B->tmem_full[as]);
+            if (last_of_x) umma_commit(&B->x_free);
+          }
+        }
+        __syncwarp();
+        if (++ws == CP_WSTAGES) { ws = 0; wphase ^= 1; }
+      }
+    }
+  } else {
+    // epilogue: warps w and w+4 share a TMEM lane quarter and take 64 columns (one plane) each
+    const int q = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const size_t M = (size_t)g.nclips * g.mclip;
+    int acc_it = 0;
+    for (int i = i0; i < i1; ++i, ++acc_it) {
+      const int mt = i / g.n_tiles, nt = i - mt * g.n_tiles;
+      const size_t tile_base = ((size_t)mt * 8 + q * 2) * 1024;  // + h * 1024 + j * 128 + lane * 4
+      const int as = acc_it & 1;
+      mbar_wait(&B->tmem_full[as], (uint32_t)((acc_it >> 1) & 1));
+      tc_fence_after();
+      const int n_plane0 = nt * TBN + colhalf * 64;  // first column of this warp's plane
+      if (n_plane0 < g.N) {
+        float* plane = g.out + (size_t)(n_plane0 >> 6) * M * 64 + tile_base;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TBN + colhalf * 64 + h * 32), v);
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n_plane0 + h * 32);
+          float4* dst = reinterpret_cast<float4*>(plane + h * 1024) + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            dst[j * 32] = make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace
 
 bool conv_gemm_tc_supported(const ConvGemm& g) {
@@ -615,6 +806,57 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
   const int grid = std::min(total, sms);
   conv_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, g, e,
                                                                   tiles_per_clip, n_tiles, total);
+  count_launch();
+  NSW_CUDA(cudaGetLastError());
+  return NSW_OK;
+}
+
+// X-resident mel-conditioning projection: out planes (ALL row-interleaved) = X[clip, m + a_off, :] . W + bias.
+// X_hi/X_lo [nclips, L, 256]; Bt_hi/Bt_lo [N, 256]; N % 64 == 0; mclip % 128 == 0.
+int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X_hi, const __half* X_lo,
+                 const __half* Bt_hi, const __half* Bt_lo, const float* bias, float* out_tiled,
+                 cudaStream_t stream) {
+  NSW_CHECK(mclip % TBM == 0 && N % 64 == 0 && nclips >= 1, NSW_EINVAL,
+            "cond_proj_tc: needs mclip %% 128 == 0 and N %% 64 == 0 (got %d, %d)", mclip, N);
+  EncodeTiledFn enc;
+  NSW_TRY(get_encode_fn(&enc));
+  const int K = 4 * TBK;
+  CUtensorMap mxh, mxl, mwh, mwl;
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)L, (uint64_t)nclips};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)L * K * 2};
+    const uint32_t box[3] = {TBK, TBM, 1};
+    NSW_TRY(make_map(enc, &mxh, X_hi, 3, dims, strides, box));
+    NSW_TRY(make_map(enc, &mxl, X_lo, 3, dims, strides, box));
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {TBK, TBN};
+    NSW_TRY(make_map(enc, &mwh, Bt_hi, 2, dims, strides, box));
+    NSW_TRY(make_map(enc, &mwl, Bt_lo, 2, dims, strides, box));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSW_CUDA(cudaFuncSetAttribute(cond_proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)CP_SMEM_BYTES));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CondProj g;
+  g.nclips = nclips;
+  g.mclip = mclip;
+  g.a_off = a_off;
+  g.N = N;
+  g.tiles_per_clip = mclip / TBM;
+  g.n_tiles = (N + TBN - 1) / TBN;
+  const long long items = (long long)nclips * g.tiles_per_clip * g.n_tiles;
+  g.bias = bias;
+  g.out = out_tiled;
+  const int grid = (int)std::min<long long>(items, sms);
+  cond_proj_tc_kernel<<<grid, CP_THREADS, CP_SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, g);
   count_launch();
   NSW_CUDA(cudaGetLastError());
   return NSW_OK;

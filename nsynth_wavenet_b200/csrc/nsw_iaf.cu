@@ -269,7 +269,10 @@ struct HeadSmem {
 };
 
 struct HeadParams {
-  const float* l;
+  const float* l;       // fp32 residual rows, or NULL when l_hi / l_lo (split fp16 pair) are given
+  const __half* l_hi;
+  const __half* l_lo;
+  int cond_tiled;       // out1 plane stored row-interleaved (EpiParams::tiled_planes layout)
   const float* cond;  // out1 plane, natural channel order, biases folded
   const float* W1;
   const float* wm;
@@ -309,14 +312,47 @@ __global__ void __launch_bounds__(HK_THREADS, 2) iaf_head_kernel(HeadParams p) {
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const size_t row0 = (size_t)tile * HK_TT;
-    for (int i = tid; i < HK_TT * (C / 4); i += HK_THREADS)
-      cp_async16(&S.A[i >> 4][(i & 15) * 4], p.l + (row0 + (i >> 4)) * C + (i & 15) * 4, true);
+    if (p.l) {
+      for (int i = tid; i < HK_TT * (C / 4); i += HK_THREADS)
+        cp_async16(&S.A[i >> 4][(i & 15) * 4], p.l + (row0 + (i >> 4)) * C + (i & 15) * 4, true);
+    } else {
+      // split fp16 pair (tcgen05 layer engines): l = hi + lo
+      for (int i = tid; i < HK_TT * (C / 8); i += HK_THREADS) {
+        const size_t off = (row0 + (i >> 3)) * C + (i & 7) * 8;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.l_hi + off));
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.l_lo + off));
+        const __half2* hp = reinterpret_cast<const __half2*>(&h);
+        const __half2* lp = reinterpret_cast<const __half2*>(&l);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __half22float2(hp[e]), b = __half22float2(lp[e]);
+          o[2 * e] = a.x + b.x;
+          o[2 * e + 1] = a.y + b.y;
+        }
+        float* dst = &S.A[i >> 3][(i & 7) * 8];
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
     cp_async_commit();
     const int r0 = warp * HK_RT;
     float2 cnd[HK_RT];
+    if (p.cond_tiled) {
+      // element (row, col) of a row-interleaved plane: ((row/128*8 + row%128/32*2 + col/32) * 1024
+      //                                                + (col%32)/4*128 + (row%32)*4 + col%4
+      const size_t col_off = (size_t)(lane >> 4) * 1024 + ((lane & 15) >> 1) * 128 + (lane & 1) * 2;
 #pragma unroll
-    for (int i = 0; i < HK_RT; ++i)
-      cnd[i] = __ldg(reinterpret_cast<const float2*>(p.cond + (row0 + r0 + i) * C) + lane);
+      for (int i = 0; i < HK_RT; ++i) {
+        const size_t grow = row0 + r0 + i;
+        cnd[i] = __ldg(reinterpret_cast<const float2*>(
+            p.cond + ((grow >> 7) * 8 + ((grow & 127) >> 5) * 2) * 1024 + (grow & 31) * 4 + col_off));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < HK_RT; ++i)
+        cnd[i] = __ldg(reinterpret_cast<const float2*>(p.cond + (row0 + r0 + i) * C) + lane);
+    }
     cp_async_wait_all();
     __syncthreads();
 
@@ -765,8 +801,10 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       e.mode = EPI_PLANES;
       e.bias = fw.bc.as<float>();
       e.out_f32 = h->cond.as<float>();
-      e.tiled_planes = tc3 ? fw.L : 0;
-      if (tc)
+      if (tc3)  // activation tile resident in shared memory, every plane row-interleaved
+        NSW_TRY(cond_proj_tc(B, Lc, T, left, g.N, me_hi, me_lo, fw.Wct_hi.as<__half>(), fw.Wct_lo.as<__half>(),
+                             fw.bc.as<float>(), h->cond.as<float>(), st));
+      else if (tc)
         NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, fw.Wct_hi.as<__half>(),
                              fw.Wct_lo.as<__half>(), e, st));
       else
@@ -830,7 +868,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
                                  cudaMemcpyDeviceToDevice, st));
     }
     }
-    if (tc_layers && fw.L > 0) {  // the head consumes fp32 rows
+    if (tc_layers && !tc3 && fw.L > 0) {  // the head consumes fp32 rows (tc3: it reads the split pair itself)
       iaf_merge_split_kernel<<<(unsigned)((rows * C / 8 + 255) / 256), 256, 0, st>>>(
           ls_hi[cur], ls_lo[cur], l_buf[cur], rows * C / 8);
       count_launch();
@@ -840,7 +878,10 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     // 4. head + affine + running composition
     rec(0);
     HeadParams hp;
-    hp.l = l_buf[cur];
+    hp.l = (tc3 && fw.L > 0) ? nullptr : l_buf[cur];
+    hp.l_hi = ls_hi[cur];
+    hp.l_lo = ls_lo[cur];
+    hp.cond_tiled = tc3 ? 1 : 0;
     hp.cond = h->cond.as<float>() + (size_t)fw.L * rows * C;
     hp.W1 = fw.W1.as<float>();
     hp.wm = fw.wm.as<float>();
