@@ -349,6 +349,15 @@ def main():
     layer_launch_ms = stage['layers'] / n_layers
     hbm_peak, tc_peak, peak_kind = measured_peaks()
     layer_gbs = LAYER_BYTES_PER_SAMPLE * B * T / (layer_launch_ms * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per layer pass,
+    # like bytes_per_launch); only valid for the shape and engine it was captured on
+    traffic, traffic_src = None, None
+    ncu_json = os.path.join(ROOT, 'profiles', 'r01', 'flow_tc_ncu_run21.json')
+    if eng.engine == 'tc3' and (B, T) == (8, 7680) and os.path.exists(ncu_json):
+        with open(ncu_json) as f:
+            cap = json.load(f)['launches'][0]
+        traffic = (float(cap['dram__bytes_read.sum']['value']) + float(cap['dram__bytes_write.sum']['value'])) * 1e6 / 10
+        traffic_src = 'profiles/r01/flow_tc_ncu_run21.json (dram__bytes_read+write of one 10-layer launch / 10)'
     cond_tflops = COND_FLOP_PER_SAMPLE_PLANE * n_planes * B * T / (stage['cond'] * 1e-3) / 1e12
 
     line = {
@@ -369,15 +378,17 @@ def main():
         'clocks': sampler.summary(),
         'roofline': {
             'kernel': {'tc3': 'iaf_flow_tc_kernel', 'tc2': 'iaf_layer_tc_kernel'}.get(eng.engine, 'iaf_layer_kernel'), 'bound': 'hbm', 'achieved': layer_gbs, 'peak': hbm_peak,
-            'unit': 'GB/s', 'frac': layer_gbs / hbm_peak, 'traffic': None,
+            'unit': 'GB/s', 'frac': layer_gbs / hbm_peak, 'traffic': traffic, 'traffic_source': traffic_src,
+            'unit_of_launch': 'one residual layer over the whole batch (engine tc3 runs all layers of a flow '
+                              'in one persistent launch; time = layers stage / number of layers)',
             'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
             'bytes_per_launch': LAYER_BYTES_PER_SAMPLE * B * T, 'launch_ms': layer_launch_ms,
             'share_of_step': stage['layers'] / stage['total'],
         },
         'roofline_cond_gemm': {
-            'kernel': 'conv_gemm (cond projections)', 'bound': 'tensor', 'achieved': cond_tflops,
+            'kernel': 'cond_proj_tc_kernel' if eng.engine == 'tc3' else 'conv_gemm (cond projections)', 'bound': 'tensor', 'achieved': cond_tflops,
             'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': cond_tflops / tc_peak,
-            'note': 'algorithmic fp32-equivalent flops; the tcgen05 engine issues 3 bf16 MMAs per product',
+            'note': 'algorithmic fp32-equivalent flops; the tcgen05 engine issues 3 fp16 MMAs per product',
         },
         'stage_ms': stage,
     }
