@@ -135,6 +135,19 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return tanhf(v);
 }
 
+// ParallelWavenet._clip_quant_scale (parallel_wavenet.py:348-359)
+__device__ __forceinline__ float clip_quant_scale_dev(float x, float Q, int use_mu_law) {
+  x = fminf(fmaxf(x, -1.0f), 1.0f - 2.0f / Q);
+  const float q = floorf(x * Q * 0.5f);  // utils.cast_quantize (utils.py:142-154)
+  if (!use_mu_law) return q / (Q * 0.5f);  // utils.inv_cast_quantize (utils.py:157-159)
+  // utils.inv_mu_law (utils.py:108-122)
+  const float mu = 255.0f;
+  float out = (q + 0.5f) * 2.0f / (mu + 1.0f);
+  const float sgn = out > 0.0f ? 1.0f : (out < 0.0f ? -1.0f : 0.0f);
+  out = sgn / mu * (powf(1.0f + mu, fabsf(out)) - 1.0f);
+  return q == 0.0f ? q : out;
+}
+
 // Philox4x32-10 (counter-based; one call gives 4 x 32 random bits)
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

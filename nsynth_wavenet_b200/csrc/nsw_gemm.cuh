@@ -85,10 +85,25 @@ int layer_tc_launch(const void* const map_act[2][2], const void* map_wdh, const 
 
 // ---- tcgen05 fused IAF flow, residual stream resident in shared memory (nsw_iaf_flow_tc.cu) ----
 int flow_tc_clips_per_launch(int T, int num_sms);  // 0 = shape not supported
+// head fused behind the last layer (NULL = publish the final rows for iaf_head_kernel instead)
+struct FlowHead {
+  int w_tile;  // 64-row tile index of W1^T (hi / lo) in the Wd tensor maps
+  const float* wm;
+  const float* ws;
+  float bm, bs;
+  const float* x_in;
+  const float* z;
+  float* x_out;
+  float* mean_tot;
+  float* scale_tot;
+  float* log_scale_tot;
+  int first, last, quantize, use_mu_law;
+  float quant_chann;
+};
 int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
                    const void* map_wrh, const void* map_wrl, const float* cond_tiled, size_t cond_plane,
                    const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
-                   unsigned int* sync_words, int num_sms, cudaStream_t stream);
+                   unsigned int* sync_words, int num_sms, const FlowHead* head, cudaStream_t stream);
 
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
 struct DeconvLayer {

@@ -289,18 +289,6 @@ struct HeadParams {
   int n_tiles;
 };
 
-__device__ __forceinline__ float clip_quant_scale_dev(float x, float Q, int use_mu_law) {
-  x = fminf(fmaxf(x, -1.0f), 1.0f - 2.0f / Q);
-  const float q = floorf(x * Q * 0.5f);  // utils.cast_quantize (utils.py:142-154)
-  if (!use_mu_law) return q / (Q * 0.5f);  // utils.inv_cast_quantize (utils.py:157-159)
-  // utils.inv_mu_law (utils.py:108-122)
-  const float mu = 255.0f;
-  float out = (q + 0.5f) * 2.0f / (mu + 1.0f);
-  const float sgn = out > 0.0f ? 1.0f : (out < 0.0f ? -1.0f : 0.0f);
-  out = sgn / mu * (powf(1.0f + mu, fabsf(out)) - 1.0f);
-  return q == 0.0f ? q : out;
-}
-
 __global__ void __launch_bounds__(HK_THREADS, 2) iaf_head_kernel(HeadParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HeadSmem& S = *reinterpret_cast<HeadSmem*>(smem_raw);
@@ -540,7 +528,8 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
   NSW_TRY(upload(fw.wm, wm, C * sizeof(float)));
   NSW_TRY(upload(fw.ws, wsc, C * sizeof(float)));
   if (cfg.engine >= NSW_ENGINE_TC2) {
-    std::vector<float> wdt((size_t)L * 3 * C * C), wrt((size_t)L * C * HALF), brn((size_t)L * C);
+    // [L][3] dilated-conv tap tiles + one more tile: W1^T of out1 (the fused head of engine tc3)
+    std::vector<float> wdt(((size_t)L * 3 + 1) * C * C), wrt((size_t)L * C * HALF), brn((size_t)L * C);
     for (int i = 0; i < L; ++i) {
       const std::string li = std::to_string(i + 1);
       const float* wd = tm.get(p + "/dilated_conv_" + li + "/W", 3 * C * C);
@@ -555,6 +544,8 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
         for (int j = 0; j < HALF; ++j) wrt[((size_t)i * C + c) * HALF + j] = wr[(size_t)j * C + c];
       for (int c = 0; c < C; ++c) brn[(size_t)i * C + c] = brr[c];
     }
+    for (int n = 0; n < C; ++n)
+      for (int k = 0; k < C; ++k) wdt[((size_t)L * 3 * C + n) * C + k] = w1[(size_t)k * C + n];
     std::vector<__half> hi(wdt.size()), lo(wdt.size());
     split_f16(wdt.data(), wdt.size(), hi.data(), lo.data());
     NSW_TRY(upload(fw.WdT_hi, hi.data(), hi.size() * 2));
@@ -564,8 +555,8 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
     NSW_TRY(upload(fw.WrT_hi, hi.data(), hi.size() * 2));
     NSW_TRY(upload(fw.WrT_lo, lo.data(), lo.size() * 2));
     NSW_TRY(upload(fw.br_nat, brn.data(), brn.size() * 4));
-    NSW_TRY(layer_tc_make_weight_map(fw.map_wdh, fw.WdT_hi.as<__half>(), L * 3 * C, C));
-    NSW_TRY(layer_tc_make_weight_map(fw.map_wdl, fw.WdT_lo.as<__half>(), L * 3 * C, C));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdh, fw.WdT_hi.as<__half>(), (L * 3 + 1) * C, C));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdl, fw.WdT_lo.as<__half>(), (L * 3 + 1) * C, C));
     NSW_TRY(layer_tc_make_weight_map(fw.map_wrh, fw.WrT_hi.as<__half>(), L * C, HALF));
     NSW_TRY(layer_tc_make_weight_map(fw.map_wrl, fw.WrT_lo.as<__half>(), L * C, HALF));
   }
@@ -822,6 +813,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     lap(3, 0, 1);
     rec(0);
     int cur = 0;
+    bool head_fused = false;
     if (h->tap_flow == f && h->tap_layer == 0)
       NSW_CUDA(cudaMemcpyAsync(h->tap_dst, l_buf[cur], rows * C * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
@@ -835,11 +827,21 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       while (l0 < fw.L) {
         const int l1 = (l0 < split_at) ? split_at : fw.L;
         if (tc3) {
+          FlowHead fh;
+          fh.w_tile = fw.L * 3;
+          fh.wm = fw.wm.as<float>(); fh.ws = fw.ws.as<float>(); fh.bm = fw.bm; fh.bs = fw.bs;
+          fh.x_in = x_cur; fh.z = h->z.as<float>(); fh.x_out = h->x.as<float>();
+          fh.mean_tot = h->mean_tot.as<float>(); fh.scale_tot = h->scale_tot.as<float>();
+          fh.log_scale_tot = h->log_scale_tot.as<float>();
+          fh.first = (f == 0); fh.last = (f == cfg.num_flows - 1); fh.quantize = quantize;
+          fh.use_mu_law = cfg.use_mu_law; fh.quant_chann = cfg.use_mu_law ? 256.0f : 65536.0f;
+          head_fused = (l0 == 0 && l1 == fw.L && h->tap_flow != f);  // not when a debug tap wants this flow's rows
           for (int c0 = 0; c0 < B; c0 += tc3_clips)
             NSW_TRY(flow_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
                                    h->cond.as<float>() + (size_t)l0 * rows * C, rows * C,
                                    fw.br_nat.as<float>(), T, c0, std::min(tc3_clips, B - c0), cur, l0, l1,
-                                   cfg.num_stages, h->sync_words.as<unsigned int>(), h->num_sms, st));
+                                   cfg.num_stages, h->sync_words.as<unsigned int>(), h->num_sms,
+                                   head_fused ? &fh : nullptr, st));
         } else {
           NSW_TRY(layer_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
                                   h->cond.as<float>() + (size_t)l0 * rows * C, rows * C, ls_hi, ls_lo,
@@ -900,8 +902,10 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     hp.use_mu_law = cfg.use_mu_law;
     hp.quant_chann = cfg.use_mu_law ? 256.0f : 65536.0f;
     hp.n_tiles = (int)(rows / HK_TT);
-    iaf_head_kernel<<<std::min(hp.n_tiles, 2 * h->num_sms), HK_THREADS, sizeof(HeadSmem), st>>>(hp);
-    count_launch();
+    if (!head_fused) {
+      iaf_head_kernel<<<std::min(hp.n_tiles, 2 * h->num_sms), HK_THREADS, sizeof(HeadSmem), st>>>(hp);
+      count_launch();
+    }
     rec(1);
     lap(3, 0, 1);
   }

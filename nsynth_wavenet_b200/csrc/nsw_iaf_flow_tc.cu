@@ -271,6 +271,23 @@ struct FlowTcParams {
   int cta_base, cta_rem;  // clip c (0-based within the launch) is split over cta_base + (c < cta_rem) CTAs
   int reach_tiles;        // 2 * max dilation / 128 (how far ahead a published tile is read)
   long long* dbg;
+  // fused head (parallel_wavenet.py:256-277, 316-330, 348-359): a pseudo-layer after layer l1-1 whose
+  // "conv" is the 1x1 out1 on relu(l) (weights = tile head_w_tile of the Wd maps) accumulated on the
+  // out1 conditioning plane, and whose epilogue is out2_mean / out2_scale + the affine composition
+  int fuse_head;
+  int head_w_tile;        // 64-row tile index of W1^T in the Wd tensor maps
+  const float* wm;        // out2_mean W [64]
+  const float* ws;        // out2_scale W [64]
+  float bm, bs;
+  const float* x_in;      // input of this flow [B*T]
+  const float* z;         // noise [B*T]
+  float* x_out;
+  float* mean_tot;
+  float* scale_tot;
+  float* log_scale_tot;
+  int T;                  // samples per clip
+  int first, last, quantize, use_mu_law;
+  float quant_chann;
 };
 
 struct Range {  // the tiles a CTA owns
@@ -352,7 +369,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
   const Range R = ft_range(p, (int)blockIdx.x);
   const int K = R.K;
   const int nl = p.l1 - p.l0;
-  const int total = nl * K;
+  const int total = nl * K;                           // gate / residual tasks
+  const int total1 = (nl + (p.fuse_head ? 1 : 0)) * K;  // MMA1 / E1 tasks (+ the head pseudo-layer)
   const int gclip = p.clip0 + R.clip;                 // clip coordinate in the tensor maps
   const int gt0 = gclip * p.tiles_per_clip + R.tk0;   // global tile id of own tile 0
   const long long tk_start = clock64();
@@ -360,7 +378,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 
   // does the output of (own tile k, layer li) have a reader outside this CTA?
   auto published = [&](int k, int li) -> bool {
-    if (li == nl - 1) return true;                                // the head reads every row
+    if (li == nl - 1) return p.fuse_head == 0;                    // the head kernel reads every row
     if ((1 << ((p.l0 + li + 1) % p.num_stages)) >= BM) return true;  // next layer reads whole foreign tiles
     return k == K - 1;                                            // next CTA's halo
   };
@@ -437,6 +455,12 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
               foreign(li, src, mh, ml);
             }
         }
+      }
+      if (p.fuse_head) {  // W1^T (hi, lo) into the current-tap weight slot once the last layer's MMA1s retired
+        ft_wait(&B->wd_free, (uint32_t)((nl - 1) & 1), "wd_free (head)");
+        ft_expect_tx(&B->wd_full, 2 * WD_TILE);
+        ft_tma_load_2d(sbase + OFF_WDH + 2 * WD_TILE, &map_wdh, &B->wd_full, 0, p.head_w_tile * 64);
+        ft_tma_load_2d(sbase + OFF_WDL + 2 * WD_TILE, &map_wdl, &B->wd_full, 0, p.head_w_tile * 64);
       }
     }
   } else if (warp == 1) {
@@ -533,6 +557,20 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
           __syncwarp();
         }
       }
+      if (p.fuse_head) {
+        // head pseudo-layer: D1 = cond_out1 (preloaded) + relu(l) . W1, one "tap" on the tile itself
+        ft_wait(&B->wd_full, (uint32_t)(nl & 1), "wd_full (head)");
+        for (int kk = 0; kk < K; ++kk, ++j) {
+          const int k = K - 1 - kk;
+          const int b = j & 1;
+          ft_wait(&B->d1_empty[b], (uint32_t)((j >> 1) & 1), "d1_empty (head)");
+          wait_ready(k, nl);
+          ft_fence_after();
+          issue_tap(tmem_u + b * 64, (uint32_t)(1 + k) * TILE_B, 2);
+          if (ft_elect()) ft_commit(&B->d1_full[b]);
+          __syncwarp();
+        }
+      }
     }
   } else if (warp == 19) {
     // =================================== MMA2 issuer ===================================
@@ -593,17 +631,17 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       __syncwarp();
       if (lane == 0) ft_arrive(&B->d1_empty[b]);
     };
-    for (int j = 0; j < 2 && j < total; ++j) {
+    for (int j = 0; j < 2 && j < total1; ++j) {
       float4 cn[8];
       const float4* src = cond_ptr(j);
 #pragma unroll
       for (int i = 0; i < 8; ++i) cn[i] = __ldg(src + i * 32);
       preload(j, cn);
     }
-    for (int j = 0; j < total; ++j) {
+    for (int j = 0; j < total1; ++j) {
       const int b = j & 1;
       float4 cn[8];
-      if (j + 2 < total) {
+      if (j + 2 < total1) {
         const float4* src = cond_ptr(j + 2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) cn[i] = __ldg(src + i * 32);
@@ -614,7 +652,58 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       uint32_t d[32];
       ft_tmem_ld32(tmem + lane_sel + b * 64 + half * 32, d);
       ft_tmem_ld_wait();
-      if (j + 2 < total) preload(j + 2, cn);
+      if (j + 2 < total1) preload(j + 2, cn);
+      if (j >= total) {
+        // ---------------- head epilogue (pseudo-layer task) ----------------
+        // d = out1(relu(l)) + cond_out1 for this thread's 32 channels; out2_mean / out2_scale are 64-wide
+        // dot products: the two warps sharing the rows exchange their partial sums through the (now idle)
+        // tap-0 weight slot
+        const int k = K - 1 - (j - total);
+        const float4* wm4 = reinterpret_cast<const float4*>(p.wm) + half * 8;
+        const float4* ws4 = reinterpret_cast<const float4*>(p.ws) + half * 8;
+        float pm = 0.f, ps = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 wmv = __ldg(wm4 + i), wsv = __ldg(ws4 + i);
+          const float h0 = fmaxf(__uint_as_float(d[4 * i]), 0.f), h1 = fmaxf(__uint_as_float(d[4 * i + 1]), 0.f);
+          const float h2 = fmaxf(__uint_as_float(d[4 * i + 2]), 0.f), h3 = fmaxf(__uint_as_float(d[4 * i + 3]), 0.f);
+          pm = fmaf(h0, wmv.x, fmaf(h1, wmv.y, fmaf(h2, wmv.z, fmaf(h3, wmv.w, pm))));
+          ps = fmaf(h0, wsv.x, fmaf(h1, wsv.y, fmaf(h2, wsv.z, fmaf(h3, wsv.w, ps))));
+        }
+        const int row = qd * 32 + lane;
+        const uint32_t exch = sbase + OFF_WDH + (uint32_t)(j & 1) * 1024u + (uint32_t)row * 8u;
+        if (half == 1) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(exch), "f"(pm), "f"(ps) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+        if (half == 0) {
+          float qm, qs;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(qm), "=f"(qs) : "r"(exch) : "memory");
+          const size_t grow = (size_t)gclip * p.T + (size_t)(R.tk0 + k) * BM + row;
+          const float mean = pm + qm + p.bm;
+          const float sp = softplusf_acc(ps + qs + p.bs);
+          const float scale = fminf(fmaxf(sp, 1.2340980408667956e-4f /*e^-9*/), 1096.6331584284585f /*e^7*/);
+          const float log_scale = logf(scale);
+          float mt, st, lt;
+          if (p.first) {
+            mt = mean; st = scale; lt = log_scale;
+          } else {
+            mt = fmaf(p.mean_tot[grow], scale, mean);
+            st = p.scale_tot[grow] * scale;
+            lt = p.log_scale_tot[grow] + log_scale;
+          }
+          float xo = fmaf(p.x_in[grow], scale, mean);
+          if (p.last) {
+            st = fminf(st, 1096.6331584284585f);
+            lt = fminf(lt, 7.0f);
+            xo = fmaf(p.z[grow], st, mt);  // new_x = x * scale_tot + mean_tot (:330)
+            if (p.quantize) xo = clip_quant_scale_dev(xo, p.quant_chann, p.use_mu_law);
+          }
+          p.mean_tot[grow] = mt;
+          p.scale_tot[grow] = st;
+          p.log_scale_tot[grow] = lt;
+          p.x_out[grow] = xo;
+        }
+        continue;
+      }
       // G[b] was last read by MMA2 of task j-2 (issued by another warp): wait until it has retired
       if (j >= 2) ft_wait(&B->g_free[b], (uint32_t)((((j - 2) >> 1)) & 1), "g_free");
       uint32_t ghi[8], glo[8];
@@ -698,13 +787,15 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       if (np > 0) ft_wait(&B->pub_done[k], (np - 1) & 1, "pub_done");
       const uint32_t cur_lo = sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
       const uint32_t cur_hi = sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+      const bool relu_out = p.fuse_head && li == nl - 1;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const uint32_t coff = (uint32_t)(((4 * half + jj) ^ (row & 7)) * 16);
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float o0 = __uint_as_float(d[8 * jj + 2 * e]), o1 = __uint_as_float(d[8 * jj + 2 * e + 1]);
+          float o0 = __uint_as_float(d[8 * jj + 2 * e]), o1 = __uint_as_float(d[8 * jj + 2 * e + 1]);
+          if (relu_out) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }  // the head's out1 consumes relu(l)
           const float a0 = __half2float(__float2half_rn(o0));
           const float a1 = __half2float(__float2half_rn(o1));
           hw[e] = ft_pack_f16(a0, a1);
@@ -781,7 +872,8 @@ int flow_tc_clips_per_launch(int T, int num_sms) {
 int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
                    const void* map_wrh, const void* map_wrl, const float* cond_tiled, size_t cond_plane,
                    const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
-                   unsigned int* sync_words /* >= nclips*T/128 + num_sms */, int num_sms, cudaStream_t stream) {
+                   unsigned int* sync_words /* >= nclips*T/128 + num_sms */, int num_sms, const FlowHead* head,
+                   cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     NSW_CUDA(cudaFuncSetAttribute(iaf_flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -815,6 +907,22 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
   p.flags = sync_words;
   p.cons = sync_words + n_flags;
   NSW_CUDA(cudaMemsetAsync(sync_words, 0, (n_flags + grid) * sizeof(unsigned int), stream));
+  p.fuse_head = head != nullptr;
+  if (head) {
+    p.head_w_tile = head->w_tile;
+    p.wm = head->wm; p.ws = head->ws; p.bm = head->bm; p.bs = head->bs;
+    p.x_in = head->x_in; p.z = head->z; p.x_out = head->x_out;
+    p.mean_tot = head->mean_tot; p.scale_tot = head->scale_tot; p.log_scale_tot = head->log_scale_tot;
+    p.first = head->first; p.last = head->last; p.quantize = head->quantize; p.use_mu_law = head->use_mu_law;
+    p.quant_chann = head->quant_chann;
+  } else {
+    p.head_w_tile = 0;
+    p.wm = p.ws = p.x_in = p.z = nullptr;
+    p.x_out = p.mean_tot = p.scale_tot = p.log_scale_tot = nullptr;
+    p.bm = p.bs = p.quant_chann = 0.f;
+    p.first = p.last = p.quantize = p.use_mu_law = 0;
+  }
+  p.T = T;
   p.dbg = nullptr;
   static long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr;
