@@ -100,10 +100,17 @@ struct FlowHead {
   int first, last, quantize, use_mu_law;
   float quant_chann;
 };
+// start conv fused in front of layer 0 (NULL = the rows were written by iaf_start_conv_kernel)
+struct FlowStart {
+  const float* x;  // input of the flow [B*T]; must not alias FlowHead::x_out
+  const float* w;  // start_conv W [3][64]
+  const float* b;  // [64]
+};
 int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
                    const void* map_wrh, const void* map_wrl, const float* cond_tiled, size_t cond_plane,
                    const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
-                   unsigned int* sync_words, int num_sms, const FlowHead* head, cudaStream_t stream);
+                   unsigned int* sync_words, int num_sms, const FlowHead* head, const FlowStart* start,
+                   cudaStream_t stream);
 
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
 struct DeconvLayer {

@@ -448,7 +448,8 @@ struct nsw_iaf {
   // workspace
   int ws_B = 0, ws_F = 0;
   DevBuf mel, mel_en, mel_en_split, cond, l0, l1, x, z, mean_tot, scale_tot, log_scale_tot,
-      deconv_scratch, ls0, ls1, grid_counter, sync_words;  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
+      deconv_scratch, ls0, ls1, grid_counter, sync_words, x2;
+  float* x_final = nullptr;  // which of x / x2 holds the last forward's output  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
   alignas(64) unsigned char map_act[2][2][128];  // [buffer][hi, lo]
   int map_B = 0, map_T = 0;
   // debug tap
@@ -668,6 +669,7 @@ static int ensure_workspace(nsw_iaf* h, int B, int F) {
     h->map_B = h->map_T = 0;  // buffers may have moved
   }
   NSW_TRY(h->x.ensure(rows * sizeof(float)));
+  NSW_TRY(h->x2.ensure(rows * sizeof(float)));
   NSW_TRY(h->z.ensure(rows * sizeof(float)));
   NSW_TRY(h->mean_tot.ensure(rows * sizeof(float)));
   NSW_TRY(h->scale_tot.ensure(rows * sizeof(float)));
@@ -681,7 +683,7 @@ extern "C" size_t nsw_iaf_workspace_bytes(const nsw_iaf* h) {
   if (!h) return 0;
   return h->mel.bytes + h->mel_en.bytes + h->mel_en_split.bytes + h->cond.bytes + h->l0.bytes +
          h->l1.bytes + h->ls0.bytes + h->ls1.bytes + h->x.bytes + h->z.bytes + h->mean_tot.bytes + h->scale_tot.bytes +
-         h->log_scale_tot.bytes + h->deconv_scratch.bytes;
+         h->log_scale_tot.bytes + h->deconv_scratch.bytes + h->x2.bytes + h->sync_words.bytes;
 }
 
 extern "C" int nsw_iaf_set_tap(nsw_iaf* h, int32_t flow, int32_t layer, float* d_l) {
@@ -805,10 +807,18 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     }
     // 3. start conv + residual layers
     rec(0);
-    const float* x_cur = (f == 0) ? h->z.as<float>() : h->x.as<float>();
-    iaf_start_conv_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256, 0, st>>>(
-        x_cur, l_buf[0], fw.start_w.as<float>(), fw.start_b.as<float>(), T, rows, ls_hi[0], ls_lo[0]);
-    count_launch();
+    // engine tc3 fuses the start conv (reads x of rows owned by OTHER CTAs) and the head (writes x) into one
+    // unsynchronised persistent kernel, so the flow's input and output must be different buffers
+    float* xbuf[2] = {h->x.as<float>(), tc3 ? h->x2.as<float>() : h->x.as<float>()};
+    const float* x_cur = (f == 0) ? h->z.as<float>() : xbuf[(f - 1) & 1];
+    float* x_next = xbuf[f & 1];
+    h->x_final = x_next;
+    const bool fuse_ends = tc3 && h->tap_flow != f;  // start conv + head inside the flow kernel
+    if (!fuse_ends) {
+      iaf_start_conv_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256, 0, st>>>(
+          x_cur, l_buf[0], fw.start_w.as<float>(), fw.start_b.as<float>(), T, rows, ls_hi[0], ls_lo[0]);
+      count_launch();
+    }
     rec(1);
     lap(3, 0, 1);
     rec(0);
@@ -830,18 +840,19 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
           FlowHead fh;
           fh.w_tile = fw.L * 3;
           fh.wm = fw.wm.as<float>(); fh.ws = fw.ws.as<float>(); fh.bm = fw.bm; fh.bs = fw.bs;
-          fh.x_in = x_cur; fh.z = h->z.as<float>(); fh.x_out = h->x.as<float>();
+          fh.x_in = x_cur; fh.z = h->z.as<float>(); fh.x_out = x_next;
           fh.mean_tot = h->mean_tot.as<float>(); fh.scale_tot = h->scale_tot.as<float>();
           fh.log_scale_tot = h->log_scale_tot.as<float>();
           fh.first = (f == 0); fh.last = (f == cfg.num_flows - 1); fh.quantize = quantize;
           fh.use_mu_law = cfg.use_mu_law; fh.quant_chann = cfg.use_mu_law ? 256.0f : 65536.0f;
-          head_fused = (l0 == 0 && l1 == fw.L && h->tap_flow != f);  // not when a debug tap wants this flow's rows
+          head_fused = fuse_ends && l0 == 0 && l1 == fw.L;  // not when a debug tap wants this flow's rows
+          FlowStart fs{x_cur, fw.start_w.as<float>(), fw.start_b.as<float>()};
           for (int c0 = 0; c0 < B; c0 += tc3_clips)
             NSW_TRY(flow_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
                                    h->cond.as<float>() + (size_t)l0 * rows * C, rows * C,
                                    fw.br_nat.as<float>(), T, c0, std::min(tc3_clips, B - c0), cur, l0, l1,
                                    cfg.num_stages, h->sync_words.as<unsigned int>(), h->num_sms,
-                                   head_fused ? &fh : nullptr, st));
+                                   head_fused ? &fh : nullptr, head_fused ? &fs : nullptr, st));
         } else {
           NSW_TRY(layer_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
                                   h->cond.as<float>() + (size_t)l0 * rows * C, rows * C, ls_hi, ls_lo,
@@ -892,7 +903,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     hp.bs = fw.bs;
     hp.x_in = x_cur;
     hp.z = h->z.as<float>();
-    hp.x_out = h->x.as<float>();
+    hp.x_out = x_next;
     hp.mean_tot = h->mean_tot.as<float>();
     hp.scale_tot = h->scale_tot.as<float>();
     hp.log_scale_tot = h->log_scale_tot.as<float>();
@@ -934,7 +945,7 @@ extern "C" int nsw_iaf_forward_device(nsw_iaf* h, const float* d_mel, const floa
   if (d_z) NSW_CUDA(cudaMemcpyAsync(h->z.p, d_z, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
   NSW_TRY(iaf_forward_internal(h, B, F, d_z != nullptr, seed, quantize, st));
   const size_t nb = rows * sizeof(float);
-  if (d_x) NSW_CUDA(cudaMemcpyAsync(d_x, h->x.p, nb, cudaMemcpyDeviceToDevice, st));
+  if (d_x) NSW_CUDA(cudaMemcpyAsync(d_x, h->x_final, nb, cudaMemcpyDeviceToDevice, st));
   if (d_mean_tot) NSW_CUDA(cudaMemcpyAsync(d_mean_tot, h->mean_tot.p, nb, cudaMemcpyDeviceToDevice, st));
   if (d_scale_tot) NSW_CUDA(cudaMemcpyAsync(d_scale_tot, h->scale_tot.p, nb, cudaMemcpyDeviceToDevice, st));
   if (d_log_scale_tot)
@@ -958,7 +969,7 @@ extern "C" int nsw_iaf_forward_host(nsw_iaf* h, const float* mel, const float* z
   if (z) NSW_CUDA(cudaMemcpyAsync(h->z.p, z, rows * sizeof(float), cudaMemcpyHostToDevice, st));
   NSW_TRY(iaf_forward_internal(h, B, F, z != nullptr, seed, quantize, st));
   const size_t nb = rows * sizeof(float);
-  if (x) NSW_CUDA(cudaMemcpyAsync(x, h->x.p, nb, cudaMemcpyDeviceToHost, st));
+  if (x) NSW_CUDA(cudaMemcpyAsync(x, h->x_final, nb, cudaMemcpyDeviceToHost, st));
   if (mean_tot) NSW_CUDA(cudaMemcpyAsync(mean_tot, h->mean_tot.p, nb, cudaMemcpyDeviceToHost, st));
   if (scale_tot) NSW_CUDA(cudaMemcpyAsync(scale_tot, h->scale_tot.p, nb, cudaMemcpyDeviceToHost, st));
   if (log_scale_tot)

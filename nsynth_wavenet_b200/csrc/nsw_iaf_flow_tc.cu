@@ -73,6 +73,7 @@ struct FtBars {
   uint64_t d1_full[2], d1_empty[2], g_full[2], g_free[2];
   uint64_t d2_full[KMAX];  // per own tile: MMA2 of the current layer has retired
   uint64_t l_init;
+  uint64_t halo0;  // fused start conv: the halo rows of layer 0 are in shared memory
   uint32_t tmem_base;
 };
 static_assert(sizeof(FtBars) <= 1024, "barrier block grew");
@@ -288,6 +289,12 @@ struct FlowTcParams {
   int T;                  // samples per clip
   int first, last, quantize, use_mu_law;
   float quant_chann;
+  // fused start conv (parallel_wavenet.py:222-225): l0[t] = b + W0 x[t-3] + W1 x[t-2] + W2 x[t-1] computed by
+  // the residual warps from start_x instead of loading the rows a separate kernel wrote (needs l0 == 0)
+  int fuse_start;
+  const float* start_x;   // input of this flow [B*T]
+  const float* start_w;   // [3][64]
+  const float* start_b;   // [64]
 };
 
 struct Range {  // the tiles a CTA owns
@@ -335,7 +342,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int k = 0; k < KMAX; ++k) {
-      ft_mbar_init(&B->own_loaded[k], 1);
+      ft_mbar_init(&B->own_loaded[k], p.fuse_start ? 8 : 1);
       ft_mbar_init(&B->tile_ready[k], 8);
       ft_mbar_init(&B->pub_done[k], 1);
       ft_mbar_init(&B->d2_full[k], 1);
@@ -345,6 +352,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
     ft_mbar_init(&B->wd_full, 1);
     ft_mbar_init(&B->wd_free, 1);
     ft_mbar_init(&B->l_init, 8);
+    ft_mbar_init(&B->halo0, 8);
     for (int b = 0; b < 2; ++b) {
       ft_mbar_init(&B->wr_full[b], 1);
       ft_mbar_init(&B->wr_free[b], 1);
@@ -406,7 +414,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       load_wd(p.l0);
       load_wr(p.l0, 0);
       if (nl > 1) load_wr(p.l0 + 1, 1);
-      {
+      if (!p.fuse_start) {
         const CUtensorMap* mh = (p.buf0 & 1) ? &map_h1 : &map_h0;
         const CUtensorMap* ml = (p.buf0 & 1) ? &map_l1 : &map_l0;
         for (int k = K - 1; k >= 0; --k) {
@@ -445,7 +453,9 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         const CUtensorMap* mh = rb ? &map_h1 : &map_h0;
         const CUtensorMap* ml = rb ? &map_l1 : &map_l0;
         if (2 * d <= BM) {
-          foreign(li, R.tk0 - 1, mh, ml);  // halo for own tile 0 (the last task of the layer)
+          // halo for own tile 0 (the last task of the layer); with the fused start conv the residual
+          // warps compute layer 0's halo themselves
+          if (!(p.fuse_start && li == 0)) foreign(li, R.tk0 - 1, mh, ml);
         } else {
           const int dt = d / BM;
           for (int k = K - 1; k >= 0; --k)
@@ -514,12 +524,14 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
           issue_tap(d1, (uint32_t)(1 + k) * TILE_B, 2);
           if (small) {
             // windows [128k - o, 128k - o + 128) of [halo | own], o = d, 2d
+            const bool own_halo = p.fuse_start && li == 0;
             if (k >= 1) wait_ready(k - 1, li);
+            else if (own_halo) ft_wait(&B->halo0, 0, "halo0");
             else ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full (halo)");
             ft_fence_after();
             issue_tap(d1, (uint32_t)((1 + k) * BM - d) * 128u, 1);
             issue_tap(d1, (uint32_t)((1 + k) * BM - 2 * d) * 128u, 0);
-            if (k == 0) {
+            if (k == 0 && !own_halo) {
               if (ft_elect()) ft_commit(&B->ring_free);
               __syncwarp();
               ++n_ring;
@@ -734,6 +746,50 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
     const int qd = warp & 3;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     const int row = qd * 32 + lane;  // row inside a tile
+    if (p.fuse_start) {
+      // init: start conv of the own tiles (-> TMEM master + smem planes) and of the halo (smem only;
+      // zeros at the start of a clip: the layer input is zero-padded, masked.py:203-204)
+      const float4* w4 = reinterpret_cast<const float4*>(p.start_w) + half * 8;
+      const float4* b4 = reinterpret_cast<const float4*>(p.start_b) + half * 8;
+      for (int k = K - 1; k >= -1; --k) {
+        const int t = (R.tk0 + k) * BM + row;  // time index inside the clip (negative only for the halo of tile 0)
+        const float* xr = p.start_x + (size_t)gclip * p.T + t;
+        const float x1 = t >= 1 ? __ldg(xr - 1) : 0.f, x2 = t >= 2 ? __ldg(xr - 2) : 0.f, x3 = t >= 3 ? __ldg(xr - 3) : 0.f;
+        const uint32_t cur_lo = sbase + OFF_LO + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+        const uint32_t cur_hi = sbase + OFF_HI + (uint32_t)(1 + k) * TILE_B + (uint32_t)row * 128u;
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w0 = __ldg(w4 + i), w1 = __ldg(w4 + 16 + i), w2 = __ldg(w4 + 32 + i), bb = __ldg(b4 + i);
+          float o[4];
+          o[0] = fmaf(w2.x, x1, fmaf(w1.x, x2, fmaf(w0.x, x3, bb.x)));
+          o[1] = fmaf(w2.y, x1, fmaf(w1.y, x2, fmaf(w0.y, x3, bb.y)));
+          o[2] = fmaf(w2.z, x1, fmaf(w1.z, x2, fmaf(w0.z, x3, bb.z)));
+          o[3] = fmaf(w2.w, x1, fmaf(w1.w, x2, fmaf(w0.w, x3, bb.w)));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[4 * i + e] = __float_as_uint(t >= 0 ? o[e] : 0.f);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t coff = (uint32_t)(((4 * half + jj) ^ (row & 7)) * 16);
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float o0 = __uint_as_float(v[8 * jj + 2 * e]), o1 = __uint_as_float(v[8 * jj + 2 * e + 1]);
+            const float a0 = __half2float(__float2half_rn(o0));
+            const float a1 = __half2float(__float2half_rn(o1));
+            hw[e] = ft_pack_f16(a0, a1);
+            lw[e] = ft_pack_f16(o0 - a0, o1 - a1);
+          }
+          ft_sts128(cur_hi + coff, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          ft_sts128(cur_lo + coff, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+        }
+        if (k >= 0) ft_tmem_st32(tmem + lane_sel + TM_L + k * 64 + half * 32, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) ft_arrive(k >= 0 ? &B->own_loaded[k] : &B->halo0);
+      }
+    } else {
     // init: L[k] = hi + lo of the start-conv output the loader fetched
     for (int k = K - 1; k >= 0; --k) {
       ft_wait(&B->own_loaded[k], 0, "own_loaded (E2)");
@@ -754,6 +810,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         }
       }
       ft_tmem_st32(tmem + lane_sel + TM_L + k * 64 + half * 32, v);
+    }
     }
     ft_tmem_st_wait();
     ft_fence_before();
@@ -873,7 +930,7 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
                    const void* map_wrh, const void* map_wrl, const float* cond_tiled, size_t cond_plane,
                    const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
                    unsigned int* sync_words /* >= nclips*T/128 + num_sms */, int num_sms, const FlowHead* head,
-                   cudaStream_t stream) {
+                   const FlowStart* start, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     NSW_CUDA(cudaFuncSetAttribute(iaf_flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -923,6 +980,10 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
     p.first = p.last = p.quantize = p.use_mu_law = 0;
   }
   p.T = T;
+  p.fuse_start = (start != nullptr && l0 == 0) ? 1 : 0;
+  p.start_x = start ? start->x : nullptr;
+  p.start_w = start ? start->w : nullptr;
+  p.start_b = start ? start->b : nullptr;
   p.dbg = nullptr;
   static long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr;
