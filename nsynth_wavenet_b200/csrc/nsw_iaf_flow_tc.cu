@@ -504,56 +504,96 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         }
         __syncwarp();
       };
+      // One burst per task: every wait and every descriptor is done BEFORE the first tcgen05.mma of the
+      // task, because the tensor pipe only buffers a few instructions: a pause between two taps
+      // (barrier test, fence, descriptor arithmetic) is a pipe bubble.  Only foreign whole-tile taps
+      // (d >= 128, one shared landing slot) are issued separately, after the burst.
+      auto issue_burst = [&](uint32_t d1, const uint32_t (&a_bytes)[3], const int (&taps)[3], int n) {
+        uint64_t alo[3], ahi[3], wh[3], wl[3];
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          alo[s2] = ft_desc_sw128(sbase_u + OFF_LO + a_bytes[s2]);
+          ahi[s2] = ft_desc_sw128(sbase_u + OFF_HI + a_bytes[s2]);
+          wh[s2] = ft_desc_sw128(sbase_u + OFF_WDH + taps[s2] * WD_TILE);
+          wl[s2] = ft_desc_sw128(sbase_u + OFF_WDL + taps[s2] * WD_TILE);
+        }
+        if (ft_elect()) {
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2) {
+            if (s2 < n) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ft_mma_ss(d1, alo[s2] + 2 * k, wh[s2] + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                ft_mma_ss(d1, ahi[s2] + 2 * k, wl[s2] + 2 * k, idesc, 1);
+                ft_mma_ss(d1, ahi[s2] + 2 * k, wh[s2] + 2 * k, idesc, 1);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      };
       int stage_mod = p.l0 % p.num_stages;
       int n_ring = 0, j = 0;
       for (int li = 0; li < nl; ++li) {
         const int d = 1 << stage_mod;
         if (++stage_mod == p.num_stages) stage_mod = 0;
         const bool small = 2 * d <= BM;
+        const int dt = d / BM;
         ft_wait(&B->wd_full, (uint32_t)(li & 1), "wd_full");
+        if (dbg && lane == 0 && li < 32) p.dbg[80 + li] = clock64() - tk_start;
         for (int kk = 0; kk < K; ++kk, ++j) {
           const int k = K - 1 - kk;
           const int b = j & 1;
           const uint32_t d1 = tmem_u + b * 64;
+          uint32_t a_bytes[3] = {(uint32_t)(1 + k) * TILE_B, 0u, 0u};
+          int taps[3] = {2, 1, 0};
+          int n = 1;
+          bool foreign[2] = {false, false};  // [tap] of the d >= 128 layers
+          bool halo_used = false;
           // D1[b] holds the conditioning rows of this task (written by the gate warps)
           ft_wait(&B->d1_empty[b], (uint32_t)((j >> 1) & 1), "d1_empty");
           if (dbg && j < 8 && lane == 0) p.dbg[64 + 2 * j] = clock64() - tk_start;
           wait_ready(k, li);
-          if (dbg && j < 8 && lane == 0) p.dbg[2 * j] = clock64() - tk_start;
-          ft_fence_after();
-          issue_tap(d1, (uint32_t)(1 + k) * TILE_B, 2);
           if (small) {
             // windows [128k - o, 128k - o + 128) of [halo | own], o = d, 2d
             const bool own_halo = p.fuse_start && li == 0;
             if (k >= 1) wait_ready(k - 1, li);
             else if (own_halo) ft_wait(&B->halo0, 0, "halo0");
-            else ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full (halo)");
-            ft_fence_after();
-            issue_tap(d1, (uint32_t)((1 + k) * BM - d) * 128u, 1);
-            issue_tap(d1, (uint32_t)((1 + k) * BM - 2 * d) * 128u, 0);
-            if (k == 0 && !own_halo) {
-              if (ft_elect()) ft_commit(&B->ring_free);
-              __syncwarp();
-              ++n_ring;
-            }
+            else { ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full (halo)"); halo_used = true; }
+            a_bytes[1] = (uint32_t)((1 + k) * BM - d) * 128u;
+            a_bytes[2] = (uint32_t)((1 + k) * BM - 2 * d) * 128u;
+            n = 3;
           } else {
-            const int dt = d / BM;
             for (int tap = 1; tap >= 0; --tap) {
               const int src = R.tk0 + k - (2 - tap) * dt;
               if (src < 0) continue;  // causal zeros
               if (src >= R.tk0) {
                 wait_ready(src - R.tk0, li);
-                ft_fence_after();
-                issue_tap(d1, (uint32_t)(1 + src - R.tk0) * TILE_B, tap);
+                a_bytes[n] = (uint32_t)(1 + src - R.tk0) * TILE_B;
+                taps[n] = tap;
+                ++n;
               } else {
-                ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full");
-                ft_fence_after();
-                issue_tap(d1, 0u, tap);
-                if (ft_elect()) ft_commit(&B->ring_free);
-                __syncwarp();
-                ++n_ring;
+                foreign[tap] = true;
               }
             }
+          }
+          if (dbg && j < 8 && lane == 0) p.dbg[2 * j] = clock64() - tk_start;
+          ft_fence_after();
+          issue_burst(d1, a_bytes, taps, n);
+          if (halo_used) {
+            if (ft_elect()) ft_commit(&B->ring_free);
+            __syncwarp();
+            ++n_ring;
+          }
+          for (int tap = 1; tap >= 0; --tap) {  // same order as the loader: t-d, then t-2d
+            if (!foreign[tap]) continue;
+            ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full");
+            ft_fence_after();
+            issue_tap(d1, 0u, tap);
+            if (ft_elect()) ft_commit(&B->ring_free);
+            __syncwarp();
+            ++n_ring;
           }
           if (ft_elect()) {
             ft_commit(&B->d1_full[b]);

@@ -130,14 +130,16 @@ __global__ void __launch_bounds__(128 + 512, 1) rate_kernel(long long* out, int 
 // the exact MMA1 operand pattern of iaf_flow_tc_kernel: hi / lo activation planes 80 KB apart, row-shifted
 // windows, 3 taps x (lo.Wh, hi.Wl, hi.Wh) x 4 k-steps = 36 MMAs per task, one commit per task
 template <int VARIANT>
-__global__ void __launch_bounds__(128, 1) pattern_kernel(long long* out, int tasks) {
+__global__ void __launch_bounds__(640, 1) pattern_kernel(long long* out, int tasks) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t dummy[8];
   __shared__ uint32_t tmem_s;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    for (int c = 0; c < 8; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy[c])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < (208 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -149,6 +151,16 @@ __global__ void __launch_bounds__(128, 1) pattern_kernel(long long* out, int tas
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp >= 4 && VARIANT >= 10) {
+    // warps parked in an mbarrier.try_wait spin (like the role warps of the flow kernel)
+    uint32_t ok = 0;
+    while (!ok) {
+      if (VARIANT == 10 || (threadIdx.x & 31) == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(&dummy[7])), "r"(0u) : "memory");
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+    }
+  }
   if (warp == 0) {
     const uint32_t tmem = __reduce_or_sync(0xffffffffu, tmem_s);
     const uint32_t sb = __reduce_or_sync(0xffffffffu, smem_u32(smem));
@@ -180,6 +192,11 @@ __global__ void __launch_bounds__(128, 1) pattern_kernel(long long* out, int tas
                          "l"(ahi + 2 * kk), "l"(wh + 2 * kk), "r"(idesc), "r"(1u) : "memory");
           }
         }
+        if (VARIANT >= 3 && VARIANT < 10) {
+          const int nc = VARIANT == 3 ? 1 : (VARIANT == 4 ? 3 : 5);
+          for (int c = 0; c < nc; ++c)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[c])) : "memory");
+        }
       }
       __syncwarp();
     }
@@ -187,11 +204,30 @@ __global__ void __launch_bounds__(128, 1) pattern_kernel(long long* out, int tas
     __syncwarp();
     mbar_wait(&bar, 0);
     long long t2 = clock64();
-    if (threadIdx.x == 0) { out[0] = t2 - t0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = t2 - t0; }
+    if (VARIANT >= 10 && threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&dummy[7])) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(512u) : "memory");
+}
+template <int VARIANT>
+void run_pattern_grid(const char* name, long long* d, int grid, int tasks) {
+  const size_t smem = 208 * 1024 + 2048;
+  cudaFuncSetAttribute(pattern_kernel<VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long h[2];
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  pattern_kernel<VARIANT><<<grid, 128, smem>>>(d, tasks);
+  cudaEventRecord(e0);
+  pattern_kernel<VARIANT><<<grid, 128, smem>>>(d, tasks);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("%-40s grid %3d tasks %6d: %.1f cyc per task (one CTA's clock64), %.3f ms -> %.0f MHz effective, %.1f ns per task\n", name, grid, tasks,
+         (double)h[0] / tasks, ms, (double)h[0] / (ms * 1e3), ms * 1e6 / tasks);
 }
 template <int VARIANT>
 void run_pattern(const char* name, long long* d) {
@@ -199,7 +235,7 @@ void run_pattern(const char* name, long long* d) {
   cudaFuncSetAttribute(pattern_kernel<VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long h[2];
   for (int rep = 0; rep < 2; ++rep) {
-    pattern_kernel<VARIANT><<<1, 128, smem>>>(d, 64);
+    pattern_kernel<VARIANT><<<1, VARIANT >= 10 ? 640 : 128, smem>>>(d, 64);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
   }
@@ -229,6 +265,14 @@ int main() {
   run_pattern<0>("flow kernel MMA1 pattern", d);
   run_pattern<1>("pattern, lo plane aliased onto hi plane", d);
   run_pattern<2>("pattern, Wl aliased onto Wh", d);
+  run_pattern_grid<0>("pattern, whole chip", d, 148, 20000);
+  run_pattern_grid<0>("pattern, one CTA", d, 1, 20000);
+  run_pattern_grid<0>("pattern, 74 CTAs", d, 74, 20000);
+  run_pattern<10>("pattern + 16 warps (all lanes) in try_wait", d);
+  run_pattern<11>("pattern + 16 warps (lane 0) in try_wait", d);
+  run_pattern<3>("pattern + 1 commit per task", d);
+  run_pattern<4>("pattern + 3 commits per task", d);
+  run_pattern<5>("pattern + 5 commits per task", d);
   run<64, 1, 0, 0>("SS same accumulator", d);
   run<64, 2, 0, 0>("SS 2 accumulators", d);
   run<64, 4, 0, 0>("SS 4 accumulators", d);
