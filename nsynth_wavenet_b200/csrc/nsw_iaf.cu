@@ -433,6 +433,7 @@ struct FlowWeights {
   DevBuf WdT_hi, WdT_lo;    // [L][3][64 pos][64 cin]
   DevBuf WrT_hi, WrT_lo;    // [L][64 c][32 j]
   DevBuf br_nat;            // [L][64] natural channel order
+  DevBuf br_cum;            // [L][64] running sum of br over layers (engine tc3 keeps the biases out of TMEM)
   alignas(64) unsigned char map_wdh[128], map_wdl[128], map_wrh[128], map_wrl[128];
   float bm = 0.f, bs = 0.f;
   int deconv_index = 0;     // which DeconvStack feeds this flow
@@ -556,6 +557,12 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
     NSW_TRY(upload(fw.WrT_hi, hi.data(), hi.size() * 2));
     NSW_TRY(upload(fw.WrT_lo, lo.data(), lo.size() * 2));
     NSW_TRY(upload(fw.br_nat, brn.data(), brn.size() * 4));
+    std::vector<float> brc(brn.size());
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.f;  // fp32 like the reference's sequential l += ... + br
+      for (int i = 0; i < L; ++i) { acc += brn[(size_t)i * C + c]; brc[(size_t)i * C + c] = acc; }
+    }
+    NSW_TRY(upload(fw.br_cum, brc.data(), brc.size() * 4));
     NSW_TRY(layer_tc_make_weight_map(fw.map_wdh, fw.WdT_hi.as<__half>(), (L * 3 + 1) * C, C));
     NSW_TRY(layer_tc_make_weight_map(fw.map_wdl, fw.WdT_lo.as<__half>(), (L * 3 + 1) * C, C));
     NSW_TRY(layer_tc_make_weight_map(fw.map_wrh, fw.WrT_hi.as<__half>(), L * C, HALF));
@@ -850,7 +857,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
           for (int c0 = 0; c0 < B; c0 += tc3_clips)
             NSW_TRY(flow_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
                                    h->cond.as<float>() + (size_t)l0 * rows * C, rows * C,
-                                   fw.br_nat.as<float>(), T, c0, std::min(tc3_clips, B - c0), cur, l0, l1,
+                                   fw.br_cum.as<float>(), T, c0, std::min(tc3_clips, B - c0), cur, l0, l1,
                                    cfg.num_stages, h->sync_words.as<unsigned int>(), h->num_sms,
                                    head_fused ? &fh : nullptr, head_fused ? &fs : nullptr, st));
         } else {

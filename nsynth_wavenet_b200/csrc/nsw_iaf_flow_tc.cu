@@ -264,7 +264,7 @@ __device__ __forceinline__ uint32_t ft_pack_f16(float a, float b) {
 struct FlowTcParams {
   const float* cond;      // tiled conditioning plane of layer l0 (see file header)
   size_t cond_plane;      // floats between consecutive layers' planes
-  const float* br;        // [L][64] residual bias, natural channel order
+  const float* br;        // [L][64] RUNNING SUM over layers of the residual biases, natural channel order
   unsigned int* flags;    // [clips * tiles_per_clip] layers published per tile   (zeroed per launch)
   unsigned int* cons;     // [grid] layers whose foreign loads a CTA has finished (zeroed per launch)
   int buf0, l0, l1, num_stages;
@@ -601,7 +601,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
               ft_commit(&B->wd_free);
               // every foreign tile of this layer has landed in shared memory: the global buffer it
               // came from may be overwritten (two layers from now) as far as this CTA is concerned
-              asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.cons + blockIdx.x), "r"((unsigned int)(li + 1))
+              // relaxed is enough: the foreign reads completed before the mbarrier flip this thread observed
+              asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.cons + blockIdx.x), "r"((unsigned int)(li + 1))
                            : "memory");
             }
             if (dbg && j < 8) p.dbg[2 * j + 1] = clock64() - tk_start;
@@ -780,8 +781,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
   } else if (warp < 18) {
     // =================================== E2: residual (8 warps) ===================================
     // The fp32 residual rows of the own tiles live in TMEM (L[k]); MMA2 accumulates g.Wr into them.
-    // E2 adds the bias, writes the sum back, and refreshes the tile's fp16 hi / lo planes in shared
-    // memory (the next layer's MMA operand, and what the publisher stores).
+    // E2 adds the running sum of the residual biases (kept out of TMEM so nothing is written back) and
+    // refreshes the tile's fp16 hi / lo planes in shared memory (the next layer's MMA operand, and what the publisher stores).
     const int half = (warp - 10) >> 2;
     const int qd = warp & 3;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
@@ -861,10 +862,20 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
     for (int j = 0; j < total; ++j) {
       const int b = j & 1;
       const int k = K - 1 - kk;
+      // TMEM holds l without the residual biases; p.br is their running sum over the layers (the sum up to
+      // layer l0-1 is already inside the rows this launch started from)
       const float4* bptr = reinterpret_cast<const float4*>(p.br + (size_t)(p.l0 + li) * C) + half * 8;
       float4 bb[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) bb[i] = __ldg(bptr + i);
+      if (p.l0 > 0) {
+        const float4* b0 = reinterpret_cast<const float4*>(p.br + (size_t)(p.l0 - 1) * C) + half * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = __ldg(b0 + i);
+          bb[i].x -= q.x; bb[i].y -= q.y; bb[i].z -= q.z; bb[i].w -= q.w;
+        }
+      }
       ft_wait(&B->d2_full[k], (uint32_t)(li & 1), "d2_full");
       if (dbg && warp == 10 && lane == 0 && j < 8) p.dbg[48 + 2 * j] = clock64() - tk_start;
       ft_fence_after();
@@ -878,7 +889,6 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         d[4 * i + 2] = __float_as_uint(__uint_as_float(d[4 * i + 2]) + bb[i].z);
         d[4 * i + 3] = __float_as_uint(__uint_as_float(d[4 * i + 3]) + bb[i].w);
       }
-      ft_tmem_st32(tmem + lane_sel + TM_L + k * 64 + half * 32, d);
       // the TMA store of this tile's previous published value must have finished reading it
       const uint32_t np = (npub >> (8 * k)) & 0xffu;
       if (np > 0) ft_wait(&B->pub_done[k], (np - 1) & 1, "pub_done");
@@ -901,7 +911,6 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         ft_sts128(cur_hi + coff, make_uint4(hw[0], hw[1], hw[2], hw[3]));
         ft_sts128(cur_lo + coff, make_uint4(lw[0], lw[1], lw[2], lw[3]));
       }
-      ft_tmem_st_wait();
       ft_fence_before();
       // generic-proxy writes to shared memory -> tcgen05.mma / TMA store reads (async proxy)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
