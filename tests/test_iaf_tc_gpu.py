@@ -75,3 +75,19 @@ def test_tc_and_ffma_engines_agree_at_full_size(student_hp, engine):
     again = a.forward_host(mel, z, quantize=False, want=KEYS)
     for k in KEYS:
         assert np.array_equal(again[k], oa[k])  # deterministic
+
+
+def test_tc3_many_clips_and_long_clip_paths(student_hp):
+    """engine tc3 beyond one launch: (a) more clips than one persistent launch takes (clip groups),
+    (b) a clip too long for the shared-memory-resident kernel (falls back to the tc2 layer kernel)."""
+    hp = student_hp
+    a, _ = make_engine(hp, 'tc3')
+    b, _ = make_engine(hp, 'ffma')
+    for batch, frames in ((80, 6), (1, 390)):   # 80 x 1024 samples: 74 clips per launch; 1 x 77824 samples: 608 tiles
+        mel, z = synth_inputs(hp, batch, frames)
+        oa = a.forward_host(mel, z, quantize=False, want=KEYS)
+        ob = b.forward_host(mel, z, quantize=False, want=KEYS)
+        for k in KEYS:
+            err = float(np.abs(oa[k] - ob[k]).max())
+            print('tc3 vs ffma', batch, 'x', frames, k, err)
+            assert err < TOL, (batch, frames, k, err)
