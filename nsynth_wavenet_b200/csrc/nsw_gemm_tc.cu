@@ -13,6 +13,8 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
+
 namespace nsw {
 
 namespace {
@@ -580,7 +582,7 @@ constexpr uint32_t CP_OFF_BARS = CP_OFF_W + CP_WSTAGES * CP_W_STAGE;
 constexpr size_t CP_SMEM_BYTES = CP_OFF_BARS + 1024 + 1024;
 
 struct CpBars {
-  uint64_t x_full, x_free;
+  uint64_t x_full[4], x_free[4];  // per 64-wide k-block of the resident activation tile
   uint64_t w_full[CP_WSTAGES], w_empty[CP_WSTAGES];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
@@ -589,10 +591,27 @@ struct CpBars {
 struct CondProj {
   int nclips, mclip, a_off, N;
   int tiles_per_clip, n_tiles;  // n-tiles of 128 columns
+  int cluster;                  // 1, or 2: CTA pairs work on two m-tiles in lock step and each CTA fetches half
+                                // of every weight stage, multicast into both (halves the L2 reads of W)
   const float* bias;
   float* out;  // [N/64] planes of nclips*mclip rows, row-interleaved
 };
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ bool tc_elect() {
   uint32_t pred;
   asm volatile(
@@ -606,6 +625,7 @@ __device__ __forceinline__ bool tc_elect() {
 __global__ void __launch_bounds__(CP_THREADS, 1)
 cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                    const __grid_constant__ CUtensorMap map_wh2, const __grid_constant__ CUtensorMap map_wl2,
                     CondProj g) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -614,9 +634,8 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   if (threadIdx.x == 0) {
-    mbar_init(&B->x_full, 1);
-    mbar_init(&B->x_free, 1);
-    for (int s = 0; s < CP_WSTAGES; ++s) { mbar_init(&B->w_full[s], 1); mbar_init(&B->w_empty[s], 1); }
+    for (int kb = 0; kb < 4; ++kb) { mbar_init(&B->x_full[kb], 1); mbar_init(&B->x_free[kb], 1); }
+    for (int s = 0; s < CP_WSTAGES; ++s) { mbar_init(&B->w_full[s], 1); mbar_init(&B->w_empty[s], (uint32_t)g.cluster); }
     for (int a = 0; a < 2; ++a) { mbar_init(&B->tmem_full[a], 1); mbar_init(&B->tmem_empty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -630,10 +649,18 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = B->tmem_base;
-  // work items = (m-tile, n-tile) pairs in m-major order; every CTA takes an equal contiguous share and
-  // (re)loads the activation tile whenever its share crosses into a new m-tile
-  const long long items = (long long)g.nclips * g.tiles_per_clip * g.n_tiles;
-  const int i0 = (int)(items * blockIdx.x / gridDim.x), i1 = (int)(items * (blockIdx.x + 1) / gridDim.x);
+  // work items = (m-tile, n-tile) pairs in m-major order; every CTA (or CTA pair: then an "m-tile" of the
+  // item list is a PAIR of m-tiles, one per CTA) takes an equal contiguous share and (re)loads the
+  // activation tile whenever its share crosses into a new m-tile
+  const int CS = g.cluster;
+  const int crank = CS == 2 ? (int)(blockIdx.x & 1) : 0;
+  const int n_groups = (int)gridDim.x / CS, group = (int)blockIdx.x / CS;
+  const long long items = (long long)(g.nclips * g.tiles_per_clip / CS) * g.n_tiles;
+  const int i0 = (int)(items * group / n_groups), i1 = (int)(items * (group + 1) / n_groups);
+  if (CS == 2) {
+    // barriers of both CTAs must be initialised before the peer multicasts into / arrives on them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -641,25 +668,38 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
       uint32_t wphase = 0;
       int xit = 0, cur_mt = -1;
       for (int i = i0; i < i1; ++i) {
-        const int mt = i / g.n_tiles, nt = i - mt * g.n_tiles;
-        if (mt != cur_mt) {
+        const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+        const int mt = mtg * CS + crank;
+        const bool new_x = mt != cur_mt;
+        int clip = 0, m0 = 0;
+        if (new_x) {
           cur_mt = mt;
-          const int clip = mt / g.tiles_per_clip;
-          const int m0 = (mt - clip * g.tiles_per_clip) * TBM;
-          if (xit > 0) mbar_wait(&B->x_free, (uint32_t)((xit - 1) & 1));
+          clip = mt / g.tiles_per_clip;
+          m0 = (mt - clip * g.tiles_per_clip) * TBM;
           ++xit;
-          mbar_expect_tx(&B->x_full, CP_X_BYTES);
-          for (int kb = 0; kb < 4; ++kb) {
-            tma_load_3d(sbase + (2 * kb) * TILE_BYTES, &map_xh, &B->x_full, kb * TBK, m0 + g.a_off, clip);
-            tma_load_3d(sbase + (2 * kb + 1) * TILE_BYTES, &map_xl, &B->x_full, kb * TBK, m0 + g.a_off, clip);
-          }
         }
         for (int kb = 0; kb < 4; ++kb) {
+          if (new_x) {
+            // k-block kb of the activation tile may be replaced as soon as the previous tile's last
+            // column block has consumed it: the reload overlaps the tail of the previous tile
+            if (xit > 1) mbar_wait(&B->x_free[kb], (uint32_t)((xit - 2) & 1));
+            mbar_expect_tx(&B->x_full[kb], 2 * TILE_BYTES);
+            tma_load_3d(sbase + (2 * kb) * TILE_BYTES, &map_xh, &B->x_full[kb], kb * TBK, m0 + g.a_off, clip);
+            tma_load_3d(sbase + (2 * kb + 1) * TILE_BYTES, &map_xl, &B->x_full[kb], kb * TBK, m0 + g.a_off, clip);
+          }
           mbar_wait(&B->w_empty[ws], wphase ^ 1);
           const uint32_t dst = sbase + CP_OFF_W + ws * CP_W_STAGE;
           mbar_expect_tx(&B->w_full[ws], CP_W_STAGE);
-          tma_load_2d(dst, &map_wh, &B->w_full[ws], kb * TBK, nt * TBN);
-          tma_load_2d(dst + TILE_BYTES, &map_wl, &B->w_full[ws], kb * TBK, nt * TBN);
+          if (CS == 1) {
+            tma_load_2d(dst, &map_wh, &B->w_full[ws], kb * TBK, nt * TBN);
+            tma_load_2d(dst + TILE_BYTES, &map_wl, &B->w_full[ws], kb * TBK, nt * TBN);
+          } else {
+            // this CTA fetches 64 of the 128 weight rows of both planes and multicasts them to the pair;
+            // the peer's half arrives the same way and completes the same transaction count
+            const uint32_t half = (uint32_t)crank * (TILE_BYTES / 2);
+            tma_load_2d_mc(dst + half, &map_wh2, &B->w_full[ws], kb * TBK, nt * TBN + crank * 64, 3);
+            tma_load_2d_mc(dst + TILE_BYTES + half, &map_wl2, &B->w_full[ws], kb * TBK, nt * TBN + crank * 64, 3);
+          }
           if (++ws == CP_WSTAGES) { ws = 0; wphase ^= 1; }
         }
       }
@@ -672,10 +712,10 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     uint32_t wphase = 0;
     int xit = 0, cur_mt = -1, acc_it = 0;
     for (int i = i0; i < i1; ++i, ++acc_it) {
-      const int mt = i / g.n_tiles;
-      if (mt != cur_mt) {
+      const int mt = i / g.n_tiles;  // m-tile (pair) index: only used to detect a change of activation tile
+      const bool first_of_x = mt != cur_mt;
+      if (first_of_x) {
         cur_mt = mt;
-        mbar_wait(&B->x_full, (uint32_t)(xit & 1));
         ++xit;
       }
       const bool last_of_x = (i + 1 == i1) || ((i + 1) / g.n_tiles != mt);
@@ -684,6 +724,7 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + (uint32_t)(as * TBN);
       for (int kb = 0; kb < 4; ++kb) {
+        if (first_of_x) mbar_wait(&B->x_full[kb], (uint32_t)((xit - 1) & 1));
         mbar_wait(&B->w_full[ws], wphase);
         tc_fence_after();
         const uint64_t xh = umma_desc_sw128(sbase_u + (2 * kb) * TILE_BYTES);
@@ -698,11 +739,10 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
             umma_f16(d_tmem, xh + adv, wl + adv, idesc, 1);
             umma_f16(d_tmem, xh + adv, wh + adv, idesc, 1);
           }
-          umma_commit(&B->w_empty[ws]);
-          if (kb == 3) {
-            umma_commit(&B->tmem_full[as]);
-            if (last_of_x) umma_commit(&B->x_free);
-          }
+          if (CS == 1) umma_commit(&B->w_empty[ws]);
+          else umma_commit_mc(&B->w_empty[ws], 3);  // the stage is refilled by BOTH CTAs of the pair
+          if (last_of_x) umma_commit(&B->x_free[kb]);
+          if (kb == 3) umma_commit(&B->tmem_full[as]);
         }
         __syncwarp();
         if (++ws == CP_WSTAGES) { ws = 0; wphase ^= 1; }
@@ -715,7 +755,8 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     const size_t M = (size_t)g.nclips * g.mclip;
     int acc_it = 0;
     for (int i = i0; i < i1; ++i, ++acc_it) {
-      const int mt = i / g.n_tiles, nt = i - mt * g.n_tiles;
+      const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+      const int mt = mtg * CS + crank;
       const size_t tile_base = ((size_t)mt * 8 + q * 2) * 1024;  // + h * 1024 + j * 128 + lane * 4
       const int as = acc_it & 1;
       mbar_wait(&B->tmem_full[as], (uint32_t)((acc_it >> 1) & 1));
@@ -744,6 +785,10 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (CS == 2) {
+    // do not exit while the peer may still multicast into this CTA's shared memory or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -836,6 +881,14 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
     NSW_TRY(make_map(enc, &mwh, Bt_hi, 2, dims, strides, box));
     NSW_TRY(make_map(enc, &mwl, Bt_lo, 2, dims, strides, box));
   }
+  CUtensorMap mwh2, mwl2;  // half-height weight boxes for the CTA-pair multicast
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {TBK, TBN / 2};
+    NSW_TRY(make_map(enc, &mwh2, Bt_hi, 2, dims, strides, box));
+    NSW_TRY(make_map(enc, &mwl2, Bt_lo, 2, dims, strides, box));
+  }
   static bool attr_set = false;
   if (!attr_set) {
     NSW_CUDA(cudaFuncSetAttribute(cond_proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -855,8 +908,36 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
   const long long items = (long long)nclips * g.tiles_per_clip * g.n_tiles;
   g.bias = bias;
   g.out = out_tiled;
-  const int grid = (int)std::min<long long>(items, sms);
-  cond_proj_tc_kernel<<<grid, CP_THREADS, CP_SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, g);
+  const bool pair = getenv("NSW_COND_NOCLUSTER") == nullptr && (nclips * g.tiles_per_clip) % 2 == 0 && sms >= 2;
+  g.cluster = pair ? 2 : 1;
+  if (pair) {
+    const long long pair_items = items / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms & ~1);
+    cfg.blockDim = dim3(CP_THREADS);
+    cfg.dynamicSmemBytes = CP_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // the shares are static, so every pair must be resident at once: GPCs with an odd SM count cannot
+    // pair their last SM
+    static int max_pairs = -1;
+    if (max_pairs < 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, cond_proj_tc_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+      max_pairs = n;
+    }
+    cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(pair_items, std::min(max_pairs, sms / 2)));
+    NSW_CUDA(cudaLaunchKernelEx(&cfg, cond_proj_tc_kernel, mxh, mxl, mwh, mwl, mwh2, mwl2, g));
+  } else {
+    const int grid = (int)std::min<long long>(items, sms);
+    cond_proj_tc_kernel<<<grid, CP_THREADS, CP_SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, mwh2, mwl2, g);
+  }
   count_launch();
   NSW_CUDA(cudaGetLastError());
   return NSW_OK;
