@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace nsw {
 
@@ -450,7 +451,13 @@ struct nsw_iaf {
   int ws_B = 0, ws_F = 0;
   DevBuf mel, mel_en, mel_en_split, cond, l0, l1, x, z, mean_tot, scale_tot, log_scale_tot,
       deconv_scratch, ls0, ls1, grid_counter, sync_words, x2;
-  float* x_final = nullptr;  // which of x / x2 holds the last forward's output  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
+  float* x_final = nullptr;  // which of x / x2 holds the last forward's output
+  // the forward of a given (B, F, quantize) replayed as a CUDA graph from its third call on (engine tc3)
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_B = 0, graph_F = 0, graph_quant = -1, graph_seen = 0;
+  uint64_t graph_launches = 0;  // kernels inside the captured graph
+  float* graph_x_final = nullptr;
+  cudaEvent_t graph_ev_in = nullptr, graph_ev_out = nullptr;  // hand-over when the caller's stream is the legacy one  // ls*: fp16 hi plane then lo plane of l0 / l1 (tc2 engine)
   alignas(64) unsigned char map_act[2][2][128];  // [buffer][hi, lo]
   int map_B = 0, map_T = 0;
   // debug tap
@@ -651,6 +658,9 @@ extern "C" void nsw_iaf_destroy(nsw_iaf* h) {
   if (h->ev_ready)
     for (auto& e : h->ev) cudaEventDestroy(e);
   if (h->pin) cudaFreeHost(h->pin);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->graph_ev_in) cudaEventDestroy(h->graph_ev_in);
+  if (h->graph_ev_out) cudaEventDestroy(h->graph_ev_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -937,6 +947,75 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
   return NSW_OK;
 }
 
+// Forward with launch overhead removed: the sequence of ~11 launches (memsets, cooperative kernels)
+// of one (B, F, quantize) shape is captured once and replayed as a CUDA graph; noise is drawn
+// outside the graph because its seed changes per call.  Anything unusual (profiling, debug tap,
+// other engines, capture failure) takes the direct path.
+static int iaf_forward_graphed(nsw_iaf* h, int B, int F, bool have_z, uint64_t seed, int quantize,
+                               cudaStream_t st) {
+  // measured gain on B200: 0.5 % of the step (the launches already queue ahead of the GPU), so it is opt-in
+  static const bool use_graph = getenv("NSW_USE_GRAPH") != nullptr;
+  const bool eligible = use_graph && h->cfg.engine == NSW_ENGINE_TC3 && !h->profiling && h->tap_flow < 0;
+  if (!eligible) return iaf_forward_internal(h, B, F, have_z, seed, quantize, st);
+  if (h->graph_B != B || h->graph_F != F || h->graph_quant != quantize) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    h->graph_B = B; h->graph_F = F; h->graph_quant = quantize; h->graph_seen = 0;
+  }
+  if (h->graph_seen >= 0) ++h->graph_seen;
+  if (h->graph_seen >= 0 && h->graph_seen < 3) return iaf_forward_internal(h, B, F, have_z, seed, quantize, st);
+  // the legacy default stream cannot be captured: run on the handle's own stream, ordered by events
+  cudaStream_t user = st;
+  const bool handover = (st == nullptr || st == cudaStreamLegacy);
+  if (handover) {
+    if (!h->graph_ev_in) {
+      NSW_CUDA(cudaEventCreateWithFlags(&h->graph_ev_in, cudaEventDisableTiming));
+      NSW_CUDA(cudaEventCreateWithFlags(&h->graph_ev_out, cudaEventDisableTiming));
+    }
+    st = h->own_stream;
+    NSW_CUDA(cudaEventRecord(h->graph_ev_in, user));
+    NSW_CUDA(cudaStreamWaitEvent(st, h->graph_ev_in, 0));
+  }
+  struct Rejoin {
+    nsw_iaf* h; cudaStream_t user, st; bool on;
+    ~Rejoin() { if (on) { cudaEventRecord(h->graph_ev_out, st); cudaStreamWaitEvent(user, h->graph_ev_out, 0); } }
+  } rejoin{h, user, st, handover};
+  if (!have_z) {
+    const size_t rows = (size_t)B * nsw_iaf_length(h, F);
+    const size_t n4 = (rows + 3) / 4;
+    iaf_noise_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(h->z.as<float>(), rows, seed,
+                                                                    h->cfg.loss_type == NSW_LOSS_GAUSS);
+    count_launch();
+  }
+  if (!h->graph_exec && h->graph_seen >= 0) {
+    cudaGraph_t graph = nullptr;
+    const uint64_t l0 = g_launch_count.load();
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int rc = NSW_OK;
+    if (ok) {
+      rc = iaf_forward_internal(h, B, F, true, seed, quantize, st);
+      ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && rc == NSW_OK && graph != nullptr;
+    }
+    h->graph_launches = g_launch_count.load() - l0;
+    g_launch_count.fetch_sub(h->graph_launches);  // counted when the graph is launched
+    if (ok) ok = cudaGraphInstantiate(&h->graph_exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      h->graph_exec = nullptr;
+      h->graph_seen = -1;  // do not try again for this shape
+      return iaf_forward_internal(h, B, F, true, seed, quantize, st);
+    }
+    h->graph_x_final = h->x_final;
+  }
+  if (h->graph_exec) {
+    NSW_CUDA(cudaGraphLaunch(h->graph_exec, st));
+    count_launch((int)h->graph_launches);
+    h->x_final = h->graph_x_final;
+    return NSW_OK;
+  }
+  return iaf_forward_internal(h, B, F, true, seed, quantize, st);
+}
+
 extern "C" int nsw_iaf_forward_device(nsw_iaf* h, const float* d_mel, const float* d_z,
                                       uint64_t seed, int32_t B, int32_t F, int32_t quantize,
                                       float* d_x, float* d_mean_tot, float* d_scale_tot,
@@ -950,7 +1029,7 @@ extern "C" int nsw_iaf_forward_device(nsw_iaf* h, const float* d_mel, const floa
   NSW_CUDA(cudaMemcpyAsync(h->mel.p, d_mel, (size_t)B * F * h->cfg.num_mel * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
   if (d_z) NSW_CUDA(cudaMemcpyAsync(h->z.p, d_z, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  NSW_TRY(iaf_forward_internal(h, B, F, d_z != nullptr, seed, quantize, st));
+  NSW_TRY(iaf_forward_graphed(h, B, F, d_z != nullptr, seed, quantize, st));
   const size_t nb = rows * sizeof(float);
   if (d_x) NSW_CUDA(cudaMemcpyAsync(d_x, h->x_final, nb, cudaMemcpyDeviceToDevice, st));
   if (d_mean_tot) NSW_CUDA(cudaMemcpyAsync(d_mean_tot, h->mean_tot.p, nb, cudaMemcpyDeviceToDevice, st));
@@ -974,7 +1053,7 @@ extern "C" int nsw_iaf_forward_host(nsw_iaf* h, const float* mel, const float* z
   NSW_CUDA(cudaMemcpyAsync(h->mel.p, mel, (size_t)B * F * h->cfg.num_mel * sizeof(float),
                            cudaMemcpyHostToDevice, st));
   if (z) NSW_CUDA(cudaMemcpyAsync(h->z.p, z, rows * sizeof(float), cudaMemcpyHostToDevice, st));
-  NSW_TRY(iaf_forward_internal(h, B, F, z != nullptr, seed, quantize, st));
+  NSW_TRY(iaf_forward_graphed(h, B, F, z != nullptr, seed, quantize, st));
   const size_t nb = rows * sizeof(float);
   if (x) NSW_CUDA(cudaMemcpyAsync(x, h->x_final, nb, cudaMemcpyDeviceToHost, st));
   if (mean_tot) NSW_CUDA(cudaMemcpyAsync(mean_tot, h->mean_tot.p, nb, cudaMemcpyDeviceToHost, st));

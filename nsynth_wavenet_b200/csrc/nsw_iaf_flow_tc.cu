@@ -382,6 +382,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
   const int gclip = p.clip0 + R.clip;                 // clip coordinate in the tensor maps
   const int gt0 = gclip * p.tiles_per_clip + R.tk0;   // global tile id of own tile 0
   const long long tk_start = clock64();
+  unsigned long long gt_start = 0;
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_start));
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
 
   // does the output of (own tile k, layer li) have a reader outside this CTA?
@@ -958,7 +960,12 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 
   ft_fence_before();
   __syncthreads();
-  if (dbg && threadIdx.x == 0) p.dbg[127] = clock64() - tk_start;
+  if (dbg && threadIdx.x == 0) {
+    p.dbg[127] = clock64() - tk_start;
+    unsigned long long gt_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_end));
+    p.dbg[126] = (long long)(gt_end - gt_start);  // ns
+  }
   if (warp == 1) {
     ft_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -1046,15 +1053,20 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
                   const_cast<void*>(map_wdh), const_cast<void*>(map_wdl), const_cast<void*>(map_wrh),
                   const_cast<void*>(map_wrl), &p};
   // cooperative launch: the per-tile flags need every CTA to be co-resident
-  NSW_CUDA(cudaLaunchCooperativeKernel((void*)iaf_flow_tc_kernel, dim3(grid), dim3(FT_THREADS), args,
-                                       FT_SMEM_BYTES, stream));
+  static const bool no_coop = getenv("NSW_FLOW_NOCOOP") != nullptr;  // timing experiment
+  if (no_coop)
+    NSW_CUDA(cudaLaunchKernel((void*)iaf_flow_tc_kernel, dim3(grid), dim3(FT_THREADS), args, FT_SMEM_BYTES, stream));
+  else
+    NSW_CUDA(cudaLaunchCooperativeKernel((void*)iaf_flow_tc_kernel, dim3(grid), dim3(FT_THREADS), args,
+                                         FT_SMEM_BYTES, stream));
   count_launch();
   NSW_CUDA(cudaGetLastError());
   if (want_dbg) {
     long long h[128];
     NSW_CUDA(cudaStreamSynchronize(stream));
     NSW_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[flow_tc dbg layers %d..%d grid %d] end %lld\n", l0, l1, grid, h[127]);
+    fprintf(stderr, "[flow_tc dbg layers %d..%d grid %d] end %lld cycles in %lld ns = %.0f MHz\n", l0, l1, grid, h[127], h[126],
+            h[126] > 0 ? 1e3 * (double)h[127] / (double)h[126] : 0.0);
     const char* names[4] = {"MMA1 (operands ready, issued)", "MMA2 (g ready, issued)", "E1   (D1 ready, g stored)",
                             "E2   (D2 ready, tile stored)"};
     for (int r = 0; r < 4; ++r) {
