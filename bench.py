@@ -351,16 +351,28 @@ def main():
     n_planes = n_layers + len(hp.num_iaf_layers)
     layer_launch_ms = stage['layers'] / n_layers
     hbm_peak, tc_peak, peak_kind = measured_peaks()
-    layer_gbs = LAYER_BYTES_PER_SAMPLE * B * T / (layer_launch_ms * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per layer pass,
-    # like bytes_per_launch); only valid for the shape and engine it was captured on
-    traffic, traffic_src = None, None
-    ncu_json = os.path.join(ROOT, 'profiles', 'r01', 'flow_tc_ncu_run21.json')
-    if eng.engine == 'tc3' and (B, T) == (8, 7680) and os.path.exists(ncu_json):
+    n_flows = len(hp.num_iaf_layers)
+    fused = eng.engine == 'tc3'
+    # algorithmic bytes of the 'layers' stage: 768 B per (sample, layer); engine tc3 also runs the
+    # start conv (read x 4 B + write l 256 B) and the head (l 256 + cond 256 + ~40 B of x / totals) of every
+    # flow inside the same kernel, so they are part of both the bytes and the time
+    stage_bytes = B * T * (LAYER_BYTES_PER_SAMPLE * n_layers + (n_flows * (260 + 552) if fused else 0))
+    n_launches = n_flows if fused else n_layers
+    layer_gbs = stage_bytes / (stage['layers'] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (one 10-layer flow launch);
+    # only valid for the shape and engine it was captured on
+    traffic, traffic_src, traffic_alg = None, None, None
+    ncu_json = os.path.join(ROOT, 'profiles', 'r01', 'tc3_ncu_run28.json')
+    if fused and (B, T) == (8, 7680) and os.path.exists(ncu_json):
         with open(ncu_json) as f:
-            cap = json.load(f)['launches'][0]
-        traffic = (float(cap['dram__bytes_read.sum']['value']) + float(cap['dram__bytes_write.sum']['value'])) * 1e6 / 10
-        traffic_src = 'profiles/r01/flow_tc_ncu_run21.json (dram__bytes_read+write of one 10-layer launch / 10)'
+            caps = [c for c in json.load(f)['launches'] if 'iaf_flow_tc' in c['kernel']]
+        if caps:
+            cap = caps[0]
+            traffic = (float(cap['dram__bytes_read.sum']['value']) + float(cap['dram__bytes_write.sum']['value'])) * 1e6
+            traffic_alg = B * T * (LAYER_BYTES_PER_SAMPLE * 10 + 812)
+            traffic_src = ('profiles/r01/tc3_ncu_run28.json: dram__bytes_read+write of one iaf_flow_tc_kernel launch '
+                           '(10-layer flow incl. start conv and head); traffic_launch_algorithmic_bytes is the same '
+                           'launch under the 768 B model')
     cond_tflops = COND_FLOP_PER_SAMPLE_PLANE * n_planes * B * T / (stage['cond'] * 1e-3) / 1e12
 
     line = {
@@ -368,8 +380,10 @@ def main():
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {
-            'workload': 'configs[2]: parallel WaveNet 4-flow IAF student ({}), batch {}x{} samples '
-                        'per GPU, synthetic mel, device-drawn noise'.format(CONFIGS[args.config], B, T),
+            'workload': ('configs[2]: parallel WaveNet 4-flow IAF student ({}), batch {}x{} samples '
+                         'per GPU, synthetic mel, device-drawn noise' if args.config == 'student' else
+                         'configs[3] per-GPU share: ClariNet Gaussian IAF ({}), batch {}x{} samples per GPU, '
+                         'synthetic mel, device-drawn noise').format(CONFIGS[args.config], B, T),
             'clips_per_gpu': B, 'samples_per_clip': T, 'engine': eng.engine,
             'l2': 'flushed between timed iterations (256 MB write)', 'parallelism': 'clips x{}'.format(world),
         },
@@ -381,11 +395,13 @@ def main():
         'clocks': sampler.summary(),
         'roofline': {
             'kernel': {'tc3': 'iaf_flow_tc_kernel', 'tc2': 'iaf_layer_tc_kernel'}.get(eng.engine, 'iaf_layer_kernel'), 'bound': 'hbm', 'achieved': layer_gbs, 'peak': hbm_peak,
-            'unit': 'GB/s', 'frac': layer_gbs / hbm_peak, 'traffic': traffic, 'traffic_source': traffic_src,
-            'unit_of_launch': 'one residual layer over the whole batch (engine tc3 runs all layers of a flow '
-                              'in one persistent launch; time = layers stage / number of layers)',
+            'unit': 'GB/s', 'frac': layer_gbs / hbm_peak, 'traffic': traffic,
+            'traffic_launch_algorithmic_bytes': traffic_alg, 'traffic_source': traffic_src,
+            'unit_of_launch': ('one flow (start conv + all residual layers + head) over the whole batch; '
+                               'bytes_per_launch and launch_ms are the averages over the flows'
+                               if fused else 'one residual layer over the whole batch'),
             'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
-            'bytes_per_launch': LAYER_BYTES_PER_SAMPLE * B * T, 'launch_ms': layer_launch_ms,
+            'bytes_per_launch': stage_bytes / n_launches, 'launch_ms': stage['layers'] / n_launches,
             'share_of_step': stage['layers'] / stage['total'],
         },
         'roofline_cond_gemm': {
