@@ -243,6 +243,50 @@ void run_pattern(const char* name, long long* d) {
   printf("%-50s: %.1f cyc per 36-MMA task = %.1f cyc/MMA\n", name, (double)h[0] / 64, (double)h[0] / 64 / 36);
 }
 
+__global__ void __launch_bounds__(128, 1) depth_kernel(long long* out, int n) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_s;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) {
+    const uint32_t tmem = __reduce_or_sync(0xffffffffu, tmem_s);
+    const uint32_t sb = __reduce_or_sync(0xffffffffu, smem_u32(smem));
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc = (uint64_t)((sb >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint64_t bdesc = (uint64_t)(((sb + 32768) >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    long long t0 = clock64(), t1 = 0;
+    if (elect()) {
+      for (int i = 0; i < n; ++i)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+                     "l"(adesc + 2 * (i & 3)), "l"(bdesc + 2 * (i & 3)), "r"(idesc), "r"(1u) : "memory");
+      t1 = clock64();
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      out[0] = t1 - t0;
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) out[1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(512u) : "memory");
+}
+
 template <int N, int NACC, int ROWSHIFT, int TS, int NOISE = 0>
 void run(const char* name, long long* d) {
   const int iters = 64;
@@ -261,7 +305,18 @@ void run(const char* name, long long* d) {
 
 int main() {
   long long* d;
-  cudaMalloc(&d, 16);
+  cudaMalloc(&d, 64);
+  {
+    const size_t smem = 64 * 1024 + 2048;
+    cudaFuncSetAttribute(depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int ns[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+    for (int n : ns) {
+      long long h[2];
+      for (int rep = 0; rep < 2; ++rep) { depth_kernel<<<1, 128, smem>>>(d, n); cudaDeviceSynchronize(); }
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      printf("queue depth probe: %2d SS MMAs (N=64) from an idle pipe: issue returns after %5lld cycles, all complete after %5lld\n", n, h[0], h[1]);
+    }
+  }
   run_pattern<0>("flow kernel MMA1 pattern", d);
   run_pattern<1>("pattern, lo plane aliased onto hi plane", d);
   run_pattern<2>("pattern, Wl aliased onto Wh", d);
