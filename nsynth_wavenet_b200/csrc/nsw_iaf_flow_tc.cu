@@ -237,6 +237,15 @@ __device__ __forceinline__ void ft_tmem_st32(uint32_t taddr, const uint32_t* r) 
 }
 __device__ __forceinline__ void ft_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// streaming 16-byte load that does not allocate in L1: the L1 / shared-memory data array is the scarce resource
+// of this kernel (the SS MMAs alone fetch their operands at ~125 of its 128 B/clk)
+__device__ __forceinline__ float4 ft_ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void ft_sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
@@ -690,7 +699,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       float4 cn[8];
       const float4* src = cond_ptr(j);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cn[i] = __ldg(src + i * 32);
+      for (int i = 0; i < 8; ++i) cn[i] = ft_ldg_stream(src + i * 32);
       preload(j, cn);
     }
     for (int j = 0; j < total1; ++j) {
@@ -699,7 +708,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       if (j + 2 < total1) {
         const float4* src = cond_ptr(j + 2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cn[i] = __ldg(src + i * 32);
+        for (int i = 0; i < 8; ++i) cn[i] = ft_ldg_stream(src + i * 32);
       }
       ft_wait(&B->d1_full[b], (uint32_t)((j >> 1) & 1), "d1_full");
       if (dbg && warp == 2 && lane == 0 && j < 8) p.dbg[32 + 2 * j] = clock64() - tk_start;

@@ -243,6 +243,125 @@ void run_pattern(const char* name, long long* d) {
   printf("%-50s: %.1f cyc per 36-MMA task = %.1f cyc/MMA\n", name, (double)h[0] / 64, (double)h[0] / 64 / 36);
 }
 
+// TMEM contention: 8 warps loop over tcgen05.ld.x32 (+ optional tcgen05.st.x32) on their own columns while
+// warp 0 issues the flow kernel's MMA pattern (or just spins for the same time): iterations per warp tell how
+// much the epilogues' TMEM traffic is slowed down by the accumulating MMAs and vice versa
+template <int MMA_ON, int WITH_ST>
+__global__ void __launch_bounds__(128 + 256, 1) tmem_contention_kernel(long long* out, int tasks) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_s;
+  __shared__ volatile int stop_flag;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    stop_flag = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < (208 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) {
+    const uint32_t tmem = __reduce_or_sync(0xffffffffu, tmem_s);
+    const uint32_t sb = __reduce_or_sync(0xffffffffu, smem_u32(smem));
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto desc = [](uint32_t a) -> uint64_t {
+      return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    };
+    const uint32_t OFF_LO = 81920, OFF_WDH = 163840, OFF_WDL = OFF_WDH + 24576;
+    long long t0 = clock64();
+    if (MMA_ON) {
+      for (int t = 0; t < tasks; ++t) {
+        const int k = 3 - (t & 3);
+        if (elect()) {
+#pragma unroll
+          for (int seg = 0; seg < 3; ++seg) {
+            const uint32_t arow = (uint32_t)((1 + k) * 128 - seg * 4) * 128u;
+            const uint64_t alo = desc(sb + OFF_LO + arow), ahi = desc(sb + arow);
+            const uint64_t wh = desc(sb + OFF_WDH + (2 - seg) * 8192), wl = desc(sb + OFF_WDL + (2 - seg) * 8192);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (t & 1) * 64),
+                           "l"(alo + 2 * kk), "l"(wh + 2 * kk), "r"(idesc), "r"(1u) : "memory");
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (t & 1) * 64),
+                           "l"(ahi + 2 * kk), "l"(wl + 2 * kk), "r"(idesc), "r"(1u) : "memory");
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (t & 1) * 64),
+                           "l"(ahi + 2 * kk), "l"(wh + 2 * kk), "r"(idesc), "r"(1u) : "memory");
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (elect()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      __syncwarp();
+      mbar_wait(&bar, 0);
+    } else {
+      while (clock64() - t0 < (long long)tasks * 1736) {}
+    }
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t2 - t0; stop_flag = 1; }
+  }
+  if (warp >= 4) {
+    long long iters = 0;
+    uint32_t r[32];
+    for (int i = 0; i < 32; ++i) r[i] = i;
+    const uint32_t addr = tmem_s + ((uint32_t)((warp & 3) * 32) << 16) + 192 + ((warp >> 2) & 1) * 32;
+    while (!stop_flag) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+            "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+            "=r"(r[30]), "=r"(r[31])
+          : "r"(addr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (WITH_ST) {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(addr),
+            "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+            "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+            "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+            "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      ++iters;
+    }
+    if (threadIdx.x == 128) out[2] = iters;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(512u) : "memory");
+}
+template <int MMA_ON, int WITH_ST>
+void run_tmem(const char* name, long long* d) {
+  const size_t smem = 208 * 1024 + 2048;
+  cudaFuncSetAttribute(tmem_contention_kernel<MMA_ON, WITH_ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long h[3];
+  for (int rep = 0; rep < 2; ++rep) {
+    tmem_contention_kernel<MMA_ON, WITH_ST><<<1, 384, smem>>>(d, 64);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("%-46s: %.1f cyc per 36-MMA task; each of 8 warps did one 4 KB TMEM ld%s every %.1f cycles\n", name, (double)h[0] / 64,
+         WITH_ST ? "+st" : "", (double)h[0] / (double)(h[2] > 0 ? h[2] : 1));
+}
+
 __global__ void __launch_bounds__(128, 1) depth_kernel(long long* out, int n) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -306,6 +425,10 @@ void run(const char* name, long long* d) {
 int main() {
   long long* d;
   cudaMalloc(&d, 64);
+  run_tmem<0, 0>("TMEM ld loop, no MMAs", d);
+  run_tmem<1, 0>("TMEM ld loop + MMA pattern", d);
+  run_tmem<0, 1>("TMEM ld+st loop, no MMAs", d);
+  run_tmem<1, 1>("TMEM ld+st loop + MMA pattern", d);
   {
     const size_t smem = 64 * 1024 + 2048;
     cudaFuncSetAttribute(depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
