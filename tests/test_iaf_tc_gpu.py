@@ -91,3 +91,19 @@ def test_tc3_many_clips_and_long_clip_paths(student_hp):
             err = float(np.abs(oa[k] - ob[k]).max())
             print('tc3 vs ffma', batch, 'x', frames, k, err)
             assert err < TOL, (batch, frames, k, err)
+
+
+@pytest.mark.parametrize('batch,frames', [(1, 3), (3, 13), (5, 39), (2, 160)])
+def test_tc3_odd_shapes_agree_with_ffma(student_hp, batch, frames):
+    """tiles per CTA from 1 to 4, clips that do not divide the SM count, a single 512-sample clip"""
+    hp = student_hp
+    a, _ = make_engine(hp, 'tc3')
+    b, _ = make_engine(hp, 'ffma')
+    mel, z = synth_inputs(hp, batch, frames)
+    oa = a.forward_host(mel, z, quantize=True, want=('x',) + KEYS)
+    ob = b.forward_host(mel, z, quantize=True, want=('x',) + KEYS)
+    for k in KEYS:
+        err = float(np.abs(oa[k] - ob[k]).max())
+        assert err < TOL, (batch, frames, k, err)
+    # quantised output: identical up to one 16-bit step where x sits on a rounding boundary
+    assert np.abs(oa['x'] - ob['x']).max() <= 1.0 / 32768 + 1e-7
