@@ -1,5 +1,7 @@
 #!/bin/bash
 # timing experiments on the flow kernel (results numerically wrong by construction): what slows the MMA1 burst?
+# NOTE: needs the NSW_FLOW_EXP instrumentation patch (strip switches in iaf_flow_tc_kernel) that was applied for this
+# run only and is not part of the committed kernel; the numbers it produced are in profiles/r01/README.md
 mkdir -p gpurun_out
 for e in 0 31 1 2 4 8 16 6 30; do
   NSW_FLOW_EXP=$e timeout 300 python bench.py --steps 10 --warmup 3 --no-fastgen --no-distill --no-cpu-baseline > gpurun_out/exp22_$e.json 2> gpurun_out/exp22_$e.err

@@ -1,4 +1,6 @@
 #!/bin/bash
+# CUDA-graph replay A/B.  NOTE: at the time of this run the switch was NSW_NO_GRAPH (graph on by default); the committed
+# code has it opt-in as NSW_USE_GRAPH=1 because the gain was 0.5 %
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_iaf_tc_gpu.py tests/test_iaf_gpu.py -x -q --timeout 600 > gpurun_out/test27.log 2>&1; echo "iaf tests rc=$?"
 tail -3 gpurun_out/test27.log
