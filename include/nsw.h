@@ -200,6 +200,14 @@ int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tenso
                           int32_t n_tensors, float* blocks, int64_t blocks_cap, float* cond_w,
                           float* cond_b, int64_t* sizes);
 
+/* TEST HOOK (host only, no CUDA): work split and publish / read plan of one launch of the persistent IAF flow kernel
+ * (engine NSW_ENGINE_TC3), computed by the same integer functions the kernel uses.  Per CTA: {clip, first tile, tiles,
+ * CTAs of the clip} then (l1-l0)*tiles records {published, source of tap t-2d, source of tap t-d} with source >= 0 a
+ * foreign tile of the clip read from the published global copy, -1 own shared memory, -2 causal zeros.  Returns the
+ * grid size (>0) or a negative NSW_E* code; *n_out = number of ints written (or needed when cap is too small). */
+int nsw_flow_plan_host(int32_t T, int32_t nclips, int32_t num_sms, int32_t l0, int32_t l1, int32_t num_stages,
+                       int32_t fuse_head, int32_t* out, int64_t cap, int64_t* n_out);
+
 /* ---- teacher full-sequence forward + distillation cross-entropy (BASELINE config 5) --------
  * replaces: Wavenet.feed_forward (wavenet.py:180-291) as called by
  * ParallelWavenet.kl_loss_logistic (parallel_wavenet.py:382) — every contraction on tcgen05. */

@@ -306,34 +306,55 @@ struct FlowTcParams {
   const float* start_b;   // [64]
 };
 
+// ---- work split and publish rules: plain integer functions shared by the kernel and by the host test hook
+//      nsw_flow_plan_host (tests/test_flow_plan.py checks on the CPU that every cross-CTA read has a publish) ----
 struct Range {  // the tiles a CTA owns
   int clip, tk0, K, idx, n_c;
 };
-__device__ __forceinline__ Range ft_range(const FlowTcParams& p, int b) {
+__host__ __device__ __forceinline__ Range ft_range_of(int tiles_per_clip, int cta_base, int cta_rem, int b) {
   Range r;
-  const int big = p.cta_rem * (p.cta_base + 1);
+  const int big = cta_rem * (cta_base + 1);
   int c;
   if (b < big) {
-    c = b / (p.cta_base + 1);
-    r.idx = b - c * (p.cta_base + 1);
-    r.n_c = p.cta_base + 1;
+    c = b / (cta_base + 1);
+    r.idx = b - c * (cta_base + 1);
+    r.n_c = cta_base + 1;
   } else {
     const int bb = b - big;
-    c = p.cta_rem + bb / p.cta_base;
-    r.idx = bb - (c - p.cta_rem) * p.cta_base;
-    r.n_c = p.cta_base;
+    c = cta_rem + bb / cta_base;
+    r.idx = bb - (c - cta_rem) * cta_base;
+    r.n_c = cta_base;
   }
   r.clip = c;
-  const int bt = p.tiles_per_clip / r.n_c, rt = p.tiles_per_clip - bt * r.n_c;
+  const int bt = tiles_per_clip / r.n_c, rt = tiles_per_clip - bt * r.n_c;
   r.K = bt + (r.idx < rt ? 1 : 0);
-  r.tk0 = r.idx * bt + min(r.idx, rt);
+  r.tk0 = r.idx * bt + (r.idx < rt ? r.idx : rt);
   return r;
 }
+__device__ __forceinline__ Range ft_range(const FlowTcParams& p, int b) {
+  return ft_range_of(p.tiles_per_clip, p.cta_base, p.cta_rem, b);
+}
 // index (within its clip's CTA group) of the CTA that owns tile tk of a clip split over n_c CTAs
-__device__ __forceinline__ int ft_owner(int tiles_per_clip, int n_c, int tk) {
+__host__ __device__ __forceinline__ int ft_owner(int tiles_per_clip, int n_c, int tk) {
   const int bt = tiles_per_clip / n_c, rt = tiles_per_clip - bt * n_c;
   const int big = rt * (bt + 1);
   return tk < big ? tk / (bt + 1) : rt + (tk - big) / bt;
+}
+// does the output of (own tile k of K, launch-relative layer li of nl) have a reader outside its CTA?
+__host__ __device__ __forceinline__ bool ft_published(int k, int K, int li, int nl, int l0, int num_stages,
+                                                      int fuse_head) {
+  if (li == nl - 1) return fuse_head == 0;                      // the head kernel reads every row
+  if ((1 << ((l0 + li + 1) % num_stages)) >= BM) return true;   // next layer reads whole foreign tiles
+  return k == K - 1;                                            // next CTA's halo
+}
+// where tap `tap` (0: t-2d, 1: t-d) of own tile k comes from in a layer with dilation d:
+//   >= 0 : foreign tile (index inside the clip) fetched from the published global copy
+//   -1   : own shared memory (including the current tile itself)      -2 : causal zeros, nothing is read
+// (for d <= 64 the only foreign tile is the halo tk0-1 of own tile 0, shared by both taps)
+__host__ __device__ __forceinline__ int ft_tap_source(int tk0, int k, int tap, int d) {
+  if (2 * d <= BM) return (k == 0) ? (tk0 >= 1 ? tk0 - 1 : -2) : -1;
+  const int src = tk0 + k - (2 - tap) * (d / BM);
+  return src < 0 ? -2 : (src >= tk0 ? -1 : src);
 }
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
@@ -397,9 +418,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 
   // does the output of (own tile k, layer li) have a reader outside this CTA?
   auto published = [&](int k, int li) -> bool {
-    if (li == nl - 1) return p.fuse_head == 0;                    // the head kernel reads every row
-    if ((1 << ((p.l0 + li + 1) % p.num_stages)) >= BM) return true;  // next layer reads whole foreign tiles
-    return k == K - 1;                                            // next CTA's halo
+    return ft_published(k, K, li, nl, p.l0, p.num_stages, p.fuse_head);
   };
 
   if (warp == 0) {
@@ -991,6 +1010,13 @@ int flow_tc_clips_per_launch(int T, int num_sms) {
   return num_sms / need;
 }
 
+// CTAs per clip for a launch: clip c gets cta_base + (c < cta_rem)
+static void flow_tc_split(int tiles, int nclips, int num_sms, int* cta_base, int* cta_rem) {
+  const int per_clip = std::min(num_sms / nclips, tiles);
+  *cta_base = per_clip;
+  *cta_rem = per_clip < tiles ? std::min(num_sms - per_clip * nclips, nclips) : 0;
+}
+
 int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
                    const void* map_wrh, const void* map_wrl, const float* cond_tiled, size_t cond_plane,
                    const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
@@ -1018,9 +1044,7 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
   p.tiles_per_clip = tiles;
   p.clip0 = clip0;
   p.nclips = nclips;
-  int per_clip = std::min(num_sms / nclips, tiles);
-  p.cta_base = per_clip;
-  p.cta_rem = per_clip < tiles ? std::min(num_sms - per_clip * nclips, nclips) : 0;
+  flow_tc_split(tiles, nclips, num_sms, &p.cta_base, &p.cta_rem);
   // the remainder CTAs only help if they lower some clip's tiles per CTA; harmless otherwise
   const int grid = p.cta_base * nclips + p.cta_rem;
   p.reach_tiles = std::max(1, 2 * (1 << (num_stages - 1)) / BM);
@@ -1091,3 +1115,36 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
 }
 
 }  // namespace nsw
+
+// TEST HOOK (host only, no CUDA): the work split and the publish / read plan of one flow-kernel launch, produced by the
+// same integer functions the kernel uses.  out[] receives, per CTA, a header {clip, tk0, K, n_c} followed by
+// (l1 - l0) * K records {published, source of tap t-2d, source of tap t-d} (see ft_tap_source); *n_out = ints written
+// (or needed, if cap is too small); returns the grid size, or a negative NSW_E* code.
+extern "C" int nsw_flow_plan_host(int32_t T, int32_t nclips, int32_t num_sms, int32_t l0, int32_t l1, int32_t num_stages,
+                                  int32_t fuse_head, int32_t* out, int64_t cap, int64_t* n_out) {
+  using namespace nsw;
+  NSW_CHECK(T > 0 && T % BM == 0 && nclips >= 1 && l1 > l0 && num_stages >= 1 && n_out, NSW_EINVAL,
+            "nsw_flow_plan_host: bad argument");
+  NSW_CHECK(nclips <= flow_tc_clips_per_launch(T, num_sms), NSW_EINVAL, "nsw_flow_plan_host: clips do not fit one launch");
+  const int tiles = T / BM, nl = l1 - l0;
+  int cta_base, cta_rem;
+  flow_tc_split(tiles, nclips, num_sms, &cta_base, &cta_rem);
+  const int grid = cta_base * nclips + cta_rem;
+  int64_t n = 0;
+  auto put = [&](int v) { if (out && n < cap) out[n] = v; ++n; };
+  for (int b = 0; b < grid; ++b) {
+    const Range r = ft_range_of(tiles, cta_base, cta_rem, b);
+    put(r.clip); put(r.tk0); put(r.K); put(r.n_c);
+    for (int li = 0; li < nl; ++li) {
+      const int d = 1 << ((l0 + li) % num_stages);
+      for (int k = 0; k < r.K; ++k) {
+        put(ft_published(k, r.K, li, nl, l0, num_stages, fuse_head) ? 1 : 0);
+        put(ft_tap_source(r.tk0, k, 0, d));
+        put(ft_tap_source(r.tk0, k, 1, d));
+      }
+    }
+  }
+  *n_out = n;
+  return grid;
+}
+
