@@ -72,6 +72,8 @@ struct FgParams {
   float* audio;                 // [T] or NULL
   float* out;                   // [T][O] or NULL
   int T, L, O, loss_type;
+  int l2_last;                  // weight blocks of phases < l2_last are loaded L2::evict_last, the rest evict_first (0 = no hints)
+  int poll_delay;               // poll group starts polling this many cycles after S1 (0 = at once)
   int flags;                    // experiment switches: 1 = sequential polls, 2 = volatile ld/st, 4 = one replica
   unsigned long long seed;
   float quant;                  // quant_chann
@@ -95,7 +97,14 @@ struct FgSmem {
   int hoff[MAX_PH];      // entry offset of the layer's history ring
   int pos[MAX_PH];       // t mod (2*dil+1), advanced once per step
   unsigned long long mbar[3];
+  // bulk-copy exchange / history path (flags 1024 / 2048)
+  alignas(128) unsigned long long inbox[XSLOT];      // one exchange slot, tagged entries
+  alignas(128) unsigned long long hstage[2][1024];   // [l[t-2d] (512) | l[t-d] (512)] tagged, by phase parity
+  unsigned long long xbar, hbar[2];
+  int pflag[2][4];
 };
+
+static_assert(sizeof(FgSmem) <= 227 * 1024, "fastgen shared memory");
 
 __device__ __forceinline__ void fg_die(const char* what) {
   printf("nsw fastgen: watchdog in %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
@@ -150,6 +159,13 @@ __device__ __forceinline__ void publish(unsigned long long* p, float v, uint32_t
                : "memory");
 }
 
+// tag in the high word grows monotonically per slot, so an L2-side 64-bit max IS the store; atomics
+// reach L2 faster than strong stores (scripts/probes/xchg_probe.cu)
+__device__ __forceinline__ void publish_red(unsigned long long* p, float v, uint32_t tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | __float_as_uint(v);
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+
 __device__ __forceinline__ void fg_mbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t ok = 0;
   long long t0 = 0;
@@ -179,6 +195,33 @@ __device__ __forceinline__ void bulk_load(float* dst, const float* src, uint32_t
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
           "r"(smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes,
+                                          unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void bulk_load_hint(float* dst, const float* src, uint32_t bytes,
+                                               unsigned long long* bar, bool keep) {
+  unsigned long long pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  mbar_expect(bar, bytes);
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
 
@@ -249,6 +292,9 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   if (tid == 0) {
     for (int s = 0; s < 3; ++s)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[s])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.xbar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.hbar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.hbar[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     S.xnext = 0.f;
   }
@@ -283,14 +329,23 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   const int nrep = (P.flags & 4) ? 1 : XREP;
   const bool f_nostream = (P.flags & 8) != 0;  // TIMING EXPERIMENT ONLY: reuse stale weights, results are wrong
   const bool f_cgld = (P.flags & 16) != 0, f_cgst = (P.flags & 32) != 0;
-  auto PUB = [&](unsigned long long* p, float v, uint32_t tg) { if (f_cgst) publish_cg(p, v, tg); else if (f_vol) publish_vol(p, v, tg); else publish(p, v, tg); };
+  const bool f_pipe = (P.flags & 64) != 0;  // two poll rounds in flight
+  const bool f_nohist = (P.flags & 128) != 0;   // TIMING EXPERIMENT ONLY: no history loads, results are wrong
+  const bool f_nopast = (P.flags & 256) != 0;   // TIMING EXPERIMENT ONLY: no past-tap dot, results are wrong
+  const bool f_red = (P.flags & 512) != 0;    // publish with red.max.u64
+  const bool f_bulk = (P.flags & 1024) != 0;  // poll the exchange slot with one cp.async.bulk per round
+  const bool f_hpre = (P.flags & 2048) != 0;  // history vectors prefetched one phase ahead with cp.async.bulk
+  uint32_t xpar = 0, hpar = 0;
+  auto PUB = [&](unsigned long long* p, float v, uint32_t tg) { if (f_red) publish_red(p, v, tg); else if (f_cgst) publish_cg(p, v, tg); else if (f_vol) publish_vol(p, v, tg); else publish(p, v, tg); };
   auto LDX = [&](const unsigned long long* p) -> uint4 { return f_cgld ? ldv4_cg(p) : (f_vol ? ldv4_vol(p) : ldv4(p)); };
   float x1 = 0.f, x2 = 0.f;  // inputs of the two previous steps (conv_start queues, rate 1)
   float ls0 = 0.f, ls1 = 0.f, sk = 0.f;  // warps 2,3: two residual channels; warps 0,1: one skip channel
   long long q = 0;           // global phase counter -> weight ring slot / parity
   int vb = 0;                // which S.v buffer the current phase reads
-  long long tEnd = 0;
+  long long tEnd = 0, tPollEnd = 0;
   const long long total_q = (long long)T * NPH;
+  int slot3 = 0;          // q % 3
+  uint32_t wpar = 1u;     // per-slot parity of the next weight-ring wait (slot 0 is consumed right here)
   fg_mbar_wait(&S.mbar[0], 0);  // weights of the very first phase
   __syncthreads();
 
@@ -311,24 +366,56 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
     if (tid < NPH) cnext = load_cond(t + 1, tid);  // consumed one step later
     const float(*cnd)[4] = S.cnd[t & 1];
 
-    for (int ph = 1; ph <= NPH; ++ph, ++q, vb ^= 1) {
+    for (int ph = 1; ph <= NPH; ++ph, ++q, vb ^= 1, slot3 = (slot3 == 2) ? 0 : slot3 + 1) {
       __syncthreads();  // S1 (the only CTA-wide barrier of a phase): S.v[vb], S.pv, S.cnd complete
       long long tS1 = 0;
       if (P.dbg) {
         tS1 = clock64();
         if (tid == 0 && tEnd) P.dbg[16 * c + 4] += tS1 - tEnd;  // wait at S1 after my slack
+        if (tid == 128 && tPollEnd) P.dbg[16 * c + 7] += tS1 - tPollEnd;  // poll group waits for the slack
       }
       const float* v = S.v[vb];
-      const int slot = (int)(q % 3);
+      const int slot = slot3;  // q % 3, kept incrementally (no 64-bit division on the critical path)
       if (warp >= 4) {
         // ======================= poll group (warps 4-7) =======================
         // receives THIS phase's exchange (what the compute groups of all CTAs publish below)
         // into S.v[vb^1] for the next phase; it never waits for this CTA's own compute
         if (tid == 128) {
           const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
-          if (qn < total_q && !(f_nostream && qn >= 3))
-            bulk_load(S.ring[qn % 3], my_blocks + (size_t)(qn % NPH) * phase_stride, BLOCK_BYTES,
-                      &S.mbar[qn % 3]);
+          if (qn < total_q && !(f_nostream && qn >= 3)) {
+            const int bph = (ph + 1 >= NPH) ? ph + 1 - NPH : ph + 1;  // qn % NPH
+            const int qs = (slot >= 1) ? slot - 1 : 2;                 // qn % 3
+            if (P.l2_last > 0)
+              bulk_load_hint(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
+                             &S.mbar[qs], bph < P.l2_last);
+            else
+              bulk_load(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
+                        &S.mbar[qs]);
+          }
+        }
+        if (f_hpre && tid == 128) {
+          // history of the layer whose past taps the NEXT phase's slack computes: >= 30 phases old
+          const int sph = (ph == NPH) ? 1 : ph + 1, st = (ph == NPH) ? t + 1 : t;
+          const int tph = (sph == NPH) ? 1 : sph + 1, tt = (sph == NPH) ? st + 1 : st;
+          if (tph <= L && tt < T) {
+            const int d = S.dil[tph];
+            const int R = 2 * d + 1;
+            const unsigned long long* hb = P.hist + S.hoff[tph];
+            int pn = S.pos[tph] + (tt - t);
+            if (pn >= R) pn -= R;
+            int p1 = pn - d;
+            if (p1 < 0) p1 += R;
+            int p2 = p1 - d;
+            if (p2 < 0) p2 += R;
+            const bool has2 = tt - 2 * d >= 0, has1 = tt - d >= 0;
+            if (has1 || has2) {
+              const int hb_i = (int)((q + 1) & 1);
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              mbar_expect(&S.hbar[hb_i], (has1 ? 4096u : 0u) + (has2 ? 4096u : 0u));
+              if (has2) bulk_copy(S.hstage[hb_i], hb + (size_t)p2 * FW, 4096u, &S.hbar[hb_i]);
+              if (has1) bulk_copy(S.hstage[hb_i] + 512, hb + (size_t)p1 * FW, 4096u, &S.hbar[hb_i]);
+            }
+          }
         }
         const int k = tid - 128;
         float* vn = S.v[vb ^ 1];
@@ -340,6 +427,70 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
         long long w0 = 0;
         int spins = 0;
+        if (P.poll_delay > 0) {
+          // nothing can arrive before the publishers' critical sections end: keep the L2 quiet until then
+          const long long tgo = clock64() + P.poll_delay;
+          while (clock64() < tgo) {}
+        }
+        if (f_bulk) {
+          // one bulk copy (48 line requests) fetches the whole slot; tags are checked in smem
+          const uint32_t nbytes = need_l ? (uint32_t)XSLOT * 8u : 256u * 8u;
+          const unsigned long long* src = need_l ? slotp : slotp + 512;
+          unsigned long long* dst = need_l ? S.inbox : S.inbox + 512;
+          for (int it = 0;; ++it) {
+            if (tid == 128) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              mbar_expect(&S.xbar, nbytes);
+              bulk_copy(dst, src, nbytes, &S.xbar);
+            }
+            fg_mbar_wait(&S.xbar, xpar);
+            xpar ^= 1u;
+            if (need_l) {
+              r0 = *reinterpret_cast<const uint4*>(S.inbox + 2 * k);
+              r1 = *reinterpret_cast<const uint4*>(S.inbox + 256 + 2 * k);
+            }
+            r2 = *reinterpret_cast<const uint4*>(S.inbox + 512 + 2 * k);
+            const bool good = (!need_l || (r0.y == tag && r0.w == tag && r1.y == tag && r1.w == tag)) &&
+                              r2.y == tag && r2.w == tag;
+            const bool wgood = __all_sync(0xffffffffu, good);
+            if (lane == 0) S.pflag[it & 1][warp - 4] = wgood;
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int* pf = S.pflag[it & 1];
+            if (pf[0] && pf[1] && pf[2] && pf[3]) break;
+            if (++spins == 4096) {
+              spins = 0;
+              if (w0 == 0) w0 = clock64();
+              else if (clock64() - w0 > FG_WATCHDOG) fg_die("exchange wait (bulk)");
+            }
+          }
+        } else if (f_pipe) {
+          // two poll rounds in flight: round B is issued before round A is examined, so the
+          // detection granularity is half a round trip
+          uint4 a0 = r0, a1 = r0, a2 = r0, b0 = r0, b1 = r0, b2 = r0;
+          if (need_l) { a0 = ldv4(pl0); a1 = ldv4(pl0 + 256); }
+          a2 = ldv4(pg);
+          for (;;) {
+            if (need_l) { b0 = ldv4(pl0); b1 = ldv4(pl0 + 256); }
+            b2 = ldv4(pg);
+            if ((!need_l || (a0.y == tag && a0.w == tag && a1.y == tag && a1.w == tag)) &&
+                a2.y == tag && a2.w == tag) {
+              r0 = a0; r1 = a1; r2 = a2;
+              break;
+            }
+            if (need_l) { a0 = ldv4(pl0); a1 = ldv4(pl0 + 256); }
+            a2 = ldv4(pg);
+            if ((!need_l || (b0.y == tag && b0.w == tag && b1.y == tag && b1.w == tag)) &&
+                b2.y == tag && b2.w == tag) {
+              r0 = b0; r1 = b1; r2 = b2;
+              break;
+            }
+            if (++spins == 4096) {
+              spins = 0;
+              if (w0 == 0) w0 = clock64();
+              else if (clock64() - w0 > FG_WATCHDOG) fg_die("exchange wait");
+            }
+          }
+        } else
         for (;;) {
           if (!ok0) r0 = LDX(pl0);
           if (!ok1 && (!f_seq || ok0)) r1 = LDX(pl0 + 256);
@@ -360,7 +511,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         }
         vn[512 + 2 * k] = __uint_as_float(r2.x);
         vn[512 + 2 * k + 1] = __uint_as_float(r2.z);
-        if (P.dbg && tid == 128) P.dbg[16 * c + 5] += clock64() - tS1;
+        if (P.dbg && tid == 128) { tPollEnd = clock64(); P.dbg[16 * c + 5] += tPollEnd - tS1; }
       } else {
         // ======================= compute group (warps 0-3) =======================
         if (ph == 1) {
@@ -368,7 +519,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         }
         const int nph = (ph == NPH) ? 1 : ph + 1;
         const int nt = (ph == NPH) ? t + 1 : t;
-        const bool do_past = (nph <= L) && (nt < T);
+        const bool do_past = (nph <= L) && (nt < T) && !f_nohist;
         const float* blk = S.ring[slot];  // arrival was checked in the previous phase's slack
         unsigned long long* xs = P.xbuf + ((size_t)ph * XREP + lane) * XSLOT;  // my replica (lane < nrep)
 
@@ -431,10 +582,24 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
           if (p2 < 0) p2 += R;
           if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
           if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
-          hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
-          hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
-          hraw[2] = hp1 ? LDX(hp1) : make_uint4(0, 0, 0, 0);
-          hraw[3] = hp1 ? LDX(hp1 + 256) : make_uint4(0, 0, 0, 0);
+          if (f_hpre) {
+            const int hb_i = (int)(q & 1);
+            if (hp1 || hp2) {
+              fg_mbar_wait(&S.hbar[hb_i], (hpar >> hb_i) & 1u);
+              hpar ^= 1u << hb_i;
+            }
+            const unsigned long long* sg = S.hstage[hb_i];
+            const uint4 z4 = make_uint4(0, 0, 0, 0);
+            hraw[0] = hp2 ? *reinterpret_cast<const uint4*>(sg + 2 * tid) : z4;
+            hraw[1] = hp2 ? *reinterpret_cast<const uint4*>(sg + 256 + 2 * tid) : z4;
+            hraw[2] = hp1 ? *reinterpret_cast<const uint4*>(sg + 512 + 2 * tid) : z4;
+            hraw[3] = hp1 ? *reinterpret_cast<const uint4*>(sg + 768 + 2 * tid) : z4;
+          } else {
+            hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
+            hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
+            hraw[2] = hp1 ? LDX(hp1) : make_uint4(0, 0, 0, 0);
+            hraw[3] = hp1 ? LDX(hp1 + 256) : make_uint4(0, 0, 0, 0);
+          }
         }
 
         // ---- slack: overlaps the exchange latency ----
@@ -457,6 +622,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
           S.hv[512 + 2 * tid] = f[2].x;   S.hv[512 + 2 * tid + 1] = f[2].y;
           S.hv[768 + 2 * tid] = f[3].x;   S.hv[768 + 2 * tid + 1] = f[3].y;
         }
+        if (P.dbg && tid == 0) P.dbg[16 * c + 1] += clock64() - tPub;  // history staged
         if (ph == 1 && tid < NPH) {
           float* dst = S.cnd[(t + 1) & 1][tid + 1];
           dst[0] = cnext.x; dst[1] = cnext.y; dst[2] = cnext.z; dst[3] = cnext.w;
@@ -469,11 +635,14 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
           a = warp_sum(a) + blk[OFF_C + 4 + warp];
           sk = (ph == 1) ? a : sk + a;
         }
+        if (P.dbg && tid == 0) P.dbg[16 * c + 2] += clock64() - tPub;  // + bar 1 + skip dot
         if (q + 1 < total_q) {
           // next phase's weights: verified here so the next critical section starts at once
-          const int nslot = (int)((q + 1) % 3);
-          if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (uint32_t)(((q + 1) / 3) & 1));
-          if (do_past) {
+          const int nslot = (slot == 2) ? 0 : slot + 1;
+          if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (wpar >> nslot) & 1u);
+          wpar ^= 1u << nslot;
+          if (P.dbg && tid == 0) P.dbg[16 * c + 8] += clock64() - tPub;  // + next weights arrived
+          if (do_past && !f_nopast) {
             const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + warp * 1024, S.hv, lane));
             if (lane == 0) S.pv[warp] = a;
           }
@@ -578,6 +747,7 @@ struct nsw_fastgen {
   DevBuf xbuf, hist, cond, enc_split, scratch, stage_in, stage_tf, stage_audio, stage_out,
       stage_mel, stage_enc;
   size_t hist_entries = 0;
+  int l2_last = 0;  // weight blocks of this many phases are kept in L2 (evict_last), the rest stream through (evict_first)
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
@@ -781,6 +951,8 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
   int coop = 0, sms = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  int l2_bytes = 0;
+  cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, device);
   NSW_CHECK(coop && sms >= NC, NSW_EINVAL,
             "fastgen needs cooperative launch and >= %d SMs (device has %d)", NC, sms);
   TensorMap tm(tensors, n);
@@ -795,6 +967,9 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
   const int N = h->L * 2 * FM + FS;
   h->NPL = N / 64;
   h->hist_entries = pk.hist_entries;
+  // the per-sample weight stream (NPH x 4.7 MB) is larger than L2 and cyclic, so plain LRU never hits: pin the
+  // blocks of the first phases in ~60 % of L2 (16 of 32 phases on B200) and let the rest stream through
+  h->l2_last = std::min(h->NPH, (int)(0.6 * (double)l2_bytes / ((double)NC * BLOCK_BYTES)));
   int rc = NSW_OK;
   const bool want_tc = cfg->engine >= NSW_ENGINE_TC;
   auto up = [&](DevBuf& b, const void* p, size_t bytes) {
@@ -940,7 +1115,11 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     P.O = h->O;
     P.loss_type = h->cfg.loss_type;
     P.seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)b;
-    P.flags = getenv("NSW_FASTGEN_FLAGS") ? atoi(getenv("NSW_FASTGEN_FLAGS")) : 0;
+    // default: red.max publish (512) + history prefetched one phase ahead by cp.async.bulk (2048);
+    // every other bit is an experiment switch (scripts/fastgen_exp.py, profiles/r01/fastgen_exchange.md)
+    P.flags = getenv("NSW_FASTGEN_FLAGS") ? atoi(getenv("NSW_FASTGEN_FLAGS")) : (512 | 2048);
+    P.l2_last = getenv("NSW_FASTGEN_L2LAST") ? atoi(getenv("NSW_FASTGEN_L2LAST")) : h->l2_last;
+    P.poll_delay = getenv("NSW_FASTGEN_POLLDELAY") ? atoi(getenv("NSW_FASTGEN_POLLDELAY")) : 0;
     P.quant = 65536.0f;
     void* args[] = {&P};
     NSW_CUDA(cudaLaunchCooperativeKernel((void*)fastgen_kernel, dim3(NC), dim3(NT), args,
@@ -951,8 +1130,8 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
       NSW_CUDA(cudaStreamSynchronize(st));
       NSW_CUDA(cudaMemcpy(host.data(), h->dbg.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       const double phases = (double)T * (h->L + 2);
-      const char* names[10] = {"crit", "crit+S2", "finalize+publish", "slack", "S1 wait", "poll(after S2)", "head",
-                               "hist issue", "ring wait", "dots+reduce"};
+      const char* names[10] = {"crit", "hist staged", "+bar1+skip", "slack", "S1 wait", "poll(after S2)", "head",
+                               "poll group waits at S1", "+weights here", "unused"};
       for (int cta : {0, 1, 64, 127}) {
         fprintf(stderr, "[nsw fastgen dbg] cta %3d cycles/phase:", cta);
         for (int i = 0; i < 10; ++i)
