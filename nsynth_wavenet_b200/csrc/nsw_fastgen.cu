@@ -38,7 +38,7 @@ constexpr int FM = 256;   // gate half (gate_width 512)
 constexpr int FS = 256;   // skip width
 constexpr int FD = 256;   // deconv width
 constexpr int NC = 128;   // CTAs
-constexpr int NT = 256;   // threads per CTA
+constexpr int NT = 384;   // threads per CTA: compute (warps 0-3), poll (4-7), past taps (8-11)
 constexpr int MAX_O = 32;
 constexpr int MAX_PH = 40;
 constexpr int XREP = 8;     // replicas of every exchange slot (CTA c polls replica c % XREP)
@@ -54,6 +54,7 @@ constexpr int BLOCK_FLOATS = OFF_P + 4 * 1024;  // 9224
 constexpr uint32_t BLOCK_BYTES = BLOCK_FLOATS * 4;
 static_assert(BLOCK_BYTES % 16 == 0 && (OFF_P * 4) % 16 == 0, "bulk copy alignment");
 
+constexpr int FG_DEFAULT_FLAGS = 512 | 2048;  // red.max publish + bulk history prefetch
 constexpr long long FG_WATCHDOG = 6000000000ll;  // ~3 s of SM clocks
 
 struct FgParams {
@@ -73,6 +74,7 @@ struct FgParams {
   float* out;                   // [T][O] or NULL
   int T, L, O, loss_type;
   int l2_last;                  // weight blocks of phases < l2_last are loaded L2::evict_last, the rest evict_first (0 = no hints)
+  int crit_delay;               // TIMING EXPERIMENT ONLY: busy-wait before the critical section
   int poll_delay;               // poll group starts polling this many cycles after S1 (0 = at once)
   int flags;                    // experiment switches: 1 = sequential polls, 2 = volatile ld/st, 4 = one replica
   unsigned long long seed;
@@ -89,7 +91,7 @@ struct FgSmem {
   float hv[1024];       // [l[t-2d] | l[t-d]] of the next layer
   float cnd[2][MAX_PH][4];
   float red_d[4][2];
-  float pv[4];
+  float pv[2][4];  // past-tap partial sums, by phase parity (written one phase ahead by the past group)
   float outv[MAX_O];
   float gum[12];
   float xnext;
@@ -106,12 +108,14 @@ struct FgSmem {
 
 static_assert(sizeof(FgSmem) <= 227 * 1024, "fastgen shared memory");
 
-__device__ __forceinline__ void fg_die(const char* what) {
+// cold path, kept out of line so that the printf argument set-up does not sit inside the phase loop
+__device__ __noinline__ void fg_die(const char* what) {
   printf("nsw fastgen: watchdog in %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
   __trap();
 }
 
-__device__ __forceinline__ float2 poll2(const unsigned long long* p, uint32_t tag) {
+// cold path (a history entry that the bulk prefetch read before it was final): out of line
+__device__ __noinline__ float2 poll2(const unsigned long long* p, uint32_t tag) {
   uint32_t a, b, c, d;
   long long t0 = 0;
   int spins = 0;
@@ -241,6 +245,21 @@ __device__ __forceinline__ float dot_rows(const float* __restrict__ w, const flo
   }
   return a0 + a1;
 }
+// same sum order as dot_rows, weights already in registers
+template <int NF4>
+__device__ __forceinline__ float dot_regs(const float4* w, const float* __restrict__ x, int lane) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NF4; ++i) {
+    const float4 ww = w[i];
+    const float4 xx = *reinterpret_cast<const float4*>(x + 128 * i + 4 * lane);
+    a0 = fmaf(ww.x, xx.x, a0);
+    a1 = fmaf(ww.y, xx.y, a1);
+    a0 = fmaf(ww.z, xx.z, a0);
+    a1 = fmaf(ww.w, xx.w, a1);
+  }
+  return a0 + a1;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -265,12 +284,25 @@ __device__ __forceinline__ uint4 ldv4(const unsigned long long* p) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.0f * sigmoid_fast(2.0f * x) - 1.0f; }
 
-// Thread roles inside a phase (after the critical section):
-//   warps 0-3 "slack group": skip accumulation + the two past taps of the NEXT layer
-//   warps 4-7 "poll group" : weight prefetch + receive the exchange for the NEXT phase
-// so the exchange latency overlaps the slack work.  lane 0 of warp w<4 owns residual channel
-// 4c+w (register ls), lane 0 of warp w<2 owns skip channel 2c+w (register sk).
-__global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
+// Thread roles inside a phase:
+//   warps 0-3  "compute group": critical section (gate pairs / residual channels -> publish), then the skip
+//              accumulation and the register preload of the next phase's critical rows
+//   warps 4-7  "poll group"   : weight + history prefetch (cp.async.bulk), receive the exchange for the NEXT phase
+//   warps 8-11 "past group"   : the two past taps of the NEXT layer (history x next weights), beside the critical
+//              section because nothing in it depends on this phase's exchange
+// lane 0 of warp w<4 owns residual channel 4c+w (register ls), lane 0 of warp w<2 owns skip channel 2c+w (sk).
+// FLAGS >= 0: the switches are compile-time constants and the cycle counters are compiled out (product build, less
+// than half the code, so the three role paths stay in the instruction caches); FLAGS < 0: run-time switches from
+// P.flags plus the counters (experiments, NSW_FASTGEN_FLAGS / NSW_FASTGEN_DEBUG).
+template <int FLAGS>
+__global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
+  FgParams P = Pin;
+  if (FLAGS >= 0) {
+    P.flags = FLAGS;
+    P.dbg = nullptr;
+    P.crit_delay = 0;
+    P.poll_delay = 0;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FgSmem& S = *reinterpret_cast<FgSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
@@ -283,7 +315,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   for (int i = tid; i < FW; i += NT) S.bcs[i] = P.bcs[i];
   if (tid < O) S.bo2[tid] = P.bo2[tid];
   for (int i = tid; i < 1024; i += NT) { S.v[0][i] = 0.f; S.v[1][i] = 0.f; S.hv[i] = 0.f; }
-  if (tid < 4) S.pv[tid] = 0.f;
+  if (tid < 8) (&S.pv[0][0])[tid] = 0.f;
   if (tid <= L) {
     S.dil[tid] = tid >= 1 ? P.dil[tid] : 1;
     S.hoff[tid] = tid >= 1 ? P.hist_off[tid] : 0;
@@ -334,6 +366,8 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   const bool f_nopast = (P.flags & 256) != 0;   // TIMING EXPERIMENT ONLY: no past-tap dot, results are wrong
   const bool f_red = (P.flags & 512) != 0;    // publish with red.max.u64
   const bool f_bulk = (P.flags & 1024) != 0;  // poll the exchange slot with one cp.async.bulk per round
+  const bool f_pastearly = (P.flags & 8192) != 0;  // past taps not gated on the publish (experiment)
+  const bool f_latepre = (P.flags & 4096) != 0;  // critical-row weights loaded inside the critical section (old behaviour)
   const bool f_hpre = (P.flags & 2048) != 0;  // history vectors prefetched one phase ahead with cp.async.bulk
   uint32_t xpar = 0, hpar = 0;
   auto PUB = [&](unsigned long long* p, float v, uint32_t tg) { if (f_red) publish_red(p, v, tg); else if (f_cgst) publish_cg(p, v, tg); else if (f_vol) publish_vol(p, v, tg); else publish(p, v, tg); };
@@ -343,17 +377,55 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
   long long q = 0;           // global phase counter -> weight ring slot / parity
   int vb = 0;                // which S.v buffer the current phase reads
   long long tEnd = 0, tPollEnd = 0;
+  long long dacc[14];  // cycle counters live in registers (a global read-modify-write per event would stall the
+                       // warp for an L2 round trip and inflate every later counter); written once at the end
+#pragma unroll
+  for (int i = 0; i < 14; ++i) dacc[i] = 0;
   const long long total_q = (long long)T * NPH;
+  // Weights of a phase's critical rows, fetched from the smem ring into registers while the compute group
+  // would otherwise idle at the phase barrier: the critical section then only loads the exchanged vector.
+  float4 wq[12];
+  float wc0 = 0.f, wc1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) wq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto preload_crit = [&](const float* blkn, int phn) {
+    if (warp >= 4) return;
+    if (warp < 2) {
+      if (phn == L + 1) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) wq[i] = *reinterpret_cast<const float4*>(blkn + OFF_S + warp * 512 + 128 * i + 4 * lane);
+        wc0 = blkn[OFF_C + 4 + warp];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) wq[i] = *reinterpret_cast<const float4*>(blkn + OFF_D + warp * 768 + 128 * i + 4 * lane);
+        if (phn <= L) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+            wq[6 + i] = *reinterpret_cast<const float4*>(blkn + OFF_D + (2 + warp) * 768 + 128 * i + 4 * lane);
+        }
+      }
+    } else if (phn <= L) {
+      const int r0 = 2 * (warp - 2);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        wq[i] = *reinterpret_cast<const float4*>(blkn + OFF_L + r0 * 256 + 128 * i + 4 * lane);
+        wq[2 + i] = *reinterpret_cast<const float4*>(blkn + OFF_L + (r0 + 1) * 256 + 128 * i + 4 * lane);
+      }
+      wc0 = blkn[OFF_C + r0];
+      wc1 = blkn[OFF_C + r0 + 1];
+    }
+  };
   int slot3 = 0;          // q % 3
   uint32_t wpar = 1u;     // per-slot parity of the next weight-ring wait (slot 0 is consumed right here)
   fg_mbar_wait(&S.mbar[0], 0);  // weights of the very first phase
   __syncthreads();
+  preload_crit(S.ring[0], 1);
 
   for (int t = 0; t < T; ++t) {
     const uint32_t tag = (uint32_t)t + 1u;
     // ---------------- conv_start on the fed-back sample (every CTA, full vector) ----------
     const float xin = S.xnext;  // written before the last __syncthreads of the previous step
-    {
+    if (tid < 256) {
       float* vc = S.v[vb];
       const int k0 = tid, k1 = tid + 256;
       vc[k0] = fmaf(S.wcs[2 * FW + k0], xin, fmaf(S.wcs[FW + k0], x1, fmaf(S.wcs[k0], x2, S.bcs[k0])));
@@ -371,28 +443,96 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
       long long tS1 = 0;
       if (P.dbg) {
         tS1 = clock64();
-        if (tid == 0 && tEnd) P.dbg[16 * c + 4] += tS1 - tEnd;  // wait at S1 after my slack
-        if (tid == 128 && tPollEnd) P.dbg[16 * c + 7] += tS1 - tPollEnd;  // poll group waits for the slack
+        if (tid == 0 && tEnd) dacc[4] += tS1 - tEnd;  // wait at S1 after my slack
+        if (tid == 128 && tPollEnd) dacc[7] += tS1 - tPollEnd;  // poll group waits for the slack
       }
       const float* v = S.v[vb];
       const int slot = slot3;  // q % 3, kept incrementally (no 64-bit division on the critical path)
-      if (warp >= 4) {
+      if (warp >= 8) {
+        // ======================= past group (warps 8-11) =======================
+        // The two past taps of the NEXT layer: history (>= 30 phases old) x the next phase's weights.  Nothing
+        // here depends on this phase's exchange, so it runs beside the critical section, not after it.
+        const int pt = tid - 256, pw = warp - 8;
+        const int nph = (ph == NPH) ? 1 : ph + 1;
+        const int nt = (ph == NPH) ? t + 1 : t;
+        const bool do_past = (nph <= L) && (nt < T) && !f_nohist;
+        // history of the next layer (>= 1 step old, so already final), requested right after this
+        // phase's publish so the strong loads never sit in front of the publishing stores
+        uint4 hraw[4];
+        const unsigned long long* hp2 = nullptr;
+        const unsigned long long* hp1 = nullptr;
+        uint32_t tag2 = 0, tag1 = 0;
+        if (do_past) {
+          const int d = S.dil[nph];
+          const int R = 2 * d + 1;
+          const unsigned long long* hb = P.hist + S.hoff[nph];
+          int pn = S.pos[nph] + (nt - t);
+          if (pn >= R) pn -= R;
+          int p1 = pn - d;
+          if (p1 < 0) p1 += R;
+          int p2 = p1 - d;
+          if (p2 < 0) p2 += R;
+          if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * pt; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
+          if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * pt; tag1 = (uint32_t)(nt - d) + 1u; }
+          if (f_hpre) {
+            const int hb_i = (int)(q & 1);
+            if (hp1 || hp2) {
+              fg_mbar_wait(&S.hbar[hb_i], (hpar >> hb_i) & 1u);
+              hpar ^= 1u << hb_i;
+            }
+            const unsigned long long* sg = S.hstage[hb_i];
+            const uint4 z4 = make_uint4(0, 0, 0, 0);
+            hraw[0] = hp2 ? *reinterpret_cast<const uint4*>(sg + 2 * pt) : z4;
+            hraw[1] = hp2 ? *reinterpret_cast<const uint4*>(sg + 256 + 2 * pt) : z4;
+            hraw[2] = hp1 ? *reinterpret_cast<const uint4*>(sg + 512 + 2 * pt) : z4;
+            hraw[3] = hp1 ? *reinterpret_cast<const uint4*>(sg + 768 + 2 * pt) : z4;
+          } else {
+            hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
+            hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
+            hraw[2] = hp1 ? LDX(hp1) : make_uint4(0, 0, 0, 0);
+            hraw[3] = hp1 ? LDX(hp1 + 256) : make_uint4(0, 0, 0, 0);
+          }
+        }
+
+        // ---- slack: overlaps the exchange latency ----
+        if (do_past) {
+          float2 f[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned long long* pp = (i < 2) ? hp2 : hp1;
+            const uint32_t tg = (i < 2) ? tag2 : tag1;
+            if (pp == nullptr) {
+              f[i] = make_float2(0.f, 0.f);
+            } else if (hraw[i].y == tg && hraw[i].w == tg) {
+              f[i] = make_float2(__uint_as_float(hraw[i].x), __uint_as_float(hraw[i].z));
+            } else {
+              f[i] = poll2(pp + ((i & 1) ? 256 : 0), tg);
+            }
+          }
+          S.hv[2 * pt] = f[0].x;         S.hv[2 * pt + 1] = f[0].y;
+          S.hv[256 + 2 * pt] = f[1].x;   S.hv[256 + 2 * pt + 1] = f[1].y;
+          S.hv[512 + 2 * pt] = f[2].x;   S.hv[512 + 2 * pt + 1] = f[2].y;
+          S.hv[768 + 2 * pt] = f[3].x;   S.hv[768 + 2 * pt + 1] = f[3].y;
+        }
+        if (P.dbg && tid == 256) dacc[1] += clock64() - tS1;  // history staged
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q + 1 < total_q) {
+          const int nslot = (slot == 2) ? 0 : slot + 1;
+          if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (wpar >> nslot) & 1u);
+          wpar ^= 1u << nslot;
+          // the 32 KB of shared-memory reads below would slow the critical section down: start after the publish
+          if (!f_pastearly) asm volatile("bar.sync 4, 256;" ::: "memory");
+          if (do_past && !f_nopast) {
+            const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + pw * 1024, S.hv, lane));
+            if (lane == 0) S.pv[(q + 1) & 1][pw] = a;
+          }
+        }
+        if (!do_past && lane == 0) S.pv[(q + 1) & 1][pw] = 0.f;
+        if (P.dbg && tid == 256) dacc[9] += clock64() - tS1;  // past taps done
+      } else if (warp >= 4) {
         // ======================= poll group (warps 4-7) =======================
         // receives THIS phase's exchange (what the compute groups of all CTAs publish below)
         // into S.v[vb^1] for the next phase; it never waits for this CTA's own compute
-        if (tid == 128) {
-          const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
-          if (qn < total_q && !(f_nostream && qn >= 3)) {
-            const int bph = (ph + 1 >= NPH) ? ph + 1 - NPH : ph + 1;  // qn % NPH
-            const int qs = (slot >= 1) ? slot - 1 : 2;                 // qn % 3
-            if (P.l2_last > 0)
-              bulk_load_hint(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
-                             &S.mbar[qs], bph < P.l2_last);
-            else
-              bulk_load(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
-                        &S.mbar[qs]);
-          }
-        }
         if (f_hpre && tid == 128) {
           // history of the layer whose past taps the NEXT phase's slack computes: >= 30 phases old
           const int sph = (ph == NPH) ? 1 : ph + 1, st = (ph == NPH) ? t + 1 : t;
@@ -410,11 +550,23 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
             const bool has2 = tt - 2 * d >= 0, has1 = tt - d >= 0;
             if (has1 || has2) {
               const int hb_i = (int)((q + 1) & 1);
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               mbar_expect(&S.hbar[hb_i], (has1 ? 4096u : 0u) + (has2 ? 4096u : 0u));
               if (has2) bulk_copy(S.hstage[hb_i], hb + (size_t)p2 * FW, 4096u, &S.hbar[hb_i]);
               if (has1) bulk_copy(S.hstage[hb_i] + 512, hb + (size_t)p1 * FW, 4096u, &S.hbar[hb_i]);
             }
+          }
+        }
+        if (tid == 128) {
+          const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
+          if (qn < total_q && !(f_nostream && qn >= 3)) {
+            const int bph = (ph + 1 >= NPH) ? ph + 1 - NPH : ph + 1;  // qn % NPH
+            const int qs = (slot >= 1) ? slot - 1 : 2;                 // qn % 3
+            if (P.l2_last > 0)
+              bulk_load_hint(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
+                             &S.mbar[qs], bph < P.l2_last);
+            else
+              bulk_load(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
+                        &S.mbar[qs]);
           }
         }
         const int k = tid - 128;
@@ -427,6 +579,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
         long long w0 = 0;
         int spins = 0;
+        if (P.dbg && tid == 128) dacc[13] += clock64() - tS1;  // prefetch issue time
         if (P.poll_delay > 0) {
           // nothing can arrive before the publishers' critical sections end: keep the L2 quiet until then
           const long long tgo = clock64() + P.poll_delay;
@@ -491,13 +644,19 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
             }
           }
         } else
-        for (;;) {
+        for (int it = 0;; ++it) {
+          long long ts = 0;
+          if (P.dbg && it == 0) ts = clock64();
           if (!ok0) r0 = LDX(pl0);
           if (!ok1 && (!f_seq || ok0)) r1 = LDX(pl0 + 256);
           if (!ok2 && (!f_seq || (ok0 && ok1))) r2 = LDX(pg);
           ok0 = ok0 || (r0.y == tag && r0.w == tag);
           ok1 = ok1 || (r1.y == tag && r1.w == tag);
           ok2 = ok2 || (r2.y == tag && r2.w == tag);
+          if (P.dbg && tid == 128) {
+            dacc[10] += 1;                              // poll sweeps
+            if (it == 0) dacc[11] += clock64() - ts;    // duration of the first sweep (3 strong loads + compare)
+          }
           if (ok0 && ok1 && ok2) break;
           if (++spins == 4096) {
             spins = 0;
@@ -505,13 +664,14 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
             else if (clock64() - w0 > FG_WATCHDOG) fg_die("exchange wait");
           }
         }
+        if (P.dbg && tid == 255) dacc[12] += clock64() - tS1;  // poll complete for the last poll thread
         if (need_l) {
           vn[2 * k] = __uint_as_float(r0.x); vn[2 * k + 1] = __uint_as_float(r0.z);
           vn[256 + 2 * k] = __uint_as_float(r1.x); vn[256 + 2 * k + 1] = __uint_as_float(r1.z);
         }
         vn[512 + 2 * k] = __uint_as_float(r2.x);
         vn[512 + 2 * k + 1] = __uint_as_float(r2.z);
-        if (P.dbg && tid == 128) { tPollEnd = clock64(); P.dbg[16 * c + 5] += tPollEnd - tS1; }
+        if (P.dbg && tid == 128) { tPollEnd = clock64(); dacc[5] += tPollEnd - tS1; }
       } else {
         // ======================= compute group (warps 0-3) =======================
         if (ph == 1) {
@@ -524,22 +684,27 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         unsigned long long* xs = P.xbuf + ((size_t)ph * XREP + lane) * XSLOT;  // my replica (lane < nrep)
 
         // ---- critical section: no CTA barrier, every warp publishes its own results ----
+        if (P.crit_delay > 0) {
+          const long long tgo = clock64() + P.crit_delay;
+          while (clock64() < tgo) {}
+        }
+        if (f_latepre) preload_crit(blk, ph);
         if (ph == L + 1) {
           if (warp < 2) {
-            const float a = warp_sum(dot_rows<2>(blk + OFF_S + warp * 512, v + 512, lane));
-            sk = fmaxf(sk + a + blk[OFF_C + 4 + warp], 0.f);  // relu(s) after the last skip
+            const float a = warp_sum(dot_regs<2>(wq, v + 512, lane));
+            sk = fmaxf(sk + a + wc0, 0.f);  // relu(s) after the last skip
             if (lane < nrep) PUB(xs + 512 + 2 * c + warp, sk, tag);
           }
         } else if (warp < 2) {
           // gate pair `warp`: rows (sig, tanh) of the dilated conv [W2 | M] . [l_{ph-2} | g_{ph-1}]
-          float a = dot_rows<6>(blk + OFF_D + warp * 768, v, lane);
-          float b = (ph <= L) ? dot_rows<6>(blk + OFF_D + (2 + warp) * 768, v, lane) : 0.f;
+          float a = dot_regs<6>(wq, v, lane);
+          float b = (ph <= L) ? dot_regs<6>(wq + 6, v, lane) : 0.f;
           warp_sum2(a, b);
           if (lane < nrep) {
             float val;
             if (ph <= L)
-              val = sigmoid_fast(a + cnd[ph][warp] + S.pv[warp]) *
-                    tanh_fast(b + cnd[ph][2 + warp] + S.pv[2 + warp]);
+              val = sigmoid_fast(a + cnd[ph][warp] + S.pv[q & 1][warp]) *
+                    tanh_fast(b + cnd[ph][2 + warp] + S.pv[q & 1][2 + warp]);
             else  // ph == L + 2: h = relu(out1 . relu(s) + cond_out1)
               val = fmaxf(a + cnd[ph][warp], 0.f);
             PUB(xs + 512 + 2 * c + warp, val, tag);
@@ -547,11 +712,11 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
         } else if (ph <= L) {
           // residual channels 4c + r0, 4c + r0 + 1:  l_{ph-1} = l_{ph-2} + Wr_{ph-1} g_{ph-1} + br_{ph-1}
           const int r0 = 2 * (warp - 2);
-          float a = dot_rows<2>(blk + OFF_L + r0 * 256, v + 512, lane);
-          float b = dot_rows<2>(blk + OFF_L + (r0 + 1) * 256, v + 512, lane);
+          float a = dot_regs<2>(wq, v + 512, lane);
+          float b = dot_regs<2>(wq + 2, v + 512, lane);
           warp_sum2(a, b);
-          ls0 += a + blk[OFF_C + r0];
-          ls1 += b + blk[OFF_C + r0 + 1];
+          ls0 += a + wc0;
+          ls1 += b + wc1;
           if (lane < nrep) {
             PUB(xs + 4 * c + r0, ls0, tag);
             PUB(xs + 4 * c + r0 + 1, ls1, tag);
@@ -561,73 +726,14 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
             PUB(hq + 1, ls1, tag);
           }
         }
+        if (!f_pastearly && q + 1 < total_q) asm volatile("bar.arrive 4, 256;" ::: "memory");
         long long tPub = 0;
-        if (P.dbg && tid == 0) { tPub = clock64(); P.dbg[16 * c + 0] += tPub - tS1; }
+        if (P.dbg && tid == 0) { tPub = clock64(); dacc[0] += tPub - tS1; }
 
-        // history of the next layer (>= 1 step old, so already final), requested right after this
-        // phase's publish so the strong loads never sit in front of the publishing stores
-        uint4 hraw[4];
-        const unsigned long long* hp2 = nullptr;
-        const unsigned long long* hp1 = nullptr;
-        uint32_t tag2 = 0, tag1 = 0;
-        if (do_past) {
-          const int d = S.dil[nph];
-          const int R = 2 * d + 1;
-          const unsigned long long* hb = P.hist + S.hoff[nph];
-          int pn = S.pos[nph] + (nt - t);
-          if (pn >= R) pn -= R;
-          int p1 = pn - d;
-          if (p1 < 0) p1 += R;
-          int p2 = p1 - d;
-          if (p2 < 0) p2 += R;
-          if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * tid; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
-          if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * tid; tag1 = (uint32_t)(nt - d) + 1u; }
-          if (f_hpre) {
-            const int hb_i = (int)(q & 1);
-            if (hp1 || hp2) {
-              fg_mbar_wait(&S.hbar[hb_i], (hpar >> hb_i) & 1u);
-              hpar ^= 1u << hb_i;
-            }
-            const unsigned long long* sg = S.hstage[hb_i];
-            const uint4 z4 = make_uint4(0, 0, 0, 0);
-            hraw[0] = hp2 ? *reinterpret_cast<const uint4*>(sg + 2 * tid) : z4;
-            hraw[1] = hp2 ? *reinterpret_cast<const uint4*>(sg + 256 + 2 * tid) : z4;
-            hraw[2] = hp1 ? *reinterpret_cast<const uint4*>(sg + 512 + 2 * tid) : z4;
-            hraw[3] = hp1 ? *reinterpret_cast<const uint4*>(sg + 768 + 2 * tid) : z4;
-          } else {
-            hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
-            hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
-            hraw[2] = hp1 ? LDX(hp1) : make_uint4(0, 0, 0, 0);
-            hraw[3] = hp1 ? LDX(hp1 + 256) : make_uint4(0, 0, 0, 0);
-          }
-        }
-
-        // ---- slack: overlaps the exchange latency ----
-        if (do_past) {
-          float2 f[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const unsigned long long* pp = (i < 2) ? hp2 : hp1;
-            const uint32_t tg = (i < 2) ? tag2 : tag1;
-            if (pp == nullptr) {
-              f[i] = make_float2(0.f, 0.f);
-            } else if (hraw[i].y == tg && hraw[i].w == tg) {
-              f[i] = make_float2(__uint_as_float(hraw[i].x), __uint_as_float(hraw[i].z));
-            } else {
-              f[i] = poll2(pp + ((i & 1) ? 256 : 0), tg);
-            }
-          }
-          S.hv[2 * tid] = f[0].x;         S.hv[2 * tid + 1] = f[0].y;
-          S.hv[256 + 2 * tid] = f[1].x;   S.hv[256 + 2 * tid + 1] = f[1].y;
-          S.hv[512 + 2 * tid] = f[2].x;   S.hv[512 + 2 * tid + 1] = f[2].y;
-          S.hv[768 + 2 * tid] = f[3].x;   S.hv[768 + 2 * tid + 1] = f[3].y;
-        }
-        if (P.dbg && tid == 0) P.dbg[16 * c + 1] += clock64() - tPub;  // history staged
         if (ph == 1 && tid < NPH) {
           float* dst = S.cnd[(t + 1) & 1][tid + 1];
           dst[0] = cnext.x; dst[1] = cnext.y; dst[2] = cnext.z; dst[3] = cnext.w;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         if (ph <= L && warp < 2) {
           // skip accumulation of the previous layer (phase 1: skip_start on l_0)
           float a = (ph == 1) ? dot_rows<4>(blk + OFF_S + warp * 512, v, lane)
@@ -635,20 +741,16 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
           a = warp_sum(a) + blk[OFF_C + 4 + warp];
           sk = (ph == 1) ? a : sk + a;
         }
-        if (P.dbg && tid == 0) P.dbg[16 * c + 2] += clock64() - tPub;  // + bar 1 + skip dot
+        if (P.dbg && tid == 0) dacc[2] += clock64() - tPub;  // + skip dot
         if (q + 1 < total_q) {
           // next phase's weights: verified here so the next critical section starts at once
           const int nslot = (slot == 2) ? 0 : slot + 1;
           if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (wpar >> nslot) & 1u);
           wpar ^= 1u << nslot;
-          if (P.dbg && tid == 0) P.dbg[16 * c + 8] += clock64() - tPub;  // + next weights arrived
-          if (do_past && !f_nopast) {
-            const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + warp * 1024, S.hv, lane));
-            if (lane == 0) S.pv[warp] = a;
-          }
+          if (P.dbg && tid == 0) dacc[8] += clock64() - tPub;  // + next weights arrived
+          if (!f_latepre) preload_crit(S.ring[nslot], nph);
         }
-        if (!do_past && lane == 0) S.pv[warp] = 0.f;
-        if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[16 * c + 3] += now - tPub; tEnd = now; }
+        if (P.dbg && tid == 0) { const long long now = clock64(); dacc[3] += now - tPub; tEnd = now; }
       }
     }
 
@@ -671,13 +773,13 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
     {
       const float* v = S.v[vb];  // g part holds h
       float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-      if (warp < O) o0 = dot_rows<2>(S.wo2t + warp * FM, v + 512, lane);
-      if (warp + 8 < O) o1 = dot_rows<2>(S.wo2t + (warp + 8) * FM, v + 512, lane);
-      if (warp + 16 < O) o2 = dot_rows<2>(S.wo2t + (warp + 16) * FM, v + 512, lane);
-      if (warp + 24 < O) o3 = dot_rows<2>(S.wo2t + (warp + 24) * FM, v + 512, lane);
+      if (warp < 8 && warp < O) o0 = dot_rows<2>(S.wo2t + warp * FM, v + 512, lane);
+      if (warp < 8 && warp + 8 < O) o1 = dot_rows<2>(S.wo2t + (warp + 8) * FM, v + 512, lane);
+      if (warp < 8 && warp + 16 < O) o2 = dot_rows<2>(S.wo2t + (warp + 16) * FM, v + 512, lane);
+      if (warp < 8 && warp + 24 < O) o3 = dot_rows<2>(S.wo2t + (warp + 24) * FM, v + 512, lane);
       warp_sum2(o0, o1);
       warp_sum2(o2, o3);
-      if (lane == 0) {
+      if (lane == 0 && warp < 8) {
         if (warp < O) S.outv[warp] = o0 + S.bo2[warp];
         if (warp + 8 < O) S.outv[warp + 8] = o1 + S.bo2[warp + 8];
         if (warp + 16 < O) S.outv[warp + 16] = o2 + S.bo2[warp + 16];
@@ -717,7 +819,12 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams P) {
       S.pos[tid] = pn >= R ? 0 : pn;
     }
     __syncthreads();
-    if (P.dbg && tid == 0) { const long long now = clock64(); P.dbg[16 * c + 6] += now - tEnd; tEnd = now; }
+    if (P.dbg && tid == 0) { const long long now = clock64(); dacc[6] += now - tEnd; tEnd = now; }
+  }
+  if (P.dbg && (tid == 0 || tid == 128 || tid == 256 || tid == 255)) {
+#pragma unroll
+    for (int i = 0; i < 14; ++i)
+      if (dacc[i]) P.dbg[16 * c + i] = dacc[i];  // thread 0 and thread 128 own disjoint counters
   }
 }
 
@@ -1000,8 +1107,10 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
   if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * XREP * XSLOT * 8);
   if (rc == NSW_OK) rc = h->hist.ensure(h->hist_entries * 8);
   if (rc == NSW_OK) {
-    cudaError_t e = cudaFuncSetAttribute(fastgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fastgen_kernel<FG_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(FgSmem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fastgen_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgSmem));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
@@ -1117,25 +1226,29 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     P.seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)b;
     // default: red.max publish (512) + history prefetched one phase ahead by cp.async.bulk (2048);
     // every other bit is an experiment switch (scripts/fastgen_exp.py, profiles/r01/fastgen_exchange.md)
-    P.flags = getenv("NSW_FASTGEN_FLAGS") ? atoi(getenv("NSW_FASTGEN_FLAGS")) : (512 | 2048);
+    P.flags = getenv("NSW_FASTGEN_FLAGS") ? atoi(getenv("NSW_FASTGEN_FLAGS")) : FG_DEFAULT_FLAGS;
     P.l2_last = getenv("NSW_FASTGEN_L2LAST") ? atoi(getenv("NSW_FASTGEN_L2LAST")) : h->l2_last;
+    P.crit_delay = getenv("NSW_FASTGEN_CRITDELAY") ? atoi(getenv("NSW_FASTGEN_CRITDELAY")) : 0;
     P.poll_delay = getenv("NSW_FASTGEN_POLLDELAY") ? atoi(getenv("NSW_FASTGEN_POLLDELAY")) : 0;
     P.quant = 65536.0f;
     void* args[] = {&P};
-    NSW_CUDA(cudaLaunchCooperativeKernel((void*)fastgen_kernel, dim3(NC), dim3(NT), args,
-                                         sizeof(FgSmem), st));
+    const bool lean = P.flags == FG_DEFAULT_FLAGS && !want_dbg && P.crit_delay == 0 && P.poll_delay == 0 &&
+                      getenv("NSW_FASTGEN_GENERIC") == nullptr;
+    NSW_CUDA(cudaLaunchCooperativeKernel(lean ? (void*)fastgen_kernel<FG_DEFAULT_FLAGS> : (void*)fastgen_kernel<-1>,
+                                         dim3(NC), dim3(NT), args, sizeof(FgSmem), st));
     count_launch();
     if (want_dbg) {
       std::vector<long long> host(128 * 16);
       NSW_CUDA(cudaStreamSynchronize(st));
       NSW_CUDA(cudaMemcpy(host.data(), h->dbg.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       const double phases = (double)T * (h->L + 2);
-      const char* names[10] = {"crit", "hist staged", "+bar1+skip", "slack", "S1 wait", "poll(after S2)", "head",
-                               "poll group waits at S1", "+weights here", "unused"};
+      const char* names[14] = {"crit", "past:hist staged(after S1)", "+skip", "slack", "S1 wait", "poll(after S1)", "head",
+                               "poll group waits at S1", "+weights here", "past:done(after S1)", "poll sweeps",
+                               "first sweep", "poll t255(after S1)", "prefetch issue"};
       for (int cta : {0, 1, 64, 127}) {
         fprintf(stderr, "[nsw fastgen dbg] cta %3d cycles/phase:", cta);
-        for (int i = 0; i < 10; ++i)
-          fprintf(stderr, " %s=%.0f", names[i], (double)host[16 * cta + i] / (i == 6 ? (double)T : phases));
+        for (int i = 0; i < 14; ++i)
+          fprintf(stderr, " %s=%.*f", names[i], i == 10 ? 2 : 0, (double)host[16 * cta + i] / (i == 6 ? (double)T : phases));
         fprintf(stderr, "\n");
       }
     }

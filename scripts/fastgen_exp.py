@@ -23,16 +23,20 @@ def main():
     enc = (torch.rand((1, a.steps, 256), generator=g) * 2 - 1).to('cuda:0')
     ref = None
     for spec in a.flags.split(','):
-        # spec = flags[:l2last[:polldelay]]
+        # spec = flags[:l2last[:polldelay[:critdelay]]]
         parts = spec.split(':')
         fl = parts[0]
-        if fl == 'default':   # the library's own defaults
-            for k in ('NSW_FASTGEN_FLAGS', 'NSW_FASTGEN_L2LAST', 'NSW_FASTGEN_POLLDELAY'):
+        os.environ.pop('NSW_FASTGEN_GENERIC', None)
+        if fl in ('default', 'generic'):   # the library's own defaults (lean compile-time build / run-time-switch build)
+            if fl == 'generic':
+                os.environ['NSW_FASTGEN_GENERIC'] = '1'
+            for k in ('NSW_FASTGEN_FLAGS', 'NSW_FASTGEN_L2LAST', 'NSW_FASTGEN_POLLDELAY', 'NSW_FASTGEN_CRITDELAY'):
                 os.environ.pop(k, None)
         else:
             os.environ['NSW_FASTGEN_FLAGS'] = fl
             os.environ['NSW_FASTGEN_L2LAST'] = parts[1] if len(parts) > 1 else '0'
             os.environ['NSW_FASTGEN_POLLDELAY'] = parts[2] if len(parts) > 2 else '0'
+            os.environ['NSW_FASTGEN_CRITDELAY'] = parts[3] if len(parts) > 3 else '0'
         fl = spec
         os.environ.pop('NSW_FASTGEN_DEBUG', None)
         eng.run_device(enc[:, :2048], seed=1)
