@@ -42,6 +42,7 @@ constexpr int NT = 384;   // threads per CTA: compute (warps 0-3), poll (4-7), p
 constexpr int MAX_O = 32;
 constexpr int MAX_PH = 40;
 constexpr int XREP = 8;     // replicas of every exchange slot (CTA c polls replica c % XREP)
+constexpr int XREP_MAX = 32; // buffer sized for the replica-count experiments (flags 16384 / 32768)
 constexpr int XSLOT = 768;  // entries per slot: [l (512) | g / s' / h (256)]
 
 // per-(phase, cta) weight block, in floats
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
   }
 
   const bool f_seq = (P.flags & 1) != 0, f_vol = (P.flags & 2) != 0;
-  const int nrep = (P.flags & 4) ? 1 : XREP;
+  const int nrep = (P.flags & 4) ? 1 : (P.flags & 16384) ? 16 : (P.flags & 32768) ? 32 : XREP;
   const bool f_nostream = (P.flags & 8) != 0;  // TIMING EXPERIMENT ONLY: reuse stale weights, results are wrong
   const bool f_cgld = (P.flags & 16) != 0, f_cgst = (P.flags & 32) != 0;
   const bool f_pipe = (P.flags & 64) != 0;  // two poll rounds in flight
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
         const int k = tid - 128;
         float* vn = S.v[vb ^ 1];
         const bool need_l = (ph + 1 <= L);
-        const unsigned long long* slotp = P.xbuf + ((size_t)ph * XREP + (c & (nrep - 1))) * XSLOT;
+        const unsigned long long* slotp = P.xbuf + ((size_t)ph * XREP_MAX + (c & (nrep - 1))) * XSLOT;
         const unsigned long long* pg = slotp + 512 + 2 * k;
         const unsigned long long* pl0 = slotp + 2 * k;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
         const int nt = (ph == NPH) ? t + 1 : t;
         const bool do_past = (nph <= L) && (nt < T) && !f_nohist;
         const float* blk = S.ring[slot];  // arrival was checked in the previous phase's slack
-        unsigned long long* xs = P.xbuf + ((size_t)ph * XREP + lane) * XSLOT;  // my replica (lane < nrep)
+        unsigned long long* xs = P.xbuf + ((size_t)ph * XREP_MAX + lane) * XSLOT;  // my replica (lane < nrep)
 
         // ---- critical section: no CTA barrier, every warp publishes its own results ----
         if (P.crit_delay > 0) {
@@ -720,7 +721,8 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
           if (lane < nrep) {
             PUB(xs + 4 * c + r0, ls0, tag);
             PUB(xs + 4 * c + r0 + 1, ls1, tag);
-          } else if (lane == XREP) {  // history ring of layer ph (read again d and 2d steps later)
+          }
+          if (lane == 31) {  // history ring of layer ph (read again d and 2d steps later)
             unsigned long long* hq = P.hist + S.hoff[ph] + (size_t)S.pos[ph] * FW + 4 * c + r0;
             PUB(hq, ls0, tag);
             PUB(hq + 1, ls1, tag);
@@ -1104,7 +1106,7 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
   if (rc == NSW_OK)
     rc = h->deconv.init(tm, "", cfg->num_mel, FD, cfg->num_deconv, cfg->deconv_filter,
                         cfg->deconv_stride, cfg->upsample_act, want_tc);
-  if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * XREP * XSLOT * 8);
+  if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * XREP_MAX * XSLOT * 8);
   if (rc == NSW_OK) rc = h->hist.ensure(h->hist_entries * 8);
   if (rc == NSW_OK) {
     cudaError_t e = cudaFuncSetAttribute(fastgen_kernel<FG_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1232,10 +1234,26 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     P.poll_delay = getenv("NSW_FASTGEN_POLLDELAY") ? atoi(getenv("NSW_FASTGEN_POLLDELAY")) : 0;
     P.quant = 65536.0f;
     void* args[] = {&P};
-    const bool lean = P.flags == FG_DEFAULT_FLAGS && !want_dbg && P.crit_delay == 0 && P.poll_delay == 0 &&
-                      getenv("NSW_FASTGEN_GENERIC") == nullptr;
-    NSW_CUDA(cudaLaunchCooperativeKernel(lean ? (void*)fastgen_kernel<FG_DEFAULT_FLAGS> : (void*)fastgen_kernel<-1>,
-                                         dim3(NC), dim3(NT), args, sizeof(FgSmem), st));
+    const bool lean = !want_dbg && P.crit_delay == 0 && P.poll_delay == 0 && getenv("NSW_FASTGEN_GENERIC") == nullptr;
+    void* kern = (void*)fastgen_kernel<-1>;
+    if (lean) {
+      // compile-time-flag builds: the default plus a few ablations (same switches, none of the dead code)
+      switch (P.flags) {
+        case FG_DEFAULT_FLAGS: kern = (void*)fastgen_kernel<FG_DEFAULT_FLAGS>; break;
+        case 0: kern = (void*)fastgen_kernel<0>; break;                 // round-start behaviour
+        case 512: kern = (void*)fastgen_kernel<512>; break;             // red.max publish only
+        case 2048: kern = (void*)fastgen_kernel<2048>; break;           // bulk history prefetch only
+        case 2564: kern = (void*)fastgen_kernel<2564>; break;           // default, one replica
+        case 10752: kern = (void*)fastgen_kernel<10752>; break;         // default, past taps not gated on the publish
+        case 6656: kern = (void*)fastgen_kernel<6656>; break;           // default, critical rows loaded late
+        case 2560 + 16384: kern = (void*)fastgen_kernel<2560 + 16384>; break;  // default, 16 replicas
+        case 2560 + 32768: kern = (void*)fastgen_kernel<2560 + 32768>; break;  // default, 32 replicas
+        default: break;
+      }
+    }
+    if (kern != (void*)fastgen_kernel<-1> && kern != (void*)fastgen_kernel<FG_DEFAULT_FLAGS>)
+      NSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgSmem)));
+    NSW_CUDA(cudaLaunchCooperativeKernel(kern, dim3(NC), dim3(NT), args, sizeof(FgSmem), st));
     count_launch();
     if (want_dbg) {
       std::vector<long long> host(128 * 16);
