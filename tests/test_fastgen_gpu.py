@@ -109,3 +109,29 @@ def test_gauss_head_teacher_forced(teacher_hp):
     assert out.shape == (1, T, 2) and np.abs(out - ref).max() < TOL
     a = eng.run_host(enc, seed=1)
     assert np.all(np.isfinite(a)) and a.min() >= -1.0 and a.max() < 1.0
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('env', [
+    {'NSW_FASTGEN_GENERIC': '1'},                                   # run-time-switch build, default switches
+    {'NSW_FASTGEN_FLAGS': '0', 'NSW_FASTGEN_L2LAST': '0'},          # round-start switches (st publish, LDG history)
+    {'NSW_FASTGEN_FLAGS': '2564'},                                  # one replica
+    {'NSW_FASTGEN_FLAGS': '3584', 'NSW_FASTGEN_GENERIC': '1'},      # bulk-copy polling (run-time build only)
+])
+def test_switch_variants_agree_bit_for_bit_with_the_product_build(teacher_hp, env, monkeypatch):
+    """Every publish / poll / prefetch variant moves the same fp32 values through the same arithmetic, so
+    audio and pre-sample outputs must be IDENTICAL to the compile-time-flag product kernel; 1100 steps
+    wrap every history ring with d <= 256."""
+    hp = teacher_hp
+    eng, _ = make_engine(hp)
+    rng = np.random.default_rng(23)
+    T = 1100
+    enc = rng.uniform(-1, 1, (1, T, 256)).astype(np.float32)
+    for k in ('NSW_FASTGEN_GENERIC', 'NSW_FASTGEN_FLAGS', 'NSW_FASTGEN_L2LAST', 'NSW_FASTGEN_DEBUG'):
+        monkeypatch.delenv(k, raising=False)
+    a0, o0 = eng.run_host(enc, seed=9, want_out=True)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    a1, o1 = eng.run_host(enc, seed=9, want_out=True)
+    assert np.array_equal(a0, a1)
+    assert np.array_equal(o0, o1)
