@@ -231,6 +231,15 @@ int nsw_mol_score_device(nsw_teacher* h, const float* d_te_out_params, const flo
                          uint64_t seed, int32_t num_samples, int32_t B, int32_t T, double* result,
                          void* stream);
 
+/* replaces: ParallelWavenet.kl_loss_gauss (parallel_wavenet.py:404-428) downstream of the teacher forward, with
+ * loss_func.mean_std_from_out_params (loss_func.py:66-75): closed-form KL between the student's
+ * N(mean_tot, scale_tot) and a GAUSS teacher's out_params [B,T,2], one HBM-bound reduction.
+ * result[0] = mean KL term, result[1] = mean (log s_p - log s_q)^2, result[2] = kl_loss = [0] + 4*[1]
+ * (host doubles; synchronises). */
+int nsw_gauss_kl_device(nsw_teacher* h, const float* d_te_out_params, const float* d_mean_tot,
+                        const float* d_scale_tot, const float* d_log_scale_tot, int32_t B, int32_t T,
+                        double* result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

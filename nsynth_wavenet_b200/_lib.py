@@ -90,6 +90,8 @@ PROTOTYPES = {
     'nsw_teacher_last_timing': (C.c_int, [_VP, C.POINTER(C.c_float)]),
     'nsw_mol_score_device': (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_uint64, C.c_int32, C.c_int32,
                                        C.c_int32, C.POINTER(C.c_double * 3), _VP]),
+    'nsw_gauss_kl_device': (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.POINTER(C.c_double * 3),
+                                      _VP]),
     'nsw_fastgen_pack_host': (C.c_int, [C.POINTER(nsw_wavenet_config), C.POINTER(nsw_tensor),
                                         C.c_int32, _VP, C.c_int64, _VP, _VP,
                                         C.POINTER(C.c_int64)]),

@@ -121,6 +121,42 @@ mol_score_kernel(const float* __restrict__ te /*[BT][3*nr]*/, const float* __res
   }
 }
 
+// ---- closed-form Gaussian KL (ClariNet distillation), HBM-bound: 20 bytes read per sample ----
+// kl_loss_gauss (parallel_wavenet.py:404-428) on the teacher's [BT][2] output: per sample
+//   log s_p - log s_q + (s_q^2 - s_p^2 + (m_p - m_q)^2) / (2 s_p^2),   reg = (log s_p - log s_q)^2
+// with s_p = exp(max(param, -7)) (loss_func.py:66-75).  Grid-stride, fp64 block sums, one atomic pair per block.
+__global__ void __launch_bounds__(256)
+gauss_kl_kernel(const float2* __restrict__ te /*[BT] (mean, log-scale param)*/, const float* __restrict__ mean,
+                const float* __restrict__ scale, const float* __restrict__ log_scale, size_t BT,
+                double* __restrict__ acc /*[2]: sum kl, sum reg*/) {
+  double kl_sum = 0.0, reg_sum = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < BT; i += (size_t)gridDim.x * blockDim.x) {
+    const float2 p = __ldg(te + i);
+    const float mq = __ldg(mean + i), sq = __ldg(scale + i), lq = __ldg(log_scale + i);
+    const float sp = expf(fmaxf(p.y, -7.0f));
+    const float lp = logf(sp);                         // the reference takes tf.log of the std (:418)
+    const float vq = sq * sq, vp = sp * sp;
+    const float dm = p.x - mq;
+    const float kl = lp - lq + (vq - vp + dm * dm) / (2.0f * vp);
+    const float dl = lp - lq;
+    kl_sum += (double)kl;
+    reg_sum += (double)(dl * dl);
+  }
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    kl_sum += __shfl_xor_sync(0xffffffffu, kl_sum, o);
+    reg_sum += __shfl_xor_sync(0xffffffffu, reg_sum, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = kl_sum; red[1][threadIdx.x >> 5] = reg_sum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    atomicAdd(acc, a);
+    atomicAdd(acc + 1, b);
+  }
+}
+
 }  // namespace
 }  // namespace nsw
 
@@ -400,5 +436,33 @@ extern "C" int nsw_mol_score_device(nsw_teacher* h, const float* d_te_out, const
   result[0] = H_Ps;
   result[1] = H_Ps_Pt;
   result[2] = H_Ps_Pt - H_Ps;
+  return NSW_OK;
+}
+
+// result[0] = mean KL term, result[1] = mean squared log-scale difference, result[2] = kl_loss = [0] + 4 [1]
+// (parallel_wavenet.py:422-428)
+extern "C" int nsw_gauss_kl_device(nsw_teacher* h, const float* d_te_out, const float* d_mean, const float* d_scale,
+                                   const float* d_log_scale, int32_t B, int32_t T, double* result, void* stream) {
+  NSW_CHECK(h && d_te_out && d_mean && d_scale && d_log_scale && result, NSW_EINVAL, "null argument");
+  NSW_CHECK(h->cfg.loss_type == NSW_LOSS_GAUSS && h->O == 2, NSW_EINVAL,
+            "gaussian KL needs a gauss teacher (out_width 2, got loss_type %d out_width %d)", h->cfg.loss_type, h->O);
+  NSW_CHECK(B >= 1 && T >= 1, NSW_EINVAL, "bad batch/length %d/%d", B, T);
+  NSW_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t BT = (size_t)B * T;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  // 8 resident CTAs of 256 threads per SM cover the latency of the 4 independent streams; never more CTAs than work
+  const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * 8, (BT + 255) / 256);
+  NSW_CUDA(cudaMemsetAsync(h->acc.p, 0, 2 * sizeof(double), st));
+  gauss_kl_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(d_te_out), d_mean, d_scale, d_log_scale, BT,
+                                        h->acc.as<double>());
+  count_launch();
+  double host[2];
+  NSW_CUDA(cudaMemcpyAsync(host, h->acc.p, sizeof(host), cudaMemcpyDeviceToHost, st));
+  NSW_CUDA(cudaStreamSynchronize(st));
+  result[0] = host[0] / (double)BT;
+  result[1] = host[1] / (double)BT;
+  result[2] = result[0] + 4.0 * result[1];
   return NSW_OK;
 }

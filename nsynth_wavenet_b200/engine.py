@@ -318,6 +318,17 @@ class TeacherEngine:
                                               C.byref(res), st))
         return {'H_Ps': res[0], 'H_Ps_Pt': res[1], 'kl_loss': res[2]}
 
+    def gauss_kl(self, te_out, mean_tot, scale_tot, log_scale_tot):
+        """-> dict(kl_loss, kl, reg) like ParallelWavenet.kl_loss_gauss (parallel_wavenet.py:404-428) downstream of
+        the teacher forward; needs a gauss teacher (wavenet_gauss.json).  torch CUDA inputs."""
+        import torch
+        B, T = mean_tot.shape
+        res = (C.c_double * 3)()
+        st = torch.cuda.current_stream(mean_tot.device).cuda_stream
+        L.check(self.lib.nsw_gauss_kl_device(self._h, L.ptr(te_out), L.ptr(mean_tot), L.ptr(scale_tot),
+                                             L.ptr(log_scale_tot), B, T, C.byref(res), st))
+        return {'kl': res[0], 'reg': res[1], 'kl_loss': res[2]}
+
     def last_timing(self):
         ms = C.c_float()
         L.check(self.lib.nsw_teacher_last_timing(self._h, C.byref(ms)))

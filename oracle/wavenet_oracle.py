@@ -644,3 +644,30 @@ def kl_loss_logistic(te_out, mean_tot, scale_tot, log_scale_tot, eps, quant_chan
     H_Ps_Pt = float(-lp.mean())                                         # :392-396
     H_Ps = float(log_scale_tot.mean() + 2.0)                            # :395
     return {'H_Ps': H_Ps, 'H_Ps_Pt': H_Ps_Pt, 'kl_loss': H_Ps_Pt - H_Ps}
+
+
+def mean_std_from_out_params(gauss_params, use_log_scales=True):
+    """loss_func.mean_std_from_out_params (wavenet/loss_func.py:66-75): [B,T,2] -> mean, std."""
+    mean, std_param = gauss_params[..., 0], gauss_params[..., 1]
+    if use_log_scales:
+        std = np.exp(np.maximum(std_param, gauss_params.dtype.type(-7.0)))      # :71-72
+    else:
+        sp = np.logaddexp(std_param, 0)                                        # softplus, :74
+        std = np.maximum(sp, np.exp(gauss_params.dtype.type(-7.0)))
+    return mean, std
+
+
+def kl_loss_gauss(te_out, mean_tot, scale_tot, log_scale_tot):
+    """ParallelWavenet.kl_loss_gauss (wavenet/parallel_wavenet.py:404-428) with the Gaussian teacher's
+    output `te_out` [B,T,2] given: closed-form KL(q || p) per sample between the student's N(mean_tot,
+    scale_tot) and the teacher's N(mean_p, scale_p), averaged, plus 4 x the mean squared difference of the
+    log scales (ClariNet's regulariser).  Arithmetic in the dtype of the inputs, like the TF graph."""
+    mean_p, scale_p = mean_std_from_out_params(te_out, use_log_scales=True)     # :416-417
+    log_scale_p = np.log(scale_p)                                               # :418
+    var_q = scale_tot ** 2                                                      # :420
+    var_p = scale_p ** 2                                                        # :421
+    kl_bl = (log_scale_p - log_scale_tot +
+             (var_q - var_p + (mean_p - mean_tot) ** 2) / (2 * var_p))          # :422-423
+    kl = float(kl_bl.mean(dtype=np.float64))                                    # :424
+    reg = float(((log_scale_p - log_scale_tot) ** 2).mean(dtype=np.float64))    # :425
+    return {'kl': kl, 'reg': reg, 'kl_loss': kl + 4.0 * reg}                    # :426-428

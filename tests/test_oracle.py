@@ -195,3 +195,33 @@ def test_weight_norm_folding():
     w = O.fold_weight_norm({'a/W_V': V, 'a/W_g': g, 'a/biases': np.zeros(5, np.float32)})
     nrm = np.sqrt((w['a/W'].astype(np.float64) ** 2).sum(axis=(0, 1, 2)))
     assert np.allclose(nrm, g, rtol=1e-5) and 'a/W_V' not in w
+
+
+def test_kl_loss_gauss_matches_torch_distributions():
+    """kl_loss_gauss (parallel_wavenet.py:404-428): the per-sample term is KL(N(m_q, s_q) || N(m_p, s_p)); an
+    independent implementation of that closed form exists in torch.distributions, so this pins the restatement
+    (including the -7 floor on the teacher's log-scale parameter, loss_func.py:71)."""
+    import torch
+    from torch.distributions import Normal, kl_divergence
+    rng = np.random.default_rng(41)
+    B, T = 3, 500
+    te = np.stack([rng.normal(0, 0.3, (B, T)), rng.uniform(-9, -1, (B, T))], axis=-1)      # some below the floor
+    mean = rng.normal(0, 0.3, (B, T))
+    ls = rng.uniform(-6, -1, (B, T))
+    scale = np.exp(ls)
+    got = O.kl_loss_gauss(te, mean, scale, ls)
+    lp = np.maximum(te[..., 1], -7.0)
+    q = Normal(torch.from_numpy(mean), torch.from_numpy(scale))
+    p = Normal(torch.from_numpy(te[..., 0]), torch.from_numpy(np.exp(lp)))
+    kl = float(kl_divergence(q, p).mean())
+    reg = float(((lp - ls) ** 2).mean())
+    assert abs(got['kl'] - kl) < 1e-9 * max(1.0, abs(kl))
+    assert abs(got['reg'] - reg) < 1e-12
+    assert abs(got['kl_loss'] - (kl + 4 * reg)) < 1e-9 * max(1.0, abs(kl))
+    # identical distributions: every term vanishes
+    same = O.kl_loss_gauss(np.stack([mean, ls], -1), mean, scale, ls)
+    assert abs(same['kl_loss']) < 1e-12
+    # float32 twin stays close to the float64 truth on the same inputs
+    g32 = O.kl_loss_gauss(te.astype(np.float32), mean.astype(np.float32), scale.astype(np.float32),
+                          ls.astype(np.float32))
+    assert abs(g32['kl_loss'] - got['kl_loss']) < 1e-4 * abs(got['kl_loss'])

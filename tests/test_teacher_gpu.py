@@ -1,5 +1,7 @@
 """GPU parity of the teacher full-sequence forward (a14) and the distillation cross-entropy
 (a15) against the CPU oracle.  Tolerance 1e-4 on out_params (split-bf16 tensor cores)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -93,3 +95,64 @@ def test_distillation_forward_pipeline(student_hp, teacher_hp):
     print('distillation losses', got, ref)
     assert abs(got['H_Ps'] - ref['H_Ps']) < 1e-4
     assert abs(got['H_Ps_Pt'] - ref['H_Ps_Pt']) < 0.02 * abs(ref['H_Ps_Pt'])   # different noise draws
+
+
+@pytest.mark.timeout(600)
+def test_gauss_kl_matches_oracle():
+    """nsw_gauss_kl_device == oracle kl_loss_gauss (parallel_wavenet.py:404-428) on random inputs, including
+    teacher log-scale parameters below the -7 floor and a length that is not a multiple of the block size."""
+    hp = O.load_hparams(os.path.join(os.path.dirname(__file__), '..', 'nsynth_wavenet_b200', 'config_jsons',
+                                     'wavenet_gauss.json'))
+    from nsynth_wavenet_b200 import TeacherEngine
+    w = O.init_teacher_weights(hp, seed=12345, bias_std=0.02)
+    eng = TeacherEngine(hp, w, device=0)
+    rng = np.random.default_rng(43)
+    for B, T in ((1, 77), (3, 7680), (8, 61440)):
+        te = np.stack([rng.normal(0, 0.3, (B, T)), rng.uniform(-9, -1, (B, T))], axis=-1).astype(np.float32)
+        mean = rng.normal(0, 0.3, (B, T)).astype(np.float32)
+        ls = rng.uniform(-6, -1, (B, T)).astype(np.float32)
+        scale = np.exp(ls)
+        ref = O.kl_loss_gauss(te, mean, scale, ls)
+        got = eng.gauss_kl(torch.from_numpy(te).cuda(), torch.from_numpy(mean).cuda(), torch.from_numpy(scale).cuda(),
+                           torch.from_numpy(ls).cuda())
+        print('gauss kl', B, T, got, ref)
+        # tolerance: fp32 per-sample terms (expf/logf within 2 ulp of NumPy's), fp64 accumulation on both sides
+        for k in ('kl', 'reg', 'kl_loss'):
+            assert abs(got[k] - ref[k]) < 2e-5 * max(1.0, abs(ref[k])), (B, T, k, got[k], ref[k])
+    # a mol teacher refuses
+    from nsynth_wavenet_b200._lib import NswError
+    mol_hp = O.load_hparams(os.path.join(os.path.dirname(__file__), '..', 'nsynth_wavenet_b200', 'config_jsons',
+                                         'wavenet_mol.json'))
+    mol = TeacherEngine(mol_hp, O.init_teacher_weights(mol_hp, seed=1), device=0)
+    z = torch.zeros((1, 128), device='cuda')
+    with pytest.raises(NswError):
+        mol.gauss_kl(torch.zeros((1, 128, 2), device='cuda'), z, z, z)
+
+
+@pytest.mark.timeout(900)
+def test_clarinet_distillation_forward_pipeline():
+    """ClariNet (BASELINE configs[3] model) distillation forward at reduced batch: Gaussian IAF student forward ->
+    Gaussian teacher forward on x -> closed-form KL, each stage against the oracle."""
+    from nsynth_wavenet_b200 import IAFEngine, TeacherEngine
+    cj = os.path.join(os.path.dirname(__file__), '..', 'nsynth_wavenet_b200', 'config_jsons')
+    shp = O.load_hparams(os.path.join(cj, 'parallel_wavenet_gauss.json'))
+    thp = O.load_hparams(os.path.join(cj, 'wavenet_gauss.json'))
+    st_w = O.init_student_weights(shp, seed=12345)
+    te_w = O.init_teacher_weights(thp, seed=12345, bias_std=0.02)
+    st = IAFEngine(shp, st_w, device=0)
+    te = TeacherEngine(thp, te_w, device=0)
+    rng = np.random.default_rng(44)
+    mel = torch.from_numpy(rng.uniform(0, 1, (2, 6, 80)).astype(np.float32)).cuda()
+    out = st.forward_device(mel, None, seed=5, quantize=False)
+    te_out = te.forward_device(out['x'], mel)
+    torch.cuda.synchronize()
+    x = out['x'].cpu().numpy()
+    ref_te = O.teacher_feed_forward(te_w, thp, x, mel.cpu().numpy(), np.float32)['out_params']
+    assert ref_te.shape[-1] == 2
+    assert np.abs(te_out.cpu().numpy() - ref_te).max() < TOL
+    got = te.gauss_kl(te_out, out['mean_tot'], out['scale_tot'], out['log_scale_tot'])
+    ref = O.kl_loss_gauss(ref_te, out['mean_tot'].cpu().numpy(), out['scale_tot'].cpu().numpy(),
+                          out['log_scale_tot'].cpu().numpy())
+    print('clarinet distillation', got, ref)
+    # the KL divides by var_p ~ exp(2*log-scale): a 1e-4 difference in the teacher's log-scale moves it by ~2e-4 relative
+    assert abs(got['kl_loss'] - ref['kl_loss']) < 2e-3 * max(1.0, abs(ref['kl_loss']))
