@@ -1,13 +1,19 @@
 """Weight containers for the generation path.
 
 The reference restores TF-V2 checkpoint bundles through tf.train.Saver with an
-EMA-shadow name map (wavenet/fastgen.py:12-14,81-84; wavenet/parallelgen.py:30-41).
-TensorFlow is not available here, so `checkpoint_path` is an ``.npz`` archive (or a
-directory / prefix next to which ``<prefix>.npz`` exists) whose keys are the same TF
-variable names, with or without the ``/ExponentialMovingAverage`` suffix.  When both
-spellings are present the EMA shadow wins, except for variables the reference reads
-un-shadowed (the frozen teacher deconv stack under use_teacher_deconv,
-parallelgen.py:32-39)."""
+EMA-shadow name map (wavenet/fastgen.py:12-14,81-84; wavenet/parallelgen.py:30-41) and resolves
+directories with tf.train.latest_checkpoint (eval_wavenet.py:22, eval_parallel_wavenet.py:22).
+`checkpoint_path` may therefore be
+
+* a TF-V2 bundle prefix (``model.ckpt-200000`` next to ``.index`` / ``.data-*``) or a directory
+  holding one (its ``checkpoint`` state file picks the latest) — read without TensorFlow by
+  ``tf_bundle.py``;
+* an ``.npz`` archive (or a directory / prefix next to which ``<prefix>.npz`` exists),
+
+with keys that are the TF variable names, with or without the ``/ExponentialMovingAverage`` suffix.
+When both spellings are present the EMA shadow wins, except for variables the reference reads
+un-shadowed (the frozen teacher deconv stack under use_teacher_deconv, parallelgen.py:32-39).
+Optimizer slots and counters of a training checkpoint are skipped."""
 from __future__ import annotations
 
 import os
@@ -28,34 +34,58 @@ def get_default_shadow_dict(names):
 
 
 def resolve_checkpoint(checkpoint_path):
+    """-> ('npz', file) or ('bundle', prefix)."""
+    from . import tf_bundle
     p = os.fspath(checkpoint_path)
-    cands = [p, p + '.npz']
+    if os.path.isfile(p) and p.endswith('.npz'):
+        return 'npz', p
+    if tf_bundle.is_bundle_prefix(p):
+        return 'bundle', p
+    if os.path.isfile(p) and p.endswith('.index'):
+        return 'bundle', p[:-len('.index')]
+    if os.path.isfile(p + '.npz'):
+        return 'npz', p + '.npz'
     if os.path.isdir(p):
-        cands += sorted(os.path.join(p, f) for f in os.listdir(p) if f.endswith('.npz'))[::-1]
-    for c in cands:
-        if os.path.isfile(c) and c.endswith('.npz'):
-            return c
+        prefix = tf_bundle.latest_checkpoint(p)
+        if prefix is not None:
+            return 'bundle', prefix
+        cands = sorted(os.path.join(p, f) for f in os.listdir(p) if f.endswith('.npz'))[::-1]
+        if cands:
+            return 'npz', cands[0]
     raise FileNotFoundError(
-        'no .npz weight archive found for checkpoint_path={!r}; TF-V2 bundles are not '
-        'readable without TensorFlow (export with tools/export_npz.py on the training '
-        'side)'.format(checkpoint_path))
+        'no TF-V2 checkpoint bundle (<prefix>.index + .data-*) and no .npz weight archive found for '
+        'checkpoint_path={!r}'.format(checkpoint_path))
+
+
+_SKIP_SUFFIXES = ('/Adam', '/Adam_1', '/Momentum', '/RMSProp', '/RMSProp_1')
+_SKIP_NAMES = ('global_step', 'beta1_power', 'beta2_power')
+
+
+def _is_model_variable(name):
+    return not (name.endswith(_SKIP_SUFFIXES) or name.split('/')[-1] in _SKIP_NAMES)
 
 
 def load_weights(checkpoint_path, unshadowed_substrings=()):
     """-> dict plain TF variable name -> float32 array."""
-    path = resolve_checkpoint(checkpoint_path)
-    raw = np.load(path)
+    kind, path = resolve_checkpoint(checkpoint_path)
+    if kind == 'bundle':
+        from . import tf_bundle
+        raw = tf_bundle.read_bundle(path, names=_is_model_variable)
+        files = list(raw)
+    else:
+        raw = np.load(path)
+        files = raw.files
     out = {}
-    for key in raw.files:
+    for key in files:
         name = key[:-2] if key.endswith(':0') else key
         if name.endswith(EMA_SUFFIX):
             base = name[:-len(EMA_SUFFIX)]
-            if any(s in base for s in unshadowed_substrings) and base in raw.files:
+            if any(s in base for s in unshadowed_substrings) and base in files:
                 continue
             out[base] = np.asarray(raw[key], np.float32)
         elif name not in out:
             shadow = name + EMA_SUFFIX
-            if shadow in raw.files and not any(s in name for s in unshadowed_substrings):
+            if shadow in files and not any(s in name for s in unshadowed_substrings):
                 continue
             out[name] = np.asarray(raw[key], np.float32)
     return out
