@@ -11,7 +11,9 @@
 // weight slice never changes; it is streamed from L2 through a 3-slot smem ring with
 // cp.async.bulk two phases ahead.  Per audio sample there are L+2 = 32 "phases", each ending
 // in one all-to-all exchange of a 768-float vector through an LL (value+tag in one 8-byte
-// word) buffer: no fences, no atomics, no grid barrier.
+// word) buffer: published with an L2-side 64-bit max (the tag only grows), polled with strong
+// loads; no fences, no grid barrier.  The weight stream (151 MB per sample, larger than L2) is
+// loaded with L2 eviction hints so that about half of it stays resident.
 //
 // Algebra that halves the number of exchanges (one per layer instead of two):
 //   d_i = W0_i l_{i-1}[t-2d] + W1_i l_{i-1}[t-d] + W2_i l_{i-1}[t] + b_i + cond_i[t]
@@ -19,7 +21,8 @@
 //   => W2_i l_{i-1}[t] = W2_i l_{i-2}[t] + (W2_i Wr_{i-1}) g_{i-1} + W2_i br_{i-1}
 // so phase i needs only g_{i-1} and l_{i-2}, both already exchanged; M_i = W2_i Wr_{i-1} is
 // precomputed in fp64 at create time.  The two past taps (2/3 of the dilated-conv work) only
-// depend on history and are computed in the slack while the exchange is in flight, and the
+// depend on history (prefetched by cp.async.bulk one phase ahead) and are computed by their own
+// warp group beside the critical section, and the
 // mel conditioning of the whole utterance is hoisted into one conv-GEMM (the reference
 // sketches the same hoist: Fastgen.cond_vars, wavenet.py:353-377).
 #include "nsw_gemm.cuh"
@@ -77,7 +80,8 @@ struct FgParams {
   int l2_last;                  // weight blocks of phases < l2_last are loaded L2::evict_last, the rest evict_first (0 = no hints)
   int crit_delay;               // TIMING EXPERIMENT ONLY: busy-wait before the critical section
   int poll_delay;               // poll group starts polling this many cycles after S1 (0 = at once)
-  int flags;                    // experiment switches: 1 = sequential polls, 2 = volatile ld/st, 4 = one replica
+  int flags;                    // switch word, bits documented where they are decoded at the top of the kernel;
+                                // product value FG_DEFAULT_FLAGS (compile-time instantiation)
   unsigned long long seed;
   float quant;                  // quant_chann
 };

@@ -164,3 +164,31 @@ def test_parallelgen_synthesis_writes_wavs(student_hp, tmp_path):
         rate, data = wavfile.read(p)
         assert rate == 16000 and data.dtype == np.float32
         assert len(data) == (8 * 200 // 512) * 512 and np.all(np.abs(data) <= 1.0)
+
+
+def test_parallelgen_synthesis_from_a_tf_bundle_directory(student_hp, tmp_path):
+    """The reference's call with the reference's kind of checkpoint (eval_parallel_wavenet.py:22,67): a directory
+    holding a TF-V2 bundle with EMA shadows and optimizer slots.  Same wavs as from the .npz of the same weights."""
+    from scipy.io import wavfile
+    from nsynth_wavenet_b200 import checkpoint as ckpt
+    from wavenet import parallelgen
+    from tf_bundle_writer import write_bundle
+    w = O.init_student_weights(student_hp, seed=12345)
+    d = tmp_path / 'ns_pwn-eval'
+    d.mkdir()
+    bundle = {}
+    for k, v in w.items():
+        bundle[k] = np.zeros_like(v)                                   # raw variable: must NOT be the one used
+        bundle[k + ckpt.EMA_SUFFIX] = v
+        bundle[k + '/Adam'] = np.zeros_like(v)
+    bundle['global_step'] = np.asarray(400000, np.int64)
+    write_bundle(str(d / 'model.ckpt-400000'), bundle, num_shards=2, block_size=1024)
+    (d / 'checkpoint').write_text('model_checkpoint_path: "model.ckpt-400000"\n')
+    npz = ckpt.save_weights(str(tmp_path / 'export'), w, ema=True)
+    mel, _ = synth_inputs(student_hp, 2, 8)
+    pa = [str(tmp_path / 'a0.wav'), str(tmp_path / 'a1.wav')]
+    pb = [str(tmp_path / 'b0.wav'), str(tmp_path / 'b1.wav')]
+    parallelgen.synthesis(student_hp, mel, pa, str(d), seed=3)
+    parallelgen.synthesis(student_hp, mel, pb, npz, seed=3)
+    for x, y in zip(pa, pb):
+        assert np.array_equal(wavfile.read(x)[1], wavfile.read(y)[1])
