@@ -240,6 +240,21 @@ int nsw_gauss_kl_device(nsw_teacher* h, const float* d_te_out_params, const floa
                         const float* d_scale_tot, const float* d_log_scale_tot, int32_t B, int32_t T,
                         double* result, void* stream);
 
+/* ---- mel front-end ---------------------------------------------------------
+ * replaces: auxilaries/mel_extractor.py:31-90 (melspectrogram / batch_melspectrogram; librosa STFT centre=True,
+ * reflect padding, hann window zero-padded to n_fft; Slaney filterbank; 20 log10(max(min_amp, .)); normalise
+ * against min_level_db).  twiddle_cos / twiddle_sin [win][n_bins]: window-folded DFT tables of the non-zero
+ * window taps; mel_basis [n_mel][n_bins].  frames = 1 + N / hop. */
+typedef struct nsw_mel nsw_mel;
+int nsw_mel_create(int32_t device, int32_t n_bins, int32_t win, int32_t hop, int32_t n_mel,
+                   const float* twiddle_cos, const float* twiddle_sin, const float* mel_basis, float min_amp,
+                   float min_level_db, nsw_mel** out);
+void nsw_mel_destroy(nsw_mel* h);
+int nsw_mel_frames(nsw_mel* h, int32_t n_samples);
+/* wav [B,N] (N > n_fft/2) -> mel [B, frames, n_mel] in [0,1] */
+int nsw_mel_device(nsw_mel* h, const float* d_wav, int32_t B, int32_t N, float* d_mel, void* stream);
+int nsw_mel_host(nsw_mel* h, const float* wav, int32_t B, int32_t N, float* mel);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,12 @@ PROTOTYPES = {
                                        C.c_int32, C.POINTER(C.c_double * 3), _VP]),
     'nsw_gauss_kl_device': (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.POINTER(C.c_double * 3),
                                       _VP]),
+    'nsw_mel_create': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, C.c_float,
+                                 C.c_float, C.POINTER(_VP)]),
+    'nsw_mel_destroy': (None, [_VP]),
+    'nsw_mel_frames': (C.c_int, [_VP, C.c_int32]),
+    'nsw_mel_device': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
+    'nsw_mel_host': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
     'nsw_fastgen_pack_host': (C.c_int, [C.POINTER(nsw_wavenet_config), C.POINTER(nsw_tensor),
                                         C.c_int32, _VP, C.c_int64, _VP, _VP,
                                         C.POINTER(C.c_int64)]),

@@ -64,14 +64,27 @@ def test_load_batch_pads_and_save_batch_roundtrip(tmp_path):
     assert fastgen.load_batch([str(tmp_path / 'e.npy'), str(tmp_path / 'f.npy')]).shape == (14, 3)
 
 
-def test_mel_extractor_shapes_and_range():
-    y = np.random.default_rng(0).uniform(-0.5, 0.5, 154480).astype(np.float32)
-    m = mel_extractor.melspectrogram(y)
-    assert m.shape == (773, 80) and m.dtype == np.float32
-    assert m.min() >= 0 and m.max() <= 1
-    assert mel_extractor.batch_melspectrogram(y[None, :8000]).shape == (1, 41, 80)
+def test_mel_tables_reproduce_the_oracle_stft_and_filterbank():
+    """Host-side table preparation of the GPU mel front-end (no GPU needed): the window-folded twiddle tables
+    contract a frame's 800 window taps to the same magnitudes as the oracle's zero-padded 2048-point rfft, and the
+    filterbank equals the oracle's."""
+    from oracle import mel_oracle
+    tc, ts = mel_extractor._build_twiddles()
+    assert tc.shape == (800, 1025) and ts.shape == (800, 1025)
+    rng = np.random.default_rng(0)
+    y = rng.uniform(-0.5, 0.5, 4000)
+    D = np.abs(mel_oracle._stft(y))                                   # [1025, frames], float64
+    ypad = np.pad(y, 1024, mode='reflect')
+    for j in (0, 3, D.shape[1] - 1):
+        taps = ypad[j * 200 + 624:j * 200 + 624 + 800]
+        re, im = taps @ tc.astype(np.float64), taps @ ts.astype(np.float64)
+        assert np.abs(np.sqrt(re * re + im * im) - D[:, j]).max() < 2e-5 * max(1.0, D[:, j].max())
     basis = mel_extractor._build_mel_basis()
     assert basis.shape == (80, 1025) and np.all(basis >= 0) and np.all(basis.sum(1) > 0)
+    assert np.array_equal(basis, mel_oracle._build_mel_basis())
+    m = mel_oracle.melspectrogram(rng.uniform(-0.5, 0.5, 154480).astype(np.float32))
+    assert m.shape == (773, 80) and m.dtype == np.float32 and m.min() >= 0 and m.max() <= 1
+    assert mel_oracle.batch_melspectrogram(y[None, :].astype(np.float32)).shape == (1, 21, 80)
 
 
 def test_mu_law_roundtrip_numpy():

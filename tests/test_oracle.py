@@ -225,3 +225,22 @@ def test_kl_loss_gauss_matches_torch_distributions():
     g32 = O.kl_loss_gauss(te.astype(np.float32), mean.astype(np.float32), scale.astype(np.float32),
                           ls.astype(np.float32))
     assert abs(g32['kl_loss'] - got['kl_loss']) < 1e-4 * abs(got['kl_loss'])
+
+
+def test_mel_oracle_stft_matches_scipy():
+    """The oracle's centred, reflect-padded, window-zero-padded STFT (librosa.stft as called at
+    auxilaries/mel_extractor.py:68-72) against scipy.signal.stft, an independent implementation of the framing
+    and the FFT, fed the same padded signal and the same 2048-point window."""
+    from scipy import signal
+    from oracle import mel_oracle
+    rng = np.random.default_rng(3)
+    y = rng.uniform(-0.5, 0.5, 5000)
+    D = mel_oracle._stft(y)                                            # [1025, frames]
+    win = np.zeros(2048)
+    win[624:1424] = signal.get_window('hann', 800, fftbins=True)       # periodic hann, centred in n_fft
+    ypad = np.pad(y, 1024, mode='reflect')
+    _, _, Z = signal.stft(ypad, window=win, nperseg=2048, noverlap=2048 - 200, nfft=2048, boundary=None,
+                          padded=False, return_onesided=True)
+    Z = Z * win.sum()                                                  # scipy scales by 1 / sum(window)
+    assert Z.shape == D.shape == (1025, 1 + 5000 // 200)
+    assert np.abs(Z - D).max() < 1e-9
