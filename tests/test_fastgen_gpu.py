@@ -135,3 +135,18 @@ def test_switch_variants_agree_bit_for_bit_with_the_product_build(teacher_hp, en
     a1, o1 = eng.run_host(enc, seed=9, want_out=True)
     assert np.array_equal(a0, a1)
     assert np.array_equal(o0, o1)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('T', [1, 2, 3, 5, 33])
+def test_very_short_utterances_match_oracle(teacher_hp, T):
+    """Edge cases of the one-phase-ahead history prefetch and the weight ring: utterances shorter than the
+    prefetch distance, than the first dilation cycle, and just past one ring of the d=16 layers."""
+    hp = teacher_hp
+    eng, w = make_engine(hp)
+    rng = np.random.default_rng(100 + T)
+    enc = rng.uniform(-1, 1, (1, T, 256)).astype(np.float32)
+    wav = rng.uniform(-0.5, 0.5, (1, T)).astype(np.float32)
+    _, out = eng.run_host(enc, teacher_force=wav, want_out=True)
+    ref = O.fastgen_run(w, hp, enc, np.float32, teacher_force=wav)['out']
+    assert np.abs(out - ref).max() < TOL
