@@ -58,7 +58,7 @@ constexpr int BLOCK_FLOATS = OFF_P + 4 * 1024;  // 9224
 constexpr uint32_t BLOCK_BYTES = BLOCK_FLOATS * 4;
 static_assert(BLOCK_BYTES % 16 == 0 && (OFF_P * 4) % 16 == 0, "bulk copy alignment");
 
-constexpr int FG_DEFAULT_FLAGS = 512 | 2048;  // red.max publish + bulk history prefetch
+constexpr int FG_DEFAULT_FLAGS = 512 | 2048;  // red.max publish + history requested one phase ahead
 constexpr long long FG_WATCHDOG = 6000000000ll;  // ~3 s of SM clocks
 
 struct FgParams {
@@ -104,11 +104,11 @@ struct FgSmem {
   int hoff[MAX_PH];      // entry offset of the layer's history ring
   int pos[MAX_PH];       // t mod (2*dil+1), advanced once per step
   unsigned long long mbar[3];
-  // bulk-copy exchange / history path (flags 1024 / 2048)
+  // bulk-copy exchange polling (flag 1024)
   alignas(128) unsigned long long inbox[XSLOT];      // one exchange slot, tagged entries
-  alignas(128) unsigned long long hstage[2][1024];   // [l[t-2d] (512) | l[t-d] (512)] tagged, by phase parity
-  unsigned long long xbar, hbar[2];
+  unsigned long long xbar;
   int pflag[2][4];
+  float part[4][8];   // per-poll-warp partial sums of the 8 critical dot products (on-arrival contraction)
 };
 
 static_assert(sizeof(FgSmem) <= 227 * 1024, "fastgen shared memory");
@@ -330,8 +330,6 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
     for (int s = 0; s < 3; ++s)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[s])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.xbar)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.hbar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.hbar[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     S.xnext = 0.f;
   }
@@ -363,7 +361,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
   }
 
   const bool f_seq = (P.flags & 1) != 0, f_vol = (P.flags & 2) != 0;
-  const int nrep = (P.flags & 4) ? 1 : (P.flags & 16384) ? 16 : (P.flags & 32768) ? 32 : XREP;
+  const int nrep = (P.flags & 4) ? 1 : XREP;
   const bool f_nostream = (P.flags & 8) != 0;  // TIMING EXPERIMENT ONLY: reuse stale weights, results are wrong
   const bool f_cgld = (P.flags & 16) != 0, f_cgst = (P.flags & 32) != 0;
   const bool f_pipe = (P.flags & 64) != 0;  // two poll rounds in flight
@@ -371,14 +369,14 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
   const bool f_nopast = (P.flags & 256) != 0;   // TIMING EXPERIMENT ONLY: no past-tap dot, results are wrong
   const bool f_red = (P.flags & 512) != 0;    // publish with red.max.u64
   const bool f_bulk = (P.flags & 1024) != 0;  // poll the exchange slot with one cp.async.bulk per round
-  const bool f_pastearly = (P.flags & 8192) != 0;  // past taps not gated on the publish (experiment)
   const bool f_latepre = (P.flags & 4096) != 0;  // critical-row weights loaded inside the critical section (old behaviour)
-  const bool f_hpre = (P.flags & 2048) != 0;  // history vectors prefetched one phase ahead with cp.async.bulk
-  uint32_t xpar = 0, hpar = 0;
+  const bool f_hpre = (P.flags & 2048) != 0;  // history vectors requested one phase ahead (registers)
+  uint32_t xpar = 0;
   auto PUB = [&](unsigned long long* p, float v, uint32_t tg) { if (f_red) publish_red(p, v, tg); else if (f_cgst) publish_cg(p, v, tg); else if (f_vol) publish_vol(p, v, tg); else publish(p, v, tg); };
   auto LDX = [&](const unsigned long long* p) -> uint4 { return f_cgld ? ldv4_cg(p) : (f_vol ? ldv4_vol(p) : ldv4(p)); };
   float x1 = 0.f, x2 = 0.f;  // inputs of the two previous steps (conv_start queues, rate 1)
-  float ls0 = 0.f, ls1 = 0.f, sk = 0.f;  // warps 2,3: two residual channels; warps 0,1: one skip channel
+  float ls0 = 0.f, ls1 = 0.f, sk = 0.f;
+  float lsr = 0.f;           // poll warp 5, lane>>3 = r: residual channel 4c+r (phases 2..L publish from the poll group)  // warps 2,3: two residual channels; warps 0,1: one skip channel
   long long q = 0;           // global phase counter -> weight ring slot / parity
   int vb = 0;                // which S.v buffer the current phase reads
   long long tEnd = 0, tPollEnd = 0;
@@ -480,17 +478,12 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
           if (nt - 2 * d >= 0) { hp2 = hb + (size_t)p2 * FW + 2 * pt; tag2 = (uint32_t)(nt - 2 * d) + 1u; }
           if (nt - d >= 0) { hp1 = hb + (size_t)p1 * FW + 2 * pt; tag1 = (uint32_t)(nt - d) + 1u; }
           if (f_hpre) {
-            const int hb_i = (int)(q & 1);
-            if (hp1 || hp2) {
-              fg_mbar_wait(&S.hbar[hb_i], (hpar >> hb_i) & 1u);
-              hpar ^= 1u << hb_i;
-            }
-            const unsigned long long* sg = S.hstage[hb_i];
-            const uint4 z4 = make_uint4(0, 0, 0, 0);
-            hraw[0] = hp2 ? *reinterpret_cast<const uint4*>(sg + 2 * pt) : z4;
-            hraw[1] = hp2 ? *reinterpret_cast<const uint4*>(sg + 256 + 2 * pt) : z4;
-            hraw[2] = hp1 ? *reinterpret_cast<const uint4*>(sg + 512 + 2 * pt) : z4;
-            hraw[3] = hp1 ? *reinterpret_cast<const uint4*>(sg + 768 + 2 * pt) : z4;
+            // requested by this thread one phase ago (end of the previous phase's past-group work), parked in the
+            // register file where the compute warps keep their preloaded rows
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              hraw[i] = make_uint4(__float_as_uint(wq[i].x), __float_as_uint(wq[i].y), __float_as_uint(wq[i].z),
+                                   __float_as_uint(wq[i].w));
           } else {
             hraw[0] = hp2 ? LDX(hp2) : make_uint4(0, 0, 0, 0);
             hraw[1] = hp2 ? LDX(hp2 + 256) : make_uint4(0, 0, 0, 0);
@@ -519,29 +512,15 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
           S.hv[512 + 2 * pt] = f[2].x;   S.hv[512 + 2 * pt + 1] = f[2].y;
           S.hv[768 + 2 * pt] = f[3].x;   S.hv[768 + 2 * pt + 1] = f[3].y;
         }
-        if (P.dbg && tid == 256) dacc[1] += clock64() - tS1;  // history staged
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q + 1 < total_q) {
-          const int nslot = (slot == 2) ? 0 : slot + 1;
-          if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (wpar >> nslot) & 1u);
-          wpar ^= 1u << nslot;
-          // the 32 KB of shared-memory reads below would slow the critical section down: start after the publish
-          if (!f_pastearly) asm volatile("bar.sync 4, 256;" ::: "memory");
-          if (do_past && !f_nopast) {
-            const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + pw * 1024, S.hv, lane));
-            if (lane == 0) S.pv[(q + 1) & 1][pw] = a;
-          }
-        }
-        if (!do_past && lane == 0) S.pv[(q + 1) & 1][pw] = 0.f;
-        if (P.dbg && tid == 256) dacc[9] += clock64() - tS1;  // past taps done
-      } else if (warp >= 4) {
-        // ======================= poll group (warps 4-7) =======================
-        // receives THIS phase's exchange (what the compute groups of all CTAs publish below)
-        // into S.v[vb^1] for the next phase; it never waits for this CTA's own compute
-        if (f_hpre && tid == 128) {
-          // history of the layer whose past taps the NEXT phase's slack computes: >= 30 phases old
+        if (f_hpre) {
+          // history of the layer whose past taps the NEXT phase computes (>= 29 phases old): plain L2 loads, in
+          // flight for the rest of this phase (issued as soon as the registers are free).  (As cp.async.bulk they queued behind the 37 KB weight block of
+          // the same SM and arrived a whole phase later.)
           const int sph = (ph == NPH) ? 1 : ph + 1, st = (ph == NPH) ? t + 1 : t;
           const int tph = (sph == NPH) ? 1 : sph + 1, tt = (sph == NPH) ? st + 1 : st;
+          uint4 hn[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hn[i] = make_uint4(0, 0, 0, 0);
           if (tph <= L && tt < T) {
             const int d = S.dil[tph];
             const int R = 2 * d + 1;
@@ -552,31 +531,62 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
             if (p1 < 0) p1 += R;
             int p2 = p1 - d;
             if (p2 < 0) p2 += R;
-            const bool has2 = tt - 2 * d >= 0, has1 = tt - d >= 0;
-            if (has1 || has2) {
-              const int hb_i = (int)((q + 1) & 1);
-              mbar_expect(&S.hbar[hb_i], (has1 ? 4096u : 0u) + (has2 ? 4096u : 0u));
-              if (has2) bulk_copy(S.hstage[hb_i], hb + (size_t)p2 * FW, 4096u, &S.hbar[hb_i]);
-              if (has1) bulk_copy(S.hstage[hb_i] + 512, hb + (size_t)p1 * FW, 4096u, &S.hbar[hb_i]);
+            if (tt - 2 * d >= 0) {
+              hn[0] = ldv4_cg(hb + (size_t)p2 * FW + 2 * pt);
+              hn[1] = ldv4_cg(hb + (size_t)p2 * FW + 256 + 2 * pt);
+            }
+            if (tt - d >= 0) {
+              hn[2] = ldv4_cg(hb + (size_t)p1 * FW + 2 * pt);
+              hn[3] = ldv4_cg(hb + (size_t)p1 * FW + 256 + 2 * pt);
             }
           }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            wq[i] = make_float4(__uint_as_float(hn[i].x), __uint_as_float(hn[i].y), __uint_as_float(hn[i].z),
+                                __uint_as_float(hn[i].w));
         }
-        if (tid == 128) {
-          const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
-          if (qn < total_q && !(f_nostream && qn >= 3)) {
-            const int bph = (ph + 1 >= NPH) ? ph + 1 - NPH : ph + 1;  // qn % NPH
-            const int qs = (slot >= 1) ? slot - 1 : 2;                 // qn % 3
-            if (P.l2_last > 0)
-              bulk_load_hint(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
-                             &S.mbar[qs], bph < P.l2_last);
-            else
-              bulk_load(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
-                        &S.mbar[qs]);
+        if (P.dbg && tid == 256) dacc[1] += clock64() - tS1;  // history staged
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q + 1 < total_q) {
+          const int nslot = (slot == 2) ? 0 : slot + 1;
+          if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (wpar >> nslot) & 1u);
+          wpar ^= 1u << nslot;
+          if (do_past && !f_nopast) {
+            const float a = warp_sum(dot_rows<8>(S.ring[nslot] + OFF_P + pw * 1024, S.hv, lane));
+            if (lane == 0) S.pv[(q + 1) & 1][pw] = a;
           }
         }
+        if (!do_past && lane == 0) S.pv[(q + 1) & 1][pw] = 0.f;
+        asm volatile("bar.arrive 5, 256;" ::: "memory");        // S.pv of the next phase is written
+        if (P.dbg && tid == 256) dacc[9] += clock64() - tS1;  // past taps done
+      } else if (warp >= 4) {
+        // ======================= poll group (warps 4-7) =======================
+        // receives THIS phase's exchange into S.v[vb^1] and (phases 2..L) contracts it on arrival
         const int k = tid - 128;
         float* vn = S.v[vb ^ 1];
         const bool need_l = (ph + 1 <= L);
+        // Phases 2..L: the critical dot products of the NEXT phase are contracted right here, on arrival, by the
+        // threads that receive the entries (6 entries x 8 rows per thread), reduced over the 128 poll threads and
+        // published by poll warps 4/5 -- the chain "last entry seen -> publish" has no vector write, CTA barrier,
+        // reload or 768-long dot in it.  Phases 1, L+1, L+2 keep the compute group's critical section.
+        const bool fast = need_l;
+        const int pnslot = (slot == 2) ? 0 : slot + 1;
+        if (q + 1 < total_q) {
+          if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[pnslot], (wpar >> pnslot) & 1u);
+          wpar ^= 1u << pnslot;
+        }
+        if (ph == 1 && warp == 5) lsr = v[4 * c + (lane >> 3)];   // l_0 channel from conv_start
+        float2 wg[4][3], wr[4];
+        if (fast) {
+          const float* nb = S.ring[pnslot];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int sgm = 0; sgm < 3; ++sgm)
+              wg[j][sgm] = *reinterpret_cast<const float2*>(nb + OFF_D + j * 768 + 256 * sgm + 2 * k);
+            wr[j] = *reinterpret_cast<const float2*>(nb + OFF_L + j * 256 + 2 * k);
+          }
+        }
         const unsigned long long* slotp = P.xbuf + ((size_t)ph * XREP_MAX + (c & (nrep - 1))) * XSLOT;
         const unsigned long long* pg = slotp + 512 + 2 * k;
         const unsigned long long* pl0 = slotp + 2 * k;
@@ -670,6 +680,63 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
           }
         }
         if (P.dbg && tid == 255) dacc[12] += clock64() - tS1;  // poll complete for the last poll thread
+        if (fast) {
+          const float e0 = __uint_as_float(r0.x), e1 = __uint_as_float(r0.z), e2 = __uint_as_float(r1.x),
+                      e3 = __uint_as_float(r1.z), g0 = __uint_as_float(r2.x), g1 = __uint_as_float(r2.z);
+          float a8[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = wg[j][0].x * e0;
+            a = fmaf(wg[j][0].y, e1, a);
+            a = fmaf(wg[j][1].x, e2, a);
+            a = fmaf(wg[j][1].y, e3, a);
+            a = fmaf(wg[j][2].x, g0, a);
+            a8[j] = fmaf(wg[j][2].y, g1, a);
+            a8[4 + j] = fmaf(wr[j].y, g1, wr[j].x * g0);
+          }
+          // transposing butterfly: 8 values x 32 lanes -> lane holds the warp total of value (lane >> 2) & 7
+          float b4[4], b2[2], b1;
+          const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float mine = h16 ? a8[4 + i] : a8[i], theirs = h16 ? a8[i] : a8[4 + i];
+            b4[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float mine = h8 ? b4[2 + i] : b4[i], theirs = h8 ? b4[i] : b4[2 + i];
+            b2[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+          }
+          {
+            const float mine = h4 ? b2[1] : b2[0], theirs = h4 ? b2[0] : b2[1];
+            b1 = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+          }
+          b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+          b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+          if ((lane & 3) == 0) S.part[warp - 4][(lane >> 2) & 7] = b1;
+        }
+        // poll group syncs, past group arrives: S.part complete and S.pv of the next phase written
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        if (fast && warp <= 5) {
+          const int np1 = ph + 1, rep = lane & 7;
+          unsigned long long* xn = P.xbuf + ((size_t)np1 * XREP_MAX + rep) * XSLOT;
+          if (warp == 4) {
+            if (lane < 16) {
+              const int pr = lane >> 3;   // gate pair
+              const float a = (S.part[0][pr] + S.part[1][pr]) + (S.part[2][pr] + S.part[3][pr]);
+              const float b = (S.part[0][2 + pr] + S.part[1][2 + pr]) + (S.part[2][2 + pr] + S.part[3][2 + pr]);
+              const float* pvn = S.pv[(q + 1) & 1];
+              const float val = sigmoid_fast(a + cnd[np1][pr] + pvn[pr]) * tanh_fast(b + cnd[np1][2 + pr] + pvn[2 + pr]);
+              if (rep < nrep) PUB(xn + 512 + 2 * c + pr, val, tag);
+            }
+          } else {
+            const int r = lane >> 3;      // residual channel 4c + r: l_{np1-1} = l_{np1-2} + Wr g + br
+            const float d = (S.part[0][4 + r] + S.part[1][4 + r]) + (S.part[2][4 + r] + S.part[3][4 + r]);
+            lsr += d + S.ring[pnslot][OFF_C + r];
+            if (rep < nrep) PUB(xn + 4 * c + r, lsr, tag);
+            if (rep == 0) PUB(P.hist + S.hoff[np1] + (size_t)S.pos[np1] * FW + 4 * c + r, lsr, tag);
+          }
+        }
         if (need_l) {
           vn[2 * k] = __uint_as_float(r0.x); vn[2 * k + 1] = __uint_as_float(r0.z);
           vn[256 + 2 * k] = __uint_as_float(r1.x); vn[256 + 2 * k + 1] = __uint_as_float(r1.z);
@@ -694,7 +761,9 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
           while (clock64() < tgo) {}
         }
         if (f_latepre) preload_crit(blk, ph);
-        if (ph == L + 1) {
+        if (ph > 1 && ph <= L) {
+          // published by the poll group at the end of the previous phase (on-arrival contraction)
+        } else if (ph == L + 1) {
           if (warp < 2) {
             const float a = warp_sum(dot_regs<2>(wq, v + 512, lane));
             sk = fmaxf(sk + a + wc0, 0.f);  // relu(s) after the last skip
@@ -732,7 +801,21 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
             PUB(hq + 1, ls1, tag);
           }
         }
-        if (!f_pastearly && q + 1 < total_q) asm volatile("bar.arrive 4, 256;" ::: "memory");
+        // prefetches for later phases are issued here, by a thread that has nothing critical left in this phase
+        // (issuing a bulk copy behind a weight block still in flight can stall the thread for ~1000 cycles)
+        if (tid == 0) {
+          const long long qn = q + 2;  // slot (q+2)%3 == (q-1)%3 was last read before S1
+          if (qn < total_q && !(f_nostream && qn >= 3)) {
+            const int bph = (ph + 1 >= NPH) ? ph + 1 - NPH : ph + 1;  // qn % NPH
+            const int qs = (slot >= 1) ? slot - 1 : 2;                 // qn % 3
+            if (P.l2_last > 0)
+              bulk_load_hint(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
+                             &S.mbar[qs], bph < P.l2_last);
+            else
+              bulk_load(S.ring[qs], my_blocks + (size_t)bph * phase_stride, BLOCK_BYTES,
+                        &S.mbar[qs]);
+          }
+        }
         long long tPub = 0;
         if (P.dbg && tid == 0) { tPub = clock64(); dacc[0] += tPub - tS1; }
 
@@ -754,7 +837,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
           if (!(f_nostream && q + 1 >= 3)) fg_mbar_wait(&S.mbar[nslot], (wpar >> nslot) & 1u);
           wpar ^= 1u << nslot;
           if (P.dbg && tid == 0) dacc[8] += clock64() - tPub;  // + next weights arrived
-          if (!f_latepre) preload_crit(S.ring[nslot], nph);
+          if (!f_latepre && (nph == 1 || nph > L)) preload_crit(S.ring[nslot], nph);  // phases 2..L publish from the poll group
         }
         if (P.dbg && tid == 0) { const long long now = clock64(); dacc[3] += now - tPub; tEnd = now; }
       }
@@ -1248,10 +1331,7 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
         case 512: kern = (void*)fastgen_kernel<512>; break;             // red.max publish only
         case 2048: kern = (void*)fastgen_kernel<2048>; break;           // bulk history prefetch only
         case 2564: kern = (void*)fastgen_kernel<2564>; break;           // default, one replica
-        case 10752: kern = (void*)fastgen_kernel<10752>; break;         // default, past taps not gated on the publish
         case 6656: kern = (void*)fastgen_kernel<6656>; break;           // default, critical rows loaded late
-        case 2560 + 16384: kern = (void*)fastgen_kernel<2560 + 16384>; break;  // default, 16 replicas
-        case 2560 + 32768: kern = (void*)fastgen_kernel<2560 + 32768>; break;  // default, 32 replicas
         default: break;
       }
     }
