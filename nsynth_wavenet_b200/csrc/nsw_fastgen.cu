@@ -44,8 +44,9 @@ constexpr int NC = 128;   // CTAs
 constexpr int NT = 384;   // threads per CTA: compute (warps 0-3), poll (4-7), past taps (8-11)
 constexpr int MAX_O = 32;
 constexpr int MAX_PH = 40;
-constexpr int XREP = 8;     // replicas of every exchange slot (CTA c polls replica c % XREP)
-constexpr int XREP_MAX = 32; // buffer sized for the replica-count experiments (flags 16384 / 32768)
+constexpr int XREP = 2;     // replicas of every exchange slot (CTA c polls replica c % XREP); 1 and 2 measure the same,
+                            // 4 is 0.7 % and 8 is 3 % slower now that 48 finalizer lanes publish (fastgen_exp_run57.log)
+constexpr int XREP_MAX = 8;  // buffer sized for the replica-count experiments (flags 16384 / 32768)
 constexpr int XSLOT = 768;  // entries per slot: [l (512) | g / s' / h (256)]
 
 // per-(phase, cta) weight block, in floats
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
   }
 
   const bool f_seq = (P.flags & 1) != 0, f_vol = (P.flags & 2) != 0;
-  const int nrep = (P.flags & 4) ? 1 : XREP;
+  const int nrep = (P.flags & 4) ? 1 : (P.flags & 16384) ? 4 : (P.flags & 32768) ? 8 : XREP;
   const bool f_nostream = (P.flags & 8) != 0;  // TIMING EXPERIMENT ONLY: reuse stale weights, results are wrong
   const bool f_cgld = (P.flags & 16) != 0, f_cgst = (P.flags & 32) != 0;
   const bool f_pipe = (P.flags & 64) != 0;  // two poll rounds in flight
@@ -1332,6 +1333,8 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
         case 2048: kern = (void*)fastgen_kernel<2048>; break;           // bulk history prefetch only
         case 2564: kern = (void*)fastgen_kernel<2564>; break;           // default, one replica
         case 6656: kern = (void*)fastgen_kernel<6656>; break;           // default, critical rows loaded late
+        case 2560 + 16384: kern = (void*)fastgen_kernel<2560 + 16384>; break;  // default with 4 replicas
+        case 2560 + 32768: kern = (void*)fastgen_kernel<2560 + 32768>; break;  // default with 8 replicas
         default: break;
       }
     }
