@@ -590,7 +590,10 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
         }
         const unsigned long long* slotp = P.xbuf + ((size_t)ph * XREP_MAX + (c & (nrep - 1))) * XSLOT;
         const unsigned long long* pg = slotp + 512 + 2 * k;
-        const unsigned long long* pl0 = slotp + 2 * k;
+        // the l part is read straight from the history ring of layer ph (same tagged entries, same tag: the owner
+        // publishes l_{ph-1} there anyway), so it is not published a second time into the exchange slot
+        const unsigned long long* pl0 =
+            f_bulk ? slotp + 2 * k : P.hist + S.hoff[ph <= L ? ph : L] + (size_t)S.pos[ph <= L ? ph : L] * FW + 2 * k;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
         bool ok0 = !need_l, ok1 = !need_l, ok2 = false;
         long long w0 = 0;
@@ -734,7 +737,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
             const int r = lane >> 3;      // residual channel 4c + r: l_{np1-1} = l_{np1-2} + Wr g + br
             const float d = (S.part[0][4 + r] + S.part[1][4 + r]) + (S.part[2][4 + r] + S.part[3][4 + r]);
             lsr += d + S.ring[pnslot][OFF_C + r];
-            if (rep < nrep) PUB(xn + 4 * c + r, lsr, tag);
+            if (f_bulk && rep < nrep) PUB(xn + 4 * c + r, lsr, tag);   // only the bulk-poll experiment reads l from the slot
             if (rep == 0) PUB(P.hist + S.hoff[np1] + (size_t)S.pos[np1] * FW + 4 * c + r, lsr, tag);
           }
         }
@@ -792,7 +795,7 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
           warp_sum2(a, b);
           ls0 += a + wc0;
           ls1 += b + wc1;
-          if (lane < nrep) {
+          if (f_bulk && lane < nrep) {
             PUB(xs + 4 * c + r0, ls0, tag);
             PUB(xs + 4 * c + r0 + 1, ls1, tag);
           }
