@@ -154,8 +154,11 @@ def fastgen_bench(device, steps, hbm_peak):
     return {'metric': 'fastgen audio samples/sec (wavenet_mol.json, batch 1)', 'value': sps,
             'unit': UNIT, 'rtf': sps / 16000.0, 'steps': steps, 'ms': ms,
             'us_per_step': 1e3 * ms / steps,
-            'weight_stream_gbs': weight_bytes * sps / 1e9,
+            'weight_stream_gbs': weight_bytes * sps / 1e9,          # L2/HBM -> shared memory, all CTAs
             'weight_stream_frac_of_hbm': weight_bytes * sps / 1e9 / hbm_peak,
+            # ncu capture of the same kernel (profiles/r01/fastgen_ncu_run56.json): 76.7 MB of DRAM reads per
+            # sample, the rest of the 151 MB stream is served from the L2-resident (evict_last) blocks
+            'dram_read_gbs_from_ncu_bytes': 76.7e6 * sps / 1e9,
             'note': 'includes the hoisted cond GEMM; weights stream L2/HBM -> smem every step, the blocks of '
                     'the first ~60 % of L2 worth of phases are loaded L2::evict_last (ncu: 49 % L2 hit rate)'}
 
