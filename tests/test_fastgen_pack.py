@@ -114,3 +114,53 @@ def test_pack_rejects_unsupported_configs(teacher_hp):
     assert rc == -1 and b'mol / gauss' in lib.nsw_last_error()
     rc = lib.nsw_fastgen_pack_host(C.byref(engine.wavenet_config(teacher_hp)), tensors, 1, None, 0, None, None, sizes)
     assert rc == -3 and b'missing weight tensor' in lib.nsw_last_error()
+
+
+def test_on_arrival_partition_and_butterfly_equal_the_row_dots(teacher_hp):
+    """The poll group's on-arrival contraction (nsw_fastgen.cu, phases 2..L), restated on the packed block of one
+    CTA: thread k holds entries {2k, 2k+1} of each third of the exchanged vector and the matching weights of the 8
+    critical rows; a transposing butterfly leaves value (lane >> 2) & 7 in every lane; 4 warp partials are summed by
+    the finalizer lanes.  Must equal the plain row dots (gate rows over [l | g], residual rows over g)."""
+    hp = teacher_hp
+    w = O.init_teacher_weights(hp, seed=12345, bias_std=0.02)
+    blocks, _, _ = pack(hp, w)
+    rng = np.random.default_rng(9)
+    for ph, cta in ((2, 0), (7, 37), (hp.num_layers, 127)):
+        blk = blocks[ph - 1][cta].astype(np.float64)
+        v = rng.normal(0, 1, 768)
+        k = np.arange(128)
+        acc = np.zeros((128, 8))
+        for j in range(4):
+            for sgm in range(3):
+                wj = np.stack([blk[OFF_D + j * 768 + 256 * sgm + 2 * k], blk[OFF_D + j * 768 + 256 * sgm + 2 * k + 1]], 1)
+                e = np.stack([v[256 * sgm + 2 * k], v[256 * sgm + 2 * k + 1]], 1)
+                acc[:, j] += (wj * e).sum(1)
+            wr = np.stack([blk[OFF_L + j * 256 + 2 * k], blk[OFF_L + j * 256 + 2 * k + 1]], 1)
+            acc[:, 4 + j] = (wr * np.stack([v[512 + 2 * k], v[512 + 2 * k + 1]], 1)).sum(1)
+        part = np.zeros((4, 8))
+        lane = np.arange(32)
+        for wp in range(4):
+            a8 = acc[32 * wp:32 * wp + 32]                                  # [lane, 8]
+            h16, h8, h4 = (lane & 16) != 0, (lane & 8) != 0, (lane & 4) != 0
+            b4 = np.zeros((32, 4))
+            for i in range(4):
+                mine = np.where(h16, a8[:, 4 + i], a8[:, i])
+                theirs = np.where(h16, a8[:, i], a8[:, 4 + i])
+                b4[:, i] = mine + theirs[lane ^ 16]
+            b2 = np.zeros((32, 2))
+            for i in range(2):
+                mine = np.where(h8, b4[:, 2 + i], b4[:, i])
+                theirs = np.where(h8, b4[:, i], b4[:, 2 + i])
+                b2[:, i] = mine + theirs[lane ^ 8]
+            mine = np.where(h4, b2[:, 1], b2[:, 0])
+            theirs = np.where(h4, b2[:, 0], b2[:, 1])
+            b1 = mine + theirs[lane ^ 4]
+            b1 = b1 + b1[lane ^ 2]
+            b1 = b1 + b1[lane ^ 1]
+            for ln in range(0, 32, 4):
+                part[wp, (ln >> 2) & 7] = b1[ln]
+            assert all(np.allclose(b1[ln], b1[ln | 3]) for ln in range(0, 32, 4))   # replicated over 4 lanes
+        tot = part.sum(0)
+        rows_d = blk[OFF_D:OFF_D + 3072].reshape(4, 768) @ v
+        rows_l = blk[OFF_L:OFF_L + 1024].reshape(4, 256) @ v[512:]
+        assert np.abs(tot[:4] - rows_d).max() < 1e-10 and np.abs(tot[4:] - rows_l).max() < 1e-10
