@@ -38,6 +38,7 @@ extern "C" {
 #define NSW_ECUDA (-2)    /* CUDA runtime or driver error                    */
 #define NSW_EMISSING (-3) /* a required weight tensor is missing / misshaped */
 #define NSW_ETIMEOUT (-4) /* persistent kernel watchdog fired                */
+#define NSW_ERANGE (-5)   /* an activation left the fp16 range of the split-precision tensor-core engines */
 
 #define NSW_MAX_FLOWS 8
 #define NSW_MAX_DECONV 4
@@ -118,6 +119,12 @@ const char* nsw_last_error(void);
  * gpu_launches claim is read from here, not estimated) */
 uint64_t nsw_kernel_launch_count(void);
 
+/* The tensor-core engines carry activations as fp16 hi + fp16 lo (fp32-grade, 22 mantissa bits) and therefore share
+ * fp16's range: |v| <= 65504.  Every conversion site checks it; the "_host" entry points return NSW_ERANGE instead of
+ * a silently wrong result, and after "_device" calls this function (which synchronises `device`) reports and clears
+ * the condition: NSW_OK or NSW_ERANGE. */
+int nsw_range_status(int32_t device);
+
 /* ---- parallel IAF student ------------------------------------------------
  * replaces: parallelgen.load_parallelgen (parallelgen.py:11-19) = graph build of
  * ParallelWavenet.feed_forward (parallel_wavenet.py:289-345) + _clip_quant_scale
@@ -179,7 +186,10 @@ int nsw_fastgen_encode_device(nsw_fastgen* h, const float* d_mel, int32_t B, int
 int nsw_fastgen_encode_host(nsw_fastgen* h, const float* mel, int32_t B, int32_t F,
                             float* encoding);
 
-/* the whole per-sample loop of fastgen.synthesis as ONE persistent kernel.
+/* the whole per-sample loop of fastgen.synthesis as ONE persistent kernel.  Two engines sit behind this call: the
+ * latency engine (batch rows one after the other, gate_width = width, mol / gauss heads) and the batched engine
+ * (up to 8 rows per weight pass; also double_gate_width, the ce head and mu-law input).  B >= 3 or a configuration the
+ * latency engine does not cover selects the batched one; NSW_FASTGEN_ENGINE=gn|latency overrides.
  * d_encoding [B,T,deconv_width] (fed step by step with NO centre trim,
  * fastgen.py:157); d_teacher_force [B,T] or NULL: if given the wav fed at step i
  * is teacher_force[:, i-1] (0 at i = 0) instead of the model's own sample;
@@ -190,6 +200,23 @@ int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, int32_t B, i
                            float* d_out, void* stream);
 int nsw_fastgen_run_host(nsw_fastgen* h, const float* encoding, int32_t B, int32_t T,
                          const float* teacher_force, uint64_t seed, float* audio, float* out);
+/* replaces: fastgen.load_cond_layers / calculate_cond_vars (fastgen.py:91-115) = Fastgen.cond_vars
+ * (wavenet.py:353-377): encoding [B,T,deconv_width] -> out [B,T, num_layers*gate_width + skip_width], columns
+ * [i*gate_width, (i+1)*gate_width) = mel_cond_{i+1}, the last skip_width columns = mel_cond_out1 (biases added). */
+int nsw_fastgen_cond_vars_device(nsw_fastgen* h, const float* d_encoding, int32_t B, int32_t T, float* d_out,
+                                 void* stream);
+int nsw_fastgen_cond_vars_host(nsw_fastgen* h, const float* encoding, int32_t B, int32_t T, float* out);
+
+/* PARITY HOOK: the sampler's random draws of the following nsw_fastgen_run_* calls are read from `noise` instead of
+ * the in-kernel Philox stream, so that the int32 samples can be compared with loss_func.mol_sample / gauss_sample /
+ * ce_sample (loss_func.py:140-206) evaluated on the same draws.  noise [B][T][nu] (host pointer, or device pointer if
+ * on_device != 0; copied):
+ *   mol   nu = nr_mix + 1 : u1[0..nr_mix) then u2, uniforms in [1e-5, 1 - 1e-5] as tf.random_uniform draws them
+ *                           (loss_func.py:166,181)
+ *   gauss nu = 1          : n ~ N(0,1), the draw of Normal.sample() (loss_func.py:203)
+ *   ce    nu = 1          : u in (0,1) for the inverse-CDF categorical draw
+ * B and T must match the runs that consume it.  noise = NULL returns to Philox. */
+int nsw_fastgen_set_noise(nsw_fastgen* h, const float* noise, int32_t B, int32_t T, int32_t nu, int32_t on_device);
 /* device time of the last nsw_fastgen_run_* (cond GEMM + persistent kernel) in ms */
 int nsw_fastgen_last_timing(nsw_fastgen* h, float* ms);
 /* TEST HOOK (host only, no CUDA): the create-time repacking of the TF-named tensors into
@@ -199,6 +226,12 @@ int nsw_fastgen_last_timing(nsw_fastgen* h, float* ms);
 int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tensors,
                           int32_t n_tensors, float* blocks, int64_t blocks_cap, float* cond_w,
                           float* cond_b, int64_t* sizes);
+
+/* TEST HOOK (host only, no CUDA): create-time repacking of the batched fastgen engine (nsw_fastgen_gn.cu: gate 512 or
+ * 1024, mol / gauss / ce heads, up to 8 utterances per weight pass).  sizes[0] = floats in `blocks`, [1] = floats per
+ * block, [2] = CTAs, [3] = columns of cond_w, [4] = gate_width / 2, [5] = phases per step (num_layers + 3). */
+int nsw_fastgen_gn_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tensors, int32_t n_tensors,
+                             float* blocks, int64_t blocks_cap, float* cond_w, float* cond_b, int64_t* sizes);
 
 /* TEST HOOK (host only, no CUDA): work split and publish / read plan of one launch of the persistent IAF flow kernel
  * (engine NSW_ENGINE_TC3), computed by the same integer functions the kernel uses.  Per CTA: {clip, first tile, tiles,

@@ -19,7 +19,7 @@ LOSS = {'logistic': 0, 'gauss': 1, 'mol': 2, 'ce': 3}
 ACT = {'tanh': 0, 'relu': 1, 'leaky_relu': 2}
 ENGINE = {'ffma': 0, 'tc': 1, 'tc2': 2, 'tc3': 3}
 
-ERRORS = {-1: 'NSW_EINVAL', -2: 'NSW_ECUDA', -3: 'NSW_EMISSING', -4: 'NSW_ETIMEOUT'}
+ERRORS = {-1: 'NSW_EINVAL', -2: 'NSW_ECUDA', -3: 'NSW_EMISSING', -4: 'NSW_ETIMEOUT', -5: 'NSW_ERANGE'}
 
 
 class NswError(RuntimeError):
@@ -59,6 +59,7 @@ PROTOTYPES = {
     'nsw_version': (C.c_int, []),
     'nsw_last_error': (C.c_char_p, []),
     'nsw_kernel_launch_count': (C.c_uint64, []),
+    'nsw_range_status': (C.c_int, [C.c_int32]),
     'nsw_iaf_create': (C.c_int, [C.POINTER(nsw_iaf_config), C.POINTER(nsw_tensor), C.c_int32,
                                  C.c_int32, C.POINTER(_VP)]),
     'nsw_iaf_destroy': (None, [_VP]),
@@ -82,6 +83,12 @@ PROTOTYPES = {
     'nsw_fastgen_run_host': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, C.c_uint64, _VP,
                                        _VP]),
     'nsw_fastgen_last_timing': (C.c_int, [_VP, C.POINTER(C.c_float)]),
+    'nsw_fastgen_cond_vars_device': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
+    'nsw_fastgen_cond_vars_host': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
+    'nsw_fastgen_set_noise': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'nsw_fastgen_gn_pack_host': (C.c_int, [C.POINTER(nsw_wavenet_config), C.POINTER(nsw_tensor),
+                                           C.c_int32, _VP, C.c_int64, _VP, _VP,
+                                           C.POINTER(C.c_int64)]),
     'nsw_teacher_create': (C.c_int, [C.POINTER(nsw_wavenet_config), C.POINTER(nsw_tensor), C.c_int32,
                                      C.c_int32, C.POINTER(_VP)]),
     'nsw_teacher_destroy': (None, [_VP]),

@@ -80,6 +80,7 @@ class MelExtractor:
     def __init__(self, device=0, p=mel_params):
         self.lib = L.load()
         self.p = p
+        self.dev_index = device
         tc, ts = _build_twiddles(p)
         basis = np.ascontiguousarray(_build_mel_basis(p))
         self.win = tc.shape[0]
@@ -114,6 +115,8 @@ class MelExtractor:
     def device(self, wav):
         """torch CUDA wav [B, N] -> torch CUDA [B, frames, num_mel] on the current stream."""
         import torch
+        from ..engine import _dev_tensor
+        _dev_tensor(wav, 'wav', (None, None), self.dev_index)
         B, N = wav.shape
         out = torch.empty((B, self.frames(N), self.p.num_mel), dtype=torch.float32, device=wav.device)
         st = torch.cuda.current_stream(wav.device).cuda_stream

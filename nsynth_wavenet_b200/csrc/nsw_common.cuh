@@ -80,6 +80,18 @@ struct DevBuf {
 
 int upload(DevBuf& buf, const void* host, size_t bytes);
 
+// ---- fp16-range guard of the split-precision (fp16 hi + fp16 lo) engines ------------------------------------
+// Every activation that becomes a tensor-core operand is rounded to fp16 (max 65504): a value beyond that turns
+// into inf and the result into garbage WITHOUT any fault (fminf / fmaxf in the epilogues even swallow the NaNs).
+// Each conversion site therefore tracks the largest magnitude it split and, when it is out of range, raises one
+// flag word in mapped pinned host memory (zero cost on the host: it is read after a synchronise that happens
+// anyway).  The *_host entry points and nsw_range_status() turn it into NSW_ERANGE.
+typedef int (*range_setter_fn)(unsigned int* device_visible_flag);
+void register_range_setter(range_setter_fn fn);
+int range_guard_init(int device);  // idempotent per device; called by every *_create
+// after a synchronise: NSW_OK, or NSW_ERANGE (and the flag is cleared) if any split saw |v| > 65504 or a NaN
+int range_check(const char* who);
+
 // deconv layer geometry shared by the IAF and fastgen handles
 //   out[o] = sum_q x[m-q] * K[r + q*s],  o + p = m*s + r   (masked.py:235-291)
 struct DeconvGeom {
@@ -135,17 +147,50 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return tanhf(v);
 }
 
-// ParallelWavenet._clip_quant_scale (parallel_wavenet.py:348-359)
-__device__ __forceinline__ float clip_quant_scale_dev(float x, float Q, int use_mu_law) {
-  x = fminf(fmaxf(x, -1.0f), 1.0f - 2.0f / Q);
-  const float q = floorf(x * Q * 0.5f);  // utils.cast_quantize (utils.py:142-154)
-  if (!use_mu_law) return q / (Q * 0.5f);  // utils.inv_cast_quantize (utils.py:157-159)
-  // utils.inv_mu_law (utils.py:108-122)
+static __device__ unsigned int* nsw_tu_range_ptr = nullptr;  // one instance per translation unit and device
+__device__ __forceinline__ void range_track(uint32_t& mx, float v) {
+  mx = max(mx, __float_as_uint(v) & 0x7fffffffu);  // NaN and inf compare above every finite magnitude
+}
+__device__ __forceinline__ void range_commit(uint32_t mx) {
+  if (mx > 0x477FE000u /* 65504.0f */) {
+    unsigned int* p = nsw_tu_range_ptr;
+    if (p) *p = 1u;
+  }
+}
+// one per .cu that splits activations: hands that unit's kernels the flag word
+#define NSW_RANGE_GUARD_TU(tag)                                                                       \
+  namespace {                                                                                         \
+  int range_setter_##tag(unsigned int* flag) {                                                        \
+    NSW_CUDA(cudaMemcpyToSymbol(::nsw::nsw_tu_range_ptr, &flag, sizeof(flag)));                              \
+    return NSW_OK;                                                                                    \
+  }                                                                                                   \
+  struct RangeReg_##tag {                                                                             \
+    RangeReg_##tag() { ::nsw::register_range_setter(&range_setter_##tag); }                           \
+  } range_reg_##tag;                                                                                  \
+  }
+
+// integer code q in [-Q/2, Q/2) -> audio: utils.inv_cast_quantize (utils.py:157-159, :167-169) or, with mu-law,
+// utils.inv_mu_law (utils.py:108-122, :125-139)
+__device__ __forceinline__ float inv_quant_dev(float q, float Q, int use_mu_law) {
+  if (!use_mu_law) return q / (Q * 0.5f);
   const float mu = 255.0f;
   float out = (q + 0.5f) * 2.0f / (mu + 1.0f);
   const float sgn = out > 0.0f ? 1.0f : (out < 0.0f ? -1.0f : 0.0f);
   out = sgn / mu * (powf(1.0f + mu, fabsf(out)) - 1.0f);
   return q == 0.0f ? q : out;
+}
+// ParallelWavenet._clip_quant_scale (parallel_wavenet.py:348-359)
+__device__ __forceinline__ float clip_quant_scale_dev(float x, float Q, int use_mu_law) {
+  x = fminf(fmaxf(x, -1.0f), 1.0f - 2.0f / Q);
+  return inv_quant_dev(floorf(x * Q * 0.5f) /* utils.cast_quantize, utils.py:142-154 */, Q, use_mu_law);
+}
+
+// utils.mu_law (utils.py:72-87) scaled the way Wavenet / Fastgen feed it (wavenet.py:411-414):
+// floor(sign(x) * log(1 + 255|x|) / log(256) * 128) / (Q/2)
+__device__ __forceinline__ float mu_law_scaled_dev(float x, float Q) {
+  const float sgn = x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f);
+  const float out = sgn * logf(1.0f + 255.0f * fabsf(x)) / 5.545177444479562f;  // np.log(256)
+  return floorf(out * 128.0f) / (Q * 0.5f);
 }
 
 // Philox4x32-10 (counter-based; one call gives 4 x 32 random bits)

@@ -25,7 +25,7 @@
 // warp group beside the critical section, and the
 // mel conditioning of the whole utterance is hoisted into one conv-GEMM (the reference
 // sketches the same hoist: Fastgen.cond_vars, wavenet.py:353-377).
-#include "nsw_gemm.cuh"
+#include "nsw_fastgen.cuh"
 
 #include <cooperative_groups.h>
 
@@ -75,6 +75,9 @@ struct FgParams {
   const float* wo2t;            // out2 W transposed [O][256]
   const float* bo2;             // [O]
   const float* tf;              // teacher forcing [T] or NULL
+  const float* noise;           // supplied sampler noise [T][nu] or NULL (then Philox); see nsw_fastgen_set_noise
+  int nu;                       // floats of supplied noise per step
+  int use_mu_law;               // mu-law input encoding + inv_mu_law feedback (wavenet.py:411-414, fastgen.py:163-164)
   float* audio;                 // [T] or NULL
   float* out;                   // [T][O] or NULL
   int T, L, O, loss_type;
@@ -849,17 +852,24 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
 
     // ---------------- output head + sampler (every CTA, redundantly) ----------------
     if (tid >= 224 && tid < 236) {
-      // noise for this step (Philox: counter = step, key = seed)
+      // noise for this step: Philox (counter = step, key = seed), or the caller's draws (parity hook)
       const int j = tid - 224;
       const uint4 rr = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)(j >> 2), 0x66617374u, 0u),
                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
       const uint32_t bits = (j & 3) == 0 ? rr.x : (j & 3) == 1 ? rr.y : (j & 3) == 2 ? rr.z : rr.w;
-      const float u = u01_clipped(bits);
+      const bool given = P.noise != nullptr;
+      const float ug = (given && j < P.nu) ? __ldg(P.noise + (size_t)t * P.nu + j) : 0.5f;
       if (P.loss_type == NSW_LOSS_MOL) {
-        // j < 10: Gumbel -log(-log u) (loss_func.py:168-171); j == 10: logistic noise (:182-183)
-        S.gum[j] = (j < 10) ? -logf(-logf(u)) : logf(u) - logf(1.0f - u);
+        // j < nr: Gumbel -log(-log u) (loss_func.py:166-171); j == nr: logistic noise (:181-182)
+        const float u = given ? ug : u01_clipped(bits);
+        S.gum[j] = (j < nr) ? -logf(-logf(u)) : logf(u) - logf(1.0f - u);
+      } else if (given) {
+        S.gum[j] = ug;  // gauss: gum[0] = n ~ N(0,1) as drawn by the caller
       } else {
-        S.gum[j] = u;
+        // Box-Muller wants an UNCLIPPED uniform in (0,1] for the radius: the [1e-5, 1-1e-5] clamp belongs to
+        // the logistic / Gumbel draws only (loss_func.py:166,181); Normal.sample() has untruncated tails
+        S.gum[j] = (j == 0) ? ((float)(bits >> 8) + 1.0f) * (1.0f / 16777216.0f)
+                            : ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);
       }
     }
     __syncthreads();
@@ -895,14 +905,17 @@ __global__ void __launch_bounds__(NT, 1) fastgen_kernel(FgParams Pin) {
         const float lsc = fminf(fmaxf(S.outv[2 * nr + sel], -7.0f), 7.0f);
         x = fmaf(expf(lsc), S.gum[10], mu);
       } else {
-        // loss_func.gauss_sample (loss_func.py:200-206), Box-Muller from two uniforms
-        const float n = sqrtf(-2.0f * logf(S.gum[0])) * cosf(6.283185307179586f * S.gum[1]);
+        // loss_func.gauss_sample (loss_func.py:200-206): Box-Muller from two uniforms unless n was supplied
+        const float n = P.noise ? S.gum[0]
+                                : sqrtf(-2.0f * logf(S.gum[0])) * cosf(6.283185307179586f * S.gum[1]);
         x = fmaf(expf(fmaxf(S.outv[1], -7.0f)), n, S.outv[0]);
       }
       x = fminf(fmaxf(x, -1.0f), 1.0f - 2.0f / Q);
-      const float a = floorf(x * Q * 0.5f) / (Q * 0.5f);  // cast_quantize + inv_cast_quantize_numpy
+      // cast_quantize, then inv_cast_quantize_numpy or inv_mu_law_numpy (fastgen.py:162-166)
+      const float a = clip_quant_scale_dev(x, Q, P.use_mu_law);
       const float fed = P.tf ? P.tf[t] : a;
-      S.xnext = fed;
+      // mu-law input encoding of the fed sample (wavenet.py:411-414): floor(sign(x) log(1+255|x|)/log(256) * 128) / (Q/2)
+      S.xnext = P.use_mu_law ? mu_law_scaled_dev(fed, Q) : fed;
       if (c == 0 && P.audio) P.audio[t] = fed;
     }
     if (c == 0 && P.out && tid < O) P.out[(size_t)t * O + tid] = S.outv[tid];
@@ -926,6 +939,9 @@ __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i];
+  uint32_t rmx = 0;
+  range_track(rmx, v);
+  range_commit(rmx);
   const __half h = __float2half_rn(v);
   hi[i] = h;
   lo[i] = __float2half_rn(v - __half2float(h));
@@ -951,6 +967,16 @@ struct nsw_fastgen {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
+  DevBuf noise;                    // nsw_fastgen_set_noise: [B][T][noise_nu], consumed by every run until cleared
+  int noise_nu = 0, noise_B = 0, noise_T = 0;
+  // latency engine (this file) exists only for gate 512 + mol / gauss; the batched engine (nsw_fastgen_gn.cu) is
+  // built on first use from the retained host copies of the tensors
+  bool latency_ok = false;
+  GnEngine* gn = nullptr;
+  std::vector<std::string> w_names;
+  std::vector<std::vector<float>> w_data;
+  std::vector<nsw_tensor> w_desc;
+  DevBuf cv_w, cv_b, cv_out, cv_in;  // Fastgen.cond_vars: natural-order [256][L*G + S] projection, built on first use
 };
 
 namespace nsw_fg_host {
@@ -964,17 +990,24 @@ struct FgPacked {
 int fg_check_cfg(const nsw_wavenet_config& c) {
   NSW_CHECK(c.width == FW && c.gate_width == 2 * FM && c.skip_width == FS && c.deconv_width == FD,
             NSW_EINVAL,
-            "fastgen kernel is specialised for width=512, gate_width=512, skip_width=256, "
+            "fastgen latency engine is specialised for width=512, gate_width=512, skip_width=256, "
             "deconv_width=256 (got %d, %d, %d, %d)",
             c.width, c.gate_width, c.skip_width, c.deconv_width);
   NSW_CHECK(c.filter_length == 3, NSW_EINVAL, "filter_length must be 3 (masked.py:349)");
   NSW_CHECK(c.num_layers >= 2 && c.num_layers + 2 < MAX_PH, NSW_EINVAL, "bad num_layers %d", c.num_layers);
   NSW_CHECK(c.loss_type == NSW_LOSS_MOL || c.loss_type == NSW_LOSS_GAUSS, NSW_EINVAL,
-            "fastgen: only mol / gauss heads are built (ce is a later row)");
+            "fastgen latency engine: only mol / gauss heads (ce runs on the batched engine)");
   NSW_CHECK(c.out_width >= 2 && c.out_width <= MAX_O, NSW_EINVAL, "bad out_width %d", c.out_width);
-  NSW_CHECK(!c.use_mu_law, NSW_EINVAL, "fastgen: mu-law input encoding is not built yet");
+  NSW_CHECK(c.loss_type != NSW_LOSS_MOL || (c.out_width % 3 == 0 && c.out_width / 3 <= 11), NSW_EINVAL,
+            "fastgen latency engine: at most 11 mixture components");
   NSW_CHECK(c.num_stages >= 1 && c.num_stages <= 16, NSW_EINVAL, "bad num_stages");
   return NSW_OK;
+}
+bool fg_latency_ok(const nsw_wavenet_config& c) {
+  return c.width == FW && c.gate_width == 2 * FM && c.skip_width == FS && c.deconv_width == FD &&
+         c.filter_length == 3 && c.num_layers >= 2 && c.num_layers + 2 < MAX_PH &&
+         (c.loss_type == NSW_LOSS_MOL || c.loss_type == NSW_LOSS_GAUSS) && c.out_width >= 2 && c.out_width <= MAX_O &&
+         (c.loss_type != NSW_LOSS_MOL || (c.out_width % 3 == 0 && c.out_width / 3 <= 11));
 }
 
 // all host-side repacking of the TF-named tensors into the kernel's layouts
@@ -1146,8 +1179,10 @@ extern "C" int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_te
 extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tensor* tensors,
                                   int32_t n, int32_t device, nsw_fastgen** out) {
   NSW_CHECK(cfg && tensors && out, NSW_EINVAL, "nsw_fastgen_create: null argument");
-  NSW_TRY(fg_check_cfg(*cfg));
+  const char* why = nullptr;
+  NSW_CHECK(gn_supported(*cfg, &why), NSW_EINVAL, "nsw_fastgen_create: %s", why);
   NSW_CUDA(cudaSetDevice(device));
+  NSW_TRY(range_guard_init(device));
   int coop = 0, sms = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -1156,55 +1191,88 @@ extern "C" int nsw_fastgen_create(const nsw_wavenet_config* cfg, const nsw_tenso
   NSW_CHECK(coop && sms >= NC, NSW_EINVAL,
             "fastgen needs cooperative launch and >= %d SMs (device has %d)", NC, sms);
   TensorMap tm(tensors, n);
-  FgPacked pk;
-  NSW_TRY(fg_pack(*cfg, tm, pk));
   nsw_fastgen* h = new nsw_fastgen();
   h->cfg = *cfg;
   h->device = device;
   h->L = cfg->num_layers;
   h->NPH = h->L + 2;
   h->O = cfg->out_width;
-  const int N = h->L * 2 * FM + FS;
-  h->NPL = N / 64;
-  h->hist_entries = pk.hist_entries;
-  // the per-sample weight stream (NPH x 4.7 MB) is larger than L2 and cyclic, so plain LRU never hits: pin the
-  // blocks of the first phases in ~60 % of L2 (16 of 32 phases on B200) and let the rest stream through
-  h->l2_last = std::min(h->NPH, (int)(0.6 * (double)l2_bytes / ((double)NC * BLOCK_BYTES)));
+  h->latency_ok = fg_latency_ok(*cfg);
+  // host copies of the tensors: the batched engine repacks them on first use
+  for (int i = 0; i < n; ++i) {
+    int64_t numel = 1;
+    for (int d = 0; d < tensors[i].ndim; ++d) numel *= tensors[i].shape[d];
+    if (!tensors[i].name || !tensors[i].data || numel <= 0) continue;
+    h->w_names.emplace_back(tensors[i].name);
+    h->w_data.emplace_back(tensors[i].data, tensors[i].data + numel);
+  }
+  h->w_desc.resize(h->w_names.size());
+  for (size_t i = 0, j = 0; i < (size_t)n && j < h->w_desc.size(); ++i) {
+    int64_t numel = 1;
+    for (int d = 0; d < tensors[i].ndim; ++d) numel *= tensors[i].shape[d];
+    if (!tensors[i].name || !tensors[i].data || numel <= 0) continue;
+    h->w_desc[j] = tensors[i];
+    h->w_desc[j].name = h->w_names[j].c_str();
+    h->w_desc[j].data = h->w_data[j].data();
+    ++j;
+  }
   int rc = NSW_OK;
   const bool want_tc = cfg->engine >= NSW_ENGINE_TC;
   auto up = [&](DevBuf& b, const void* p, size_t bytes) {
     if (rc == NSW_OK) rc = upload(b, p, bytes);
   };
-  up(h->blocks, pk.blocks.data(), pk.blocks.size() * 4);
-  up(h->wcs, pk.wcs.data(), pk.wcs.size() * 4);
-  up(h->bcs, pk.bcs.data(), pk.bcs.size() * 4);
-  up(h->wo2t, pk.wo2t.data(), pk.wo2t.size() * 4);
-  up(h->bo2, pk.bo2.data(), pk.bo2.size() * 4);
-  up(h->cond_b, pk.cond_b.data(), pk.cond_b.size() * 4);
-  up(h->hist_off, pk.hist_off.data(), pk.hist_off.size() * 4);
-  up(h->dil, pk.dil.data(), pk.dil.size() * 4);
-  if (want_tc) {
-    std::vector<float> bt((size_t)N * FD);
-    for (int k = 0; k < FD; ++k)
-      for (int nn = 0; nn < N; ++nn) bt[(size_t)nn * FD + k] = pk.cond_w[(size_t)k * N + nn];
-    std::vector<__half> hi(bt.size()), lo(bt.size());
-    split_f16(bt.data(), bt.size(), hi.data(), lo.data());
-    up(h->cond_wt_hi, hi.data(), hi.size() * 2);
-    up(h->cond_wt_lo, lo.data(), lo.size() * 2);
+  if (h->latency_ok) {
+    FgPacked pk;
+    rc = fg_pack(*cfg, tm, pk);
+    const int N = h->L * 2 * FM + FS;
+    h->NPL = N / 64;
+    h->hist_entries = pk.hist_entries;
+    // the per-sample weight stream (NPH x 4.7 MB) is larger than L2 and cyclic, so plain LRU never hits: pin the
+    // blocks of the first phases in ~60 % of L2 (16 of 32 phases on B200) and let the rest stream through
+    h->l2_last = std::min(h->NPH, (int)(0.6 * (double)l2_bytes / ((double)NC * BLOCK_BYTES)));
+    if (rc == NSW_OK) {
+      up(h->blocks, pk.blocks.data(), pk.blocks.size() * 4);
+      up(h->wcs, pk.wcs.data(), pk.wcs.size() * 4);
+      up(h->bcs, pk.bcs.data(), pk.bcs.size() * 4);
+      up(h->wo2t, pk.wo2t.data(), pk.wo2t.size() * 4);
+      up(h->bo2, pk.bo2.data(), pk.bo2.size() * 4);
+      up(h->cond_b, pk.cond_b.data(), pk.cond_b.size() * 4);
+      up(h->hist_off, pk.hist_off.data(), pk.hist_off.size() * 4);
+      up(h->dil, pk.dil.data(), pk.dil.size() * 4);
+      if (want_tc) {
+        std::vector<float> bt((size_t)N * FD);
+        for (int k = 0; k < FD; ++k)
+          for (int nn = 0; nn < N; ++nn) bt[(size_t)nn * FD + k] = pk.cond_w[(size_t)k * N + nn];
+        std::vector<__half> hi(bt.size()), lo(bt.size());
+        split_f16(bt.data(), bt.size(), hi.data(), lo.data());
+        up(h->cond_wt_hi, hi.data(), hi.size() * 2);
+        up(h->cond_wt_lo, lo.data(), lo.size() * 2);
+      } else {
+        up(h->cond_w, pk.cond_w.data(), pk.cond_w.size() * 4);
+      }
+    }
+    if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * XREP_MAX * XSLOT * 8);
+    if (rc == NSW_OK) rc = h->hist.ensure(h->hist_entries * 8);
+    if (rc == NSW_OK) {
+      cudaError_t e = cudaFuncSetAttribute(fastgen_kernel<FG_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(FgSmem));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fastgen_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgSmem));
+      if (e != cudaSuccess) {
+        set_error("nsw_fastgen_create: %s", cudaGetErrorString(e));
+        rc = NSW_ECUDA;
+      }
+    }
   } else {
-    up(h->cond_w, pk.cond_w.data(), pk.cond_w.size() * 4);
+    // no latency engine for this configuration: build the batched one now so that a bad checkpoint fails here
+    TensorMap own(h->w_desc.data(), (int)h->w_desc.size());
+    rc = gn_create(*cfg, own, device, &h->gn);
   }
   if (rc == NSW_OK)
     rc = h->deconv.init(tm, "", cfg->num_mel, FD, cfg->num_deconv, cfg->deconv_filter,
                         cfg->deconv_stride, cfg->upsample_act, want_tc);
-  if (rc == NSW_OK) rc = h->xbuf.ensure((size_t)(h->NPH + 1) * XREP_MAX * XSLOT * 8);
-  if (rc == NSW_OK) rc = h->hist.ensure(h->hist_entries * 8);
   if (rc == NSW_OK) {
-    cudaError_t e = cudaFuncSetAttribute(fastgen_kernel<FG_DEFAULT_FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(FgSmem));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(fastgen_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgSmem));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) {
@@ -1226,6 +1294,7 @@ extern "C" void nsw_fastgen_destroy(nsw_fastgen* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->gn) gn_destroy(h->gn);
   delete h;
 }
 
@@ -1262,6 +1331,29 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
   NSW_CHECK(B >= 1 && T >= 1, NSW_EINVAL, "bad batch/length %d/%d", B, T);
   NSW_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  const float* d_noise = nullptr;
+  if (h->noise.p) {
+    NSW_CHECK(h->noise_B == B && h->noise_T == T, NSW_EINVAL,
+              "nsw_fastgen_set_noise was given [%d][%d] draws, this run is [%d][%d]", h->noise_B, h->noise_T, B, T);
+    d_noise = h->noise.as<float>();
+  }
+  // engine choice: the latency engine runs one utterance at a time (41 us per sample each), the batched engine
+  // advances up to 8 together for about the price of one pass over the weights
+  bool use_gn = !h->latency_ok || B >= 3;
+  if (const char* e = getenv("NSW_FASTGEN_ENGINE")) {
+    if (!strcmp(e, "gn") || !strcmp(e, "batched")) use_gn = true;
+    else if (!strcmp(e, "latency") && h->latency_ok) use_gn = false;
+  }
+  if (use_gn) {
+    if (!h->gn) {
+      TensorMap own(h->w_desc.data(), (int)h->w_desc.size());
+      NSW_TRY(gn_create(h->cfg, own, h->device, &h->gn));
+    }
+    NSW_CUDA(cudaEventRecord(h->ev0, st));
+    NSW_TRY(gn_run(h->gn, d_encoding, B, T, d_teacher_force, seed, d_noise, h->noise_nu, d_audio, d_out, st));
+    NSW_CUDA(cudaEventRecord(h->ev1, st));
+    return NSW_OK;
+  }
   const int N = h->NPL * 64;
   NSW_TRY(h->cond.ensure((size_t)h->NPL * T * 64 * sizeof(float)));
   const bool tc = h->cfg.engine >= NSW_ENGINE_TC;
@@ -1323,7 +1415,10 @@ extern "C" int nsw_fastgen_run_device(nsw_fastgen* h, const float* d_encoding, i
     P.l2_last = getenv("NSW_FASTGEN_L2LAST") ? atoi(getenv("NSW_FASTGEN_L2LAST")) : h->l2_last;
     P.crit_delay = getenv("NSW_FASTGEN_CRITDELAY") ? atoi(getenv("NSW_FASTGEN_CRITDELAY")) : 0;
     P.poll_delay = getenv("NSW_FASTGEN_POLLDELAY") ? atoi(getenv("NSW_FASTGEN_POLLDELAY")) : 0;
-    P.quant = 65536.0f;
+    P.quant = h->cfg.use_mu_law ? 256.0f : 65536.0f;  // wavenet.py:117-120
+    P.use_mu_law = h->cfg.use_mu_law ? 1 : 0;
+    P.noise = d_noise ? d_noise + (size_t)b * T * h->noise_nu : nullptr;
+    P.nu = h->noise_nu;
     void* args[] = {&P};
     const bool lean = !want_dbg && P.crit_delay == 0 && P.poll_delay == 0 && getenv("NSW_FASTGEN_GENERIC") == nullptr;
     void* kern = (void*)fastgen_kernel<-1>;
@@ -1390,6 +1485,76 @@ extern "C" int nsw_fastgen_run_host(nsw_fastgen* h, const float* encoding, int32
     set_error("fastgen kernel failed: %s", cudaGetErrorString(e));
     return NSW_ECUDA;
   }
+  return range_check("nsw_fastgen_run_host");
+}
+
+// Fastgen.cond_vars (wavenet.py:353-377) as fastgen.calculate_cond_vars evaluates it (fastgen.py:100-115): the 1x1
+// mel-conditioning projection of every layer on the whole encoding, natural channel order, biases included.
+extern "C" int nsw_fastgen_cond_vars_device(nsw_fastgen* h, const float* d_encoding, int32_t B, int32_t T,
+                                            float* d_out, void* stream) {
+  NSW_CHECK(h && d_encoding && d_out, NSW_EINVAL, "null argument");
+  NSW_CHECK(B >= 1 && T >= 1, NSW_EINVAL, "bad batch/length %d/%d", B, T);
+  NSW_CUDA(cudaSetDevice(h->device));
+  const int L = h->L, G = h->cfg.gate_width, S = h->cfg.skip_width, N = L * G + S;
+  if (!h->cv_w.p) {
+    TensorMap own(h->w_desc.data(), (int)h->w_desc.size());
+    std::vector<float> wn((size_t)FD * N), bn(N);
+    for (int i = 0; i <= L; ++i) {
+      const std::string base = i < L ? "mel_cond_" + std::to_string(i + 1) : std::string("mel_cond_out1");
+      const int width = i < L ? G : S;
+      const float* wc = own.get(base + "/W", (int64_t)FD * width);
+      const float* bc = own.get(base + "/biases", width);
+      if (!wc || !bc) return NSW_EMISSING;
+      for (int k = 0; k < FD; ++k)
+        for (int co = 0; co < width; ++co) wn[(size_t)k * N + (size_t)i * G + co] = wc[(size_t)k * width + co];
+      for (int co = 0; co < width; ++co) bn[(size_t)i * G + co] = bc[co];
+    }
+    NSW_TRY(upload(h->cv_w, wn.data(), wn.size() * 4));
+    NSW_TRY(upload(h->cv_b, bn.data(), bn.size() * 4));
+  }
+  ConvGemm g;
+  g.nclips = 1; g.L = B * T; g.cin = FD; g.ntaps = 1; g.a_off = 0; g.mclip = B * T; g.N = N;
+  EpiParams e{};
+  e.mode = EPI_ROWS;
+  e.bias = h->cv_b.as<float>();
+  e.out_f32 = d_out;
+  e.ld_out = N;
+  return conv_gemm_ffma(g, d_encoding, h->cv_w.as<float>(), e, (cudaStream_t)stream);
+}
+
+extern "C" int nsw_fastgen_cond_vars_host(nsw_fastgen* h, const float* encoding, int32_t B, int32_t T, float* out) {
+  NSW_CHECK(h && encoding && out, NSW_EINVAL, "null argument");
+  NSW_CUDA(cudaSetDevice(h->device));
+  const int N = h->L * h->cfg.gate_width + h->cfg.skip_width;
+  const size_t ne = (size_t)B * T * FD * 4, no = (size_t)B * T * N * 4;
+  NSW_TRY(h->cv_in.ensure(ne));
+  NSW_TRY(h->cv_out.ensure(no));
+  cudaStream_t st = h->own_stream;
+  NSW_CUDA(cudaMemcpyAsync(h->cv_in.p, encoding, ne, cudaMemcpyHostToDevice, st));
+  NSW_TRY(nsw_fastgen_cond_vars_device(h, h->cv_in.as<float>(), B, T, h->cv_out.as<float>(), st));
+  NSW_CUDA(cudaMemcpyAsync(out, h->cv_out.p, no, cudaMemcpyDeviceToHost, st));
+  NSW_CUDA(cudaStreamSynchronize(st));
+  return NSW_OK;
+}
+
+extern "C" int nsw_fastgen_set_noise(nsw_fastgen* h, const float* noise, int32_t B, int32_t T, int32_t nu,
+                                     int32_t on_device) {
+  NSW_CHECK(h, NSW_EINVAL, "null handle");
+  NSW_CUDA(cudaSetDevice(h->device));
+  if (!noise) {
+    h->noise.release();
+    h->noise_nu = h->noise_B = h->noise_T = 0;
+    return NSW_OK;
+  }
+  const int want = h->cfg.loss_type == NSW_LOSS_MOL ? h->O / 3 + 1 : 1;
+  NSW_CHECK(nu == want && B >= 1 && T >= 1, NSW_EINVAL,
+            "nsw_fastgen_set_noise: this head consumes %d draws per step (got nu=%d, B=%d, T=%d)", want, nu, B, T);
+  const size_t bytes = (size_t)B * T * nu * sizeof(float);
+  NSW_TRY(h->noise.ensure(bytes));
+  NSW_CUDA(cudaMemcpy(h->noise.p, noise, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  h->noise_nu = nu;
+  h->noise_B = B;
+  h->noise_T = T;
   return NSW_OK;
 }
 
@@ -1399,3 +1564,5 @@ extern "C" int nsw_fastgen_last_timing(nsw_fastgen* h, float* ms) {
   NSW_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return NSW_OK;
 }
+
+NSW_RANGE_GUARD_TU(fastgen)

@@ -19,6 +19,11 @@ __device__ __forceinline__ void store_epi(const ConvGemm& g, const EpiParams& e,
     const size_t plane = (size_t)(n >> 6);
     float* dst = e.out_f32 + (plane * (size_t)M + (size_t)r) * 64 + (n & 63);
     *reinterpret_cast<float4*>(dst) = v;
+  } else if (e.mode == EPI_ROWS) {
+    // plain row-major result (+ bias): out[row * ld_out + n]
+    const float4 b = *reinterpret_cast<const float4*>(e.bias + n);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    *reinterpret_cast<float4*>(e.out_f32 + (size_t)r * e.ld_out + n) = v;
   } else {
     const int clip = r / g.mclip, m = r - clip * g.mclip;
     const int rr = n / e.cout, co = n - rr * e.cout;
@@ -35,10 +40,13 @@ __device__ __forceinline__ void store_epi(const ConvGemm& g, const EpiParams& e,
       float f[4] = {v.x, v.y, v.z, v.w};
       __half hi[4], lo[4];
 #pragma unroll
+      uint32_t rmx = 0;
       for (int i = 0; i < 4; ++i) {
+        range_track(rmx, f[i]);
         hi[i] = __float2half_rn(f[i]);
         lo[i] = __float2half_rn(f[i] - __half2float(hi[i]));
       }
+      range_commit(rmx);
       *reinterpret_cast<uint2*>(e.out_hi + off) = *reinterpret_cast<uint2*>(hi);
       *reinterpret_cast<uint2*>(e.out_lo + off) = *reinterpret_cast<uint2*>(lo);
     }
@@ -267,3 +275,5 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __hal
 }
 
 }  // namespace nsw
+
+NSW_RANGE_GUARD_TU(gemm_ffma)

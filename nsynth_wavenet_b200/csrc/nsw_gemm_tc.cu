@@ -276,11 +276,14 @@ __device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiPa
       for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
     }
     float h[32], l[32];
+    uint32_t rmx = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
+      range_track(rmx, f[j]);
       h[j] = __half2float(__float2half_rn(f[j]));
       l[j] = f[j] - h[j];
     }
+    range_commit(rmx);
     const uint4 hi[4] = {pack8_f16(h), pack8_f16(h + 8), pack8_f16(h + 16), pack8_f16(h + 24)};
     const uint4 lo[4] = {pack8_f16(l), pack8_f16(l + 8), pack8_f16(l + 16), pack8_f16(l + 24)};
     const size_t pb = (size_t)e.ld_split * 2;
@@ -364,6 +367,12 @@ __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams&
     __syncwarp();
   }
   if (e.mode == EPI_DECONV && e.out_hi) {
+    {
+      uint32_t rmx = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) range_track(rmx, f[j]);
+      range_commit(rmx);
+    }
     // fp16 split planes: 32 values = 64 B per row per plane; both planes share one pass
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
@@ -944,3 +953,5 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
 }
 
 }  // namespace nsw
+
+NSW_RANGE_GUARD_TU(gemm_tc)

@@ -95,10 +95,13 @@ iaf_start_conv_kernel(const float* __restrict__ x, float* __restrict__ l,
     const float f[4] = {o.x, o.y, o.z, o.w};
     __align__(8) __half hi[4], lo[4];
 #pragma unroll
+    uint32_t rmx = 0;
     for (int i = 0; i < 4; ++i) {
+      range_track(rmx, f[i]);
       hi[i] = __float2half_rn(f[i]);
       lo[i] = __float2half_rn(f[i] - __half2float(hi[i]));
     }
+    range_commit(rmx);
     *reinterpret_cast<uint2*>(l_hi + row * C + c) = *reinterpret_cast<uint2*>(hi);
     *reinterpret_cast<uint2*>(l_lo + row * C + c) = *reinterpret_cast<uint2*>(lo);
   }
@@ -611,6 +614,7 @@ extern "C" int nsw_iaf_create(const nsw_iaf_config* cfg, const nsw_tensor* tenso
   NSW_CHECK(cfg->loss_type == NSW_LOSS_LOGISTIC || cfg->loss_type == NSW_LOSS_GAUSS, NSW_EINVAL,
             "student loss_type must be logistic or gauss");
   NSW_CUDA(cudaSetDevice(device));
+  NSW_TRY(range_guard_init(device));
   nsw_iaf* h = new nsw_iaf();
   h->cfg = *cfg;
   h->device = device;
@@ -1062,5 +1066,7 @@ extern "C" int nsw_iaf_forward_host(nsw_iaf* h, const float* mel, const float* z
     NSW_CUDA(cudaMemcpyAsync(log_scale_tot, h->log_scale_tot.p, nb, cudaMemcpyDeviceToHost, st));
   if (rand_input) NSW_CUDA(cudaMemcpyAsync(rand_input, h->z.p, nb, cudaMemcpyDeviceToHost, st));
   NSW_CUDA(cudaStreamSynchronize(st));
-  return NSW_OK;
+  return range_check("nsw_iaf_forward_host");
 }
+
+NSW_RANGE_GUARD_TU(iaf)

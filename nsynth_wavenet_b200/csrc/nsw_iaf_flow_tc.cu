@@ -281,6 +281,7 @@ struct FlowTcParams {
   int cta_base, cta_rem;  // clip c (0-based within the launch) is split over cta_base + (c < cta_rem) CTAs
   int reach_tiles;        // 2 * max dilation / 128 (how far ahead a published tile is read)
   long long* dbg;
+  int dbg_cta;            // block whose timeline NSW_LAYER_DEBUG records
   // fused head (parallel_wavenet.py:256-277, 316-330, 348-359): a pseudo-layer after layer l1-1 whose
   // "conv" is the 1x1 out1 on relu(l) (weights = tile head_w_tile of the Wd maps) accumulated on the
   // out1 conditioning plane, and whose epilogue is out2_mean / out2_scale + the affine composition
@@ -413,8 +414,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
   const int gt0 = gclip * p.tiles_per_clip + R.tk0;   // global tile id of own tile 0
   const long long tk_start = clock64();
   unsigned long long gt_start = 0;
-  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_start));
-  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+  if (p.dbg != nullptr && (int)blockIdx.x == p.dbg_cta && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_start));
+  const bool dbg = p.dbg != nullptr && (int)blockIdx.x == p.dbg_cta;
 
   // does the output of (own tile k, layer li) have a reader outside this CTA?
   auto published = [&](int k, int li) -> bool {
@@ -572,6 +573,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
         const int dt = d / BM;
         ft_wait(&B->wd_full, (uint32_t)(li & 1), "wd_full");
         if (dbg && lane == 0 && li < 32) p.dbg[80 + li] = clock64() - tk_start;
+        long long w_d1 = 0, w_rdy = 0, w_ring = 0;  // NSW_LAYER_DEBUG: where this layer's issuer time went
         for (int kk = 0; kk < K; ++kk, ++j) {
           const int k = K - 1 - kk;
           const int b = j & 1;
@@ -581,8 +583,10 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
           int n = 1;
           bool foreign[2] = {false, false};  // [tap] of the d >= 128 layers
           bool halo_used = false;
+          long long tw0 = dbg ? clock64() : 0;
           // D1[b] holds the conditioning rows of this task (written by the gate warps)
           ft_wait(&B->d1_empty[b], (uint32_t)((j >> 1) & 1), "d1_empty");
+          if (dbg) { const long long now = clock64(); w_d1 += now - tw0; tw0 = now; }
           if (dbg && j < 8 && lane == 0) p.dbg[64 + 2 * j] = clock64() - tk_start;
           wait_ready(k, li);
           if (small) {
@@ -608,6 +612,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
               }
             }
           }
+          if (dbg) { const long long now = clock64(); w_rdy += now - tw0; tw0 = now; }
           if (dbg && j < 8 && lane == 0) p.dbg[2 * j] = clock64() - tk_start;
           ft_fence_after();
           issue_burst(d1, a_bytes, taps, n);
@@ -618,7 +623,9 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
           }
           for (int tap = 1; tap >= 0; --tap) {  // same order as the loader: t-d, then t-2d
             if (!foreign[tap]) continue;
+            tw0 = dbg ? clock64() : 0;
             ft_wait(&B->ring_full, (uint32_t)(n_ring & 1), "ring_full");
+            if (dbg) w_ring += clock64() - tw0;
             ft_fence_after();
             issue_tap(d1, 0u, tap);
             if (ft_elect()) ft_commit(&B->ring_free);
@@ -638,6 +645,11 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
             if (dbg && j < 8) p.dbg[2 * j + 1] = clock64() - tk_start;
           }
           __syncwarp();
+        }
+        if (dbg && lane == 0 && li < 32) {
+          p.dbg[128 + li] = w_d1;
+          p.dbg[160 + li] = w_rdy;
+          p.dbg[192 + li] = w_ring;
         }
       }
       if (p.fuse_head) {
@@ -817,6 +829,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
     const int qd = warp & 3;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     const int row = qd * 32 + lane;  // row inside a tile
+    uint32_t rmx = 0;                // fp16-range guard: largest magnitude this thread split
     if (p.fuse_start) {
       // init: start conv of the own tiles (-> TMEM master + smem planes) and of the halo (smem only;
       // zeros at the start of a clip: the layer input is zero-padded, masked.py:203-204)
@@ -838,7 +851,10 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
           o[2] = fmaf(w2.z, x1, fmaf(w1.z, x2, fmaf(w0.z, x3, bb.z)));
           o[3] = fmaf(w2.w, x1, fmaf(w1.w, x2, fmaf(w0.w, x3, bb.w)));
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[4 * i + e] = __float_as_uint(t >= 0 ? o[e] : 0.f);
+          for (int e = 0; e < 4; ++e) {
+            v[4 * i + e] = __float_as_uint(t >= 0 ? o[e] : 0.f);
+            range_track(rmx, __uint_as_float(v[4 * i + e]));
+          }
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -932,6 +948,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float o0 = __uint_as_float(d[8 * jj + 2 * e]), o1 = __uint_as_float(d[8 * jj + 2 * e + 1]);
+          range_track(rmx, o0);
+          range_track(rmx, o1);
           if (relu_out) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }  // the head's out1 consumes relu(l)
           const float a0 = __half2float(__float2half_rn(o0));
           const float a1 = __half2float(__float2half_rn(o1));
@@ -950,6 +968,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       if (dbg && warp == 10 && lane == 0 && j < 8) p.dbg[48 + 2 * j + 1] = clock64() - tk_start;
       if (++kk == K) { kk = 0; ++li; }
     }
+    range_commit(rmx);
   } else if (warp == 18) {
     // =================================== publisher ===================================
     if (lane == 0) {
@@ -1001,6 +1020,9 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 }
 
 }  // namespace
+}  // namespace nsw
+NSW_RANGE_GUARD_TU(flow_tc)
+namespace nsw {
 
 // how many clips one launch can take: every clip needs ceil(tiles / KMAX) CTAs of its own
 int flow_tc_clips_per_launch(int T, int num_sms) {
@@ -1074,11 +1096,12 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
   p.start_w = start ? start->w : nullptr;
   p.start_b = start ? start->b : nullptr;
   p.dbg = nullptr;
+  p.dbg_cta = getenv("NSW_LAYER_DEBUG_CTA") ? atoi(getenv("NSW_LAYER_DEBUG_CTA")) : 0;
   static long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr;
   if (want_dbg) {
-    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 128 * sizeof(long long)));
-    NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * sizeof(long long), stream));
+    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
+    NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), stream));
     p.dbg = dbg_buf;
   }
   void* args[] = {const_cast<void*>(map_act[0][0]), const_cast<void*>(map_act[0][1]),
@@ -1095,7 +1118,7 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
   count_launch();
   NSW_CUDA(cudaGetLastError());
   if (want_dbg) {
-    long long h[128];
+    long long h[256];
     NSW_CUDA(cudaStreamSynchronize(stream));
     NSW_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[flow_tc dbg layers %d..%d grid %d] end %lld cycles in %lld ns = %.0f MHz\n", l0, l1, grid, h[127], h[126],
@@ -1110,6 +1133,15 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
     fprintf(stderr, "  %-30s:", "MMA1 D1 buffer free at");
     for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[64 + 2 * i]);
     fprintf(stderr, "\n");
+    fprintf(stderr, "  %-30s:", "layer start (MMA1 sees weights)");
+    for (int i = 0; i < std::min(l1 - l0, 32); ++i) fprintf(stderr, " %lld", h[80 + i]);
+    fprintf(stderr, "  [cta %d]\n", p.dbg_cta);
+    const char* wn[3] = {"MMA1 waits: D1 buffer", "MMA1 waits: operand tiles/halo", "MMA1 waits: foreign ring"};
+    for (int r = 0; r < 3; ++r) {
+      fprintf(stderr, "  %-30s:", wn[r]);
+      for (int i = 0; i < std::min(l1 - l0, 32); ++i) fprintf(stderr, " %lld", h[128 + 32 * r + i]);
+      fprintf(stderr, "\n");
+    }
   }
   return NSW_OK;
 }

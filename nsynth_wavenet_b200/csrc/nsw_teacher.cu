@@ -43,10 +43,13 @@ teacher_start_kernel(const float* __restrict__ x, const float* __restrict__ w /*
   *reinterpret_cast<float4*>(ls + row * TLS + c) = make_float4(f[0], f[1], f[2], f[3]);
   __align__(8) __half h[4], l[4];
 #pragma unroll
+  uint32_t rmx = 0;
   for (int i = 0; i < 4; ++i) {
+    range_track(rmx, f[i]);
     h[i] = __float2half_rn(f[i]);
     l[i] = __float2half_rn(f[i] - __half2float(h[i]));
   }
+  range_commit(rmx);
   *reinterpret_cast<uint2*>(hi + row * TLS + c) = *reinterpret_cast<uint2*>(h);
   *reinterpret_cast<uint2*>(lo + row * TLS + c) = *reinterpret_cast<uint2*>(l);
 }
@@ -216,6 +219,7 @@ extern "C" int nsw_teacher_create(const nsw_wavenet_config* cfg, const nsw_tenso
             cfg->out_width);
   NSW_CHECK(cfg->num_layers >= 1 && cfg->num_layers <= 64, NSW_EINVAL, "bad num_layers");
   NSW_CUDA(cudaSetDevice(device));
+  NSW_TRY(range_guard_init(device));
   TensorMap tm(tensors, n);
   nsw_teacher* h = new nsw_teacher();
   h->cfg = *cfg;
@@ -402,7 +406,7 @@ extern "C" int nsw_teacher_forward_host(nsw_teacher* h, const float* wav, const 
   NSW_CUDA(cudaMemcpyAsync(out, h->out_dev.p, no, cudaMemcpyDeviceToHost, st));
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { set_error("teacher forward failed: %s", cudaGetErrorString(e)); return NSW_ECUDA; }
-  return NSW_OK;
+  return range_check("nsw_teacher_forward_host");
 }
 
 extern "C" int nsw_teacher_last_timing(nsw_teacher* h, float* ms) {
@@ -466,3 +470,5 @@ extern "C" int nsw_gauss_kl_device(nsw_teacher* h, const float* d_te_out, const 
   result[2] = result[0] + 4.0 * result[1];
   return NSW_OK;
 }
+
+NSW_RANGE_GUARD_TU(teacher)

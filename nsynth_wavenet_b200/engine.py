@@ -20,7 +20,7 @@ def _get(hp, name, default):
 
 
 def default_engine():
-    # tc2 = conv-GEMMs and the IAF residual layers on tcgen05 (fp32-grade via split bf16)
+    # tc3 = conv-GEMMs and the IAF residual layers on tcgen05 (fp32-grade via split fp16: hi + lo, three products)
     return os.environ.get('NSW_ENGINE', 'tc3')
 
 
@@ -103,6 +103,29 @@ def fold_weight_norm(weights):
     return out
 
 
+def _dev_tensor(x, name, shape, device):
+    """The C ABI takes raw device pointers: reject anything whose memory is not what the kernels index
+    (CUDA, float32, contiguous, on the handle's device, expected shape; None in `shape` = any extent)."""
+    import torch
+    if x is None:
+        return None
+    if not isinstance(x, torch.Tensor):
+        raise TypeError('{}: expected a torch CUDA tensor, got {}'.format(name, type(x).__name__))
+    if not x.is_cuda:
+        raise ValueError('{}: must live on the GPU (got a {} tensor)'.format(name, x.device))
+    if x.device.index != device:
+        raise ValueError('{}: lives on cuda:{} but the engine was created on cuda:{}'.format(
+            name, x.device.index, device))
+    if x.dtype != torch.float32:
+        raise ValueError('{}: must be float32 (got {})'.format(name, x.dtype))
+    if not x.is_contiguous():
+        raise ValueError('{}: must be contiguous (call .contiguous())'.format(name))
+    if shape is not None:
+        if x.dim() != len(shape) or any(e is not None and int(d) != int(e) for d, e in zip(x.shape, shape)):
+            raise ValueError('{}: shape {} does not match {}'.format(name, tuple(x.shape), tuple(shape)))
+    return x
+
+
 class IAFEngine:
     """4-flow IAF student on one GPU."""
 
@@ -155,15 +178,16 @@ class IAFEngine:
         """torch CUDA tensors in, torch CUDA tensors out; enqueues on the current
         torch stream (or `stream`) and does not synchronise."""
         import torch
-        assert mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous()
+        _dev_tensor(mel, 'mel', (None, None, self.num_mel), self.device)
         B, F, _ = mel.shape
         T = self.length(F)
         names = ('x', 'mean_tot', 'scale_tot', 'log_scale_tot', 'rand_input')
         if out is None:
             out = {n: torch.empty((B, T), dtype=torch.float32, device=mel.device)
                    for n in names[:4]}
-        if z is not None:
-            assert z.is_cuda and z.is_contiguous() and tuple(z.shape) == (B, T)
+        for n, v in out.items():
+            _dev_tensor(v, 'out[{!r}]'.format(n), (B, T), self.device)
+        _dev_tensor(z, 'z', (B, T), self.device)
         st = stream if stream is not None else torch.cuda.current_stream(mel.device).cuda_stream
         L.check(self.lib.nsw_iaf_forward_device(
             self._h, L.ptr(mel), L.ptr(z), seed, B, F, int(bool(quantize)),
@@ -172,6 +196,7 @@ class IAFEngine:
 
     def deconv_device(self, mel, stack=0):
         import torch
+        _dev_tensor(mel, 'mel', (None, None, self.num_mel), self.device)
         B, F, _ = mel.shape
         stride = int(np.prod([dc[1] for dc in self.hparams.deconv_config]))
         enc = torch.empty((B, F * stride, self.hparams.deconv_width), dtype=torch.float32,
@@ -181,6 +206,7 @@ class IAFEngine:
         return enc
 
     def set_tap(self, flow, layer, dst):
+        _dev_tensor(dst, 'dst', None, self.device)
         L.check(self.lib.nsw_iaf_set_tap(self._h, flow, layer, L.ptr(dst)))
 
     def set_profiling(self, on):
@@ -205,6 +231,7 @@ class FastgenEngine:
         self.num_mel = num_mel
         cfg = wavenet_config(hparams, num_mel, engine)
         self.out_width = cfg.out_width
+        self.gate_width = cfg.gate_width
         tensors, keep = L.make_tensors(fold_weight_norm(weights))
         h = C.c_void_p()
         L.check(self.lib.nsw_fastgen_create(C.byref(cfg), tensors, len(tensors), device,
@@ -231,8 +258,42 @@ class FastgenEngine:
         L.check(self.lib.nsw_fastgen_encode_host(self._h, L.ptr(mel), B, F, L.ptr(enc)))
         return enc
 
+    def cond_vars_host(self, encoding):
+        """Fastgen.cond_vars (wavenet.py:353-377): dict layer name -> np[B, T, width] of the mel-conditioning
+        projections (mel_cond_1..L: gate_width columns each, mel_cond_out1: skip_width)."""
+        encoding = np.ascontiguousarray(encoding, np.float32)
+        B, T, _ = encoding.shape
+        Lr, G, S = self.hparams.num_layers, self.gate_width, self.hparams.skip_width
+        flat = np.empty((B, T, Lr * G + S), np.float32)
+        L.check(self.lib.nsw_fastgen_cond_vars_host(self._h, L.ptr(encoding), B, T, L.ptr(flat)))
+        out = {'mel_cond_%d' % (i + 1): flat[:, :, i * G:(i + 1) * G] for i in range(Lr)}
+        out['mel_cond_out1'] = flat[:, :, Lr * G:]
+        return out
+
+    def noise_width(self):
+        """floats of sampler noise per step: mol nr_mix + 1 (u1, u2), gauss 1 (n), ce 1 (u)."""
+        return self.out_width // 3 + 1 if self.hparams.loss_type == 'mol' else 1
+
+    def set_noise(self, noise):
+        """Parity hook (nsw_fastgen_set_noise): the following runs read their random draws from `noise`
+        [B, T, noise_width()] (NumPy or torch CUDA) instead of the in-kernel Philox stream; None restores Philox."""
+        if noise is None:
+            L.check(self.lib.nsw_fastgen_set_noise(self._h, None, 0, 0, 0, 0))
+            return
+        if isinstance(noise, np.ndarray):
+            noise = np.ascontiguousarray(noise, np.float32)
+            on_dev = 0
+        else:
+            _dev_tensor(noise, 'noise', (None, None, self.noise_width()), self.device)
+            on_dev = 1
+        B, T, nu = noise.shape
+        L.check(self.lib.nsw_fastgen_set_noise(self._h, L.ptr(noise), B, T, nu, on_dev))
+
     def run_host(self, encoding, teacher_force=None, seed=0, want_out=False):
         encoding = np.ascontiguousarray(encoding, np.float32)
+        if encoding.ndim != 3 or encoding.shape[2] != self.hparams.deconv_width:
+            raise ValueError('encoding must be [B, T, {}], got {}'.format(self.hparams.deconv_width,
+                                                                          encoding.shape))
         B, T, _ = encoding.shape
         audio = np.empty((B, T), np.float32)
         out = np.empty((B, T, self.out_width), np.float32) if want_out else None
@@ -246,7 +307,9 @@ class FastgenEngine:
 
     def run_device(self, encoding, teacher_force=None, seed=0, want_out=False):
         import torch
+        _dev_tensor(encoding, 'encoding', (None, None, self.hparams.deconv_width), self.device)
         B, T, _ = encoding.shape
+        _dev_tensor(teacher_force, 'teacher_force', (B, T), self.device)
         audio = torch.empty((B, T), dtype=torch.float32, device=encoding.device)
         out = (torch.empty((B, T, self.out_width), dtype=torch.float32, device=encoding.device)
                if want_out else None)
@@ -269,6 +332,8 @@ class TeacherEngine:
     def __init__(self, hparams, weights, device=0, num_mel=80):
         self.lib = L.load()
         self.hparams = hparams
+        self.device = device
+        self.num_mel = num_mel
         cfg = wavenet_config(hparams, num_mel, 'tc')
         self.out_width = cfg.out_width
         tensors, keep = L.make_tensors(fold_weight_norm(weights))
@@ -299,6 +364,8 @@ class TeacherEngine:
 
     def forward_device(self, wav_scaled, mel):
         import torch
+        _dev_tensor(wav_scaled, 'wav_scaled', (None, None), self.device)
+        _dev_tensor(mel, 'mel', (wav_scaled.shape[0], None, self.num_mel), self.device)
         B, T = wav_scaled.shape
         F = mel.shape[1]
         out = torch.empty((B, T, self.out_width), dtype=torch.float32, device=wav_scaled.device)
@@ -310,7 +377,12 @@ class TeacherEngine:
     def mol_score(self, te_out, mean_tot, scale_tot, log_scale_tot, num_samples=100, eps=None, seed=0):
         """-> dict(H_Ps, H_Ps_Pt, kl_loss) like ParallelWavenet.kl_loss_logistic (torch CUDA inputs)."""
         import torch
+        _dev_tensor(mean_tot, 'mean_tot', (None, None), self.device)
         B, T = mean_tot.shape
+        _dev_tensor(te_out, 'te_out', (B, T, self.out_width), self.device)
+        _dev_tensor(scale_tot, 'scale_tot', (B, T), self.device)
+        _dev_tensor(log_scale_tot, 'log_scale_tot', (B, T), self.device)
+        _dev_tensor(eps, 'eps', (num_samples, B, T), self.device)
         res = (C.c_double * 3)()
         st = torch.cuda.current_stream(mean_tot.device).cuda_stream
         L.check(self.lib.nsw_mol_score_device(self._h, L.ptr(te_out), L.ptr(mean_tot), L.ptr(scale_tot),
@@ -322,7 +394,11 @@ class TeacherEngine:
         """-> dict(kl_loss, kl, reg) like ParallelWavenet.kl_loss_gauss (parallel_wavenet.py:404-428) downstream of
         the teacher forward; needs a gauss teacher (wavenet_gauss.json).  torch CUDA inputs."""
         import torch
+        _dev_tensor(mean_tot, 'mean_tot', (None, None), self.device)
         B, T = mean_tot.shape
+        _dev_tensor(te_out, 'te_out', (B, T, self.out_width), self.device)
+        _dev_tensor(scale_tot, 'scale_tot', (B, T), self.device)
+        _dev_tensor(log_scale_tot, 'log_scale_tot', (B, T), self.device)
         res = (C.c_double * 3)()
         st = torch.cuda.current_stream(mean_tot.device).cuda_stream
         L.check(self.lib.nsw_gauss_kl_device(self._h, L.ptr(te_out), L.ptr(mean_tot), L.ptr(scale_tot),

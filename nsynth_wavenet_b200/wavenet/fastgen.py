@@ -74,6 +74,26 @@ def encode(hparams, wav_data, checkpoint_path, device=0, engine=None):
     return encoding
 
 
+def load_cond_layers(hparams, batch_size=1, en_length=320, weights=None, device=0, engine=None):
+    """fastgen.py:91-97: the handle that evaluates Fastgen.cond_vars on an encoding placeholder."""
+    if weights is None:
+        raise ValueError('load_cond_layers needs `weights`')
+    eng = FastgenEngine(hparams, weights, device=device, engine=engine)
+    return {'engine': eng, 'encoding_in': (batch_size, en_length, hparams.deconv_width),
+            'cond_vars': 'cond_vars'}
+
+
+def calculate_cond_vars(hparams, encoding, checkpoint_path, device=0, engine=None):
+    """fastgen.py:100-115: encoding [B, L, deconv_width] -> dict 'mel_cond_i' / 'mel_cond_out1' -> np[B, L, width]
+    (the hoisted conditioning GEMM the persistent kernels consume, in the reference's channel order)."""
+    batch_size, en_length, _ = encoding.shape
+    weights = ckpt.load_weights(checkpoint_path)
+    cond = load_cond_layers(hparams, batch_size, en_length, weights=weights, device=device, engine=engine)
+    cond_vars = cond['engine'].cond_vars_host(encoding)
+    cond['engine'].close()
+    return cond_vars
+
+
 def load_fastgen(hparams, batch_size=1, weights=None, device=0, engine=None):
     """fastgen.py:118-125."""
     if weights is None:

@@ -512,6 +512,21 @@ def mol_loss(mol_params, targets, quant_chann):
     return -mol_log_probs(mol_params, targets, quant_chann).mean()
 
 
+def ce_sample(out, quant_chann, u):
+    """loss_func.ce_sample (loss_func.py:140-151): one draw from Categorical(logits=out), shifted to
+    [-Q/2, Q/2).  The reference draws through tf.distributions.Categorical -> tf.multinomial, whose noise
+    stream cannot be reproduced outside TensorFlow; with the uniform u [B] given, the draw is defined here by
+    the inverse CDF, k = min{k : sum_{i<=k} p_i > u * sum_i p_i} with p = exp(out - max(out)), which has the
+    same distribution.  out [B, Q] -> int32 [B]."""
+    out = np.asarray(out, np.float64)
+    p = np.exp(out - out.max(axis=-1, keepdims=True))
+    cdf = np.cumsum(p, axis=-1)
+    thr = np.asarray(u, np.float64) * cdf[..., -1]
+    k = (cdf > thr[..., None]).argmax(axis=-1)
+    k = np.where(cdf[..., -1] > thr, k, out.shape[-1] - 1)
+    return (k - quant_chann // 2).astype(np.int32)
+
+
 # --------------------------------------------------------------------------
 # Autoregressive fastgen (wavenet/wavenet.py:379-514, masked.py:328-405,
 # wavenet/fastgen.py:128-169)
@@ -612,7 +627,7 @@ def fastgen_run(w, hp, encoding, dtype=np.float32, teacher_force=None,
         elif hp.loss_type == 'gauss':
             q = gauss_sample(out.astype(np.float32), Q, n[:, i])
         else:
-            raise NotImplementedError('ce sampling parity is distributional only')
+            q = ce_sample(out.astype(np.float32), Q, n[:, i])   # n carries the uniform of the inverse-CDF draw
         a = inv_mu_law(q) if hp.use_mu_law else inv_cast_quantize(q, Q)
         audio = a.reshape(B, 1).astype(dtype)
         samples[:, i] = a

@@ -150,3 +150,81 @@ def test_very_short_utterances_match_oracle(teacher_hp, T):
     _, out = eng.run_host(enc, teacher_force=wav, want_out=True)
     ref = O.fastgen_run(w, hp, enc, np.float32, teacher_force=wav)['out']
     assert np.abs(out - ref).max() < TOL
+
+
+def _write_wav(path, n, seed=0):
+    from scipy.io import wavfile
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 16000.0
+    x = 0.4 * np.sin(2 * np.pi * 220 * t) + 0.05 * rng.standard_normal(n)
+    wavfile.write(path, 16000, (np.clip(x, -1, 1) * 32767).astype(np.int16))
+    return path
+
+
+@pytest.mark.timeout(600)
+def test_fastgen_encode_and_synthesis_entry_points(teacher_hp, tmp_path):
+    """The reference-facing calls themselves (eval_wavenet.py:65-69): wav files -> fastgen.load_batch ->
+    fastgen.encode (mel on the GPU + deconv stack, fastgen.py:69-88) -> fastgen.synthesis (fastgen.py:128-169) -> wav
+    files of length F*200, F = 1 + N // 200."""
+    from scipy.io import wavfile
+    from nsynth_wavenet_b200 import checkpoint as ckpt
+    from nsynth_wavenet_b200.auxilaries import mel_extractor
+    from wavenet import fastgen
+    hp = teacher_hp
+    w = O.init_teacher_weights(hp, seed=12345, bias_std=0.02)
+    ck = ckpt.save_weights(str(tmp_path / 'model.ckpt-200000'), w, ema=True)
+    files = [_write_wav(str(tmp_path / 'a.wav'), 2500, 1), _write_wav(str(tmp_path / 'b.wav'), 1900, 2)]
+    batch = fastgen.load_batch(files, sample_length=-1)
+    assert batch.shape == (2, 2500)
+    enc = fastgen.encode(hp, batch, ck)
+    F = 1 + 2500 // 200
+    assert enc.shape == (2, F * 200, 256) and enc.dtype == np.float32
+    ref = O.deconv_stack(mel_extractor.batch_melspectrogram(batch), w, hp, '', np.float64)
+    assert np.abs(enc - ref).max() < 2e-5
+    assert fastgen.encode(hp, batch[0], ck).shape == (1, F * 200, 256)           # 1-D input (fastgen.py:70-71)
+    out = [str(tmp_path / 'gen_a.wav'), str(tmp_path / 'gen_b.wav')]
+    fastgen.synthesis(hp, enc[:, :1200], out, ck, seed=4)
+    for p in out:
+        rate, data = wavfile.read(p)
+        assert rate == 16000 and data.dtype == np.float32 and len(data) == 1200
+        assert data.min() >= -1.0 and data.max() <= 1.0 - 2.0 / 65536
+        assert np.all(data * 32768 == np.floor(data * 32768))
+    # the wavs are what the engine generates for that seed, and the oracle follows the same trajectory
+    from nsynth_wavenet_b200 import FastgenEngine
+    eng = FastgenEngine(hp, w, device=0)
+    audio, o = eng.run_host(enc[:, :1200], seed=4, want_out=True)
+    assert np.array_equal(audio[0], wavfile.read(out[0])[1]) and np.array_equal(audio[1], wavfile.read(out[1])[1])
+    tf_ref = O.fastgen_run(w, hp, enc[:, :300], np.float32, teacher_force=audio[:, :300])['out']
+    assert np.abs(o[:, :300] - tf_ref).max() < TOL
+
+
+@pytest.mark.timeout(300)
+def test_encode_whole_reference_length_file(teacher_hp, tmp_path):
+    """154 480 samples (the reference's tests/test_data/test.wav length) -> 773 frames -> 154 600 encoding steps
+    (SURVEY 8c-iii)."""
+    from nsynth_wavenet_b200 import checkpoint as ckpt
+    from wavenet import fastgen
+    w = O.init_teacher_weights(teacher_hp, seed=12345)
+    ck = ckpt.save_weights(str(tmp_path / 'm'), w, ema=True)
+    f = _write_wav(str(tmp_path / 'long.wav'), 154480, 3)
+    batch = fastgen.load_batch([f], sample_length=-1)
+    enc = fastgen.encode(teacher_hp, batch, ck)
+    assert enc.shape == (1, 154600, 256) and np.all(np.isfinite(enc))
+
+
+@pytest.mark.timeout(300)
+def test_cond_vars_helpers_match_oracle(teacher_hp, tmp_path):
+    """fastgen.load_cond_layers / calculate_cond_vars (fastgen.py:91-115, Fastgen.cond_vars wavenet.py:353-377):
+    the hoisted mel-conditioning projections of every layer."""
+    from nsynth_wavenet_b200 import checkpoint as ckpt
+    from wavenet import fastgen
+    hp = teacher_hp
+    w = O.init_teacher_weights(hp, seed=12345, bias_std=0.02)
+    ck = ckpt.save_weights(str(tmp_path / 'm'), w, ema=True)
+    rng = np.random.default_rng(31)
+    enc = rng.uniform(-1, 1, (2, 70, 256)).astype(np.float32)
+    cv = fastgen.calculate_cond_vars(hp, enc, ck)
+    assert sorted(cv) == sorted(['mel_cond_%d' % (i + 1) for i in range(hp.num_layers)] + ['mel_cond_out1'])
+    for name, v in cv.items():
+        ref = enc.astype(np.float64) @ w[name + '/W'][0, 0].astype(np.float64) + w[name + '/biases']
+        assert v.shape == ref.shape and np.abs(v - ref).max() < 2e-5, name
