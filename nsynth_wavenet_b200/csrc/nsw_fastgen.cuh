@@ -23,8 +23,8 @@ constexpr int GN_MAX_L = 60;
 struct GnLayout {
   int MH, PPC, nD, K1;
   int off_d, off_p, off_l, off_s, off_c, block_floats;
-  __host__ __device__ static GnLayout make(int mh) {
-    GnLayout g;
+  __host__ __device__ static constexpr GnLayout make(int mh) {
+    GnLayout g{};
     g.MH = mh;
     g.PPC = mh / GN_NC;          // gate pairs per CTA
     g.nD = 2 * g.PPC;            // dilated-conv rows per CTA: [sigmoid rows | tanh rows]

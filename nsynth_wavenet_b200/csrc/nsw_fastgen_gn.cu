@@ -220,15 +220,17 @@ struct GnParams {
   unsigned long long seed;  // row b uses seed + golden * (b0 + b): seed_b0 carries b0
   int b0;
   float quant;
+  long long* dbg;          // NSW_FASTGEN_DEBUG: [NC][8] cycle sums of thread 0 (NULL = off)
+  int flags;               // experiment switches (NSW_GN_FLAGS): 1 = red.release arrive
 };
 
 template <int MH, int BT>
 struct GnSmem {
-  float xin[BT][GN_W + MH];  // fresh inputs of a phase: [l_{ph-2} | g_{ph-1}]; s / h in the first 256 for the head
-  float hv[BT][2 * GN_W];    // [l[t-2d] | l[t-d]] of the phase's layer
-  float wcs[3 * GN_W];
-  float bcs[GN_W];
-  float outv[BT][GN_MAX_O];
+  // weight blocks of two consecutive phases (cp.async.bulk, one phase ahead)
+  alignas(128) float wring[2][GnLayout::make(MH).block_floats];
+  alignas(128) float xl[BT][GN_W];    // fresh l_{ph-2} | head phases: s / h, rows of 256 | sampler: out, rows of O
+  alignas(128) float xg[BT][MH];      // fresh g_{ph-1}
+  alignas(128) float hv[2][BT][GN_W];  // [0] = l[t-2d], [1] = l[t-d] of the phase's layer
   float rsum[16][BT];
   float pv[8][BT];
   float cnd[8][BT];
@@ -236,18 +238,52 @@ struct GnSmem {
   float sst[2][BT];          // owned skip channels 2c, 2c+1
   float xn[BT], x1[BT], x2[BT];
   int dil[GN_MAX_L + 4], hoff[GN_MAX_L + 4], pos[GN_MAX_L + 4];
+  unsigned long long wbar[2], hbar, fbar;
 };
 
+static_assert(sizeof(GnSmem<512, GN_MAX_BT>) <= 227 * 1024, "batched fastgen shared memory");
+
 __device__ __noinline__ void gn_die(const char* what) {
-  printf("nsw fastgen(gn): watchdog in %s (block %d)\n", what, blockIdx.x);
+  printf("nsw fastgen(gn): watchdog in %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
   __trap();
 }
 
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void gn_mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void gn_expect(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gn_bulk(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void gn_mbar_wait(unsigned long long* bar, uint32_t parity, const char* what) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins == 1024) {
+      spins = 0;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > GN_WATCHDOG) gn_die(what);
+    }
+  }
+}
 
-// acc[b] = sum_i w[i] . x[b][128 i + 4 lane .. +3]  (per-lane partial; x rows are xs floats apart)
+// acc[b] += sum_{i<NF} w[i] . x[b * xs + 128 i + 4 lane .. +3]   (per-lane partial sums)
 template <int NF, int BT>
-__device__ __forceinline__ void dot_bt(const float4* w, const float* x, int xs, int lane, float (&acc)[BT]) {
+__device__ __forceinline__ void dot_seg(const float4* w, const float* x, int xs, int lane, float (&acc)[BT]) {
 #pragma unroll
   for (int b = 0; b < BT; ++b) {
     float a0 = 0.f, a1 = 0.f;
@@ -259,50 +295,74 @@ __device__ __forceinline__ void dot_bt(const float4* w, const float* x, int xs, 
       a0 = fmaf(w[i].z, xx.z, a0);
       a1 = fmaf(w[i].w, xx.w, a1);
     }
-    acc[b] = a0 + a1;
+    acc[b] += a0 + a1;
   }
 }
+// transposing butterfly: BT per-lane partials -> warp totals; the lanes with (lane & (32 / BT - 1)) == 0 write
+// total number lane / (32 / BT) into dst
 template <int BT>
-__device__ __forceinline__ void dot_n(int nf, const float4* w, const float* x, int xs, int lane, float (&acc)[BT]) {
-  switch (nf) {
-    case 2: dot_bt<2, BT>(w, x, xs, lane, acc); break;
-    case 4: dot_bt<4, BT>(w, x, xs, lane, acc); break;
-    case 6: dot_bt<6, BT>(w, x, xs, lane, acc); break;
-    default: dot_bt<8, BT>(w, x, xs, lane, acc); break;
-  }
-}
-template <int BT>
-__device__ __forceinline__ void reduce_store(float (&acc)[BT], float* dst, int lane) {
+__device__ __forceinline__ void reduce_store(float (&a)[BT], float* dst, int lane) {
+  constexpr unsigned F = 0xffffffffu;
+  float v;
+  if (BT == 8) {
+    float b4[4], b2[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
-  for (int b = 0; b < BT; ++b) {
-    float v = acc[b];
+    for (int i = 0; i < 4; ++i) b4[i] = (h16 ? a[4 + i] : a[i]) + __shfl_xor_sync(F, h16 ? a[i] : a[4 + i], 16);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) dst[b] = v;
+    for (int i = 0; i < 2; ++i) b2[i] = (h8 ? b4[2 + i] : b4[i]) + __shfl_xor_sync(F, h8 ? b4[i] : b4[2 + i], 8);
+    v = (h4 ? b2[1] : b2[0]) + __shfl_xor_sync(F, h4 ? b2[0] : b2[1], 4);
+    v += __shfl_xor_sync(F, v, 2);
+    v += __shfl_xor_sync(F, v, 1);
+    if ((lane & 3) == 0) dst[lane >> 2] = v;
+  } else if (BT == 4) {
+    float b2[2];
+    const bool h16 = lane & 16, h8 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) b2[i] = (h16 ? a[2 + i] : a[i]) + __shfl_xor_sync(F, h16 ? a[i] : a[2 + i], 16);
+    v = (h8 ? b2[1] : b2[0]) + __shfl_xor_sync(F, h8 ? b2[0] : b2[1], 8);
+    v += __shfl_xor_sync(F, v, 4);
+    v += __shfl_xor_sync(F, v, 2);
+    v += __shfl_xor_sync(F, v, 1);
+    if ((lane & 7) == 0) dst[lane >> 3] = v;
+  } else if (BT == 2) {
+    const bool h16 = lane & 16;
+    v = (h16 ? a[BT - 1] : a[0]) + __shfl_xor_sync(F, h16 ? a[0] : a[BT - 1], 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(F, v, o);
+    if ((lane & 15) == 0) dst[lane >> 4] = v;
+  } else {
+    v = a[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(F, v, o);
+    if (lane == 0) dst[0] = v;
   }
 }
 
 __device__ __forceinline__ float gn_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gn_tanh(float x) { return 2.0f * gn_sigmoid(2.0f * x) - 1.0f; }
 
+// Warp 15 is the "comm" warp: its lane 0 streams the weight blocks (one phase ahead) and the history taps (as soon as
+// the previous past-tap dots are done) into shared memory with cp.async.bulk, polls the grid barrier of the previous
+// phase WHILE the other warps do their barrier-independent work, and fetches the fresh inputs the moment it opens.
 template <int MH, int BT>
 __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
-  constexpr int W = GN_W, S = GN_S, XS = GN_W + MH, NT = GN_NT, NC = GN_NC;
+  constexpr int W = GN_W, S = GN_S, NT = GN_NT, NC = GN_NC;
   constexpr int PPC = MH / NC, nD = 2 * PPC, K1 = W + MH, G = 2 * MH;
   constexpr int OFF_D = 0, OFF_P = OFF_D + nD * K1, OFF_L = OFF_P + nD * 2 * W, OFF_S = OFF_L + 4 * MH,
                 OFF_C = OFF_S + 2 * W, BF = OFF_C + 16;
-  constexpr int NFD = K1 / 128, NFM = MH / 128;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NFM = MH / 128;
+  constexpr int COMM = NT / 32 - 1;
+  static_assert(nD + 6 <= COMM, "row warps and the comm warp must not overlap");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   using Smem = GnSmem<MH, BT>;
   Smem& Sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x;
   const int L = P.L, O = P.O, T = P.T, NPH = L + 3;
   const int RO = (O + NC - 1) / NC;
+  const bool comm = warp == COMM && lane == 0;
+  float* outv = &Sm.xl[0][0];  // sampler view of the head outputs, rows of O floats
 
-  for (int i = tid; i < 3 * W; i += NT) Sm.wcs[i] = P.wcs[i];
-  for (int i = tid; i < W; i += NT) Sm.bcs[i] = P.bcs[i];
-  for (int i = tid; i < BT * XS; i += NT) (&Sm.xin[0][0])[i] = 0.f;
-  for (int i = tid; i < BT * 2 * W; i += NT) (&Sm.hv[0][0])[i] = 0.f;
   if (tid <= L) {
     const int d = tid >= 1 ? P.dil[tid] : 1;
     Sm.dil[tid] = d;
@@ -314,205 +374,92 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
     Sm.x1[tid] = P.xstate[4 * tid + 1];
     Sm.x2[tid] = P.xstate[4 * tid + 2];
   }
+  if (tid == 0) {
+    gn_mbar_init(&Sm.wbar[0], 1);
+    gn_mbar_init(&Sm.wbar[1], 1);
+    gn_mbar_init(&Sm.hbar, 1);
+    gn_mbar_init(&Sm.fbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
+  const size_t ring_entry = (size_t)BT * W;
+  constexpr uint32_t ENTRY_B = BT * W * 4, G_B = BT * MH * 4, S_B = BT * S * 4, BLOCK_B = BF * 4;
+  // ---- comm-lane helpers ----
+  auto issue_weights = [&](int ph0 /* 0-based phase */, int slot) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot was read through the generic proxy
+    gn_expect(&Sm.wbar[slot], BLOCK_B);
+    gn_bulk(Sm.wring[slot], P.blocks + ((size_t)ph0 * NC + c) * BF, BLOCK_B, &Sm.wbar[slot]);
+  };
+  auto issue_hist = [&](int ph, int t, int pos) {  // taps of layer ph for step t; pos = ring slot of step t
+    const int d = Sm.dil[ph], R = 2 * d + 1;
+    int p1 = pos - d; if (p1 < 0) p1 += R;
+    int p2 = p1 - d; if (p2 < 0) p2 += R;
+    const float* ring = P.hist + (size_t)Sm.hoff[ph] * ring_entry;
+    const bool ok2 = t - 2 * d >= 0, ok1 = t - d >= 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    gn_expect(&Sm.hbar, (ok2 ? ENTRY_B : 0u) + (ok1 ? ENTRY_B : 0u));
+    if (ok2) gn_bulk(&Sm.hv[0][0][0], ring + (size_t)p2 * ring_entry, ENTRY_B, &Sm.hbar);
+    if (ok1) gn_bulk(&Sm.hv[1][0][0], ring + (size_t)p1 * ring_entry, ENTRY_B, &Sm.hbar);
+  };
   unsigned int bar_target = 0;
+  auto poll_grid = [&]() {  // comm lane: every CTA has published the previous phase
+    long long t0 = 0;
+    int spins = 0;
+    for (;;) {
+      unsigned int seen;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.bar) : "memory");
+      if ((int)(seen - bar_target) >= 0) break;
+      if (++spins == 1024) {
+        spins = 0;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > GN_WATCHDOG) gn_die("grid barrier");
+      }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy publishes -> the bulk copies issued next
+  };
   auto arrive = [&]() {
     __syncthreads();
     if (tid == 0) {
-      __threadfence();
-      atomicAdd(P.bar, 1u);
+      if (P.flags & 1) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.bar) : "memory");
+      } else {
+        __threadfence();
+        atomicAdd(P.bar, 1u);
+      }
     }
     bar_target += NC;
   };
-  auto wait = [&]() {
-    if (tid == 0) {
-      long long t0 = 0;
-      int spins = 0;
-      for (;;) {
-        unsigned int seen;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.bar) : "memory");
-        if ((int)(seen - bar_target) >= 0) break;
-        if (++spins == 1024) {
-          spins = 0;
-          if (t0 == 0) t0 = clock64();
-          else if (clock64() - t0 > GN_WATCHDOG) gn_die("grid barrier");
-        }
-      }
-      __threadfence();
-    }
-    __syncthreads();
-  };
 
-  const size_t ring_entry = (size_t)BT * W;
-  for (int t = P.t0; t < P.t1; ++t) {
-    const int tl = t - P.t0;
-    for (int ph = 1; ph <= NPH; ++ph) {
-      const float* blk = P.blocks + ((size_t)(ph - 1) * NC + c) * BF;
-      if (tid == 0) {  // pull the block two phases ahead into L2 (the stream is larger than L2: plain LRU never hits)
-        const int pn = ph + 1 >= NPH ? ph + 1 - NPH : ph + 1;  // 0-based index of phase ph + 2
-        const float* nxt = P.blocks + ((size_t)pn * NC + c) * BF;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((uint32_t)(BF * 4)) : "memory");
-      }
-      // ------------------------------- before the barrier in flight -------------------------------
-      float4 wp[8], wf[8];
-      int nf = 0, xoff = 0;  // fresh row of this warp: nf float4 per lane against xin[b][xoff ...]
-      const bool has_past = ph <= L && warp < nD;
-      if (has_past) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wp[i] = __ldg(reinterpret_cast<const float4*>(blk + OFF_P + warp * 2 * W + 128 * i + 4 * lane));
-      }
-      {
-        const float* row = nullptr;
-        if (ph <= L) {
-          if (warp < nD) { row = blk + OFF_D + warp * K1; nf = NFD; xoff = 0; }
-          else if (warp < nD + 4) { if (ph >= 2) { row = blk + OFF_L + (warp - nD) * MH; nf = NFM; xoff = W; } }
-          else if (warp < nD + 6) {
-            row = blk + OFF_S + (warp - nD - 4) * W;
-            if (ph == 1) { nf = W / 128; xoff = 0; } else { nf = NFM; xoff = W; }
-          }
-        } else if (ph == L + 1) {
-          if (warp >= nD + 4 && warp < nD + 6) { row = blk + OFF_S + (warp - nD - 4) * W; nf = NFM; xoff = W; }
-        } else if (ph == L + 2) {
-          if (warp < 2) { row = blk + OFF_D + warp * K1; nf = S / 128; xoff = 0; }
-        } else {
-          if (warp < RO && c * RO + warp < O) { row = blk + OFF_D + warp * K1; nf = S / 128; xoff = 0; }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < nf) wf[i] = __ldg(reinterpret_cast<const float4*>(row + 128 * i + 4 * lane));
-      }
-      if (ph <= L) {
-        const int d = Sm.dil[ph], R = 2 * d + 1;
-        const int pos = Sm.pos[ph];
-        int p1 = pos - d; if (p1 < 0) p1 += R;
-        int p2 = p1 - d; if (p2 < 0) p2 += R;
-        const float* ring = P.hist + (size_t)Sm.hoff[ph] * ring_entry;
-        const bool ok2 = t - 2 * d >= 0, ok1 = t - d >= 0;
-        for (int i = tid; i < BT * (W / 4); i += NT) {  // one float4 of each tap per iteration
-          const int b = i / (W / 4), k4 = i - b * (W / 4);
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 a2 = ok2 ? ldcg4(ring + (size_t)p2 * ring_entry + (size_t)b * W + 4 * k4) : z;
-          const float4 a1 = ok1 ? ldcg4(ring + (size_t)p1 * ring_entry + (size_t)b * W + 4 * k4) : z;
-          *reinterpret_cast<float4*>(&Sm.hv[b][4 * k4]) = a2;
-          *reinterpret_cast<float4*>(&Sm.hv[b][W + 4 * k4]) = a1;
-        }
-        if (tid < nD * BT) {
-          const int j = tid / BT, b = tid - j * BT;
-          const int n = (ph - 1) * G + c * nD + j;
-          Sm.cnd[j][b] = __ldg(P.cond + (size_t)b * P.cond_bstride + ((size_t)(n >> 6) * P.Tc + tl) * 64 + (n & 63));
-        }
-      } else if (ph == L + 2) {
-        if (tid < 2 * BT) {
-          const int j = tid / BT, b = tid - j * BT;
-          const int n = L * G + 2 * c + j;
-          Sm.cnd[j][b] = __ldg(P.cond + (size_t)b * P.cond_bstride + ((size_t)(n >> 6) * P.Tc + tl) * 64 + (n & 63));
-        }
-      }
-      __syncthreads();  // hv / cnd staged
-      if (has_past) {
-        float acc[BT];
-        dot_bt<8, BT>(wp, &Sm.hv[0][0], 2 * W, lane, acc);
-        reduce_store<BT>(acc, Sm.pv[warp], lane);
-      }
-      // ------------------------------- the exchange of the previous phase -------------------------------
-      wait();
-      if (ph == 1) {
-        // conv_start on the fed-back sample, every CTA the full vector (causal_linear rate 1, masked.py:352-376)
-        for (int i = tid; i < BT * W; i += NT) {
-          const int b = i / W, k = i - b * W;
-          Sm.xin[b][k] = fmaf(Sm.wcs[2 * W + k], Sm.xn[b], fmaf(Sm.wcs[W + k], Sm.x1[b], fmaf(Sm.wcs[k], Sm.x2[b], Sm.bcs[k])));
-        }
-        for (int i = tid; i < BT * MH; i += NT) Sm.xin[i / MH][W + i % MH] = 0.f;  // no gate output before layer 1
-      } else if (ph <= L) {
-        const float* lsrc = P.hist + ((size_t)Sm.hoff[ph - 1] + Sm.pos[ph - 1]) * ring_entry;  // l_{ph-2} of this step
-        const float* gsrc = P.gbuf + (size_t)((ph - 1) & 1) * BT * MH;
-        for (int i = tid; i < BT * (W / 4); i += NT) {
-          const int b = i / (W / 4), k4 = i - b * (W / 4);
-          *reinterpret_cast<float4*>(&Sm.xin[b][4 * k4]) = ldcg4(lsrc + (size_t)b * W + 4 * k4);
-        }
-        for (int i = tid; i < BT * (MH / 4); i += NT) {
-          const int b = i / (MH / 4), k4 = i - b * (MH / 4);
-          *reinterpret_cast<float4*>(&Sm.xin[b][W + 4 * k4]) = ldcg4(gsrc + (size_t)b * MH + 4 * k4);
-        }
-      } else if (ph == L + 1) {
-        const float* gsrc = P.gbuf + (size_t)(L & 1) * BT * MH;
-        for (int i = tid; i < BT * (MH / 4); i += NT) {
-          const int b = i / (MH / 4), k4 = i - b * (MH / 4);
-          *reinterpret_cast<float4*>(&Sm.xin[b][W + 4 * k4]) = ldcg4(gsrc + (size_t)b * MH + 4 * k4);
-        }
-      } else {
-        const float* src = ph == L + 2 ? P.sbuf : P.hbuf;
-        for (int i = tid; i < BT * (S / 4); i += NT) {
-          const int b = i / (S / 4), k4 = i - b * (S / 4);
-          *reinterpret_cast<float4*>(&Sm.xin[b][4 * k4]) = ldcg4(src + (size_t)b * S + 4 * k4);
-        }
-      }
-      __syncthreads();
-      if (ph == 1 && tid < BT) {  // conv_start's two queues (rate 1)
-        Sm.x2[tid] = Sm.x1[tid];
-        Sm.x1[tid] = Sm.xn[tid];
-      }
-      if (nf > 0) {
-        float acc[BT];
-        dot_n<BT>(nf, wf, &Sm.xin[0][0] + xoff, XS, lane, acc);
-        reduce_store<BT>(acc, Sm.rsum[warp], lane);
-      }
-      __syncthreads();
-      // ------------------------------- epilogues: one thread per (row, batch row) -------------------------------
-      if (ph <= L) {
-        if (tid < PPC * BT) {
-          const int pr = tid / BT, b = tid - pr * BT;
-          const float a = Sm.rsum[pr][b] + Sm.pv[pr][b] + Sm.cnd[pr][b];
-          const float q = Sm.rsum[PPC + pr][b] + Sm.pv[PPC + pr][b] + Sm.cnd[PPC + pr][b];
-          __stcg(P.gbuf + (size_t)(ph & 1) * BT * MH + (size_t)b * MH + c * PPC + pr, gn_sigmoid(a) * gn_tanh(q));
-        } else if (tid >= 64 && tid < 64 + 4 * BT) {
-          const int r = (tid - 64) / BT, b = (tid - 64) - r * BT;
-          // l_{ph-1} = l_{ph-2} + Wr_{ph-1} g_{ph-1} + br_{ph-1}  (phase 1: l_0 from conv_start)
-          const float l = ph == 1 ? Sm.xin[b][4 * c + r] : Sm.lst[r][b] + Sm.rsum[nD + r][b] + __ldg(blk + OFF_C + r);
-          Sm.lst[r][b] = l;
-          __stcg(P.hist + ((size_t)Sm.hoff[ph] + Sm.pos[ph]) * ring_entry + (size_t)b * W + 4 * c + r, l);
-        } else if (tid >= 128 && tid < 128 + 2 * BT) {
-          const int r = (tid - 128) / BT, b = (tid - 128) - r * BT;
-          const float a = Sm.rsum[nD + 4 + r][b] + __ldg(blk + OFF_C + 4 + r);
-          Sm.sst[r][b] = ph == 1 ? a : Sm.sst[r][b] + a;  // skip_start, then skip_{ph-1}
-        }
-      } else if (ph == L + 1) {
-        if (tid >= 128 && tid < 128 + 2 * BT) {
-          const int r = (tid - 128) / BT, b = (tid - 128) - r * BT;
-          const float s = Sm.sst[r][b] + Sm.rsum[nD + 4 + r][b] + __ldg(blk + OFF_C + 4 + r);
-          __stcg(P.sbuf + (size_t)b * S + 2 * c + r, fmaxf(s, 0.f));  // relu(s) (wavenet.py:494)
-        }
-      } else if (ph == L + 2) {
-        if (tid < 2 * BT) {
-          const int r = tid / BT, b = tid - r * BT;
-          __stcg(P.hbuf + (size_t)b * S + 2 * c + r, fmaxf(Sm.rsum[r][b] + Sm.cnd[r][b], 0.f));
-        }
-      } else {
-        if (tid < RO * BT) {
-          const int r = tid / BT, b = tid - r * BT;
-          const int o = c * RO + r;
-          if (o < O) __stcg(P.obuf + (size_t)b * O + o, Sm.rsum[r][b] + __ldg(blk + OFF_C + 6 + r));
-        }
-      }
-      arrive();
-    }
-    // ------------------------------- head: every CTA samples every row, redundantly -------------------------------
-    wait();
-    for (int i = tid; i < BT * O; i += NT) {
-      const int b = i / O, o = i - b * O;
-      Sm.outv[b][o] = __ldcg(P.obuf + (size_t)b * O + o);
-    }
+  if (comm) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    issue_weights(0, 0);
+    issue_hist(1, P.t0, Sm.pos[1]);
+  }
+  uint32_t nh = 0, nfr = 0;  // completed uses of hbar / fbar (parities)
+  long long gq = 0;          // phases since launch
+  long long dacc[6] = {0, 0, 0, 0, 0, 0};
+  const bool dbg = P.dbg != nullptr && tid == 0;
+
+  // sample step ts from obuf (all CTAs, redundantly); runs between the grid barrier of its phase L+3 and phase 1
+  auto sample_step = [&](int ts) {
+    for (int i = tid; i < BT * O; i += NT) outv[i] = __ldcg(P.obuf + i);
     __syncthreads();
+    if (c == 0 && P.out) {
+      for (int i = tid; i < P.nb * O; i += NT) {
+        const int b = i / O, o = i - b * O;
+        P.out[((size_t)b * T + ts) * O + o] = outv[i];
+      }
+    }
     if (warp < BT) {
       const int b = warp;
-      const float* ov = Sm.outv[b];
+      const float* ov = outv + (size_t)b * O;
       const float Q = P.quant;
       const unsigned long long sd = P.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(P.b0 + b);
       const uint2 key = make_uint2((uint32_t)sd, (uint32_t)(sd >> 32));
-      const float* nz = (P.noise && b < P.nb) ? P.noise + ((size_t)b * T + t) * P.nu : nullptr;
+      const float* nz = (P.noise && b < P.nb) ? P.noise + ((size_t)b * T + ts) * P.nu : nullptr;
       auto bits_of = [&](int j) -> uint32_t {  // same stream as the latency engine: counter (t, j / 4), word j % 4
-        const uint4 rr = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)(j >> 2), 0x66617374u, 0u), key);
+        const uint4 rr = philox4x32_10(make_uint4((uint32_t)ts, (uint32_t)(j >> 2), 0x66617374u, 0u), key);
         return (j & 3) == 0 ? rr.x : (j & 3) == 1 ? rr.y : (j & 3) == 2 ? rr.z : rr.w;
       };
       float a;  // dequantised sample
@@ -585,24 +532,203 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
         a = inv_quant_dev((float)k - 0.5f * Q, Q, P.use_mu_law);  // fastgen.py:162-166
       }
       if (lane == 0) {
-        const float fed = (P.tf && b < P.nb) ? P.tf[(size_t)b * T + t] : a;
+        const float fed = (P.tf && b < P.nb) ? P.tf[(size_t)b * T + ts] : a;
         Sm.xn[b] = P.use_mu_law ? mu_law_scaled_dev(fed, Q) : fed;  // wavenet.py:411-414
-        if (c == 0 && P.audio && b < P.nb) P.audio[(size_t)b * T + t] = fed;
+        if (c == 0 && P.audio && b < P.nb) P.audio[(size_t)b * T + ts] = fed;
       }
     }
-    if (c == 0 && P.out) {
-      for (int i = tid; i < P.nb * O; i += NT) {
-        const int b = i / O, o = i - b * O;
-        P.out[((size_t)b * T + t) * O + o] = Sm.outv[b][o];
+    __syncthreads();
+  };
+
+  for (int t = P.t0; t < P.t1; ++t) {
+    const int tl = t - P.t0;
+    for (int ph = 1; ph <= NPH; ++ph, ++gq) {
+      const int slot = (int)(gq & 1);
+      const float* blk = Sm.wring[slot];
+      long long tq = dbg ? clock64() : 0;
+      auto lap = [&](int i) { if (dbg) { const long long now = clock64(); dacc[i] += now - tq; tq = now; } };
+      const bool last_phase = (t + 1 == P.t1) && ph == NPH;
+      // ---------------- comm lane: next weights, then the previous phase's exchange ----------------
+      if (comm) {
+        // (the next weight block is requested AFTER the fresh inputs: bulk copies are served in order, and 37-78 KB
+        // of weights in front of them would delay the critical path by their transfer time)
+        if (ph >= 2 || t > P.t0) poll_grid();
+        if (ph >= 2) {
+          // fresh inputs of this phase (xl / xg were last read before the previous arrive)
+          if (ph <= L) {
+            gn_expect(&Sm.fbar, ENTRY_B + G_B);
+            gn_bulk(&Sm.xl[0][0], P.hist + ((size_t)Sm.hoff[ph - 1] + Sm.pos[ph - 1]) * ring_entry, ENTRY_B, &Sm.fbar);
+            gn_bulk(&Sm.xg[0][0], P.gbuf + (size_t)((ph - 1) & 1) * BT * MH, G_B, &Sm.fbar);
+          } else if (ph == L + 1) {
+            gn_expect(&Sm.fbar, G_B);
+            gn_bulk(&Sm.xg[0][0], P.gbuf + (size_t)(L & 1) * BT * MH, G_B, &Sm.fbar);
+          } else {
+            gn_expect(&Sm.fbar, S_B);
+            gn_bulk(&Sm.xl[0][0], ph == L + 2 ? P.sbuf : P.hbuf, S_B, &Sm.fbar);
+          }
+        }
+        if (!last_phase) issue_weights(ph == NPH ? 0 : ph, slot ^ 1);
       }
+      // ---------------- everything that does not depend on the exchange in flight ----------------
+      gn_mbar_wait(&Sm.wbar[slot], (uint32_t)((gq >> 1) & 1), "weight block");
+      float4 wp[8], wf[8];
+      // fresh row of this warp: nfl float4 per lane against xl (rows xs apart), then nfg against xg
+      int nfl = 0, nfg = 0, xs = W;
+      const bool has_past = ph <= L && warp < nD;
+      bool ok2 = false, ok1 = false;
+      if (ph <= L) {
+        const int d = Sm.dil[ph];
+        ok2 = t - 2 * d >= 0;
+        ok1 = t - d >= 0;
+      }
+      if (has_past) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wp[i] = *reinterpret_cast<const float4*>(blk + OFF_P + warp * 2 * W + 128 * i + 4 * lane);
+      }
+      {
+        const float* row = nullptr;
+        if (ph <= L) {
+          if (warp < nD) { row = blk + OFF_D + warp * K1; nfl = W / 128; nfg = NFM; }
+          else if (warp < nD + 4) { if (ph >= 2) { row = blk + OFF_L + (warp - nD) * MH; nfg = NFM; } }
+          else if (warp < nD + 6) {
+            row = blk + OFF_S + (warp - nD - 4) * W;
+            if (ph == 1) nfl = W / 128; else nfg = NFM;
+          }
+        } else if (ph == L + 1) {
+          if (warp >= nD + 4 && warp < nD + 6) { row = blk + OFF_S + (warp - nD - 4) * W; nfg = NFM; }
+        } else if (ph == L + 2) {
+          if (warp < 2) { row = blk + OFF_D + warp * K1; nfl = S / 128; xs = S; }
+        } else {
+          if (warp < RO && c * RO + warp < O) { row = blk + OFF_D + warp * K1; nfl = S / 128; xs = S; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < nfl + nfg) wf[i] = *reinterpret_cast<const float4*>(row + 128 * i + 4 * lane);
+      }
+      if (ph <= L) {
+        if (tid >= 256 && tid < 256 + nD * BT) {
+          const int j = (tid - 256) / BT, b = (tid - 256) - j * BT;
+          const int n = (ph - 1) * G + c * nD + j;
+          Sm.cnd[j][b] = __ldg(P.cond + (size_t)b * P.cond_bstride + ((size_t)(n >> 6) * P.Tc + tl) * 64 + (n & 63));
+        }
+        if (has_past) {
+          gn_mbar_wait(&Sm.hbar, nh & 1u, "history taps");
+          float acc[BT];
+#pragma unroll
+          for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+          if (ok2) dot_seg<4, BT>(wp, &Sm.hv[0][0][0], W, lane, acc);
+          if (ok1) dot_seg<4, BT>(wp + 4, &Sm.hv[1][0][0], W, lane, acc);
+          reduce_store<BT>(acc, Sm.pv[warp], lane);
+        }
+        ++nh;
+      } else if (ph == L + 2) {
+        if (tid >= 256 && tid < 256 + 2 * BT) {
+          const int j = (tid - 256) / BT, b = (tid - 256) - j * BT;
+          const int n = L * G + 2 * c + j;
+          Sm.cnd[j][b] = __ldg(P.cond + (size_t)b * P.cond_bstride + ((size_t)(n >> 6) * P.Tc + tl) * 64 + (n & 63));
+        }
+      }
+      __syncthreads();  // S1: past taps done (hv is free), cnd / pv staged; the comm lane has seen the grid barrier
+      lap(0);
+      if (comm && !last_phase) {
+        // history taps of the next phase with a dilated conv (phase 1 of the next step after the head phases)
+        if (ph < L) issue_hist(ph + 1, t, Sm.pos[ph + 1]);
+        else if (ph == NPH) {
+          const int R = 2 * Sm.dil[1] + 1;
+          const int pn = Sm.pos[1] + 1;
+          issue_hist(1, t + 1, pn >= R ? 0 : pn);
+        }
+      }
+      // ---------------- fresh inputs ----------------
+      if (ph == 1) {
+        if (t > P.t0) sample_step(t - 1);
+        // conv_start on the fed-back sample, every CTA the full vector (causal_linear rate 1, masked.py:352-376)
+        for (int i = tid; i < BT * W; i += NT) {
+          const int b = i / W, k = i - b * W;
+          Sm.xl[b][k] = fmaf(__ldg(P.wcs + 2 * W + k), Sm.xn[b],
+                             fmaf(__ldg(P.wcs + W + k), Sm.x1[b], fmaf(__ldg(P.wcs + k), Sm.x2[b], __ldg(P.bcs + k))));
+        }
+        for (int i = tid; i < BT * MH; i += NT) (&Sm.xg[0][0])[i] = 0.f;  // no gate output before layer 1
+        __syncthreads();
+        if (tid < BT) {  // conv_start's two queues (rate 1)
+          Sm.x2[tid] = Sm.x1[tid];
+          Sm.x1[tid] = Sm.xn[tid];
+        }
+      } else {
+        gn_mbar_wait(&Sm.fbar, nfr & 1u, "fresh inputs");
+        ++nfr;
+      }
+      lap(1);
+      if (nfl + nfg > 0) {
+        float acc[BT];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+        // compile-time register indices only (a dynamically indexed weight array would live in local memory)
+        if (nfl == 4) {
+          dot_seg<4, BT>(wf, &Sm.xl[0][0], xs, lane, acc);
+          if (nfg > 0) dot_seg<NFM, BT>(wf + 4, &Sm.xg[0][0], MH, lane, acc);
+        } else if (nfl == 2) {
+          dot_seg<2, BT>(wf, &Sm.xl[0][0], xs, lane, acc);
+        } else {
+          dot_seg<NFM, BT>(wf, &Sm.xg[0][0], MH, lane, acc);
+        }
+        reduce_store<BT>(acc, Sm.rsum[warp], lane);
+      }
+      __syncthreads();  // S2
+      lap(2);
+      // ---------------- epilogues: one thread per (row, batch row) ----------------
+      if (ph <= L) {
+        if (tid < PPC * BT) {
+          const int pr = tid / BT, b = tid - pr * BT;
+          const float a = Sm.rsum[pr][b] + Sm.pv[pr][b] + Sm.cnd[pr][b];
+          const float q = Sm.rsum[PPC + pr][b] + Sm.pv[PPC + pr][b] + Sm.cnd[PPC + pr][b];
+          __stcg(P.gbuf + (size_t)(ph & 1) * BT * MH + (size_t)b * MH + c * PPC + pr, gn_sigmoid(a) * gn_tanh(q));
+        } else if (tid >= 64 && tid < 64 + 4 * BT) {
+          const int r = (tid - 64) / BT, b = (tid - 64) - r * BT;
+          // l_{ph-1} = l_{ph-2} + Wr_{ph-1} g_{ph-1} + br_{ph-1}  (phase 1: l_0 from conv_start)
+          const float l = ph == 1 ? Sm.xl[b][4 * c + r] : Sm.lst[r][b] + Sm.rsum[nD + r][b] + blk[OFF_C + r];
+          Sm.lst[r][b] = l;
+          __stcg(P.hist + ((size_t)Sm.hoff[ph] + Sm.pos[ph]) * ring_entry + (size_t)b * W + 4 * c + r, l);
+        } else if (tid >= 128 && tid < 128 + 2 * BT) {
+          const int r = (tid - 128) / BT, b = (tid - 128) - r * BT;
+          const float a = Sm.rsum[nD + 4 + r][b] + blk[OFF_C + 4 + r];
+          Sm.sst[r][b] = ph == 1 ? a : Sm.sst[r][b] + a;  // skip_start, then skip_{ph-1}
+        }
+      } else if (ph == L + 1) {
+        if (tid >= 128 && tid < 128 + 2 * BT) {
+          const int r = (tid - 128) / BT, b = (tid - 128) - r * BT;
+          const float s = Sm.sst[r][b] + Sm.rsum[nD + 4 + r][b] + blk[OFF_C + 4 + r];
+          __stcg(P.sbuf + (size_t)b * S + 2 * c + r, fmaxf(s, 0.f));  // relu(s) (wavenet.py:494)
+        }
+      } else if (ph == L + 2) {
+        if (tid < 2 * BT) {
+          const int r = tid / BT, b = tid - r * BT;
+          __stcg(P.hbuf + (size_t)b * S + 2 * c + r, fmaxf(Sm.rsum[r][b] + Sm.cnd[r][b], 0.f));
+        }
+      } else {
+        if (tid < RO * BT) {
+          const int r = tid / BT, b = tid - r * BT;
+          const int o = c * RO + r;
+          if (o < O) __stcg(P.obuf + (size_t)b * O + o, Sm.rsum[r][b] + blk[OFF_C + 6 + r]);
+        }
+      }
+      lap(3);
+      arrive();
+      lap(4);
     }
-    if (tid >= 1 && tid <= L) {
+    if (tid >= 1 && tid <= L) {  // ring slot of step t+1 (the comm lane already used pos[1] + 1 for its prefetch)
       const int R = 2 * Sm.dil[tid] + 1;
       const int pn = Sm.pos[tid] + 1;
       Sm.pos[tid] = pn >= R ? 0 : pn;
     }
     __syncthreads();
   }
+  // the last step of this launch: its head outputs are behind the last grid barrier
+  if (comm) poll_grid();
+  __syncthreads();
+  sample_step(P.t1 - 1);
+  if (dbg)
+    for (int i = 0; i < 5; ++i) P.dbg[8 * c + i] = dacc[i];
   if (c == 0 && tid < BT) {
     P.xstate[4 * tid] = Sm.xn[tid];
     P.xstate[4 * tid + 1] = Sm.x1[tid];
@@ -643,7 +769,7 @@ struct GnEngine {
   size_t hist_entries = 0;
   int chunk = 2048;
   DevBuf blocks, wcs, bcs, cond_w, cond_wt_hi, cond_wt_lo, cond_b, hist_off, dil;
-  DevBuf hist, gbuf, sbuf, hbuf, obuf, xstate, bar, cond, enc_split;
+  DevBuf hist, gbuf, sbuf, hbuf, obuf, xstate, bar, cond, enc_split, dbg;
 };
 
 int gn_create(const nsw_wavenet_config& cfg, const TensorMap& tm, int device, GnEngine** out) {
@@ -765,6 +891,14 @@ int gn_run(GnEngine* g, const float* d_encoding, int B, int T, const float* d_tf
       P.L = L; P.O = O; P.loss_type = g->cfg.loss_type; P.use_mu_law = g->cfg.use_mu_law ? 1 : 0; P.nu = nu;
       P.seed = seed; P.b0 = b0;
       P.quant = g->cfg.use_mu_law ? 256.0f : 65536.0f;
+      P.dbg = nullptr;
+      P.flags = getenv("NSW_GN_FLAGS") ? atoi(getenv("NSW_GN_FLAGS")) : 0;
+      const bool want_dbg = getenv("NSW_FASTGEN_DEBUG") != nullptr;
+      if (want_dbg) {
+        NSW_TRY(g->dbg.ensure(GN_NC * 8 * sizeof(long long)));
+        NSW_CUDA(cudaMemsetAsync(g->dbg.p, 0, GN_NC * 8 * sizeof(long long), st));
+        P.dbg = g->dbg.as<long long>();
+      }
       int rc;
       if (MH == 256) {
         rc = BT == 1 ? gn_launch<256, 1>(P, st) : BT == 2 ? gn_launch<256, 2>(P, st)
@@ -774,6 +908,18 @@ int gn_run(GnEngine* g, const float* d_encoding, int B, int T, const float* d_tf
              : BT == 4 ? gn_launch<512, 4>(P, st) : gn_launch<512, 8>(P, st);
       }
       NSW_TRY(rc);
+      if (want_dbg) {
+        std::vector<long long> host(GN_NC * 8);
+        NSW_CUDA(cudaStreamSynchronize(st));
+        NSW_CUDA(cudaMemcpy(host.data(), g->dbg.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const double phases = (double)tcn * (L + 3);
+        const char* names[5] = {"weights + past taps (to S1)", "fresh inputs arrived", "dots", "epilogue", "arrive"};
+        for (int cta : {0, 1, 64, 127}) {
+          fprintf(stderr, "[nsw fastgen gn dbg BT=%d MH=%d] cta %3d cycles/phase:", BT, MH, cta);
+          for (int i = 0; i < 5; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)host[8 * cta + i] / phases);
+          fprintf(stderr, "\n");
+        }
+      }
     }
   }
   return NSW_OK;
