@@ -2,14 +2,20 @@
 """Headline benchmark: parallelgen IAF audio samples/s on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N ...            # CPU restatement of the reference
+  python bench.py --impl reference --gpus N ...            # CPU restatement of the reference, same config
 
-Workload (config.workload): BASELINE configs[2] — parallel WaveNet 4-flow IAF student
+Workload (config.workload): BASELINE configs[2] -- parallel WaveNet 4-flow IAF student
 (parallel_wavenet.json, random init seed 12345), batch 8 x 7680 samples per GPU, synthetic
 mel ~ U[0,1), noise drawn on the device.  One "step" = one full forward of that batch
 (deconv stack, cond projections, 60 residual layers, 4 heads, quantise).  N > 1 shards
 independent clips across ranks (weak scaling, 8 clips per GPU); NCCL is used once, to
 broadcast the weight blob from rank 0, never in the timed loop.
+
+Beside the contract keys the line carries: `sustained` (the same step looped for >= 2 s), `e2e` (C-ABI host call,
+pinned buffers), `e2e_python` (wavenet.parallelgen.synthesis: pageable arrays, checkpoint on disk, wav files written),
+`roofline` (+ `frac_model_hbm`, `frac_dram`, `frac_tensor`), `roofline_cond_gemm`, `roofline_teacher`, `fastgen`
+(configs[1]: latency engine at batch 1, batched engine at batch 8, its own e2e and cpu_baseline), `clarinet`
+(configs[3] per-GPU share) and `distill` (configs[4] forward), the last two timed as max over ranks at every N.
 """
 from __future__ import annotations
 
@@ -17,6 +23,7 @@ import argparse
 import json
 import os
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,12 +39,19 @@ CONFIGS = {'student': 'parallel_wavenet.json', 'clarinet': 'parallel_wavenet_gau
 # algorithmic bytes of the fused residual layer per (sample, layer):
 # read l (64*4) + read cond (64*4) + write l (64*4)
 LAYER_BYTES_PER_SAMPLE = 768
+# algorithmic flops (2 * MAC) per (sample, layer): 3-tap 64->64 conv + 32->64 residual 1x1
+LAYER_FLOP_PER_SAMPLE = 2 * (3 * 64 * 64 + 32 * 64)
+HEAD_FLOP_PER_SAMPLE = 2 * (64 * 64 + 2 * 64)        # out1 + out2_mean / out2_scale, per (sample, flow)
 COND_FLOP_PER_SAMPLE_PLANE = 2 * 256 * 64
+SPLIT_PRODUCTS = 3                                   # hi*hi + hi*lo + lo*hi fp16 MMAs per fp32-grade product
+FASTGEN_ALGORITHMIC_BYTES = 29697024 * 4             # weights touched per autoregressive step
+TEACHER_FLOP_PER_SAMPLE = 67.4e6                     # full-sequence teacher, per output sample
 
 
 def load_hparams(name):
     from argparse import Namespace
-    with open(os.path.join(ROOT, 'nsynth_wavenet_b200', 'config_jsons', CONFIGS[name])) as f:
+    fname = CONFIGS.get(name, name)
+    with open(os.path.join(ROOT, 'nsynth_wavenet_b200', 'config_jsons', fname)) as f:
         return Namespace(**json.load(f))
 
 
@@ -50,6 +64,26 @@ def measured_peaks():
     return 6650.0, 1590.0, 'fallback'
 
 
+def ncu_capture(name):
+    """Committed ncu --set full summary of a kernel (profiles/r02 first, else r01): dict of metrics or None."""
+    for rnd, fname in (('r02', 'flow_cond_ncu.json'), ('r01', 'tc3_ncu_run28.json')):
+        p = os.path.join(ROOT, 'profiles', rnd, fname)
+        if not os.path.exists(p):
+            continue
+        with open(p) as f:
+            caps = [c for c in json.load(f)['launches'] if name in c['kernel']]
+        if caps:
+            return caps[0], 'profiles/{}/{}'.format(rnd, fname)
+    return None, None
+
+
+def metric_value(cap, key):
+    v = cap.get(key)
+    if isinstance(v, dict):
+        v = v.get('value')
+    return None if v is None else float(v)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi-equivalent clock / throttle-reason sampling through NVML during the timed region."""
 
@@ -57,6 +91,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
+        self.power = []
         self.reasons = set()
         self.max_mhz = None
         self.stop_flag = False
@@ -85,6 +120,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -95,25 +134,37 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.05)
 
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return self.summary()
+
     def summary(self):
         if not self.ok or not self.samples:
             return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
-        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
-                'reasons': sorted(self.reasons)}
+        out = {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+               'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+        if self.power:
+            out['power_w_max'] = float(np.max(self.power))
+        return out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/): cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------------------------
 def cpu_reference_run(hp, batch, frames, steps, warmup, seed=12345):
     """Times the torch-CPU restatement of the reference's graph (oracle/torch_port.py) with
     every host thread.  Returns (samples_per_s, ms_per_step, cores, sample description)."""
     import torch
-    from oracle import torch_port, wavenet_oracle as O
+    from oracle import torch_port
+    from nsynth_wavenet_b200.weights_init import init_student_weights
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    w = O.init_student_weights(hp, seed=seed)
+    w = init_student_weights(hp, seed=seed)
     port = torch_port.StudentPort(w, hp)
     rng = np.random.default_rng(54321)
     mel = rng.uniform(0, 1, (batch, frames, 80)).astype(np.float32)
-    T = O.iaf_length(frames, hp)
+    T = (frames * 200 // 512) * 512
     gauss = getattr(hp, 'loss_type', 'logistic') != 'logistic'
     times = []
     for i in range(warmup + steps):
@@ -121,7 +172,8 @@ def cpu_reference_run(hp, batch, frames, steps, warmup, seed=12345):
         if gauss:
             z = rng.standard_normal((batch, T)).astype(np.float32)
         else:
-            z = O.logistic_from_uniform(rng.uniform(1e-5, 1 - 1e-5, (batch, T))).astype(np.float32)
+            u = rng.uniform(1e-5, 1 - 1e-5, (batch, T))
+            z = (np.log(u) - np.log1p(-u)).astype(np.float32)
         port.forward(mel, z, quantize=True)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
@@ -131,96 +183,260 @@ def cpu_reference_run(hp, batch, frames, steps, warmup, seed=12345):
             len(times), batch, T, cores)
 
 
-def fastgen_bench(device, steps, hbm_peak):
-    """Teacher WaveNet (wavenet_mol.json, 30 layers, random init) free-running generation at
-    batch 1 through the persistent kernel; encoding resident in HBM, in-kernel RNG."""
+def cpu_fastgen_run(steps):
+    """the reference's per-sample loop (fastgen.py:156-168) restated on torch-CPU,
+    wavenet_mol.json, batch 1, free-running MoL sampling."""
     import torch
-    from argparse import Namespace
+    from oracle import torch_port
+    from nsynth_wavenet_b200.weights_init import init_teacher_weights
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = load_hparams('wavenet_mol.json')
+    port = torch_port.FastgenPort(init_teacher_weights(hp, seed=12345), hp, 1)
+    rng = np.random.default_rng(1)
+    enc = rng.uniform(-1, 1, (1, steps + 64, 256)).astype(np.float32)
+    port.run(enc, 64)
+    port.reset()
+    t0 = time.perf_counter()
+    port.run(enc, steps)
+    dt = time.perf_counter() - t0
+    return {'value': steps / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'rtf': steps / dt / 16000.0,
+            'sample': '{} autoregressive steps, batch 1, one Python iteration per sample like fastgen.py:156, '
+                      'torch-CPU fp32, {} threads'.format(steps, cores)}
+
+
+def run_reference(args, emit):
+    """--impl reference: the reference's own CPU path restated (TF 1.x is not installable
+    here), same config as the b200 arm, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    hp = load_hparams(args.config)
+    batch = args.ref_batch
+    v, ms, cores, sample = cpu_reference_run(hp, batch, args.frames, args.steps, max(1, args.warmup))
+    T = (args.frames * 200 // 512) * 512
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.config, batch, T, None, args.gpus),
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'rtf': v / 16000.0,
+        'note': 'TensorFlow 1.x is absent: this is the fp32 torch-CPU restatement of the '
+                'reference graph (oracle/torch_port.py), all host threads, one process (rank 0)',
+    }
+    emit(line)
+
+
+def workload_config(config, B, T, engine, world):
+    cfg = {
+        'workload': ('configs[2]: parallel WaveNet 4-flow IAF student ({}), batch {}x{} samples '
+                     'per GPU, synthetic mel, device-drawn noise' if config == 'student' else
+                     'configs[3] per-GPU share: ClariNet Gaussian IAF ({}), batch {}x{} samples per GPU, '
+                     'synthetic mel, device-drawn noise').format(CONFIGS[config], B, T),
+        'clips_per_gpu': B, 'samples_per_clip': T,
+        'l2': 'flushed between timed iterations (256 MB write)', 'parallelism': 'clips x{}'.format(world),
+    }
+    if engine is not None:
+        cfg['engine'] = engine
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# secondary blocks
+# ------------------------------------------------------------------------------------------------------------------
+def time_steps(fn, steps, warmup, flush, dev, barrier):
+    """fn(i) enqueues one step; returns per-step CUDA-event times in ms."""
+    import torch
+    for i in range(warmup):
+        fn(i)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        if flush is not None:
+            flush.zero_()
+        evs[i][0].record()
+        fn(i)
+        evs[i][1].record()
+    barrier()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def fastgen_bench(device, steps, hbm_peak, with_cpu):
+    """BASELINE configs[1]: teacher WaveNet (wavenet_mol.json, 30 layers, random init) free-running generation.
+    `value` = batch 1 on the latency engine; `batched` = 8 utterances on the batched engine; encoding resident in
+    HBM, in-kernel RNG; `e2e` goes through nsw_fastgen_run_host (encoding H2D + audio D2H inside)."""
+    import torch
     from nsynth_wavenet_b200 import FastgenEngine
-    from oracle import wavenet_oracle as O
-    with open(os.path.join(ROOT, 'nsynth_wavenet_b200', 'config_jsons', 'wavenet_mol.json')) as f:
-        hp = Namespace(**json.load(f))
-    w = O.init_teacher_weights(hp, seed=12345)
-    eng = FastgenEngine(hp, w, device=device)
+    from nsynth_wavenet_b200.weights_init import init_teacher_weights
+    hp = load_hparams('wavenet_mol.json')
+    eng = FastgenEngine(hp, init_teacher_weights(hp, seed=12345), device=device)
     g = torch.Generator(device='cpu').manual_seed(1)
-    enc = (torch.rand((1, steps, 256), generator=g) * 2 - 1).to('cuda:%d' % device)
-    eng.run_device(enc[:, :2048], seed=1)       # warm-up
+    enc_h = (torch.rand((1, steps, 256), generator=g) * 2 - 1)
+    enc = enc_h.to('cuda:%d' % device)
+    eng.run_device(enc[:, :2048].contiguous(), seed=1)       # warm-up
     torch.cuda.synchronize()
     eng.run_device(enc, seed=2)
     torch.cuda.synchronize()
     ms = eng.last_timing()
     sps = steps / (ms * 1e-3)
-    weight_bytes = 32 * 128 * 9224 * 4          # per-step streamed weight blocks (all CTAs)
-    return {'metric': 'fastgen audio samples/sec (wavenet_mol.json, batch 1)', 'value': sps,
-            'unit': UNIT, 'rtf': sps / 16000.0, 'steps': steps, 'ms': ms,
-            'us_per_step': 1e3 * ms / steps,
-            'weight_stream_gbs': weight_bytes * sps / 1e9,          # L2/HBM -> shared memory, all CTAs
-            'weight_stream_frac_of_hbm': weight_bytes * sps / 1e9 / hbm_peak,
-            # ncu capture of the same kernel (profiles/r01/fastgen_ncu_run56.json): 76.7 MB of DRAM reads per
-            # sample, the rest of the 151 MB stream is served from the L2-resident (evict_last) blocks
-            'dram_read_gbs_from_ncu_bytes': 76.7e6 * sps / 1e9,
-            'note': 'includes the hoisted cond GEMM; weights stream L2/HBM -> smem every step, the blocks of '
-                    'the first ~60 % of L2 worth of phases are loaded L2::evict_last (ncu: 49 % L2 hit rate)'}
+    blocks_bytes = 32 * 128 * 9224 * 4          # per-step weight blocks streamed L2 -> shared memory (all CTAs)
+    out = {'metric': 'fastgen audio samples/sec (wavenet_mol.json, batch 1)', 'value': sps,
+           'unit': UNIT, 'rtf': sps / 16000.0, 'steps': steps, 'ms': ms, 'us_per_step': 1e3 * ms / steps,
+           'engine': 'latency (one persistent kernel, tagged-word exchange, no grid barrier)',
+           'roofline': {
+               'bound': 'hbm', 'unit': 'GB/s', 'peak': hbm_peak,
+               # SURVEY 8d K5: 118.8 MB of weights touched per step is the algorithmic traffic
+               'achieved': FASTGEN_ALGORITHMIC_BYTES * sps / 1e9,
+               'frac': FASTGEN_ALGORITHMIC_BYTES * sps / 1e9 / hbm_peak,
+               # measured DRAM reads of the kernel (profiles/r01/fastgen_ncu_run56.json: 76.7 MB per sample; the rest
+               # of the stream is served from the L2-resident evict_last blocks)
+               'dram_read_gbs': 76.7e6 * sps / 1e9, 'frac_dram': 76.7e6 * sps / 1e9 / hbm_peak,
+               # L2 -> shared-memory traffic (not HBM): 151 MB per step incl. the precomputed M = W2 Wr matrices
+               'l2_to_smem_gbs': blocks_bytes * sps / 1e9,
+               'note': 'the step is bound by 32 exchange hops (~1.3 us each), not by bandwidth'}}
+    # end to end through the C ABI host call: 8000 steps, encoding (8 MB) copied H2D, audio D2H inside
+    Te = min(steps, 8000)
+    enc_np = enc_h[:, :Te].contiguous().numpy()
+    eng.run_host(enc_np, seed=3)                 # same length: the workspace (cond planes) is grown once, like a warm server
+    t0 = time.perf_counter()
+    eng.run_host(enc_np, seed=4)
+    dt = time.perf_counter() - t0
+    out['e2e'] = {'value': Te / dt, 'unit': UNIT, 'rtf': Te / dt / 16000.0, 'steps': Te,
+                  'h2d_bytes_per_step': 256 * 4, 'd2h_bytes_per_step': 4,
+                  'note': 'nsw_fastgen_run_host: pageable encoding H2D + hoisted cond GEMM + kernel + audio D2H'}
+    # batched engine: 8 utterances per weight pass
+    Bb, Tb = 8, min(steps, 8000)
+    encb = (torch.rand((Bb, Tb, 256), generator=g) * 2 - 1).to('cuda:%d' % device)
+    eng.run_device(encb[:, :512].contiguous(), seed=5)
+    torch.cuda.synchronize()
+    eng.run_device(encb, seed=6)
+    torch.cuda.synchronize()
+    msb = eng.last_timing()
+    out['batched'] = {'batch': Bb, 'steps': Tb, 'value': Bb * Tb / (msb * 1e-3), 'unit': UNIT,
+                      'rtf_aggregate': Bb * Tb / (msb * 1e-3) / 16000.0, 'us_per_step': 1e3 * msb / Tb,
+                      'engine': 'batched (one grid barrier per layer, weights streamed once for all rows)'}
+    eng.close()
+    # wavenet_ce.json as shipped: gate 1024 (double_gate_width default), mu-law, 256-way softmax head
+    try:
+        hpc = load_hparams('wavenet_ce.json')
+        ce = FastgenEngine(hpc, init_teacher_weights(hpc, seed=12345), device=device)
+        ce.run_device(encb[:, :256].contiguous(), seed=7)
+        torch.cuda.synchronize()
+        Tc = min(Tb, 4000)
+        ce.run_device(encb[:, :Tc].contiguous(), seed=8)
+        torch.cuda.synchronize()
+        msc = ce.last_timing()
+        out['ce_double_gate_batched'] = {'batch': Bb, 'steps': Tc, 'value': Bb * Tc / (msc * 1e-3), 'unit': UNIT,
+                                         'rtf_aggregate': Bb * Tc / (msc * 1e-3) / 16000.0,
+                                         'us_per_step': 1e3 * msc / Tc}
+        ce.close()
+    except Exception as ex:
+        out['ce_double_gate_batched'] = {'error': str(ex)[:200]}
+    if with_cpu:
+        out['cpu_baseline'] = cpu_fastgen_run(2000)
+    return out
 
 
-def distill_bench(device, hbm_peak):
-    """BASELINE configs[4] forward pieces on one GPU at the author's per-GPU batch (7 x 7680):
-    student forward + teacher full-sequence forward on the student's output + 100-sample MoL
-    cross-entropy (parallel_wavenet.py:361-402).  Secondary metric, reported not optimised."""
+def distill_bench(device, tc_peak, world, dev, barrier, max_over_ranks):
+    """BASELINE configs[4] forward on every rank at the author's per-GPU batch (7 x 7680: the reference's
+    total_batch_size 28 is 4 GPUs x 7; N GPUs here hold 7 N clips, weak scaling): student forward + teacher
+    full-sequence forward on the student's output + 100-sample MoL cross-entropy (parallel_wavenet.py:361-402), the
+    loss all-reduced over ranks (the forward's only collective)."""
     import torch
-    from argparse import Namespace
+    import torch.distributed as dist
     from nsynth_wavenet_b200 import IAFEngine, TeacherEngine
-    from oracle import wavenet_oracle as O
-    cfgdir = os.path.join(ROOT, 'nsynth_wavenet_b200', 'config_jsons')
-    with open(os.path.join(cfgdir, 'wavenet_mol.json')) as f:
-        thp = Namespace(**json.load(f))
+    from nsynth_wavenet_b200.weights_init import init_student_weights, init_teacher_weights
+    thp = load_hparams('wavenet_mol.json')
     shp = load_hparams('student')
-    st = IAFEngine(shp, O.init_student_weights(shp, seed=12345), device=device)
-    te = TeacherEngine(thp, O.init_teacher_weights(thp, seed=12345), device=device)
-    dev = 'cuda:%d' % device
-    mel = torch.rand((7, 39, 80), device=dev)
+    st = IAFEngine(shp, init_student_weights(shp, seed=12345), device=device)
+    te = TeacherEngine(thp, init_teacher_weights(thp, seed=12345), device=device)
+    g = torch.Generator(device='cpu').manual_seed(100 + int(os.environ.get('RANK', '0')))
+    mel = torch.rand((7, 39, 80), generator=g).to(dev)
     res = None
-    evs = []
-    for i in range(4):
+    evs, tes = [], []
+    barrier()
+    for i in range(5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = st.forward_device(mel, None, seed=i, quantize=False)
         te_out = te.forward_device(out['x'], mel)
         res = te.mol_score(te_out, out['mean_tot'], out['scale_tot'], out['log_scale_tot'],
                            num_samples=100, seed=i)
+        if world > 1:
+            lt = torch.tensor([res['kl_loss']], dtype=torch.float64, device=dev)
+            dist.all_reduce(lt)
+            res = dict(res, kl_loss_mean_over_ranks=float(lt.item()) / world)
         e1.record()
         torch.cuda.synchronize()
         evs.append(e0.elapsed_time(e1))
-    ms = float(np.median(evs[1:]))
-    return {'metric': 'distillation forward (student + teacher + 100-sample MoL CE), 7x7680 per GPU',
-            'ms': ms, 'teacher_forward_ms': te.last_timing(), 'clips_per_s': 7 / (ms * 1e-3),
-            'losses': res}
+        tes.append(te.last_timing())
+    ms = max_over_ranks(float(np.median(evs[1:])))
+    te_ms = float(np.median(tes[1:]))
+    n = 7 * 7680
+    issued = TEACHER_FLOP_PER_SAMPLE * n * SPLIT_PRODUCTS / (te_ms * 1e-3) / 1e12
+    st.close()
+    te.close()
+    return {'metric': 'configs[4] distillation forward (student + teacher + 100-sample MoL CE), 7x7680 per GPU, '
+                      '{} GPU(s): {} clips'.format(world, 7 * world),
+            'ms': ms, 'clips_per_s': 7 * world / (ms * 1e-3), 'teacher_forward_ms': te_ms, 'losses': res,
+            'roofline_teacher': {
+                'kernel': 'conv_gemm_tc_kernel (teacher layers)', 'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': tc_peak,
+                'achieved': issued, 'frac': issued / tc_peak,
+                'achieved_fp32_equivalent': issued / SPLIT_PRODUCTS,
+                'note': 'issued fp16 tensor flops = 3 x the algorithmic 67.4 MFLOP per sample (split-fp16 products)'}}
 
 
-def run_reference(args, emit):
-    """--impl reference: the reference's own CPU path restated (TF 1.x is not installable
-    here), bounded sample, rank 0 only."""
-    rank = int(os.environ.get('RANK', '0'))
+def clarinet_bench(device, rank, world, dev, flush, barrier, max_over_ranks, steps):
+    """BASELINE configs[3]: ClariNet Gaussian IAF (parallel_wavenet_gauss.json, four separate deconv stacks),
+    8 clips of 7680 samples per GPU (64 x 7680 over 8 GPUs), weights broadcast from rank 0."""
+    from nsynth_wavenet_b200 import IAFEngine, parallel
+    from nsynth_wavenet_b200.weights_init import init_student_weights
+    import torch
+    hp = load_hparams('clarinet')
+    w0 = init_student_weights(hp, seed=12345)
     if rank != 0:
-        return
-    hp = load_hparams(args.config)
-    # bounded: 1 clip of 7680 samples per step keeps K=10,W=3 within a few minutes
-    batch = args.ref_batch
-    v, ms, cores, sample = cpu_reference_run(hp, batch, args.frames, args.steps, max(1, args.warmup))
-    line = {
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[2]: parallel WaveNet 4-flow IAF student ({}), '
-                               '8x7680 per GPU; reference arm runs a bounded sample of it on host '
-                               'cores'.format(CONFIGS[args.config])},
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'rtf': v / 16000.0,
-        'note': 'TensorFlow 1.x is absent: this is the fp32 torch-CPU restatement of the '
-                'reference graph (oracle/torch_port.py), all host threads',
-    }
-    emit(line)
+        w0 = {k: np.zeros_like(v) for k, v in w0.items()}
+    eng = IAFEngine(hp, parallel.broadcast_weights(w0, device=dev), device=device)
+    g = torch.Generator(device='cpu').manual_seed(200 + rank)
+    mel = torch.rand((8, 39, 80), generator=g).to(dev)
+    T = eng.length(39)
+    out = {k: torch.empty((8, T), dtype=torch.float32, device=dev) for k in ('x', 'mean_tot', 'scale_tot', 'log_scale_tot')}
+    ts = time_steps(lambda i: eng.forward_device(mel, None, seed=i, quantize=True, out=out), steps, 3, flush, dev, barrier)
+    total = max_over_ranks(float(np.sum(ts)))
+    eng.close()
+    return {'metric': 'configs[3] ClariNet Gaussian IAF samples/s, 8x7680 per GPU, {} GPU(s)'.format(world),
+            'value': world * 8 * T * steps / (total * 1e-3), 'unit': UNIT, 'ms_per_step': total / steps,
+            'rtf': world * 8 * T * steps / (total * 1e-3) / 16000.0}
+
+
+def python_e2e(hp, B, F, T, reps):
+    """The call a user of the reference makes: wavenet.parallelgen.synthesis(hparams, mel, save_paths, checkpoint_path)
+    with pageable NumPy arrays, the checkpoint on disk and wav files written (parallelgen.py:22-51).  First call =
+    checkpoint read + engine build; repeat calls hit the engine cache (checkpoint.cached_engine)."""
+    from nsynth_wavenet_b200 import checkpoint as ckpt
+    from nsynth_wavenet_b200.weights_init import init_student_weights
+    from wavenet import parallelgen
+    rng = np.random.default_rng(777)
+    mel = rng.uniform(0, 1, (B, F, 80)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        ck = ckpt.save_weights(os.path.join(d, 'model.ckpt-1'), init_student_weights(hp, seed=12345), ema=True)
+        paths = [os.path.join(d, 'gen_%d.wav' % i) for i in range(B)]
+        t0 = time.perf_counter()
+        parallelgen.synthesis(hp, mel, paths, ck, seed=1)
+        first = time.perf_counter() - t0
+        ts = []
+        for i in range(reps):
+            t0 = time.perf_counter()
+            parallelgen.synthesis(hp, mel, paths, ck, seed=2 + i)
+            ts.append(time.perf_counter() - t0)
+        ckpt.clear_engine_cache()
+    rep = float(np.median(ts))
+    return {'value': B * T / rep, 'unit': UNIT, 'repeat_call_ms': 1e3 * rep, 'first_call_s': first,
+            'h2d_bytes_per_step': int(B * F * 80 * 4), 'd2h_bytes_per_step': int(B * T * 4),
+            'note': 'parallelgen.synthesis end to end: pageable mel H2D, forward, audio D2H, {} float32 wav files '
+                    'written; repeat calls reuse the cached engine (keyed on checkpoint path + mtime)'.format(B)}
 
 
 def main():
@@ -233,11 +449,15 @@ def main():
     ap.add_argument('--batch', type=int, default=8, help='clips per GPU')
     ap.add_argument('--frames', type=int, default=39, help='mel frames per clip (39 -> 7680 samples)')
     ap.add_argument('--engine', default=None, choices=[None, 'ffma', 'tc', 'tc2', 'tc3'])
-    ap.add_argument('--ref-batch', type=int, default=1)
+    ap.add_argument('--ref-batch', type=int, default=8, help='clips per step of the CPU arms (same config as the GPU arm)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--sustained-seconds', type=float, default=2.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fastgen', action='store_true')
     ap.add_argument('--no-distill', action='store_true')
+    ap.add_argument('--no-clarinet', action='store_true')
+    ap.add_argument('--no-sustained', action='store_true')
+    ap.add_argument('--no-python-e2e', action='store_true')
     ap.add_argument('--fastgen-steps', type=int, default=32000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -258,8 +478,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from nsynth_wavenet_b200 import IAFEngine, _lib
-    from oracle import wavenet_oracle as O  # weights init + cpu_baseline leg only
+    from nsynth_wavenet_b200 import IAFEngine, _lib, parallel
+    from nsynth_wavenet_b200.weights_init import init_student_weights
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -271,10 +491,17 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        return parallel.max_over_ranks(v, device=dev)
+
     hp = load_hparams(args.config)
     # ---- weights: rank 0 initialises, NCCL broadcasts one flat blob (the only collective) ----
-    from nsynth_wavenet_b200 import parallel
-    w0 = O.init_student_weights(hp, seed=12345)
+    w0 = init_student_weights(hp, seed=12345)
     if rank != 0:  # only rank 0's values survive: proves the broadcast carries the weights
         w0 = {k: np.zeros_like(v) for k, v in w0.items()}
     weights = parallel.broadcast_weights(w0, device=dev)
@@ -293,11 +520,6 @@ def main():
     def step(i):
         eng.forward_device(mel_d, None, seed=1000 + i, quantize=True, out=out)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -315,21 +537,37 @@ def main():
         evs[i][1].record()
     barrier()
     launches = lib.nsw_kernel_launch_count() - launches0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    clocks = sampler.finish()
     gpu_ms = sum(a.elapsed_time(b) for a, b in evs)
-    total_ms = parallel.max_over_ranks(gpu_ms, device=dev)
+    total_ms = max_over_ranks(gpu_ms)
     ms_per_step = total_ms / args.steps
     value = world * B * T * args.steps / (total_ms * 1e-3)
+
+    # ---- sustained: the same step (same L2 flush between steps) looped for >= 2 s of wall clock ----
+    sustained = None
+    if not args.no_sustained:
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        per = []
+        t_start = time.perf_counter()
+        block = 0
+        while time.perf_counter() - t_start < args.sustained_seconds:
+            per += time_steps(step, 100, 0, flush, dev, lambda: torch.cuda.synchronize())
+            block += 1
+        wall = time.perf_counter() - t_start
+        sc = s2.finish()
+        med = max_over_ranks(float(np.median(per)))
+        sustained = {'ms_per_step_median': med, 'ms_per_step_mean': float(np.mean(per)),
+                     'ms_per_step_p95': float(np.percentile(per, 95)), 'steps': len(per), 'wall_s': wall,
+                     'value': world * B * T / (med * 1e-3), 'unit': UNIT, 'clocks': sc}
 
     # ---- e2e: the reference-facing host call, pinned host buffers, H2D + D2H inside ----
     x_h = np.empty((B, T), np.float32)
     x_pin = torch.from_numpy(x_h).pin_memory()
-    mel_np = mel_h.numpy()
+    mel_np = np.array(mel_h.numpy())       # pageable copy
     for i in range(2):
         eng.forward_host(mel_np, None, seed=i, quantize=True)
     barrier()
-    names5 = ('x', 'mean_tot', 'scale_tot', 'log_scale_tot', 'rand_input')
     e2e_s = 0.0
     for i in range(args.steps):
         flush.zero_()                      # same L2 hygiene as the device-timed loop (not timed)
@@ -338,13 +576,21 @@ def main():
         _lib.check(lib.nsw_iaf_forward_host(eng._h, mel_h.data_ptr(), None, 2000 + i, B, F, 1,
                                             x_pin.data_ptr(), None, None, None, None))
         e2e_s += time.perf_counter() - t0
-    e2e_value = world * B * T * args.steps / parallel.max_over_ranks(e2e_s, device=dev)
+    e2e_value = world * B * T * args.steps / max_over_ranks(e2e_s)
+    pg_s = 0.0
+    for i in range(args.steps):            # the same call with pageable NumPy arrays (what Python callers hold)
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.forward_host(mel_np, None, seed=3000 + i, quantize=True)
+        pg_s += time.perf_counter() - t0
+    e2e_pageable = world * B * T * args.steps / max_over_ranks(pg_s)
 
-    # ---- roofline of the dominant kernel (iaf_layer_kernel), measured live with CUDA events
-    #      on the launch stream inside the library (separate profiled passes) ----
+    # ---- rooflines of the dominant kernels, measured live with CUDA events on the launch stream inside the
+    #      library (separate profiled passes) ----
     eng.set_profiling(True)
     prof = []
-    for i in range(3):
+    for i in range(5):
         flush.zero_()
         step(i)
         torch.cuda.synchronize()
@@ -352,10 +598,9 @@ def main():
     eng.set_profiling(False)
     stage = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
     n_layers = int(sum(hp.num_iaf_layers))
-    n_planes = n_layers + len(hp.num_iaf_layers)
-    layer_launch_ms = stage['layers'] / n_layers
-    hbm_peak, tc_peak, peak_kind = measured_peaks()
     n_flows = len(hp.num_iaf_layers)
+    n_planes = n_layers + n_flows
+    hbm_peak, tc_peak, peak_kind = measured_peaks()
     fused = eng.engine == 'tc3'
     # algorithmic bytes of the 'layers' stage: 768 B per (sample, layer); engine tc3 also runs the
     # start conv (read x 4 B + write l 256 B) and the head (l 256 + cond 256 + ~40 B of x / totals) of every
@@ -363,77 +608,108 @@ def main():
     stage_bytes = B * T * (LAYER_BYTES_PER_SAMPLE * n_layers + (n_flows * (260 + 552) if fused else 0))
     n_launches = n_flows if fused else n_layers
     layer_gbs = stage_bytes / (stage['layers'] * 1e-3) / 1e9
+    # issued tensor-core flops of the same stage: 3 split-fp16 products per algorithmic MAC
+    stage_flop = B * T * (LAYER_FLOP_PER_SAMPLE * n_layers + (HEAD_FLOP_PER_SAMPLE * n_flows if fused else 0))
+    issued_tflops = stage_flop * SPLIT_PRODUCTS / (stage['layers'] * 1e-3) / 1e12
+    kernel_name = {'tc3': 'iaf_flow_tc_kernel', 'tc2': 'iaf_layer_tc_kernel'}.get(eng.engine, 'iaf_layer_kernel')
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (one 10-layer flow launch);
     # only valid for the shape and engine it was captured on
-    traffic, traffic_src, traffic_alg = None, None, None
-    ncu_json = os.path.join(ROOT, 'profiles', 'r01', 'tc3_ncu_run28.json')
-    if fused and (B, T) == (8, 7680) and os.path.exists(ncu_json):
-        with open(ncu_json) as f:
-            caps = [c for c in json.load(f)['launches'] if 'iaf_flow_tc' in c['kernel']]
-        if caps:
-            cap = caps[0]
-            traffic = (float(cap['dram__bytes_read.sum']['value']) + float(cap['dram__bytes_write.sum']['value'])) * 1e6
-            traffic_alg = B * T * (LAYER_BYTES_PER_SAMPLE * 10 + 812)
-            traffic_src = ('profiles/r01/tc3_ncu_run28.json: dram__bytes_read+write of one iaf_flow_tc_kernel launch '
-                           '(10-layer flow incl. start conv and head); traffic_launch_algorithmic_bytes is the same '
-                           'launch under the 768 B model')
+    traffic, traffic_src, traffic_alg, frac_dram, ncu_extra = None, None, None, None, None
+    cap, cap_src = ncu_capture('iaf_flow_tc') if fused and (B, T) == (8, 7680) else (None, None)
+    if cap:
+        rd, wr = metric_value(cap, 'dram__bytes_read.sum'), metric_value(cap, 'dram__bytes_write.sum')
+        scale = 1e6 if rd is not None and rd < 1e5 else 1.0     # r01 summaries are in MB
+        traffic = (rd + wr) * scale
+        traffic_alg = B * T * (LAYER_BYTES_PER_SAMPLE * 10 + 812)
+        traffic_src = cap_src + ': dram__bytes_read+write of one iaf_flow_tc_kernel launch (10-layer flow incl. start conv and head)'
+        # the four flows move 60 / 10 x this; divide by the live stage time
+        frac_dram = traffic * (n_layers / 10.0) / (stage['layers'] * 1e-3) / 1e9 / hbm_peak
+        ncu_extra = {k: metric_value(cap, k) for k in cap
+                     if k.startswith(('sm__pipe_tensor', 'l1tex__data_pipe', 'smsp__issue_active', 'sm__inst_executed_pipe',
+                                      'l1tex__data_bank', 'smsp__average_warp'))}
     cond_tflops = COND_FLOP_PER_SAMPLE_PLANE * n_planes * B * T / (stage['cond'] * 1e-3) / 1e12
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {
-            'workload': ('configs[2]: parallel WaveNet 4-flow IAF student ({}), batch {}x{} samples '
-                         'per GPU, synthetic mel, device-drawn noise' if args.config == 'student' else
-                         'configs[3] per-GPU share: ClariNet Gaussian IAF ({}), batch {}x{} samples per GPU, '
-                         'synthetic mel, device-drawn noise').format(CONFIGS[args.config], B, T),
-            'clips_per_gpu': B, 'samples_per_clip': T, 'engine': eng.engine,
-            'l2': 'flushed between timed iterations (256 MB write)', 'parallelism': 'clips x{}'.format(world),
-        },
+        'config': workload_config(args.config, B, T, eng.engine, world),
         'rtf': value / 16000.0,
         'rtf_per_gpu': value / 16000.0 / world,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * F * 80 * 4),
-                'd2h_bytes_per_step': int(B * T * 4)},
+                'd2h_bytes_per_step': int(B * T * 4), 'value_pageable_buffers': e2e_pageable},
         'gpu_launches': int(launches),
-        'clocks': sampler.summary(),
+        'clocks': clocks,
+        'sustained': sustained,
         'roofline': {
-            'kernel': {'tc3': 'iaf_flow_tc_kernel', 'tc2': 'iaf_layer_tc_kernel'}.get(eng.engine, 'iaf_layer_kernel'), 'bound': 'hbm', 'achieved': layer_gbs, 'peak': hbm_peak,
-            'unit': 'GB/s', 'frac': layer_gbs / hbm_peak, 'traffic': traffic,
-            'traffic_launch_algorithmic_bytes': traffic_alg, 'traffic_source': traffic_src,
+            'kernel': kernel_name,
+            # what bounds the kernel: the tensor pipe's operand fetch (N=64 SS MMAs are shared-memory-bandwidth
+            # bound at 49 instead of 32 cycles; profiles/r02 ncu: shared-memory data pipe vs DRAM), NOT HBM
+            'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': tc_peak,
+            'achieved': issued_tflops, 'frac': issued_tflops / tc_peak, 'frac_tensor': issued_tflops / tc_peak,
+            'achieved_fp32_equivalent': issued_tflops / SPLIT_PRODUCTS,
+            # SURVEY's per-layer-kernel byte model (768 B per sample and layer) against the HBM peak: a model
+            # throughput, kept for continuity with round 1 -- the fused kernel never moves those bytes
+            'frac_model_hbm': layer_gbs / hbm_peak, 'model_gbs': layer_gbs, 'hbm_peak_gbs': hbm_peak,
+            # real DRAM traffic (ncu bytes of the committed capture, scaled to the 60 layers) / live stage time / peak
+            'frac_dram': frac_dram,
+            'traffic': traffic, 'traffic_launch_algorithmic_bytes': traffic_alg, 'traffic_source': traffic_src,
+            'ncu': ncu_extra,
             'unit_of_launch': ('one flow (start conv + all residual layers + head) over the whole batch; '
-                               'bytes_per_launch and launch_ms are the averages over the flows'
+                               'flops_per_launch and launch_ms are the averages over the flows'
                                if fused else 'one residual layer over the whole batch'),
-            'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
-            'bytes_per_launch': stage_bytes / n_launches, 'launch_ms': stage['layers'] / n_launches,
+            'peak_source': peak_kind + ' (MEASURED_PEAKS.json bf16_tflops, burst; hbm_gbs for the *_hbm / *_dram fractions)',
+            'flops_per_launch_issued': stage_flop * SPLIT_PRODUCTS / n_launches, 'bytes_per_launch_model': stage_bytes / n_launches,
+            'launch_ms': stage['layers'] / n_launches,
             'share_of_step': stage['layers'] / stage['total'],
         },
         'roofline_cond_gemm': {
-            'kernel': 'cond_proj_tc_kernel' if eng.engine == 'tc3' else 'conv_gemm (cond projections)', 'bound': 'tensor', 'achieved': cond_tflops,
-            'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': cond_tflops / tc_peak,
-            'note': 'algorithmic fp32-equivalent flops; the tcgen05 engine issues 3 fp16 MMAs per product',
+            'kernel': 'cond_proj_tc_kernel' if eng.engine == 'tc3' else 'conv_gemm (cond projections)', 'bound': 'tensor',
+            'achieved': cond_tflops * SPLIT_PRODUCTS, 'peak': tc_peak, 'unit': 'TFLOP/s',
+            'frac': cond_tflops * SPLIT_PRODUCTS / tc_peak, 'achieved_fp32_equivalent': cond_tflops,
+            'note': 'issued fp16 tensor flops = 3 x the algorithmic 2*256*64 per (sample, plane)',
         },
         'stage_ms': stage,
     }
 
-    # ---- secondary metric: autoregressive fastgen (BASELINE configs[1]), batch 1, rank 0 ----
+    # ---- the call a Python user makes: parallelgen.synthesis with a checkpoint on disk (rank 0) ----
+    if rank == 0 and not args.no_python_e2e:
+        try:
+            line['e2e_python'] = python_e2e(hp, B, F, T, 10)
+        except Exception as ex:
+            line['e2e_python'] = {'error': str(ex)[:300]}
+
+    # ---- configs[3] and configs[4] at this N (max over ranks) ----
+    if not args.no_clarinet and args.config == 'student':
+        try:
+            cl = clarinet_bench(local_rank, rank, world, dev, flush, barrier, max_over_ranks, max(5, min(args.steps, 20)))
+            if rank == 0:
+                line['clarinet'] = cl
+        except Exception as ex:
+            if rank == 0:
+                line['clarinet'] = {'error': str(ex)[:300]}
+    if not args.no_distill:
+        try:
+            ds = distill_bench(local_rank, tc_peak, world, dev, barrier, max_over_ranks)
+            if rank == 0:
+                line['distill'] = ds
+        except Exception as ex:  # reported, never silently dropped
+            if rank == 0:
+                line['distill'] = {'error': str(ex)[:300]}
+
+    # ---- secondary metric: autoregressive fastgen (BASELINE configs[1]), rank 0 ----
     if rank == 0 and not args.no_fastgen:
         try:
-            line['fastgen'] = fastgen_bench(local_rank, args.fastgen_steps, hbm_peak)
-        except Exception as ex:  # reported, never silently dropped
+            line['fastgen'] = fastgen_bench(local_rank, args.fastgen_steps, hbm_peak,
+                                            with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as ex:
             line['fastgen'] = {'error': str(ex)[:300]}
 
-    if rank == 0 and not args.no_distill:
-        try:
-            line['distill'] = distill_bench(local_rank, hbm_peak)
-        except Exception as ex:
-            line['distill'] = {'error': str(ex)[:300]}
-
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # bounded CPU sample (about cpu-seconds of work): single-clip forwards
-        v1, ms1, cores, _ = cpu_reference_run(hp, 1, F, 1, 1)
+        # bounded CPU sample (about cpu-seconds of work) of the SAME workload: 8 x 7680 per step
+        v1, ms1, cores, _ = cpu_reference_run(hp, args.ref_batch, F, 1, 1)
         reps = int(max(1, min(20, args.cpu_seconds / (ms1 * 1e-3))))
-        v, ms, cores, sample = cpu_reference_run(hp, 1, F, reps, 0)
+        v, ms, cores, sample = cpu_reference_run(hp, args.ref_batch, F, reps, 0)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                 'sample': sample}
     elif rank == 0:
@@ -441,6 +717,7 @@ def main():
     if rank == 0:
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

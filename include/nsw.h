@@ -119,6 +119,11 @@ const char* nsw_last_error(void);
  * gpu_launches claim is read from here, not estimated) */
 uint64_t nsw_kernel_launch_count(void);
 
+/* CRC-32C (Castagnoli) of `n` bytes continuing from `crc` (0 to start): the checksum of TensorFlow's V2 checkpoint
+ * bundles (index blocks and tensors), used by the TensorFlow-free bundle reader that replaces Saver.restore
+ * (fastgen.py:81-84, parallelgen.py:40-41).  Host only, little-endian byte order. */
+uint32_t nsw_crc32c(const void* data, size_t n, uint32_t crc);
+
 /* The tensor-core engines carry activations as fp16 hi + fp16 lo (fp32-grade, 22 mantissa bits) and therefore share
  * fp16's range: |v| <= 65504.  Every conversion site checks it; the "_host" entry points return NSW_ERANGE instead of
  * a silently wrong result, and after "_device" calls this function (which synchronises `device`) reports and clears

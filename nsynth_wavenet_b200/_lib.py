@@ -60,6 +60,7 @@ PROTOTYPES = {
     'nsw_last_error': (C.c_char_p, []),
     'nsw_kernel_launch_count': (C.c_uint64, []),
     'nsw_range_status': (C.c_int, [C.c_int32]),
+    'nsw_crc32c': (C.c_uint32, [_VP, C.c_size_t, C.c_uint32]),
     'nsw_iaf_create': (C.c_int, [C.POINTER(nsw_iaf_config), C.POINTER(nsw_tensor), C.c_int32,
                                  C.c_int32, C.POINTER(_VP)]),
     'nsw_iaf_destroy': (None, [_VP]),

@@ -97,3 +97,42 @@ def save_weights(path, weights, ema=True):
         path = path + '.npz'
     np.savez(path, **{(k + EMA_SUFFIX if ema else k): v for k, v in weights.items()})
     return path
+
+
+# ---- engine cache --------------------------------------------------------------------------------------------
+# The reference rebuilds its graph and restores the checkpoint on EVERY synthesis / encode call
+# (parallelgen.py:24-41, fastgen.py:73-84, 143-147).  Here a call costs about a millisecond of GPU time, so that
+# per-call set-up (reading the bundle, repacking weights, tensor maps, workspace) would be all of it: engines are kept,
+# keyed on what determines them, and dropped when the checkpoint on disk changes.
+_ENGINES = {}
+_MAX_ENGINES = 4
+
+
+def _stamp(kind, path):
+    files = [path] if kind == 'npz' else None
+    if files is None:
+        d, base = os.path.split(path)
+        files = sorted(os.path.join(d or '.', f) for f in os.listdir(d or '.')
+                       if f == base + '.index' or f.startswith(base + '.data-'))
+    return tuple((f, os.path.getmtime(f), os.path.getsize(f)) for f in files)
+
+
+def cached_engine(factory, tag, hparams, checkpoint_path, unshadowed=(), **kw):
+    """factory(hparams, weights, **kw) -> engine; one engine per (tag, checkpoint files + mtimes, hparams, kw)."""
+    kind, path = resolve_checkpoint(checkpoint_path)
+    key = (tag, kind, os.path.realpath(path), _stamp(kind, path),
+           tuple(sorted((k, repr(v)) for k, v in vars(hparams).items())), tuple(sorted(kw.items())))
+    eng = _ENGINES.get(key)
+    if eng is None or getattr(eng, '_h', None) is None:
+        for old in [k for k in _ENGINES if k[:3] == key[:3] and k != key]:   # same file, stale contents
+            _ENGINES.pop(old).close()
+        while len(_ENGINES) >= _MAX_ENGINES:
+            _ENGINES.pop(next(iter(_ENGINES))).close()
+        eng = factory(hparams, load_weights(checkpoint_path, unshadowed), **kw)
+        _ENGINES[key] = eng
+    return eng
+
+
+def clear_engine_cache():
+    while _ENGINES:
+        _ENGINES.popitem()[1].close()

@@ -87,7 +87,38 @@ int upload(DevBuf& buf, const void* host, size_t bytes) {
 
 }  // namespace nsw
 
+// CRC-32C (Castagnoli, reflected polynomial 0x82f63b78), slice-by-8: the checksum TensorFlow's V2 checkpoint bundles
+// carry for every index block and every tensor (tensorflow/core/lib/hash/crc32c.h); host only.
+static uint32_t g_crc_tab[8][256];
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82f63b78u : c >> 1;
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xff];
+}
+
 extern "C" {
+uint32_t nsw_crc32c(const void* data, size_t n, uint32_t crc) {
+  static std::once_flag once;
+  std::call_once(once, crc_init);
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t c = crc ^ 0xffffffffu;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = g_crc_tab[7][lo & 0xff] ^ g_crc_tab[6][(lo >> 8) & 0xff] ^ g_crc_tab[5][(lo >> 16) & 0xff] ^ g_crc_tab[4][lo >> 24] ^
+        g_crc_tab[3][hi & 0xff] ^ g_crc_tab[2][(hi >> 8) & 0xff] ^ g_crc_tab[1][(hi >> 16) & 0xff] ^ g_crc_tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = g_crc_tab[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  return c ^ 0xffffffffu;
+}
 int nsw_version(void) { return 100; }
 const char* nsw_last_error(void) { return nsw::g_err; }
 uint64_t nsw_kernel_launch_count(void) { return nsw::g_launch_count.load(); }

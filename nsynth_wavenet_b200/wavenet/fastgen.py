@@ -66,12 +66,9 @@ def encode(hparams, wav_data, checkpoint_path, device=0, engine=None):
         wav_data = np.expand_dims(wav_data, 0)
     mel_val = mel_extractor.batch_melspectrogram(wav_data)
     batch_size, mel_length, num_mel = mel_val.shape
-    weights = ckpt.load_weights(checkpoint_path)
-    ds = load_deconv_stack(hparams, batch_size, mel_length, num_mel, weights=weights,
-                           device=device, engine=engine)
-    encoding = ds['engine'].encode_host(mel_val)
-    ds['engine'].close()
-    return encoding
+    eng = ckpt.cached_engine(FastgenEngine, 'fastgen', hparams, checkpoint_path, device=device,
+                             num_mel=num_mel, engine=engine)
+    return eng.encode_host(mel_val)
 
 
 def load_cond_layers(hparams, batch_size=1, en_length=320, weights=None, device=0, engine=None):
@@ -86,12 +83,9 @@ def load_cond_layers(hparams, batch_size=1, en_length=320, weights=None, device=
 def calculate_cond_vars(hparams, encoding, checkpoint_path, device=0, engine=None):
     """fastgen.py:100-115: encoding [B, L, deconv_width] -> dict 'mel_cond_i' / 'mel_cond_out1' -> np[B, L, width]
     (the hoisted conditioning GEMM the persistent kernels consume, in the reference's channel order)."""
-    batch_size, en_length, _ = encoding.shape
-    weights = ckpt.load_weights(checkpoint_path)
-    cond = load_cond_layers(hparams, batch_size, en_length, weights=weights, device=device, engine=engine)
-    cond_vars = cond['engine'].cond_vars_host(encoding)
-    cond['engine'].close()
-    return cond_vars
+    eng = ckpt.cached_engine(FastgenEngine, 'fastgen', hparams, checkpoint_path, device=device,
+                             num_mel=80, engine=engine)
+    return eng.cond_vars_host(encoding)
 
 
 def load_fastgen(hparams, batch_size=1, weights=None, device=0, engine=None):
@@ -108,11 +102,9 @@ def synthesis(hparams, mel_encoding, save_paths, checkpoint_path, seed=None, dev
               engine=None):
     """fastgen.py:128-169: one sample per encoding step, queues start at zero, the
     previous dequantised sample is fed back; writes len(save_paths) wavs."""
-    batch_size = mel_encoding.shape[0]
-    weights = ckpt.load_weights(checkpoint_path)
-    fg = load_fastgen(hparams, batch_size, weights=weights, device=device, engine=engine)
+    eng = ckpt.cached_engine(FastgenEngine, 'fastgen', hparams, checkpoint_path, device=device,
+                             num_mel=80, engine=engine)
     if seed is None:
         seed = int(time.time_ns() & 0x7FFFFFFFFFFFFFFF)
-    audio_batch = fg['engine'].run_host(np.asarray(mel_encoding, np.float32), seed=seed)
-    fg['engine'].close()
+    audio_batch = eng.run_host(np.asarray(mel_encoding, np.float32), seed=seed)
     save_batch(audio_batch, save_paths)

@@ -53,10 +53,9 @@ def load_parallelgen(hparams, batch_size=1, length=7680, num_mel=80, weights=Non
 def synthesis(hparams, mel, save_paths, checkpoint_path, seed=None, device=0, engine=None):
     """parallelgen.py:22-51."""
     batch_size, length, num_mel = mel.shape
-    weights = ckpt.load_weights(checkpoint_path, _unshadowed(hparams))
-    fg_dict = load_parallelgen(hparams, batch_size, length, num_mel, weights=weights,
-                               device=device, engine=engine)
-    eng = fg_dict['engine']
+    # graph build + Saver.restore of the reference (parallelgen.py:24-41): done once per checkpoint, then cached
+    eng = ckpt.cached_engine(IAFEngine, 'iaf', hparams, checkpoint_path, _unshadowed(hparams),
+                             device=device, num_mel=num_mel, engine=engine)
     if seed is None:
         seed = int(time.time_ns() & 0x7FFFFFFFFFFFFFFF)
     start = time.time()
@@ -67,5 +66,4 @@ def synthesis(hparams, mel, save_paths, checkpoint_path, seed=None, device=0, en
     log.info('Target waveform length {:.5f}, '
              'Session run consume {:.5f} secs, '
              'Delay {:.2f}'.format(wave_length, cost, cost / wave_length))
-    eng.close()
     fastgen.save_batch(audio, save_paths)

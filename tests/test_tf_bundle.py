@@ -157,3 +157,123 @@ def test_footer_and_block_layout_are_the_published_ones(tmp_path):
     e = tf_bundle.parse_entry(ents[1][1])
     assert e['dtype'] == 1 and e['shape'] == (2, 3) and e['size'] == 24 and e['offset'] == 0
     assert tf_bundle.unmask_crc(e['crc32c']) == tf_bundle.crc32c(np.arange(6, dtype='<f4').tobytes())
+
+
+# ---- a bundle the repo's writers did NOT produce -------------------------------------------------------------------
+HANDMADE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'handmade.ckpt')
+
+
+def test_handmade_byte_level_fixture_parses_to_the_values_it_was_assembled_from():
+    """tests/golden/handmade.ckpt.* were laid out byte by byte from the TensorFlow / LevelDB format sources by
+    tests/golden/make_handmade_bundle.py (own bitwise CRC, literal protobuf bytes): two data blocks, prefix-compressed
+    keys over several restart points, varint edges (127/128/16383/16384, a 5-byte offset past 2 GiB, a 6-byte size),
+    three shards with shard 1 absent."""
+    header, entries = tf_bundle.read_index(HANDMADE + '.index')
+    assert header == {'num_shards': 3, 'endianness': 0, 'producer': 1}
+    assert sorted(entries) == ['a/big_offset', 'a/dims', 'b/scalar_i64', 'b/vec_f32',
+                               'b/vec_f32/ExponentialMovingAverage', 'c/mat_f16']
+    big = entries['a/big_offset']
+    assert (big['dtype'], big['shape'], big['shard_id'], big['offset'], big['size']) == (1, (2,), 1, 2 ** 31 + 16, 8)
+    assert tf_bundle.unmask_crc(big['crc32c']) == 0x12345678
+    dims = entries['a/dims']
+    assert dims['shape'] == (127, 128, 16383, 16384) and dims['size'] == 127 * 128 * 16383 * 16384 and dims['dtype'] == 4
+    assert entries['b/scalar_i64']['shape'] == () and entries['c/mat_f16']['dtype'] == 19
+    got = tf_bundle.read_bundle(HANDMADE, names=lambda n: not n.startswith('a/'), verify_data=True)
+    assert got['b/scalar_i64'].dtype == np.int64 and int(got['b/scalar_i64']) == 200000
+    assert np.array_equal(got['b/vec_f32'], np.asarray([1.0, -2.5, 3.25], np.float32))
+    assert np.array_equal(got['b/vec_f32/ExponentialMovingAverage'], np.asarray([0.125, 0.25, -0.5], np.float32))
+    assert np.array_equal(got['c/mat_f16'], np.asarray([[0.5, -1.0], [2.0, 65504.0]], np.float16))
+    with pytest.raises(tf_bundle.BundleError, match='missing shard'):
+        tf_bundle.read_bundle(HANDMADE)                       # shard 1 is absent on purpose
+
+
+def test_handmade_fixture_is_what_its_generator_script_writes(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('mk', os.path.join(os.path.dirname(HANDMADE), 'make_handmade_bundle.py'))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    assert open(HANDMADE + '.index', 'rb').read() == bytes(mk.index_file)
+    assert open(HANDMADE + '.data-00000-of-00003', 'rb').read() == mk.shard0
+    assert open(HANDMADE + '.data-00002-of-00003', 'rb').read() == mk.shard2
+    assert mk.crc32c_bitwise(b'123456789') == 0xe3069283 == tf_bundle.crc32c_py(b'123456789')
+
+
+def test_handmade_fixture_corruption_is_detected(tmp_path):
+    import shutil
+    for suffix in ('.index', '.data-00000-of-00003', '.data-00002-of-00003'):
+        shutil.copy(HANDMADE + suffix, str(tmp_path / ('h.ckpt' + suffix)))
+    p = str(tmp_path / 'h.ckpt')
+    raw = bytearray(open(p + '.index', 'rb').read())
+    raw[40] ^= 0x01                                           # inside data block 1
+    open(p + '.index', 'wb').write(bytes(raw))
+    with pytest.raises(tf_bundle.BundleError, match='CRC'):
+        tf_bundle.read_index(p + '.index')
+    raw[40] ^= 0x01
+    raw[-1] ^= 0xff                                           # footer magic
+    open(p + '.index', 'wb').write(bytes(raw))
+    with pytest.raises(tf_bundle.BundleError, match='magic'):
+        tf_bundle.read_index(p + '.index')
+    raw[-1] ^= 0xff
+    open(p + '.index', 'wb').write(bytes(raw))
+    d = bytearray(open(p + '.data-00002-of-00003', 'rb').read())
+    d[3] ^= 0x80
+    open(p + '.data-00002-of-00003', 'wb').write(bytes(d))
+    with pytest.raises(tf_bundle.BundleError, match='CRC'):
+        tf_bundle.read_bundle(p, names=['b/vec_f32'], verify_data=True)
+
+
+def test_native_and_python_crc_agree():
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 7, 8, 9, 255, 256, 257, 4099, 100003):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert tf_bundle.crc32c(b) == tf_bundle.crc32c_py(b), n
+    b = rng.integers(0, 256, 5000, dtype=np.uint8).tobytes()
+    assert tf_bundle.crc32c(b[1000:], tf_bundle.crc32c(b[:1000])) == tf_bundle.crc32c_py(b)
+
+
+def test_product_writer_is_read_back_by_the_reader_and_matches_the_test_writer_semantics(tmp_path):
+    """tf_bundle.write_bundle (used by tools/make_eval_model) and tests/tf_bundle_writer.py are independent
+    implementations: both must give the reader the same tensors, across several index blocks."""
+    rng = np.random.default_rng(6)
+    vars_ = teacher_like_variables(rng, n_layers=12)
+    vars_['misc/empty'] = np.zeros((0, 4), np.float32)
+    vars_['misc/f16'] = rng.normal(0, 1, (5,)).astype(np.float16)
+    a = tf_bundle.write_bundle(str(tmp_path / 'a.ckpt'), vars_, block_size=512)
+    b = str(tmp_path / 'b.ckpt')
+    write_bundle(b, vars_, num_shards=1, block_size=512)
+    ga, gb = tf_bundle.read_bundle(a, verify_data=True), tf_bundle.read_bundle(b, verify_data=True)
+    assert set(ga) == set(gb) == set(vars_)
+    for k, v in vars_.items():
+        assert ga[k].dtype == v.dtype and np.array_equal(ga[k], v) and np.array_equal(gb[k], v), k
+    ha, ea = tf_bundle.read_index(a + '.index')
+    hb, eb = tf_bundle.read_index(b + '.index')
+    assert ha == hb and ea == eb                              # identical header and entry protos (offsets, CRCs)
+
+
+def test_make_eval_model_strips_a_training_checkpoint_to_its_ema_shadows(tmp_path):
+    """tools/make_eval_model.py of the reference (:8-34): EMA variables only, under their shadow names, state file,
+    config json copied; the result loads through checkpoint.load_weights like the ns_wn-eval directories of the
+    reference's Readme."""
+    from nsynth_wavenet_b200.tools.make_eval_model import save_eval_model
+    rng = np.random.default_rng(8)
+    vars_ = teacher_like_variables(rng, n_layers=4)
+    train = tmp_path / 'logs'
+    train.mkdir()
+    write_bundle(str(train / 'model.ckpt-1234'), vars_, num_shards=2, block_size=256)
+    (train / 'checkpoint').write_text('model_checkpoint_path: "model.ckpt-1234"\n')
+    (train / 'wavenet_mol.json').write_text('{"num_layers": 4}')
+    out = tmp_path / 'eval'
+    out.mkdir()
+    (out / 'stale').write_text('x')                           # the tool starts from an empty directory (:9-11)
+    prefix = save_eval_model(str(train), str(out))
+    assert sorted(os.listdir(str(out))) == ['checkpoint', 'model.ckpt-1234.data-00000-of-00001',
+                                            'model.ckpt-1234.index', 'wavenet_mol.json']
+    assert open(str(out / 'checkpoint')).read() == 'model_checkpoint_path: "model.ckpt-1234"'
+    _, entries = tf_bundle.read_index(prefix + '.index')
+    assert entries and all('ExponentialMovingAverage' in k for k in entries)
+    assert len(entries) == sum('ExponentialMovingAverage' in k for k in vars_)
+    got = checkpoint.load_weights(str(out))
+    for k, v in vars_.items():
+        if k.endswith('/ExponentialMovingAverage'):
+            assert np.array_equal(got[k[:-len('/ExponentialMovingAverage')]], v)
+    assert tf_bundle.latest_checkpoint(str(out)) == prefix
