@@ -395,7 +395,8 @@ def write_bundle(prefix, tensors, block_size=4096):
     offset, recs = 0, []
     with open(prefix + '.data-00000-of-00001', 'wb') as f:
         for n in names:
-            arr = np.ascontiguousarray(tensors[n])
+            arr = np.asarray(tensors[n])
+            arr = arr if arr.ndim == 0 else np.ascontiguousarray(arr)       # (ascontiguousarray would turn a scalar into [1])
             if arr.dtype not in _DTYPE_ENUM:
                 raise BundleError('{}: dtype {} cannot be stored'.format(n, arr.dtype))
             raw = arr.astype(arr.dtype.newbyteorder('<'), copy=False).tobytes()
