@@ -293,6 +293,22 @@ int nsw_mel_frames(nsw_mel* h, int32_t n_samples);
 int nsw_mel_device(nsw_mel* h, const float* d_wav, int32_t B, int32_t N, float* d_mel, void* stream);
 int nsw_mel_host(nsw_mel* h, const float* wav, int32_t B, int32_t N, float* mel);
 
+/* ---- power-loss STFT ---------------------------------------------------------
+ * replaces: mel_extractor._tf_stft (mel_extractor.py:111-121) = tf.contrib.signal.stft(frame_length 800, frame_step 200,
+ * fft_length 2048, pad_end=True): frame j starts at sample j*hop, zeros past the end, ceil(N / hop) frames.  A handle
+ * created by nsw_mel_create with twiddle tables for tap n at position n is switched to that framing with
+ * nsw_mel_set_framing(h, 0, 0) (shift = sample index of tap 0 of frame 0; reflect = 1 restores librosa's centred,
+ * reflect-padded framing with shift = -win/2). */
+int nsw_mel_set_framing(nsw_mel* h, int32_t shift, int32_t reflect);
+/* wav [B,N] -> |STFT| [B, frames, n_bins] */
+int nsw_stft_mag_device(nsw_mel* h, const float* d_wav, int32_t B, int32_t N, float* d_mag, void* stream);
+/* replaces: ParallelWavenet.power_loss (parallel_wavenet.py:459-479) with the shipped switches (|STFT| features,
+ * squared difference, priority-frequency average :56-70); the longer of the two waves is centre-cropped (:430-435).
+ * d_orig [B,N_orig], d_pred [B,N_pred]; result[0] = power_loss, [1] = mean over all bins, [2] = mean over the bins
+ * below priority_freq (host doubles; synchronises). */
+int nsw_power_loss_device(nsw_mel* h, const float* d_orig, int32_t N_orig, const float* d_pred, int32_t N_pred,
+                          int32_t B, int32_t priority_freq, double* result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,10 @@ PROTOTYPES = {
     'nsw_mel_frames': (C.c_int, [_VP, C.c_int32]),
     'nsw_mel_device': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     'nsw_mel_host': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
+    'nsw_mel_set_framing': (C.c_int, [_VP, C.c_int32, C.c_int32]),
+    'nsw_stft_mag_device': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
+    'nsw_power_loss_device': (C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_double * 3), _VP]),
     'nsw_fastgen_pack_host': (C.c_int, [C.POINTER(nsw_wavenet_config), C.POINTER(nsw_tensor),
                                         C.c_int32, _VP, C.c_int64, _VP, _VP,
                                         C.POINTER(C.c_int64)]),

@@ -61,14 +61,15 @@ def _build_mel_basis(p=mel_params):
     return (weights * enorm[:, None]).astype(np.float32)
 
 
-def _build_twiddles(p=mel_params):
+def _build_twiddles(p=mel_params, centred=True):
     """Window-folded DFT tables of the non-zero window taps: [win, num_freq] cos and sin (float32 from float64).
-    Tap n of the window sits at position lpad + n of the n_fft frame (librosa pads the window to n_fft centred,
-    mel_extractor.py:68-72)."""
+    centred: tap n of the window sits at position lpad + n of the n_fft frame (librosa pads the window to n_fft
+    centred, mel_extractor.py:68-72); not centred: at position n (tf.contrib.signal.stft zero-pads the windowed frame
+    at its END to fft_length, mel_extractor.py:111-121)."""
     n_fft = (p.num_freq - 1) * 2
     win_length = int(p.frame_length_ms / 1000.0 * p.sample_rate)
     win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(win_length) / win_length)       # periodic hann
-    lpad = (n_fft - win_length) // 2
+    lpad = (n_fft - win_length) // 2 if centred else 0
     pos = (np.arange(win_length) + lpad)[:, None] * np.arange(p.num_freq)[None, :]    # exact integers
     ang = 2.0 * np.pi * (pos % n_fft) / n_fft
     return (win[:, None] * np.cos(ang)).astype(np.float32), (win[:, None] * np.sin(ang)).astype(np.float32)
@@ -122,6 +123,59 @@ class MelExtractor:
         st = torch.cuda.current_stream(wav.device).cuda_stream
         L.check(self.lib.nsw_mel_device(self._h, L.ptr(wav), B, N, L.ptr(out), st))
         return out
+
+
+class TfStft(MelExtractor):
+    """mel_extractor._tf_stft (mel_extractor.py:111-121) on the GPU: tf.contrib.signal.stft(frame_length 800,
+    frame_step 200, fft_length 2048, pad_end=True) -> magnitudes, and the power loss built on it
+    (parallel_wavenet.py:459-479)."""
+
+    def __init__(self, device=0, p=mel_params):
+        self.lib = L.load()
+        self.p = p
+        self.dev_index = device
+        tc, ts = _build_twiddles(p, centred=False)
+        basis = np.ascontiguousarray(_build_mel_basis(p))
+        self.win = tc.shape[0]
+        self.hop = int(p.frame_shift_ms / 1000.0 * p.sample_rate)
+        h = C.c_void_p()
+        L.check(self.lib.nsw_mel_create(device, p.num_freq, self.win, self.hop, p.num_mel, L.ptr(tc), L.ptr(ts),
+                                        L.ptr(basis), float(p.min_amp), float(p.min_level_db), C.byref(h)))
+        self._h = h
+        L.check(self.lib.nsw_mel_set_framing(self._h, 0, 0))
+
+    def frames(self, n_samples):
+        return -(-n_samples // self.hop)      # pad_end=True: ceil
+
+    def host(self, wav):
+        raise NotImplementedError('TfStft produces STFT magnitudes (stft_mag) and the power loss, not mels')
+
+    device = host
+
+    def stft_mag(self, wav):
+        """torch CUDA wav [B, N] -> |STFT| [B, ceil(N / 200), 1025] on the current stream."""
+        import torch
+        from ..engine import _dev_tensor
+        _dev_tensor(wav, 'wav', (None, None), self.dev_index)
+        B, N = wav.shape
+        out = torch.empty((B, self.frames(N), self.p.num_freq), dtype=torch.float32, device=wav.device)
+        st = torch.cuda.current_stream(wav.device).cuda_stream
+        L.check(self.lib.nsw_stft_mag_device(self._h, L.ptr(wav), B, N, L.ptr(out), st))
+        return out
+
+    def power_loss(self, orig_wav, pred_wav, priority_freq=PRIORITY_FREQ):
+        """ParallelWavenet.power_loss (parallel_wavenet.py:459-479), torch CUDA [B, N_orig] / [B, N_pred] ->
+        dict(power_loss, all_bins, priority_bins)."""
+        import torch
+        from ..engine import _dev_tensor
+        _dev_tensor(orig_wav, 'orig_wav', (None, None), self.dev_index)
+        _dev_tensor(pred_wav, 'pred_wav', (orig_wav.shape[0], None), self.dev_index)
+        res = (C.c_double * 3)()
+        st = torch.cuda.current_stream(orig_wav.device).cuda_stream
+        L.check(self.lib.nsw_power_loss_device(self._h, L.ptr(orig_wav), orig_wav.shape[1], L.ptr(pred_wav),
+                                               pred_wav.shape[1], orig_wav.shape[0], int(priority_freq),
+                                               C.byref(res), st))
+        return {'power_loss': res[0], 'all_bins': res[1], 'priority_bins': res[2]}
 
 
 def _extractor(device=0):

@@ -30,13 +30,14 @@ struct MelGeom {
   int win;        // 800 non-zero window taps
   int hop;        // 200
   int n_mel;      // 80
-  int shift;      // sample index of tap 0 of frame 0: lpad - n_fft/2 = -win/2
+  int shift;      // sample index of tap 0 of frame 0: lpad - n_fft/2 = -win/2 (librosa, centred); 0 for tf.contrib.signal.stft
+  int reflect;    // 1: np.pad(mode='reflect') outside [0, N) (librosa centre=True); 0: zeros (tf stft, pad_end=True)
 };
 
 __global__ void __launch_bounds__(MF_THREADS)
-stft_mag_kernel(const float* __restrict__ wav /*[B][N]*/, const float* __restrict__ tc /*[win][n_bins]*/,
+stft_mag_kernel(const float* __restrict__ wav /*[B][stride], the clip at +off*/, const float* __restrict__ tc /*[win][n_bins]*/,
                 const float* __restrict__ ts, float* __restrict__ mag /*[B][frames][n_bins]*/, MelGeom g, int N,
-                int frames) {
+                int frames, int stride, int off) {
   extern __shared__ float sm[];
   const int span = (MF_FRAMES - 1) * g.hop + g.win;
   float* xs = sm;                          // [span]
@@ -44,13 +45,15 @@ stft_mag_kernel(const float* __restrict__ wav /*[B][N]*/, const float* __restric
   float* ss = cs + MF_KC * MF_BINS;        // [MF_KC][MF_BINS]
   const int tid = threadIdx.x, tx = tid & (MF_BINS - 1), ty = tid / MF_BINS;  // ty in 0..3
   const int f0 = blockIdx.x * MF_FRAMES, b0 = blockIdx.y * MF_BINS, b = blockIdx.z;
-  const float* w = wav + (size_t)b * N;
+  const float* w = wav + (size_t)b * stride + off;
   // stage the span; np.pad(mode='reflect') semantics: index -m -> m, N-1+m -> N-1-m
   const int base = f0 * g.hop + g.shift;
   for (int i = tid; i < span; i += MF_THREADS) {
     int m = base + i;
-    if (m < 0) m = -m;
-    if (m >= N) m = 2 * (N - 1) - m;
+    if (g.reflect) {
+      if (m < 0) m = -m;
+      if (m >= N) m = 2 * (N - 1) - m;
+    }
     xs[i] = (m >= 0 && m < N) ? w[m] : 0.f;   // frames past the last one of a ragged tile read zeros
   }
   float re[8], im[8];
@@ -102,6 +105,36 @@ mel_log_kernel(const float* __restrict__ mag /*[BF][n_bins]*/, const float* __re
   }
 }
 
+// sum over all (frame, bin) of (a - b)^2, and over the bins below `priority` (PWNHelper.diff_fn / avg_loss_fn,
+// parallel_wavenet.py:56-70, with USE_L1_LOSS = False): fp64 block sums, two atomics per block
+__global__ void __launch_bounds__(256)
+power_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t rows, int n_bins, int priority,
+                  double* __restrict__ acc /*[2]*/) {
+  double s_all = 0.0, s_pri = 0.0;
+  const size_t n = rows * (size_t)n_bins;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    const double q = (double)d * (double)d;
+    s_all += q;
+    if ((int)(i % n_bins) < priority) s_pri += q;
+  }
+  __shared__ double sh[2][256];
+  sh[0][threadIdx.x] = s_all;
+  sh[1][threadIdx.x] = s_pri;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(acc, sh[0][0]);
+    atomicAdd(acc + 1, sh[1][0]);
+  }
+}
+
 }  // namespace
 }  // namespace nsw
 
@@ -111,7 +144,7 @@ struct nsw_mel {
   int device = 0;
   MelGeom g{};
   float min_amp = 1e-5f, min_level_db = -140.f;
-  DevBuf tc, ts, basis_t, mag, stage_wav, stage_mel;
+  DevBuf tc, ts, basis_t, mag, mag2, acc, stage_wav, stage_wav2, stage_mel;
   cudaStream_t own_stream = nullptr;
 };
 
@@ -130,6 +163,7 @@ extern "C" int nsw_mel_create(int32_t device, int32_t n_bins, int32_t win, int32
   h->g.hop = hop;
   h->g.n_mel = n_mel;
   h->g.shift = -win / 2;   // centre=True: frame j is centred on sample j*hop, the window on the frame
+  h->g.reflect = 1;
   h->min_amp = min_amp;
   h->min_level_db = min_level_db;
   std::vector<float> bt((size_t)n_bins * n_mel);
@@ -181,8 +215,9 @@ extern "C" int nsw_mel_device(nsw_mel* h, const float* d_wav, int32_t B, int32_t
   NSW_TRY(h->mag.ensure((size_t)B * frames * h->g.n_bins * sizeof(float)));
   const size_t smem = ((size_t)(MF_FRAMES - 1) * h->g.hop + h->g.win + 2 * MF_KC * MF_BINS) * sizeof(float);
   dim3 grid((frames + MF_FRAMES - 1) / MF_FRAMES, (h->g.n_bins + MF_BINS - 1) / MF_BINS, B);
+  NSW_CHECK(h->g.reflect == 1, NSW_EINVAL, "this handle was switched to tf.contrib.signal.stft framing (nsw_mel_set_framing)");
   stft_mag_kernel<<<grid, MF_THREADS, smem, st>>>(d_wav, h->tc.as<float>(), h->ts.as<float>(), h->mag.as<float>(),
-                                                  h->g, N, frames);
+                                                  h->g, N, frames, N, 0);
   count_launch();
   mel_log_kernel<<<(unsigned)((size_t)B * frames), 128, h->g.n_bins * sizeof(float), st>>>(
       h->mag.as<float>(), h->basis_t.as<float>(), d_mel, h->g, h->min_amp, h->min_level_db);
@@ -203,5 +238,80 @@ extern "C" int nsw_mel_host(nsw_mel* h, const float* wav, int32_t B, int32_t N, 
   NSW_TRY(nsw_mel_device(h, h->stage_wav.as<float>(), B, N, h->stage_mel.as<float>(), h->own_stream));
   NSW_CUDA(cudaMemcpyAsync(mel, h->stage_mel.p, nm, cudaMemcpyDeviceToHost, h->own_stream));
   NSW_CUDA(cudaStreamSynchronize(h->own_stream));
+  return NSW_OK;
+}
+
+
+// ---- power-loss STFT ------------------------------------------------------------------------------
+// mel_extractor._tf_stft (mel_extractor.py:111-121) = tf.contrib.signal.stft(y, frame_length, frame_step, fft_length,
+// pad_end=True): frame j starts AT sample j*hop (not centred), zeros past the end, ceil(N / hop) frames, the periodic
+// hann window on the first frame_length samples of the fft_length frame.  The twiddle tables of such a handle are
+// built for tap n at position n (the Python side does that) and the framing is switched here.
+extern "C" int nsw_mel_set_framing(nsw_mel* h, int32_t shift, int32_t reflect) {
+  NSW_CHECK(h, NSW_EINVAL, "null handle");
+  h->g.shift = shift;
+  h->g.reflect = reflect ? 1 : 0;
+  return NSW_OK;
+}
+
+static int stft_frames_of(const nsw_mel* h, int N) {
+  return h->g.reflect ? 1 + N / h->g.hop : (N + h->g.hop - 1) / h->g.hop;
+}
+
+// |STFT| of wav [B][N] -> mag [B][frames][n_bins]; frames = ceil(N / hop) (tf framing) or 1 + N / hop (librosa)
+extern "C" int nsw_stft_mag_device(nsw_mel* h, const float* d_wav, int32_t B, int32_t N, float* d_mag, void* stream) {
+  NSW_CHECK(h && d_wav && d_mag, NSW_EINVAL, "null argument");
+  NSW_CHECK(B >= 1 && N >= 1, NSW_EINVAL, "bad batch/length %d/%d", B, N);
+  NSW_CUDA(cudaSetDevice(h->device));
+  const int frames = stft_frames_of(h, N);
+  const size_t smem = ((size_t)(MF_FRAMES - 1) * h->g.hop + h->g.win + 2 * MF_KC * MF_BINS) * sizeof(float);
+  dim3 grid((frames + MF_FRAMES - 1) / MF_FRAMES, (h->g.n_bins + MF_BINS - 1) / MF_BINS, B);
+  stft_mag_kernel<<<grid, MF_THREADS, smem, (cudaStream_t)stream>>>(d_wav, h->tc.as<float>(), h->ts.as<float>(), d_mag,
+                                                                    h->g, N, frames, N, 0);
+  count_launch();
+  NSW_CUDA(cudaGetLastError());
+  return NSW_OK;
+}
+
+// replaces: ParallelWavenet.power_loss (parallel_wavenet.py:459-479) with the shipped switches (SPEC_ENHANCE_FACTOR 1:
+// |STFT|; USE_L1_LOSS False: squared difference; USE_PRIORITY_FREQ True: 0.5 mean(all bins) + 0.5 mean(bins below
+// priority_freq); NORM_FEAT False).  The longer wave is centre-cropped (_trim, :430-435).  result[0] = power_loss,
+// [1] = mean squared difference over all bins, [2] = over the priority bins (host doubles; synchronises).
+extern "C" int nsw_power_loss_device(nsw_mel* h, const float* d_orig, int32_t N_orig, const float* d_pred,
+                                     int32_t N_pred, int32_t B, int32_t priority_freq, double* result, void* stream) {
+  NSW_CHECK(h && d_orig && d_pred && result, NSW_EINVAL, "null argument");
+  NSW_CHECK(B >= 1 && N_orig >= 1 && N_pred >= 1, NSW_EINVAL, "bad shapes");
+  NSW_CHECK(h->g.reflect == 0, NSW_EINVAL, "power loss needs a handle with tf.contrib.signal.stft framing");
+  NSW_CHECK(priority_freq >= 0 && priority_freq <= h->g.n_bins, NSW_EINVAL, "bad priority_freq %d", priority_freq);
+  NSW_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = std::min(N_orig, N_pred);
+  const int off_o = (N_orig - N) / 2, off_p = (N_pred - N) / 2;   // tf.slice(x, [0, trim_len // 2], ...)
+  const int frames = stft_frames_of(h, N);
+  const size_t nm = (size_t)B * frames * h->g.n_bins;
+  NSW_TRY(h->mag.ensure(nm * sizeof(float)));
+  NSW_TRY(h->mag2.ensure(nm * sizeof(float)));
+  NSW_TRY(h->acc.ensure(2 * sizeof(double)));
+  const size_t smem = ((size_t)(MF_FRAMES - 1) * h->g.hop + h->g.win + 2 * MF_KC * MF_BINS) * sizeof(float);
+  dim3 grid((frames + MF_FRAMES - 1) / MF_FRAMES, (h->g.n_bins + MF_BINS - 1) / MF_BINS, B);
+  stft_mag_kernel<<<grid, MF_THREADS, smem, st>>>(d_orig, h->tc.as<float>(), h->ts.as<float>(), h->mag.as<float>(), h->g,
+                                                  N, frames, N_orig, off_o);
+  stft_mag_kernel<<<grid, MF_THREADS, smem, st>>>(d_pred, h->tc.as<float>(), h->ts.as<float>(), h->mag2.as<float>(), h->g,
+                                                  N, frames, N_pred, off_p);
+  count_launch(2);
+  NSW_CUDA(cudaMemsetAsync(h->acc.p, 0, 2 * sizeof(double), st));
+  const int blocks = (int)std::min<size_t>(592, (nm + 255) / 256);
+  power_diff_kernel<<<blocks, 256, 0, st>>>(h->mag.as<float>(), h->mag2.as<float>(), (size_t)B * frames, h->g.n_bins,
+                                           priority_freq, h->acc.as<double>());
+  count_launch();
+  NSW_CUDA(cudaGetLastError());
+  double sums[2];
+  NSW_CUDA(cudaMemcpyAsync(sums, h->acc.p, sizeof(sums), cudaMemcpyDeviceToHost, st));
+  NSW_CUDA(cudaStreamSynchronize(st));
+  const double all = sums[0] / (double)nm;
+  const double pri = priority_freq > 0 ? sums[1] / ((double)B * frames * priority_freq) : 0.0;
+  result[1] = all;
+  result[2] = pri;
+  result[0] = priority_freq > 0 ? 0.5 * all + 0.5 * pri : all;
   return NSW_OK;
 }

@@ -396,7 +396,7 @@ class TeacherEngine:
         import torch
         _dev_tensor(mean_tot, 'mean_tot', (None, None), self.device)
         B, T = mean_tot.shape
-        _dev_tensor(te_out, 'te_out', (B, T, self.out_width), self.device)
+        _dev_tensor(te_out, 'te_out', (B, T, 2), self.device)       # (a mol teacher is refused by the library)
         _dev_tensor(scale_tot, 'scale_tot', (B, T), self.device)
         _dev_tensor(log_scale_tot, 'log_scale_tot', (B, T), self.device)
         res = (C.c_double * 3)()

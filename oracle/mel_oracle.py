@@ -100,3 +100,42 @@ def batch_melspectrogram(y):
     """mel_extractor.py:38-44."""
     assert len(y.shape) == 2
     return np.array([melspectrogram(y[b]) for b in range(y.shape[0])])
+
+
+# ---- power-loss STFT (mel_extractor.py:111-121, parallel_wavenet.py:430-435, 56-70, 459-479) -------------------
+def tf_stft(y, p=mel_params):
+    """mel_extractor._tf_stft = tf.contrib.signal.stft(y, frame_length, frame_step, fft_length, pad_end=True):
+    frame j = y[j*step : j*step + frame_length] (zeros past the end), times the periodic hann window
+    (tf.contrib.signal.hann_window, periodic=True by default), zero-padded at its end to fft_length, rfft.
+    pad_end=True gives ceil(N / frame_step) frames.  y [B, N] -> complex [B, frames, num_freq].
+    (TensorFlow's tf.contrib.signal is an un-vendored dependency; restated from its documented framing.)"""
+    step = int(p.frame_shift_ms * p.sample_rate / 1000)
+    length = int(p.frame_length_ms * p.sample_rate / 1000)
+    n_fft = int(2 * (p.num_freq - 1))
+    y = np.asarray(y, np.float64)
+    B, N = y.shape
+    frames = -(-N // step)
+    ypad = np.concatenate([y, np.zeros((B, (frames - 1) * step + length - N if (frames - 1) * step + length > N else 0))], 1)
+    win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(length) / length)
+    idx = np.arange(length)[None, :] + step * np.arange(frames)[:, None]
+    return np.fft.rfft(ypad[:, idx] * win[None, None, :], n=n_fft, axis=2)
+
+
+def trim(x, trim_len):
+    """ParallelWavenet._trim (parallel_wavenet.py:430-435)."""
+    left = int(trim_len // 2)
+    return x[:, left:left + x.shape[1] - trim_len]
+
+
+def power_loss(orig_wav, pred_wav, priority_freq=PRIORITY_FREQ):
+    """ParallelWavenet.power_loss (parallel_wavenet.py:459-479) with the shipped module switches (:11-30):
+    SPEC_ENHANCE_FACTOR = 1 (features = |STFT|), USE_MEL = False, NORM_FEAT = False, USE_L1_LOSS = False (squared
+    difference), USE_PRIORITY_FREQ = True (0.5 mean over all bins + 0.5 mean over the bins below PRIORITY_FREQ)."""
+    orig_wav, pred_wav = np.asarray(orig_wav, np.float64), np.asarray(pred_wav, np.float64)
+    lp, lo = pred_wav.shape[1], orig_wav.shape[1]
+    if lp > lo:
+        pred_wav = trim(pred_wav, lp - lo)
+    elif lp < lo:
+        orig_wav = trim(orig_wav, lo - lp)
+    diff = (np.abs(tf_stft(orig_wav)) - np.abs(tf_stft(pred_wav))) ** 2
+    return 0.5 * diff.mean() + 0.5 * diff[:, :, :priority_freq].mean()

@@ -244,3 +244,34 @@ def test_mel_oracle_stft_matches_scipy():
     Z = Z * win.sum()                                                  # scipy scales by 1 / sum(window)
     assert Z.shape == D.shape == (1025, 1 + 5000 // 200)
     assert np.abs(Z - D).max() < 1e-9
+
+
+def test_power_loss_stft_oracle_is_the_documented_framing():
+    """oracle.mel_oracle.tf_stft against a literal DFT of hand-cut frames (tf.contrib.signal.stft with pad_end=True:
+    frames start at j*step, ceil(N/step) of them, zeros past the end, periodic hann on the first frame_length samples
+    of the fft_length frame), and against scipy's STFT for the frames scipy also has."""
+    import scipy.signal
+    from oracle import mel_oracle as MO
+    rng = np.random.default_rng(3)
+    N = 1530
+    y = rng.standard_normal((2, N))
+    S = MO.tf_stft(y)
+    assert S.shape == (2, 8, 1025)                       # ceil(1530 / 200) = 8 frames
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(800) / 800)
+    for j in (0, 3, 7):
+        seg = np.zeros(800)
+        chunk = y[1, j * 200:j * 200 + 800]
+        seg[:len(chunk)] = chunk
+        k = np.asarray([0, 1, 17, 512, 1024])
+        n = np.arange(800)
+        lit = (seg * win)[None, :] * np.exp(-2j * np.pi * k[:, None] * n[None, :] / 2048)
+        assert np.abs(S[1, j, k] - lit.sum(1)).max() < 1e-9
+    f, t, Z = scipy.signal.stft(y[0], window=win, nperseg=800, noverlap=600, nfft=2048, boundary=None, padded=False)
+    Z = Z * win.sum()                                    # scipy normalises by the window sum
+    assert np.abs(S[0, :Z.shape[1]].T - Z).max() < 1e-9   # the frames that lie fully inside the signal
+    # power loss: trims the longer wave about its centre, squared magnitude difference, priority bins weighted 0.5
+    a, b = rng.standard_normal((2, 1600)), rng.standard_normal((2, 1536))
+    pl = MO.power_loss(a, b)
+    d = (np.abs(MO.tf_stft(a[:, 32:32 + 1536])) - np.abs(MO.tf_stft(b))) ** 2
+    assert abs(pl - (0.5 * d.mean() + 0.5 * d[:, :, :MO.PRIORITY_FREQ].mean())) < 1e-12
+    assert MO.PRIORITY_FREQ == 384 and MO.power_loss(a, a) == 0.0
