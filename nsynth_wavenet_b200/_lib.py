@@ -129,7 +129,10 @@ def load(build_if_stale=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_stale and _build.is_stale():
+    override = os.environ.get('NSW_LIB')      # timing experiments: an alternative build of the same sources
+    if override:
+        _build.LIB_PATH = override
+    elif build_if_stale and _build.is_stale():
         _build.build_library()
     if not os.path.exists(_build.LIB_PATH):
         raise NswError('libnsw_b200.so is missing and could not be built; '

@@ -149,8 +149,21 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 static __device__ unsigned int* nsw_tu_range_ptr = nullptr;  // one instance per translation unit and device
 __device__ __forceinline__ void range_track(uint32_t& mx, float v) {
+#ifndef NSW_NO_RANGE_GUARD  // (timing experiments only)
   mx = max(mx, __float_as_uint(v) & 0x7fffffffu);  // NaN and inf compare above every finite magnitude
+#endif
 }
+// one FMNMX per value for the epilogues that sit on a kernel's critical chain (the residual stream of the flow / layer
+// kernels).  fmaxf ignores NaNs, which is enough there: every value those epilogues split is a finite combination of
+// values that passed an integer-tracked site (start conv, deconv / conditioning epilogues) unless some term overflowed
+// to inf first, and inf is caught.
+__device__ __forceinline__ void range_track_fast(float& mx, float v) {
+#ifndef NSW_NO_RANGE_GUARD
+  mx = fmaxf(mx, fabsf(v));
+#endif
+}
+__device__ __forceinline__ void range_commit(uint32_t mx);
+__device__ __forceinline__ void range_commit_fast(float mx) { range_commit(__float_as_uint(mx)); }
 __device__ __forceinline__ void range_commit(uint32_t mx) {
   if (mx > 0x477FE000u /* 65504.0f */) {
     unsigned int* p = nsw_tu_range_ptr;

@@ -39,8 +39,8 @@ __device__ __forceinline__ void store_epi(const ConvGemm& g, const EpiParams& e,
     if (e.out_hi) {
       float f[4] = {v.x, v.y, v.z, v.w};
       __half hi[4], lo[4];
-#pragma unroll
       uint32_t rmx = 0;
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
         range_track(rmx, f[i]);
         hi[i] = __float2half_rn(f[i]);

@@ -94,8 +94,8 @@ iaf_start_conv_kernel(const float* __restrict__ x, float* __restrict__ l,
   if (l_hi) {  // split-fp16 copy for the tcgen05 layer kernel's MMA operand
     const float f[4] = {o.x, o.y, o.z, o.w};
     __align__(8) __half hi[4], lo[4];
-#pragma unroll
     uint32_t rmx = 0;
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
       range_track(rmx, f[i]);
       hi[i] = __float2half_rn(f[i]);

@@ -829,7 +829,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
     const int qd = warp & 3;
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     const int row = qd * 32 + lane;  // row inside a tile
-    uint32_t rmx = 0;                // fp16-range guard: largest magnitude this thread split
+    uint32_t rmx = 0;                // fp16-range guard: largest magnitude this thread split (start conv)
+    float rmxf = 0.f;                // the same for the per-layer residual rows (one FMNMX per value)
     if (p.fuse_start) {
       // init: start conv of the own tiles (-> TMEM master + smem planes) and of the halo (smem only;
       // zeros at the start of a clip: the layer input is zero-padded, masked.py:203-204)
@@ -948,8 +949,8 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float o0 = __uint_as_float(d[8 * jj + 2 * e]), o1 = __uint_as_float(d[8 * jj + 2 * e + 1]);
-          range_track(rmx, o0);
-          range_track(rmx, o1);
+          range_track_fast(rmxf, o0);
+          range_track_fast(rmxf, o1);
           if (relu_out) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }  // the head's out1 consumes relu(l)
           const float a0 = __half2float(__float2half_rn(o0));
           const float a1 = __half2float(__float2half_rn(o1));
@@ -969,6 +970,7 @@ iaf_flow_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
       if (++kk == K) { kk = 0; ++li; }
     }
     range_commit(rmx);
+    range_commit_fast(rmxf);
   } else if (warp == 18) {
     // =================================== publisher ===================================
     if (lane == 0) {

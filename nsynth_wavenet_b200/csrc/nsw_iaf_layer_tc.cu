@@ -484,7 +484,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
     const uint32_t scr = sbase + OFF_SCR + (uint32_t)(warp - 2) * 4096u;
     int itg = 0;
-    uint32_t rmx = 0;  // fp16-range guard
+    float rmx = 0.f;  // fp16-range guard
     for (int li = 0; li < n_layers; ++li) {
       const int layer = p.l0 + li;
       const int wb = ((p.buf0 + li) & 1) ^ 1;  // buffer this layer writes
@@ -578,8 +578,8 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            range_track(rmx, o[2 * e]);
-            range_track(rmx, o[2 * e + 1]);
+            range_track_fast(rmx, o[2 * e]);
+            range_track_fast(rmx, o[2 * e + 1]);
             const float a0 = __half2float(__float2half_rn(o[2 * e]));
             const float a1 = __half2float(__float2half_rn(o[2 * e + 1]));
             hw[e] = pack_f16(a0, a1);
@@ -603,7 +603,7 @@ iaf_layer_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_con
           asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.grid_counter) : "memory");
       }
     }
-    range_commit(rmx);
+    range_commit_fast(rmx);
   }
 
   fence_before();

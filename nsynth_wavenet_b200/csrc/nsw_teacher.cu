@@ -42,8 +42,8 @@ teacher_start_kernel(const float* __restrict__ x, const float* __restrict__ w /*
   f[3] = fmaf(w2.w, x1, fmaf(w1.w, x2, fmaf(w0.w, x3, bb.w)));
   *reinterpret_cast<float4*>(ls + row * TLS + c) = make_float4(f[0], f[1], f[2], f[3]);
   __align__(8) __half h[4], l[4];
-#pragma unroll
   uint32_t rmx = 0;
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
     range_track(rmx, f[i]);
     h[i] = __float2half_rn(f[i]);

@@ -1,0 +1,9 @@
+#!/bin/bash
+# r02 run11: cost of the fp16-range guard (A/B against a -DNSW_NO_RANGE_GUARD build of the same sources)
+mkdir -p gpurun_out
+LEAN="--no-cpu-baseline --no-fastgen --no-distill --no-clarinet --no-python-e2e --no-sustained"
+for i in 1 2 3; do
+for lib in "" scripts/r02/_lib/libnsw_noguard.so; do
+NSW_LIB=$lib timeout 600 python bench.py --steps 40 --warmup 5 $LEAN 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('lib=$lib ms_per_step %.4f' % d['ms_per_step'], {k: round(v,4) for k,v in d['stage_ms'].items()})"
+done; done
