@@ -22,7 +22,10 @@ def load_audio(path, sample_length=64000, sr=16000):
                          'tools/sox_downsample.py in the reference)'.format(path, rate, sr))
     if data.ndim > 1:
         data = data.mean(axis=1)
-    if np.issubdtype(data.dtype, np.integer):
+    if data.dtype == np.uint8:
+        # 8-bit PCM is unsigned with the zero line at 128 (the only unsigned WAV sample format)
+        data = (data.astype(np.float32) - 128.0) / 128.0
+    elif np.issubdtype(data.dtype, np.integer):
         data = data.astype(np.float32) / float(np.iinfo(data.dtype).max + 1)
     audio = np.asarray(data, np.float32)
     if sample_length > 0:

@@ -80,6 +80,10 @@ struct DevBuf {
 
 int upload(DevBuf& buf, const void* host, size_t bytes);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device), whatever
+// device is current, and safely from several threads (`done` is one bit per device ordinal).
+int ensure_dynamic_smem(const void* kernel, int bytes, std::atomic<uint64_t>& done);
+
 // ---- fp16-range guard of the split-precision (fp16 hi + fp16 lo) engines ------------------------------------
 // Every activation that becomes a tensor-core operand is rounded to fp16 (max 65504): a value beyond that turns
 // into inf and the result into garbage WITHOUT any fault (fminf / fmaxf in the epilogues even swallow the NaNs).

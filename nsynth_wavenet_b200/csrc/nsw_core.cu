@@ -79,6 +79,16 @@ int range_check(const char* who) {
   return NSW_ERANGE;
 }
 
+int ensure_dynamic_smem(const void* kernel, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  NSW_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return NSW_OK;
+  NSW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));  // idempotent
+  done.fetch_or(bit, std::memory_order_release);
+  return NSW_OK;
+}
+
 int upload(DevBuf& buf, const void* host, size_t bytes) {
   NSW_TRY(buf.ensure(bytes));
   NSW_CUDA(cudaMemcpy(buf.p, host, bytes, cudaMemcpyHostToDevice));

@@ -222,6 +222,7 @@ struct GnParams {
   float quant;
   long long* dbg;          // NSW_FASTGEN_DEBUG: [NC][8] cycle sums of thread 0 (NULL = off)
   int flags;               // experiment switches (NSW_GN_FLAGS): 1 = red.release arrive
+  int l2_last;             // weight blocks of phases < l2_last are loaded L2::evict_last, the rest evict_first (0 = no hints)
 };
 
 template <int MH, int BT>
@@ -231,8 +232,11 @@ struct GnSmem {
   alignas(128) float xl[BT][GN_W];    // fresh l_{ph-2} | head phases: s / h, rows of 256 | sampler: out, rows of O
   alignas(128) float xg[BT][MH];      // fresh g_{ph-1}
   alignas(128) float hv[2][BT][GN_W];  // [0] = l[t-2d], [1] = l[t-d] of the phase's layer
-  float rsum[16][BT];
-  float pv[8][BT];
+  // K-split partial sums: a warp contracts ONE 128-float slice of the inputs against every row that uses it, so the
+  // inputs are read from shared memory once per slice instead of once per row (the dots were shared-memory-bandwidth
+  // bound: rows x K x 4 B x BT = 147 - 360 KB per phase at BT = 8)
+  float pf[12][64];          // fresh stage: [slice warp][row * BT + b] (+ 4 * BT for the skip rows)
+  float pp[8][64];           // past taps:   [tap * 4 + slice][row * BT + b]
   float cnd[8][BT];
   float lst[4][BT];          // owned residual channels 4c..4c+3
   float sst[2][BT];          // owned skip channels 2c, 2c+1
@@ -260,6 +264,18 @@ __device__ __forceinline__ void gn_bulk(void* dst, const void* src, uint32_t byt
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// weight blocks: the per-step stream (156 - 330 MB) is larger than L2 and cyclic, so plain LRU never hits; the blocks of
+// the first phases are kept (evict_last), the rest stream through (evict_first) -- as in the latency engine
+__device__ __forceinline__ void gn_bulk_hint(void* dst, const void* src, uint32_t bytes, unsigned long long* bar, bool keep) {
+  unsigned long long pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void gn_mbar_wait(unsigned long long* bar, uint32_t parity, const char* what) {
   uint32_t ok = 0;
   long long t0 = 0;
@@ -281,61 +297,54 @@ __device__ __forceinline__ void gn_mbar_wait(unsigned long long* bar, uint32_t p
   }
 }
 
-// acc[b] += sum_{i<NF} w[i] . x[b * xs + 128 i + 4 lane .. +3]   (per-lane partial sums)
-template <int NF, int BT>
-__device__ __forceinline__ void dot_seg(const float4* w, const float* x, int xs, int lane, float (&acc)[BT]) {
+// transposing butterfly over V = 2^k per-lane partials (k <= 5 halving steps with xor offsets 16, 8, ...; plain
+// xor-adds after that): afterwards a[0] holds the warp total of value number lane >> (5 - k)
+template <int N, int O>
+__device__ __forceinline__ void red_step(float* a, int lane) {
+  if constexpr (O >= 1) {
+    if constexpr (N > 1) {
+      const bool up = (lane & O) != 0;
 #pragma unroll
-  for (int b = 0; b < BT; ++b) {
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) {
-      const float4 xx = *reinterpret_cast<const float4*>(x + (size_t)b * xs + 128 * i + 4 * lane);
-      a0 = fmaf(w[i].x, xx.x, a0);
-      a1 = fmaf(w[i].y, xx.y, a1);
-      a0 = fmaf(w[i].z, xx.z, a0);
-      a1 = fmaf(w[i].w, xx.w, a1);
+      for (int i = 0; i < N / 2; ++i) {
+        const float keep = up ? a[N / 2 + i] : a[i];
+        const float send = up ? a[i] : a[N / 2 + i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+      }
+      red_step<N / 2, O / 2>(a, lane);
+    } else {
+      a[0] += __shfl_xor_sync(0xffffffffu, a[0], O);
+      red_step<1, O / 2>(a, lane);
     }
-    acc[b] += a0 + a1;
   }
 }
-// transposing butterfly: BT per-lane partials -> warp totals; the lanes with (lane & (32 / BT - 1)) == 0 write
-// total number lane / (32 / BT) into dst
-template <int BT>
-__device__ __forceinline__ void reduce_store(float (&a)[BT], float* dst, int lane) {
-  constexpr unsigned F = 0xffffffffu;
-  float v;
-  if (BT == 8) {
-    float b4[4], b2[2];
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+// One 128-float input slice (x: BT rows, xs floats apart, already at the slice) against NR <= 4 weight rows (w: rows ws
+// floats apart, already at the slice): out[r * BT + b] = sum over the slice.  NR * BT is a power of two <= 32.
+template <int NR, int BT>
+__device__ __forceinline__ void slice_rows(const float* w, int ws, const float4 (&xv)[BT], int lane, float* out) {
+  constexpr int V = NR * BT;
+  static_assert(V <= 32 && (V & (V - 1)) == 0, "slice_rows: NR * BT must be a power of two <= 32");
+  float acc[V];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) b4[i] = (h16 ? a[4 + i] : a[i]) + __shfl_xor_sync(F, h16 ? a[i] : a[4 + i], 16);
+  for (int r = 0; r < NR; ++r) {
+    const float4 wv = *reinterpret_cast<const float4*>(w + (size_t)r * ws + 4 * lane);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) b2[i] = (h8 ? b4[2 + i] : b4[i]) + __shfl_xor_sync(F, h8 ? b4[i] : b4[2 + i], 8);
-    v = (h4 ? b2[1] : b2[0]) + __shfl_xor_sync(F, h4 ? b2[0] : b2[1], 4);
-    v += __shfl_xor_sync(F, v, 2);
-    v += __shfl_xor_sync(F, v, 1);
-    if ((lane & 3) == 0) dst[lane >> 2] = v;
-  } else if (BT == 4) {
-    float b2[2];
-    const bool h16 = lane & 16, h8 = lane & 8;
+    for (int b = 0; b < BT; ++b)
+      acc[r * BT + b] = fmaf(wv.x, xv[b].x, fmaf(wv.y, xv[b].y, fmaf(wv.z, xv[b].z, wv.w * xv[b].w)));
+  }
+  red_step<V, 16>(acc, lane);
+  constexpr int STEP = 32 / V;   // lanes per value
+  if ((lane & (STEP - 1)) == 0) out[lane / STEP] = acc[0];
+}
+template <int NR, int BT>
+__device__ __forceinline__ void slice_job(const float* w, int ws, const float* x, int xs, int lane, float* out) {
+  float4 xv[BT];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) b2[i] = (h16 ? a[2 + i] : a[i]) + __shfl_xor_sync(F, h16 ? a[i] : a[2 + i], 16);
-    v = (h8 ? b2[1] : b2[0]) + __shfl_xor_sync(F, h8 ? b2[0] : b2[1], 8);
-    v += __shfl_xor_sync(F, v, 4);
-    v += __shfl_xor_sync(F, v, 2);
-    v += __shfl_xor_sync(F, v, 1);
-    if ((lane & 7) == 0) dst[lane >> 3] = v;
-  } else if (BT == 2) {
-    const bool h16 = lane & 16;
-    v = (h16 ? a[BT - 1] : a[0]) + __shfl_xor_sync(F, h16 ? a[0] : a[BT - 1], 16);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(F, v, o);
-    if ((lane & 15) == 0) dst[lane >> 4] = v;
-  } else {
-    v = a[0];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(F, v, o);
-    if (lane == 0) dst[0] = v;
+  for (int b = 0; b < BT; ++b) xv[b] = *reinterpret_cast<const float4*>(x + (size_t)b * xs + 4 * lane);
+  if constexpr (NR <= 4) {
+    slice_rows<NR, BT>(w, ws, xv, lane, out);
+  } else {  // 8 rows as two groups of 4: at most 32 accumulators live
+    slice_rows<4, BT>(w, ws, xv, lane, out);
+    slice_rows<4, BT>(w + (size_t)4 * ws, ws, xv, lane, out + 4 * BT);
   }
 }
 
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
                 OFF_C = OFF_S + 2 * W, BF = OFF_C + 16;
   constexpr int NFM = MH / 128;
   constexpr int COMM = NT / 32 - 1;
-  static_assert(nD + 6 <= COMM, "row warps and the comm warp must not overlap");
+  static_assert(4 + 2 * NFM <= COMM, "slice warps and the comm warp must not overlap");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using Smem = GnSmem<MH, BT>;
   Smem& Sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -389,7 +398,10 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
   auto issue_weights = [&](int ph0 /* 0-based phase */, int slot) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot was read through the generic proxy
     gn_expect(&Sm.wbar[slot], BLOCK_B);
-    gn_bulk(Sm.wring[slot], P.blocks + ((size_t)ph0 * NC + c) * BF, BLOCK_B, &Sm.wbar[slot]);
+    if (P.l2_last > 0)
+      gn_bulk_hint(Sm.wring[slot], P.blocks + ((size_t)ph0 * NC + c) * BF, BLOCK_B, &Sm.wbar[slot], ph0 < P.l2_last);
+    else
+      gn_bulk(Sm.wring[slot], P.blocks + ((size_t)ph0 * NC + c) * BF, BLOCK_B, &Sm.wbar[slot]);
   };
   auto issue_hist = [&](int ph, int t, int pos) {  // taps of layer ph for step t; pos = ring slot of step t
     const int d = Sm.dil[ph], R = 2 * d + 1;
@@ -571,54 +583,23 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
       }
       // ---------------- everything that does not depend on the exchange in flight ----------------
       gn_mbar_wait(&Sm.wbar[slot], (uint32_t)((gq >> 1) & 1), "weight block");
-      float4 wp[8], wf[8];
-      // fresh row of this warp: nfl float4 per lane against xl (rows xs apart), then nfg against xg
-      int nfl = 0, nfg = 0, xs = W;
-      const bool has_past = ph <= L && warp < nD;
       bool ok2 = false, ok1 = false;
       if (ph <= L) {
         const int d = Sm.dil[ph];
         ok2 = t - 2 * d >= 0;
         ok1 = t - d >= 0;
-      }
-      if (has_past) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wp[i] = *reinterpret_cast<const float4*>(blk + OFF_P + warp * 2 * W + 128 * i + 4 * lane);
-      }
-      {
-        const float* row = nullptr;
-        if (ph <= L) {
-          if (warp < nD) { row = blk + OFF_D + warp * K1; nfl = W / 128; nfg = NFM; }
-          else if (warp < nD + 4) { if (ph >= 2) { row = blk + OFF_L + (warp - nD) * MH; nfg = NFM; } }
-          else if (warp < nD + 6) {
-            row = blk + OFF_S + (warp - nD - 4) * W;
-            if (ph == 1) nfl = W / 128; else nfg = NFM;
-          }
-        } else if (ph == L + 1) {
-          if (warp >= nD + 4 && warp < nD + 6) { row = blk + OFF_S + (warp - nD - 4) * W; nfg = NFM; }
-        } else if (ph == L + 2) {
-          if (warp < 2) { row = blk + OFF_D + warp * K1; nfl = S / 128; xs = S; }
-        } else {
-          if (warp < RO && c * RO + warp < O) { row = blk + OFF_D + warp * K1; nfl = S / 128; xs = S; }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < nfl + nfg) wf[i] = *reinterpret_cast<const float4*>(row + 128 * i + 4 * lane);
-      }
-      if (ph <= L) {
         if (tid >= 256 && tid < 256 + nD * BT) {
           const int j = (tid - 256) / BT, b = (tid - 256) - j * BT;
           const int n = (ph - 1) * G + c * nD + j;
           Sm.cnd[j][b] = __ldg(P.cond + (size_t)b * P.cond_bstride + ((size_t)(n >> 6) * P.Tc + tl) * 64 + (n & 63));
         }
-        if (has_past) {
-          gn_mbar_wait(&Sm.hbar, nh & 1u, "history taps");
-          float acc[BT];
-#pragma unroll
-          for (int b = 0; b < BT; ++b) acc[b] = 0.f;
-          if (ok2) dot_seg<4, BT>(wp, &Sm.hv[0][0][0], W, lane, acc);
-          if (ok1) dot_seg<4, BT>(wp + 4, &Sm.hv[1][0][0], W, lane, acc);
-          reduce_store<BT>(acc, Sm.pv[warp], lane);
+        if (warp < 8) {
+          // past taps, K-split: warp = tap * 4 + slice; every dilated-conv row of the CTA against that slice
+          const int tap = warp >> 2, sl = warp & 3;
+          if (tap == 0 ? ok2 : ok1) {
+            gn_mbar_wait(&Sm.hbar, nh & 1u, "history taps");
+            slice_job<nD, BT>(blk + OFF_P + tap * W + sl * 128, 2 * W, &Sm.hv[tap][0][sl * 128], W, lane, Sm.pp[warp]);
+          }
         }
         ++nh;
       } else if (ph == L + 2) {
@@ -659,57 +640,79 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
         ++nfr;
       }
       lap(1);
-      if (nfl + nfg > 0) {
-        float acc[BT];
-#pragma unroll
-        for (int b = 0; b < BT; ++b) acc[b] = 0.f;
-        // compile-time register indices only (a dynamically indexed weight array would live in local memory)
-        if (nfl == 4) {
-          dot_seg<4, BT>(wf, &Sm.xl[0][0], xs, lane, acc);
-          if (nfg > 0) dot_seg<NFM, BT>(wf + 4, &Sm.xg[0][0], MH, lane, acc);
-        } else if (nfl == 2) {
-          dot_seg<2, BT>(wf, &Sm.xl[0][0], xs, lane, acc);
-        } else {
-          dot_seg<NFM, BT>(wf, &Sm.xg[0][0], MH, lane, acc);
+      // fresh rows, K-split: one warp per 128-float slice of xl (warps 0-3) and of xg (D rows: warps 4..4+NFM-1,
+      // residual + skip rows: the next NFM warps)
+      if (ph <= L) {
+        if (warp < 4) {
+          slice_job<nD, BT>(blk + OFF_D + warp * 128, K1, &Sm.xl[0][warp * 128], W, lane, Sm.pf[warp]);
+        } else if (ph == 1) {
+          if (warp < 8)  // skip_start on l_0 (K = W)
+            slice_job<2, BT>(blk + OFF_S + (warp - 4) * 128, W, &Sm.xl[0][(warp - 4) * 128], W, lane, Sm.pf[warp]);
+        } else if (warp < 4 + NFM) {
+          const int sl = warp - 4;
+          slice_job<nD, BT>(blk + OFF_D + W + sl * 128, K1, &Sm.xg[0][sl * 128], MH, lane, Sm.pf[warp]);
+        } else if (warp < 4 + 2 * NFM) {
+          const int sl = warp - 4 - NFM;
+          slice_job<4, BT>(blk + OFF_L + sl * 128, MH, &Sm.xg[0][sl * 128], MH, lane, Sm.pf[warp]);
+          slice_job<2, BT>(blk + OFF_S + sl * 128, W, &Sm.xg[0][sl * 128], MH, lane, Sm.pf[warp] + 4 * BT);
         }
-        reduce_store<BT>(acc, Sm.rsum[warp], lane);
+      } else if (ph == L + 1) {
+        if (warp >= 4 + NFM && warp < 4 + 2 * NFM) {
+          const int sl = warp - 4 - NFM;
+          slice_job<2, BT>(blk + OFF_S + sl * 128, W, &Sm.xg[0][sl * 128], MH, lane, Sm.pf[warp] + 4 * BT);
+        }
+      } else {
+        if (warp < S / 128)  // out1 (L+2) / out2 (L+3) rows, K = S, inputs in the first S floats of xl with stride S
+          slice_job<2, BT>(blk + OFF_D + warp * 128, K1, &Sm.xl[0][0] + warp * 128, S, lane, Sm.pf[warp]);
       }
       __syncthreads();  // S2
       lap(2);
       // ---------------- epilogues: one thread per (row, batch row) ----------------
+      auto sum_pf = [&](int w0, int w1, int idx) {
+        float a = 0.f;
+        for (int w = w0; w < w1; ++w) a += Sm.pf[w][idx];
+        return a;
+      };
       if (ph <= L) {
+        const int dw = ph == 1 ? 4 : 4 + NFM;  // slice warps holding partials of the dilated-conv rows
         if (tid < PPC * BT) {
           const int pr = tid / BT, b = tid - pr * BT;
-          const float a = Sm.rsum[pr][b] + Sm.pv[pr][b] + Sm.cnd[pr][b];
-          const float q = Sm.rsum[PPC + pr][b] + Sm.pv[PPC + pr][b] + Sm.cnd[PPC + pr][b];
+          float a = sum_pf(0, dw, pr * BT + b) + Sm.cnd[pr][b];
+          float q = sum_pf(0, dw, (PPC + pr) * BT + b) + Sm.cnd[PPC + pr][b];
+          if (ok2)
+            for (int w = 0; w < 4; ++w) { a += Sm.pp[w][pr * BT + b]; q += Sm.pp[w][(PPC + pr) * BT + b]; }
+          if (ok1)
+            for (int w = 4; w < 8; ++w) { a += Sm.pp[w][pr * BT + b]; q += Sm.pp[w][(PPC + pr) * BT + b]; }
           __stcg(P.gbuf + (size_t)(ph & 1) * BT * MH + (size_t)b * MH + c * PPC + pr, gn_sigmoid(a) * gn_tanh(q));
         } else if (tid >= 64 && tid < 64 + 4 * BT) {
           const int r = (tid - 64) / BT, b = (tid - 64) - r * BT;
           // l_{ph-1} = l_{ph-2} + Wr_{ph-1} g_{ph-1} + br_{ph-1}  (phase 1: l_0 from conv_start)
-          const float l = ph == 1 ? Sm.xl[b][4 * c + r] : Sm.lst[r][b] + Sm.rsum[nD + r][b] + blk[OFF_C + r];
+          const float l = ph == 1 ? Sm.xl[b][4 * c + r]
+                                  : Sm.lst[r][b] + sum_pf(4 + NFM, 4 + 2 * NFM, r * BT + b) + blk[OFF_C + r];
           Sm.lst[r][b] = l;
           __stcg(P.hist + ((size_t)Sm.hoff[ph] + Sm.pos[ph]) * ring_entry + (size_t)b * W + 4 * c + r, l);
         } else if (tid >= 128 && tid < 128 + 2 * BT) {
           const int r = (tid - 128) / BT, b = (tid - 128) - r * BT;
-          const float a = Sm.rsum[nD + 4 + r][b] + blk[OFF_C + 4 + r];
+          const float a = (ph == 1 ? sum_pf(4, 8, r * BT + b) : sum_pf(4 + NFM, 4 + 2 * NFM, 4 * BT + r * BT + b)) +
+                          blk[OFF_C + 4 + r];
           Sm.sst[r][b] = ph == 1 ? a : Sm.sst[r][b] + a;  // skip_start, then skip_{ph-1}
         }
       } else if (ph == L + 1) {
         if (tid >= 128 && tid < 128 + 2 * BT) {
           const int r = (tid - 128) / BT, b = (tid - 128) - r * BT;
-          const float s = Sm.sst[r][b] + Sm.rsum[nD + 4 + r][b] + blk[OFF_C + 4 + r];
+          const float s = Sm.sst[r][b] + sum_pf(4 + NFM, 4 + 2 * NFM, 4 * BT + r * BT + b) + blk[OFF_C + 4 + r];
           __stcg(P.sbuf + (size_t)b * S + 2 * c + r, fmaxf(s, 0.f));  // relu(s) (wavenet.py:494)
         }
       } else if (ph == L + 2) {
         if (tid < 2 * BT) {
           const int r = tid / BT, b = tid - r * BT;
-          __stcg(P.hbuf + (size_t)b * S + 2 * c + r, fmaxf(Sm.rsum[r][b] + Sm.cnd[r][b], 0.f));
+          __stcg(P.hbuf + (size_t)b * S + 2 * c + r, fmaxf(sum_pf(0, S / 128, r * BT + b) + Sm.cnd[r][b], 0.f));
         }
       } else {
         if (tid < RO * BT) {
           const int r = tid / BT, b = tid - r * BT;
           const int o = c * RO + r;
-          if (o < O) __stcg(P.obuf + (size_t)b * O + o, Sm.rsum[r][b] + blk[OFF_C + 6 + r]);
+          if (o < O) __stcg(P.obuf + (size_t)b * O + o, sum_pf(0, S / 128, r * BT + b) + blk[OFF_C + 6 + r]);
         }
       }
       lap(3);
@@ -767,6 +770,7 @@ struct GnEngine {
   nsw_wavenet_config cfg;
   int device = 0, L = 0, O = 0, MH = 0, N = 0, NPL = 0;
   size_t hist_entries = 0;
+  int l2_last = 0;
   int chunk = 2048;
   DevBuf blocks, wcs, bcs, cond_w, cond_wt_hi, cond_wt_lo, cond_b, hist_off, dil;
   DevBuf hist, gbuf, sbuf, hbuf, obuf, xstate, bar, cond, enc_split, dbg;
@@ -791,6 +795,9 @@ int gn_create(const nsw_wavenet_config& cfg, const TensorMap& tm, int device, Gn
   g->NPL = pk.N / 64;
   g->hist_entries = pk.hist_entries;
   if (const char* e = getenv("NSW_FASTGEN_CHUNK")) g->chunk = std::max(1, atoi(e));
+  int l2_bytes = 0;
+  cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, device);
+  g->l2_last = std::min(pk.L + 3, (int)(0.6 * (double)l2_bytes / ((double)GN_NC * pk.lay.block_floats * 4)));
   int rc = NSW_OK;
   auto up = [&](DevBuf& b, const void* p, size_t bytes) { if (rc == NSW_OK) rc = upload(b, p, bytes); };
   up(g->blocks, pk.blocks.data(), pk.blocks.size() * 4);
@@ -893,6 +900,7 @@ int gn_run(GnEngine* g, const float* d_encoding, int B, int T, const float* d_tf
       P.quant = g->cfg.use_mu_law ? 256.0f : 65536.0f;
       P.dbg = nullptr;
       P.flags = getenv("NSW_GN_FLAGS") ? atoi(getenv("NSW_GN_FLAGS")) : 0;
+      P.l2_last = getenv("NSW_FASTGEN_L2LAST") ? atoi(getenv("NSW_FASTGEN_L2LAST")) : g->l2_last;
       const bool want_dbg = getenv("NSW_FASTGEN_DEBUG") != nullptr;
       if (want_dbg) {
         NSW_TRY(g->dbg.ensure(GN_NC * 8 * sizeof(long long)));

@@ -604,6 +604,7 @@ struct CondProj {
                                 // of every weight stage, multicast into both (halves the L2 reads of W)
   const float* bias;
   float* out;  // [N/64] planes of nclips*mclip rows, row-interleaved
+  int exp;     // TIMING EXPERIMENTS ONLY (NSW_COND_EXP): 1 = no global stores, 2 = no MMAs (results are wrong)
 };
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -744,7 +745,9 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
           for (int k = 0; k < TBK / 16; ++k) {
             const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+            if (g.exp == 2 && k > 0) continue;
             umma_f16(d_tmem, xl + adv, wh + adv, idesc, (kb | k) != 0);
+            if (g.exp == 2) continue;
             umma_f16(d_tmem, xh + adv, wl + adv, idesc, 1);
             umma_f16(d_tmem, xh + adv, wh + adv, idesc, 1);
           }
@@ -782,7 +785,8 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(b4 + j);
-            dst[j * 32] = make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+            const float4 o = make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+            if (g.exp != 1 || o.x == 123456.789f) dst[j * 32] = o;
           }
         }
       }
@@ -801,6 +805,229 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same projection with cta_group::2 MMAs (M = 256 over a CTA pair).  Each CTA of the pair keeps its own
+// [128 x 256] activation tile resident and holds only HALF of every weight stage (64 of the 128 weight rows: the
+// tensor cores of the two SMs exchange the B operand between themselves), so the per-SM weight stream -- what bounded
+// the 1-CTA kernel: 3 stages x 32 KB in flight against ~1 us of L2 latency, tensor pipe 50 % busy, and still 0.29 of
+// 0.39 ms with 1/12 of the MMAs (profiles/r02) -- is halved and the ring is twice as deep in the same shared memory.
+//   leader (cluster rank 0): issues every tcgen05.mma.cta_group::2; its x_full / w_full barriers count the bytes of
+//   BOTH CTAs (the peer's TMA loads name the leader's barrier); commits are multicast to both CTAs; the peer's
+//   epilogue warps release an accumulator stage with a remote arrive on the leader's tmem_empty barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int CP2_WSTAGES = 6;
+constexpr uint32_t CP2_W_STAGE = TILE_BYTES;          // per CTA: W hi + lo [64 n x 64 k] = 16 KB
+constexpr uint32_t CP2_OFF_BARS = CP_OFF_W + CP2_WSTAGES * CP2_W_STAGE;
+constexpr size_t CP2_SMEM_BYTES = CP2_OFF_BARS + 1024 + 1024;
+
+struct Cp2Bars {
+  uint64_t x_full[4], x_free[4];
+  uint64_t w_full[CP2_WSTAGES], w_empty[CP2_WSTAGES];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cp2_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cp2_tma_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,
+                                           int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void cp2_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cp2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cp2_commit(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void cp2_arrive_remote(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                     const __grid_constant__ CUtensorMap map_wh2, const __grid_constant__ CUtensorMap map_wl2, CondProj g) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  Cp2Bars* B = reinterpret_cast<Cp2Bars*>(smem + CP2_OFF_BARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const int crank = (int)(blockIdx.x & 1);
+  const bool leader = crank == 0;
+  if (threadIdx.x == 0) {
+    for (int kb = 0; kb < 4; ++kb) { mbar_init(&B->x_full[kb], 1); mbar_init(&B->x_free[kb], 1); }
+    for (int s = 0; s < CP2_WSTAGES; ++s) { mbar_init(&B->w_full[s], 1); mbar_init(&B->w_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&B->tmem_full[a], 1); mbar_init(&B->tmem_empty[a], 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  // barriers of both CTAs must exist before the peer's TMA completes on / arrives at them
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = B->tmem_base;
+  const int n_groups = (int)gridDim.x / 2, group = (int)blockIdx.x / 2;
+  const long long items = (long long)(g.nclips * g.tiles_per_clip / 2) * g.n_tiles;
+  const int i0 = (int)(items * group / n_groups), i1 = (int)(items * (group + 1) / n_groups);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      int xit = 0, cur_mt = -1;
+      for (int i = i0; i < i1; ++i) {
+        const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+        const int mt = mtg * 2 + crank;
+        const bool new_x = mt != cur_mt;
+        int clip = 0, m0 = 0;
+        if (new_x) {
+          cur_mt = mt;
+          clip = mt / g.tiles_per_clip;
+          m0 = (mt - clip * g.tiles_per_clip) * TBM;
+          ++xit;
+        }
+        for (int kb = 0; kb < 4; ++kb) {
+          if (new_x) {
+            if (xit > 1) mbar_wait(&B->x_free[kb], (uint32_t)((xit - 2) & 1));
+            if (leader) mbar_expect_tx(&B->x_full[kb], 4 * TILE_BYTES);  // hi + lo of BOTH CTAs
+            const uint32_t xb = cp2_mapa(smem_u32(&B->x_full[kb]), 0);
+            cp2_tma_3d(sbase + (2 * kb) * TILE_BYTES, &map_xh, xb, kb * TBK, m0 + g.a_off, clip);
+            cp2_tma_3d(sbase + (2 * kb + 1) * TILE_BYTES, &map_xl, xb, kb * TBK, m0 + g.a_off, clip);
+          }
+          mbar_wait(&B->w_empty[ws], wphase ^ 1);
+          const uint32_t dst = sbase + CP_OFF_W + ws * CP2_W_STAGE;
+          if (leader) mbar_expect_tx(&B->w_full[ws], 2 * CP2_W_STAGE);
+          const uint32_t wb = cp2_mapa(smem_u32(&B->w_full[ws]), 0);
+          // this CTA's half of the 128 weight rows, hi then lo plane (8 KB each)
+          cp2_tma_2d(dst, &map_wh2, wb, kb * TBK, nt * TBN + crank * 64);
+          cp2_tma_2d(dst + TILE_BYTES / 2, &map_wl2, wb, kb * TBK, nt * TBN + crank * 64);
+          if (++ws == CP2_WSTAGES) { ws = 0; wphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // instruction descriptor: D = f32, A = B = f16, K-major, M = 256 (128 per CTA), N = TBN
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+      const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase);
+      int ws = 0;
+      uint32_t wphase = 0;
+      int xit = 0, cur_mt = -1, acc_it = 0;
+      for (int i = i0; i < i1; ++i, ++acc_it) {
+        const int mt = i / g.n_tiles;
+        const bool first_of_x = mt != cur_mt;
+        if (first_of_x) {
+          cur_mt = mt;
+          ++xit;
+        }
+        const bool last_of_x = (i + 1 == i1) || ((i + 1) / g.n_tiles != mt);
+        const int as = acc_it & 1;
+        mbar_wait(&B->tmem_empty[as], (uint32_t)(((acc_it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + (uint32_t)(as * TBN);
+        for (int kb = 0; kb < 4; ++kb) {
+          if (first_of_x) mbar_wait(&B->x_full[kb], (uint32_t)((xit - 1) & 1));
+          mbar_wait(&B->w_full[ws], wphase);
+          tc_fence_after();
+          const uint64_t xh = umma_desc_sw128(sbase_u + (2 * kb) * TILE_BYTES);
+          const uint64_t xl = umma_desc_sw128(sbase_u + (2 * kb + 1) * TILE_BYTES);
+          const uint64_t wh = umma_desc_sw128(sbase_u + CP_OFF_W + ws * CP2_W_STAGE);
+          const uint64_t wl = umma_desc_sw128(sbase_u + CP_OFF_W + ws * CP2_W_STAGE + TILE_BYTES / 2);
+          if (tc_elect()) {
+#pragma unroll
+            for (int k = 0; k < TBK / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+              cp2_mma(d_tmem, xl + adv, wh + adv, idesc, (kb | k) != 0);
+              cp2_mma(d_tmem, xh + adv, wl + adv, idesc, 1);
+              cp2_mma(d_tmem, xh + adv, wh + adv, idesc, 1);
+            }
+            cp2_commit(&B->w_empty[ws]);
+            if (last_of_x) cp2_commit(&B->x_free[kb]);
+            if (kb == 3) cp2_commit(&B->tmem_full[as]);
+          }
+          __syncwarp();
+          if (++ws == CP2_WSTAGES) { ws = 0; wphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // epilogue: as in the 1-CTA kernel; the accumulator stage is released on the LEADER's barrier
+    const int q = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const size_t M = (size_t)g.nclips * g.mclip;
+    int acc_it = 0;
+    for (int i = i0; i < i1; ++i, ++acc_it) {
+      const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+      const int mt = mtg * 2 + crank;
+      const size_t tile_base = ((size_t)mt * 8 + q * 2) * 1024;
+      const int as = acc_it & 1;
+      mbar_wait(&B->tmem_full[as], (uint32_t)((acc_it >> 1) & 1));
+      tc_fence_after();
+      const int n_plane0 = nt * TBN + colhalf * 64;
+      if (n_plane0 < g.N) {
+        float* plane = g.out + (size_t)(n_plane0 >> 6) * M * 64 + tile_base;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TBN + colhalf * 64 + h * 32), v);
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n_plane0 + h * 32);
+          float4* dst = reinterpret_cast<float4*>(plane + h * 1024) + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            dst[j * 32] = make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&B->tmem_empty[as]);
+        else cp2_arrive_remote(cp2_mapa(smem_u32(&B->tmem_empty[as]), 0));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  // do not exit (or free TMEM) while the peer's MMAs / TMA may still touch this CTA
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -845,12 +1072,8 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
     NSW_TRY(make_map(enc, &mwh, Bt_hi, 2, dims, strides, box));
     NSW_TRY(make_map(enc, &mwl, Bt_lo, 2, dims, strides, box));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSW_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)TC_SMEM_BYTES));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};  // per device (the attribute is per device)
+  NSW_TRY(ensure_dynamic_smem((const void*)conv_gemm_tc_kernel, (int)TC_SMEM_BYTES, attr_done));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -898,12 +1121,8 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
     NSW_TRY(make_map(enc, &mwh2, Bt_hi, 2, dims, strides, box));
     NSW_TRY(make_map(enc, &mwl2, Bt_lo, 2, dims, strides, box));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSW_CUDA(cudaFuncSetAttribute(cond_proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)CP_SMEM_BYTES));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};  // per device (the attribute is per device)
+  NSW_TRY(ensure_dynamic_smem((const void*)cond_proj_tc_kernel, (int)CP_SMEM_BYTES, attr_done));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -917,9 +1136,32 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
   const long long items = (long long)nclips * g.tiles_per_clip * g.n_tiles;
   g.bias = bias;
   g.out = out_tiled;
+  g.exp = getenv("NSW_COND_EXP") ? atoi(getenv("NSW_COND_EXP")) : 0;
   const bool pair = getenv("NSW_COND_NOCLUSTER") == nullptr && (nclips * g.tiles_per_clip) % 2 == 0 && sms >= 2;
   g.cluster = pair ? 2 : 1;
-  if (pair) {
+  // cta_group::2 MMAs (cond_proj_tc2_kernel) by default; NSW_COND_1CTA=1 keeps the pair kernel with 1-CTA MMAs
+  const bool two = pair && getenv("NSW_COND_1CTA") == nullptr && g.exp == 0;
+  if (two) {
+    static std::atomic<uint64_t> attr2_done{0};
+    NSW_TRY(ensure_dynamic_smem((const void*)cond_proj_tc2_kernel, (int)CP2_SMEM_BYTES, attr2_done));
+    const long long pair_items = items / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms & ~1);
+    cfg.blockDim = dim3(CP_THREADS);
+    cfg.dynamicSmemBytes = CP2_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, cond_proj_tc2_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+    cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(pair_items, std::min(n, sms / 2)));
+    NSW_CUDA(cudaLaunchKernelEx(&cfg, cond_proj_tc2_kernel, mxh, mxl, mwh2, mwl2, g));
+  } else if (pair) {
     const long long pair_items = items / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(sms & ~1);

@@ -1046,12 +1046,8 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
                    const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
                    unsigned int* sync_words /* >= nclips*T/128 + num_sms */, int num_sms, const FlowHead* head,
                    const FlowStart* start, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSW_CUDA(cudaFuncSetAttribute(iaf_flow_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)FT_SMEM_BYTES));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};  // per device (the attribute is per device)
+  NSW_TRY(ensure_dynamic_smem((const void*)iaf_flow_tc_kernel, (int)FT_SMEM_BYTES, attr_done));
   NSW_CHECK(T % BM == 0, NSW_EINVAL, "flow_tc: T=%d must be a multiple of %d", T, BM);
   NSW_CHECK(l1 > l0 && nclips >= 1, NSW_EINVAL, "flow_tc: empty layer or clip range");
   const int tiles = T / BM;
@@ -1099,10 +1095,14 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
   p.start_b = start ? start->b : nullptr;
   p.dbg = nullptr;
   p.dbg_cta = getenv("NSW_LAYER_DEBUG_CTA") ? atoi(getenv("NSW_LAYER_DEBUG_CTA")) : 0;
-  static long long* dbg_buf = nullptr;
+  static long long* dbg_bufs[64] = {nullptr};  // NSW_LAYER_DEBUG only: one buffer per device
   const bool want_dbg = getenv("NSW_LAYER_DEBUG") != nullptr;
+  long long* dbg_buf = nullptr;
   if (want_dbg) {
-    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
+    int dbg_dev = 0;
+    NSW_CUDA(cudaGetDevice(&dbg_dev));
+    if (!dbg_bufs[dbg_dev & 63]) NSW_CUDA(cudaMalloc(&dbg_bufs[dbg_dev & 63], 256 * sizeof(long long)));
+    dbg_buf = dbg_bufs[dbg_dev & 63];
     NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), stream));
     p.dbg = dbg_buf;
   }

@@ -674,12 +674,8 @@ int layer_tc_launch(const void* const map_act[2][2], const void* map_wdh, const 
                     __half* const hi[2], __half* const lo[2], const float* br, int T, int rows, int buf0,
                     int l0, int l1, int num_stages, unsigned int* grid_counter, int num_sms,
                     cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSW_CUDA(cudaFuncSetAttribute(iaf_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)LT_SMEM_BYTES));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};  // per device (the attribute is per device)
+  NSW_TRY(ensure_dynamic_smem((const void*)iaf_layer_tc_kernel, (int)LT_SMEM_BYTES, attr_done));
   NSW_CHECK(T % LT_BM == 0, NSW_EINVAL, "layer_tc: T=%d must be a multiple of %d", T, LT_BM);
   NSW_CHECK(l1 > l0, NSW_EINVAL, "layer_tc: empty layer range");
   LayerTcParams p;

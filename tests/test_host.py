@@ -119,3 +119,67 @@ def test_engine_fold_weight_norm_matches_oracle():
     assert set(a) == set(b) == {'x/W', 'y/kernel'}
     for k in a:
         assert np.allclose(a[k], b[k])
+
+
+def test_load_audio_sample_formats(tmp_path):
+    """utils.load_audio (utils.py:55-69 goes through librosa / soundfile): int16, int32, uint8 (offset 128) and
+    float32 wavs of the same signal load to the same [-1, 1) floats."""
+    x = np.sin(np.arange(400) / 7.0) * 0.5
+    p16, p32, p8, pf = (str(tmp_path / n) for n in ('a16.wav', 'a32.wav', 'a8.wav', 'af.wav'))
+    wavfile.write(p16, 16000, np.round(x * 32767).astype(np.int16))
+    wavfile.write(p32, 16000, np.round(x * (2 ** 31 - 1)).astype(np.int32))
+    wavfile.write(p8, 16000, np.round(x * 127 + 128).astype(np.uint8))
+    wavfile.write(pf, 16000, x.astype(np.float32))
+    ref = utils.load_audio(pf, -1)
+    assert ref.dtype == np.float32 and np.abs(ref - x).max() < 1e-6
+    assert np.abs(utils.load_audio(p16, -1) - x).max() < 1e-4
+    assert np.abs(utils.load_audio(p32, -1) - x).max() < 1e-6
+    a8 = utils.load_audio(p8, -1)
+    assert np.abs(a8 - x).max() < 1.0 / 128 and abs(a8.mean()) < 0.01     # no DC offset of +1
+    assert len(utils.load_audio(p16, 100)) == 100
+    with pytest.raises(ValueError, match='sample rate'):
+        wavfile.write(str(tmp_path / 'r.wav'), 22050, x.astype(np.float32))
+        utils.load_audio(str(tmp_path / 'r.wav'))
+
+
+def test_weights_init_matches_the_test_side_generator():
+    """nsynth_wavenet_b200.weights_init (bench.py / smoke use it) draws the same tensors as the oracle's initialiser,
+    for the student, the MoL teacher and the double-gate CE teacher."""
+    from oracle import wavenet_oracle as O
+    from nsynth_wavenet_b200 import weights_init as WI
+    from conftest import load_hparams
+    for cfg, a, b in (('parallel_wavenet.json', WI.init_student_weights, O.init_student_weights),
+                      ('parallel_wavenet_gauss.json', WI.init_student_weights, O.init_student_weights),
+                      ('wavenet_mol.json', WI.init_teacher_weights, O.init_teacher_weights),
+                      ('wavenet_ce.json', WI.init_teacher_weights, O.init_teacher_weights)):
+        hp = load_hparams(cfg)
+        if cfg == 'wavenet_ce.json':
+            hp = Namespace(**{**vars(hp), 'num_layers': 2})
+        wa, wb = a(hp, seed=7, bias_std=0.01), b(hp, seed=7, bias_std=0.01)
+        assert set(wa) == set(wb)
+        assert all(np.array_equal(wa[k], wb[k]) for k in wa), cfg
+
+
+def test_engine_cache_key_follows_the_checkpoint_file(tmp_path, monkeypatch):
+    """checkpoint.cached_engine: same checkpoint -> same engine object; rewritten checkpoint -> a new one."""
+    made = []
+
+    class Fake:
+        def __init__(self, hp, weights, **kw):
+            self._h, self.w = 1, weights
+            made.append(self)
+
+        def close(self):
+            self._h = None
+    hp = Namespace(a=1)
+    p = ckpt.save_weights(str(tmp_path / 'm'), {'x/W': np.ones(3, np.float32)})
+    e1 = ckpt.cached_engine(Fake, 'iaf', hp, p, device=0)
+    e2 = ckpt.cached_engine(Fake, 'iaf', hp, p, device=0)
+    assert e1 is e2 and len(made) == 1
+    assert ckpt.cached_engine(Fake, 'iaf', Namespace(a=2), p, device=0) is not e1      # other hparams
+    os.utime(p, (1, 1))
+    ckpt.save_weights(str(tmp_path / 'm'), {'x/W': np.zeros(3, np.float32)})
+    e3 = ckpt.cached_engine(Fake, 'iaf', hp, p, device=0)
+    assert e3 is not e1 and e1._h is None and e3.w['x/W'].sum() == 0
+    ckpt.clear_engine_cache()
+    assert e3._h is None
