@@ -237,6 +237,7 @@ struct GnSmem {
   // bound: rows x K x 4 B x BT = 147 - 360 KB per phase at BT = 8)
   float pf[12][64];          // fresh stage: [slice warp][row * BT + b] (+ 4 * BT for the skip rows)
   float pp[8][64];           // past taps:   [tap * 4 + slice][row * BT + b]
+  float pvc[64];             // past taps + conditioning (+ every folded bias) per (row, b), summed off the critical path
   float cnd[8][BT];
   float lst[4][BT];          // owned residual channels 4c..4c+3
   float sst[2][BT];          // owned skip channels 2c, 2c+1
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
                 OFF_C = OFF_S + 2 * W, BF = OFF_C + 16;
   constexpr int NFM = MH / 128;
   constexpr int COMM = NT / 32 - 1;
-  static_assert(4 + 2 * NFM <= COMM, "slice warps and the comm warp must not overlap");
+  static_assert(4 + 2 * NFM <= COMM - 1, "slice warps, the past-sum warp and the comm warp must not overlap");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using Smem = GnSmem<MH, BT>;
   Smem& Sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -611,6 +612,16 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
       }
       __syncthreads();  // S1: past taps done (hv is free), cnd / pv staged; the comm lane has seen the grid barrier
       lap(0);
+      if (warp == COMM - 1 && ph <= L) {
+        // while the fresh inputs are in flight: past-tap partials of the 8 slice warps + conditioning -> one value per
+        // (row, b), so that the epilogue on the critical path adds a single term
+        for (int idx = lane; idx < nD * BT; idx += 32) {
+          float a = Sm.cnd[idx / BT][idx % BT];
+          if (ok2) a += (Sm.pp[0][idx] + Sm.pp[1][idx]) + (Sm.pp[2][idx] + Sm.pp[3][idx]);
+          if (ok1) a += (Sm.pp[4][idx] + Sm.pp[5][idx]) + (Sm.pp[6][idx] + Sm.pp[7][idx]);
+          Sm.pvc[idx] = a;
+        }
+      }
       if (comm && !last_phase) {
         // history taps of the next phase with a dilated conv (phase 1 of the next step after the head phases)
         if (ph < L) issue_hist(ph + 1, t, Sm.pos[ph + 1]);
@@ -668,21 +679,21 @@ __global__ void __launch_bounds__(GN_NT, 1) fastgen_gn_kernel(GnParams P) {
       __syncthreads();  // S2
       lap(2);
       // ---------------- epilogues: one thread per (row, batch row) ----------------
-      auto sum_pf = [&](int w0, int w1, int idx) {
-        float a = 0.f;
-        for (int w = w0; w < w1; ++w) a += Sm.pf[w][idx];
-        return a;
+      auto sum_pf = [&](int w0, int w1, int idx) {  // two chains, fixed trip count: the loads issue together
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 12; w += 2) {
+          if (w >= w0 && w < w1) a0 += Sm.pf[w][idx];
+          if (w + 1 >= w0 && w + 1 < w1) a1 += Sm.pf[w + 1][idx];
+        }
+        return a0 + a1;
       };
       if (ph <= L) {
         const int dw = ph == 1 ? 4 : 4 + NFM;  // slice warps holding partials of the dilated-conv rows
         if (tid < PPC * BT) {
           const int pr = tid / BT, b = tid - pr * BT;
-          float a = sum_pf(0, dw, pr * BT + b) + Sm.cnd[pr][b];
-          float q = sum_pf(0, dw, (PPC + pr) * BT + b) + Sm.cnd[PPC + pr][b];
-          if (ok2)
-            for (int w = 0; w < 4; ++w) { a += Sm.pp[w][pr * BT + b]; q += Sm.pp[w][(PPC + pr) * BT + b]; }
-          if (ok1)
-            for (int w = 4; w < 8; ++w) { a += Sm.pp[w][pr * BT + b]; q += Sm.pp[w][(PPC + pr) * BT + b]; }
+          const float a = sum_pf(0, dw, pr * BT + b) + Sm.pvc[pr * BT + b];
+          const float q = sum_pf(0, dw, (PPC + pr) * BT + b) + Sm.pvc[(PPC + pr) * BT + b];
           __stcg(P.gbuf + (size_t)(ph & 1) * BT * MH + (size_t)b * MH + c * PPC + pr, gn_sigmoid(a) * gn_tanh(q));
         } else if (tid >= 64 && tid < 64 + 4 * BT) {
           const int r = (tid - 64) / BT, b = (tid - 64) - r * BT;

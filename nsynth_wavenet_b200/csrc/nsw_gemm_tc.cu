@@ -597,6 +597,10 @@ struct CpBars {
   uint32_t tmem_base;
 };
 
+#ifndef NSW_COND_STAGGER
+#define NSW_COND_STAGGER 1
+#endif
+
 struct CondProj {
   int nclips, mclip, a_off, N;
   int tiles_per_clip, n_tiles;  // n-tiles of 128 columns
@@ -606,6 +610,15 @@ struct CondProj {
   float* out;  // [N/64] planes of nclips*mclip rows, row-interleaved
   int exp;     // TIMING EXPERIMENTS ONLY (NSW_COND_EXP): 1 = no global stores, 2 = no MMAs (results are wrong)
 };
+
+// Column-tile visiting order of m-tile group `mtg`: rotated by a group-dependent offset, so that the CTAs (which all
+// sweep the same 32 weight tiles) are not all asking the same L2 lines for the same tile at the same moment.  A
+// bijection per m-tile group, so the static split of the (m-tile, n-tile) item list still covers every pair once.
+__device__ __forceinline__ int cp_ntile(int k, int mtg, int n_tiles) {
+  if (NSW_COND_STAGGER == 0) return k;
+  int nt = k + (mtg * 13) % n_tiles;
+  return nt >= n_tiles ? nt - n_tiles : nt;
+}
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                                uint16_t cta_mask) {
@@ -678,7 +691,7 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
       uint32_t wphase = 0;
       int xit = 0, cur_mt = -1;
       for (int i = i0; i < i1; ++i) {
-        const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+        const int mtg = i / g.n_tiles, nt = cp_ntile(i - mtg * g.n_tiles, mtg, g.n_tiles);
         const int mt = mtg * CS + crank;
         const bool new_x = mt != cur_mt;
         int clip = 0, m0 = 0;
@@ -767,7 +780,7 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
     const size_t M = (size_t)g.nclips * g.mclip;
     int acc_it = 0;
     for (int i = i0; i < i1; ++i, ++acc_it) {
-      const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+      const int mtg = i / g.n_tiles, nt = cp_ntile(i - mtg * g.n_tiles, mtg, g.n_tiles);
       const int mt = mtg * CS + crank;
       const size_t tile_base = ((size_t)mt * 8 + q * 2) * 1024;  // + h * 1024 + j * 128 + lane * 4
       const int as = acc_it & 1;
@@ -908,7 +921,7 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
       uint32_t wphase = 0;
       int xit = 0, cur_mt = -1;
       for (int i = i0; i < i1; ++i) {
-        const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+        const int mtg = i / g.n_tiles, nt = cp_ntile(i - mtg * g.n_tiles, mtg, g.n_tiles);
         const int mt = mtg * 2 + crank;
         const bool new_x = mt != cur_mt;
         int clip = 0, m0 = 0;
@@ -990,7 +1003,7 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
     const size_t M = (size_t)g.nclips * g.mclip;
     int acc_it = 0;
     for (int i = i0; i < i1; ++i, ++acc_it) {
-      const int mtg = i / g.n_tiles, nt = i - mtg * g.n_tiles;
+      const int mtg = i / g.n_tiles, nt = cp_ntile(i - mtg * g.n_tiles, mtg, g.n_tiles);
       const int mt = mtg * 2 + crank;
       const size_t tile_base = ((size_t)mt * 8 + q * 2) * 1024;
       const int as = acc_it & 1;
