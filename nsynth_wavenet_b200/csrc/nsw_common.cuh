@@ -100,6 +100,7 @@ int range_check(const char* who);
 //   out[o] = sum_q x[m-q] * K[r + q*s],  o + p = m*s + r   (masked.py:235-291)
 struct DeconvGeom {
   int k, s, cin, cout, ntaps, p;
+  int a_off;  // first input frame of GEMM row m is m + a_off
   int mclip(int L) const { return (s * L - 1 + p) / s + 1; }  // GEMM rows per clip
 };
 

@@ -146,29 +146,63 @@ int DeconvStack::init(const TensorMap& tm, const std::string& prefix, int num_me
     g.s = stride[i];
     g.cin = cin;
     g.cout = width;
-    NSW_CHECK(g.s > 0 && g.k % g.s == 0 && g.k >= g.s, NSW_EINVAL,
-              "deconv layer %d: filter %d must be a multiple of stride %d", i + 1, g.k, g.s);
-    NSW_CHECK(g.cin % 4 == 0 && g.cout % 64 == 0 && (g.k / g.s * g.cin) % 16 == 0, NSW_EINVAL,
-              "deconv layer %d: unsupported channel counts %d -> %d", i + 1, g.cin, g.cout);
-    g.ntaps = g.k / g.s;
-    g.p = (g.k - g.s) / 2;  // TF conv2d_transpose SAME: left pad of the forward conv
+    NSW_CHECK(g.s > 0 && g.k >= 1, NSW_EINVAL, "deconv layer %d: bad filter %d / stride %d", i + 1, g.k, g.s);
     total_stride *= g.s;
-    const std::string base = prefix + "trans_conv_" + std::to_string(i + 1);
-    const float* kern = tm.get(base + "/kernel", (int64_t)g.k * g.cout * g.cin);  // [1,k,cout,cin]
-    const float* bias = tm.get(base + "/bias", g.cout);
-    if (!kern || !bias) return NSW_EMISSING;
-    const int K = g.ntaps * g.cin, N = g.s * g.cout;
-    std::vector<float> bw((size_t)K * N);
-    for (int tp = 0; tp < g.ntaps; ++tp) {
-      const int q = g.ntaps - 1 - tp;  // X frame m-q  <->  A tap index tp (a_off = -(ntaps-1))
-      for (int c = 0; c < g.cin; ++c)
-        for (int r = 0; r < g.s; ++r) {
-          const int j = r + q * g.s;
-          for (int co = 0; co < g.cout; ++co)
-            bw[(size_t)(tp * g.cin + c) * N + r * g.cout + co] =
-                kern[((size_t)j * g.cout + co) * g.cin + c];
+    // which upsampler the checkpoint holds decides: resize_conv_i/{W,biases} (use_resize_conv, wavenet.py:37-39) or
+    // trans_conv_i/{kernel,bias}
+    const std::string rbase = prefix + "resize_conv_" + std::to_string(i + 1);
+    const bool resize = tm.has(rbase + "/W");
+    const float* bias = nullptr;
+    std::vector<float> bw;
+    if (resize) {
+      // masked.resize_conv1d (masked.py:294-322): nearest-neighbour upsampling by s (x_up[u] = x[u / s]), then a
+      // non-causal SAME conv of length k: y[o] = b + sum_j x_up[o + j - pl] W[j], pl = (k - 1) / 2.  For output phase
+      // r = o mod s the taps that fall on input frame m + q add up to ONE effective kernel, so the layer is the same
+      // conv-GEMM as the transposed conv: frames m + qmin .. m + qmax against phase-folded weights.
+      const int pl = (g.k - 1) / 2;
+      auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+      const int qmin = fdiv(-pl, g.s), qmax = fdiv(g.s - 1 + g.k - 1 - pl, g.s);
+      g.ntaps = qmax - qmin + 1;
+      g.a_off = qmin;
+      g.p = 0;
+      const float* w = tm.get(rbase + "/W", (int64_t)g.k * g.cin * g.cout);  // [1,k,cin,cout]
+      bias = tm.get(rbase + "/biases", g.cout);
+      if (!w || !bias) return NSW_EMISSING;
+      const int N = g.s * g.cout;
+      bw.assign((size_t)g.ntaps * g.cin * N, 0.f);
+      for (int r = 0; r < g.s; ++r)
+        for (int j = 0; j < g.k; ++j) {
+          const int tp = fdiv(r + j - pl, g.s) - qmin;
+          for (int c = 0; c < g.cin; ++c)
+            for (int co = 0; co < g.cout; ++co)
+              bw[(size_t)(tp * g.cin + c) * N + r * g.cout + co] += w[((size_t)j * g.cin + c) * g.cout + co];
         }
+    } else {
+      NSW_CHECK(g.k % g.s == 0 && g.k >= g.s, NSW_EINVAL,
+                "deconv layer %d: filter %d must be a multiple of stride %d", i + 1, g.k, g.s);
+      g.ntaps = g.k / g.s;
+      g.a_off = -(g.ntaps - 1);
+      g.p = (g.k - g.s) / 2;  // TF conv2d_transpose SAME: left pad of the forward conv
+      const std::string base = prefix + "trans_conv_" + std::to_string(i + 1);
+      const float* kern = tm.get(base + "/kernel", (int64_t)g.k * g.cout * g.cin);  // [1,k,cout,cin]
+      bias = tm.get(base + "/bias", g.cout);
+      if (!kern || !bias) return NSW_EMISSING;
+      const int N = g.s * g.cout;
+      bw.resize((size_t)g.ntaps * g.cin * N);
+      for (int tp = 0; tp < g.ntaps; ++tp) {
+        const int q = g.ntaps - 1 - tp;  // X frame m-q  <->  A tap index tp (a_off = -(ntaps-1))
+        for (int c = 0; c < g.cin; ++c)
+          for (int r = 0; r < g.s; ++r) {
+            const int j = r + q * g.s;
+            for (int co = 0; co < g.cout; ++co)
+              bw[(size_t)(tp * g.cin + c) * N + r * g.cout + co] =
+                  kern[((size_t)j * g.cout + co) * g.cin + c];
+          }
+      }
     }
+    NSW_CHECK(g.cin % 4 == 0 && g.cout % 64 == 0 && (g.ntaps * g.cin) % 16 == 0, NSW_EINVAL,
+              "deconv layer %d: unsupported channel counts %d -> %d", i + 1, g.cin, g.cout);
+    const int K = g.ntaps * g.cin, N = g.s * g.cout;
     NSW_TRY(upload(L.Bw, bw.data(), bw.size() * sizeof(float)));
     NSW_TRY(upload(L.bias, bias, g.cout * sizeof(float)));
     if (want_tc) {
@@ -215,7 +249,7 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __hal
     g.L = L;
     g.cin = dg.cin;
     g.ntaps = dg.ntaps;
-    g.a_off = -(dg.ntaps - 1);
+    g.a_off = dg.a_off;
     g.mclip = dg.mclip(L);
     g.N = dg.s * dg.cout;
     EpiParams e{};

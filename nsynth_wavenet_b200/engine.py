@@ -49,9 +49,8 @@ def iaf_config(hp, num_mel=80, engine=None):
     cfg.upsample_act = L.ACT[_get(hp, 'upsample_act', 'tanh')]
     cfg.use_mu_law = int(bool(hp.use_mu_law))
     cfg.engine = L.ENGINE[engine or default_engine()]
-    if _get(hp, 'use_resize_conv', False):
-        raise NotImplementedError('use_resize_conv is not used by any shipped config '
-                                  '(masked.py:294-322) and is not on the B200 path')
+    # use_resize_conv (masked.py:294-322) needs no flag: the library picks the upsampler from the variable names it is
+    # given (resize_conv_i/{W,biases} or trans_conv_i/{kernel,bias})
     return cfg
 
 
@@ -78,8 +77,6 @@ def wavenet_config(hp, num_mel=80, engine=None):
     cfg.upsample_act = L.ACT[_get(hp, 'upsample_act', 'tanh')]
     cfg.use_mu_law = int(use_mu_law)
     cfg.engine = L.ENGINE[engine or default_engine()]
-    if _get(hp, 'use_resize_conv', False):
-        raise NotImplementedError('use_resize_conv is not on the B200 path')
     return cfg
 
 

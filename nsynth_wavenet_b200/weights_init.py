@@ -24,9 +24,14 @@ def _conv(w, rng, name, k, cin, cout, std, bias_init=0.0):
 def _deconv(w, rng, prefix, hp, num_mel, std):
     cin = num_mel
     for i, (fl, _stride) in enumerate(hp.deconv_config):
-        base = '{}trans_conv_{:d}'.format(prefix, i + 1)
-        w[base + '/kernel'] = rng.normal(0.0, std, size=(1, fl, hp.deconv_width, cin)).astype(np.float32)
-        w[base + '/bias'] = np.zeros((hp.deconv_width,), np.float32)
+        if _get(hp, 'use_resize_conv', False):      # masked.resize_conv1d -> conv1d variables (masked.py:294-322)
+            base = '{}resize_conv_{:d}'.format(prefix, i + 1)
+            w[base + '/W'] = rng.normal(0.0, std, size=(1, fl, cin, hp.deconv_width)).astype(np.float32)
+            w[base + '/biases'] = np.zeros((hp.deconv_width,), np.float32)
+        else:
+            base = '{}trans_conv_{:d}'.format(prefix, i + 1)
+            w[base + '/kernel'] = rng.normal(0.0, std, size=(1, fl, hp.deconv_width, cin)).astype(np.float32)
+            w[base + '/bias'] = np.zeros((hp.deconv_width,), np.float32)
         cin = hp.deconv_width
 
 

@@ -93,10 +93,15 @@ def _conv_vars(w, rng, name, k, cin, cout, bias_init=0.0, std=0.05):
 def _deconv_vars(w, rng, prefix, hp, num_mel, std=0.05):
     cin = num_mel
     for i, (fl, s) in enumerate(hp.deconv_config):
-        base = '{}trans_conv_{:d}'.format(prefix, i + 1)
-        w[base + '/kernel'] = rng.normal(
-            0.0, std, size=(1, fl, hp.deconv_width, cin)).astype(np.float32)
-        w[base + '/bias'] = np.zeros((hp.deconv_width,), np.float32)
+        if _get(hp, 'use_resize_conv', False):   # masked.resize_conv1d creates conv1d variables (masked.py:309-318)
+            base = '{}resize_conv_{:d}'.format(prefix, i + 1)
+            w[base + '/W'] = rng.normal(0.0, std, size=(1, fl, cin, hp.deconv_width)).astype(np.float32)
+            w[base + '/biases'] = np.zeros((hp.deconv_width,), np.float32)
+        else:
+            base = '{}trans_conv_{:d}'.format(prefix, i + 1)
+            w[base + '/kernel'] = rng.normal(
+                0.0, std, size=(1, fl, hp.deconv_width, cin)).astype(np.float32)
+            w[base + '/bias'] = np.zeros((hp.deconv_width,), np.float32)
         cin = hp.deconv_width
 
 
@@ -253,14 +258,33 @@ def trans_conv1d(x, K, b, stride, act=None):
     return y
 
 
+def resize_conv1d(x, W, b, stride, act=None):
+    """masked.resize_conv1d (masked.py:294-322): tf.image.resize_nearest_neighbor to length L*stride
+    (x_up[u] = x[u // stride]), then masked.conv1d(causal=False): tf.nn.conv2d with SAME padding, stride 1, i.e.
+    y[o] = b + sum_j x_up[o + j - (k-1)//2] W[0,j] with zeros outside; then the activation."""
+    B, L, cin = x.shape
+    k = W.shape[1]
+    up = np.repeat(x, stride, axis=1)
+    pl = (k - 1) // 2
+    padded = np.concatenate([np.zeros((B, pl, cin), x.dtype), up, np.zeros((B, k - 1 - pl, cin), x.dtype)], axis=1)
+    y = np.zeros((B, L * stride, W.shape[3]), x.dtype)
+    for j in range(k):
+        y += padded[:, j:j + L * stride] @ W[0, j].astype(x.dtype)
+    y = y + b.astype(x.dtype)
+    return act(y) if act is not None else y
+
+
 def deconv_stack(mel, w, hp, prefix='', dtype=np.float32):
-    """wavenet._deconv_stack (wavenet.py:46-73) with trans_conv1d layers."""
-    assert not _get(hp, 'use_resize_conv', False), 'resize_conv path not on the hot path'
+    """wavenet._deconv_stack (wavenet.py:46-73): trans_conv1d layers, or resize_conv1d with use_resize_conv."""
     act = upsample_act(_get(hp, 'upsample_act', 'tanh'))
     x = mel.astype(dtype)
     for i, (fl, s) in enumerate(hp.deconv_config):
-        base = '{}trans_conv_{:d}'.format(prefix, i + 1)
-        x = trans_conv1d(x, w[base + '/kernel'], w[base + '/bias'], s, act)
+        if _get(hp, 'use_resize_conv', False):
+            base = '{}resize_conv_{:d}'.format(prefix, i + 1)
+            x = resize_conv1d(x, w[base + '/W'], w[base + '/biases'], s, act)
+        else:
+            base = '{}trans_conv_{:d}'.format(prefix, i + 1)
+            x = trans_conv1d(x, w[base + '/kernel'], w[base + '/bias'], s, act)
     return x
 
 

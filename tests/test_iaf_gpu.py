@@ -192,3 +192,28 @@ def test_parallelgen_synthesis_from_a_tf_bundle_directory(student_hp, tmp_path):
     parallelgen.synthesis(student_hp, mel, pb, npz, seed=3)
     for x, y in zip(pa, pb):
         assert np.array_equal(wavfile.read(x)[1], wavfile.read(y)[1])
+
+
+@pytest.mark.parametrize('engine', ['ffma', 'tc3'])
+def test_resize_conv_upsampler_matches_oracle(student_hp, engine):
+    """use_resize_conv (masked.resize_conv1d, masked.py:294-322; wavenet.py:37-39): nearest-neighbour upsampling + SAME
+    conv instead of the transposed conv, selected by the variable names of the checkpoint (resize_conv_i/{W,biases}).
+    Deconv output and the whole IAF forward against the oracle."""
+    from argparse import Namespace
+    from nsynth_wavenet_b200 import IAFEngine
+    hp = Namespace(**{**vars(student_hp), 'use_resize_conv': True})
+    w = O.init_student_weights(hp, seed=321, bias_std=0.02)
+    assert 'iaf_share/resize_conv_2/W' in w
+    eng = IAFEngine(hp, w, device=0, engine=engine)
+    rng = np.random.default_rng(6)
+    for B, F in ((1, 1), (2, 3), (1, 7)):
+        mel = rng.uniform(0, 1, (B, F, 80)).astype(np.float32)
+        ref = O.deconv_stack(mel, w, hp, 'iaf_share/', np.float64)
+        got = eng.deconv_device(torch.from_numpy(mel).cuda()).cpu().numpy()
+        assert got.shape == ref.shape == (B, F * 200, 256)
+        assert np.abs(got - ref).max() < TOL_FP32, (B, F, np.abs(got - ref).max())
+    mel, z = synth_inputs(hp, 2, 6)
+    ref = O.student_feed_forward(w, hp, mel, z, np.float64)
+    out = eng.forward_host(mel, z, quantize=False, want=('x',) + KEYS)
+    for k in KEYS + ('x',):
+        assert np.abs(out[k] - ref[k]).max() < (TOL_FP32 if engine == 'ffma' else TOL), k

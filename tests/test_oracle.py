@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/wavenet_oracle.py) against everything the reference's own
 tests pin for the generation path and against independent torch ops."""
 import os
+from argparse import Namespace
 
 import numpy as np
 import pytest
@@ -275,3 +276,32 @@ def test_power_loss_stft_oracle_is_the_documented_framing():
     d = (np.abs(MO.tf_stft(a[:, 32:32 + 1536])) - np.abs(MO.tf_stft(b))) ** 2
     assert abs(pl - (0.5 * d.mean() + 0.5 * d[:, :, :MO.PRIORITY_FREQ].mean())) < 1e-12
     assert MO.PRIORITY_FREQ == 384 and MO.power_loss(a, a) == 0.0
+
+
+def test_resize_conv_oracle_equals_nearest_upsampling_plus_same_conv():
+    """oracle.resize_conv1d (masked.resize_conv1d, masked.py:294-322) against torch: nearest-neighbour interpolation to
+    L*stride followed by a stride-1 convolution with TensorFlow's SAME padding ((k-1)//2 zeros on the left, the rest on
+    the right) -- for an even filter length the padding is asymmetric, which is what this pins."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(9)
+    for (k, s, cin, cout, L) in ((40, 10, 8, 6, 5), (80, 20, 6, 4, 3), (5, 3, 4, 4, 7), (4, 2, 4, 4, 6)):
+        x = rng.standard_normal((2, L, cin))
+        W = rng.standard_normal((1, k, cin, cout))
+        b = rng.standard_normal(cout)
+        got = O.resize_conv1d(x, W, b, s, None)
+        xt = torch.from_numpy(x).permute(0, 2, 1)                        # [B, C, L]
+        up = F.interpolate(xt, scale_factor=s, mode='nearest')
+        pl = (k - 1) // 2
+        up = F.pad(up, (pl, k - 1 - pl))
+        wt = torch.from_numpy(W[0]).permute(2, 1, 0)                     # [cout, cin, k]
+        ref = F.conv1d(up, wt, torch.from_numpy(b)).permute(0, 2, 1).numpy()
+        assert got.shape == (2, L * s, cout)
+        assert np.abs(got - ref).max() < 1e-10, (k, s)
+    hp = Namespace(deconv_config=[[40, 10], [80, 20]], deconv_width=256, use_resize_conv=True, upsample_act='leaky_relu',
+                   width=512, skip_width=256, filter_length=3, num_layers=2, num_stages=2, use_mu_law=False,
+                   loss_type='mol', mol_mix=10, double_gate_width=False)
+    w = O.init_teacher_weights(hp, seed=3)
+    assert 'resize_conv_1/W' in w and w['resize_conv_1/W'].shape == (1, 40, 80, 256) and 'trans_conv_1/kernel' not in w
+    enc = O.deconv_stack(rng.uniform(0, 1, (1, 3, 80)), w, hp, '', np.float64)
+    assert enc.shape == (1, 600, 256)
