@@ -169,14 +169,16 @@ int DeconvStack::init(const TensorMap& tm, const std::string& prefix, int num_me
       bias = tm.get(rbase + "/biases", g.cout);
       if (!w || !bias) return NSW_EMISSING;
       const int N = g.s * g.cout;
-      bw.assign((size_t)g.ntaps * g.cin * N, 0.f);
+      std::vector<double> acc((size_t)g.ntaps * g.cin * N, 0.0);  // up to s taps fold into one weight: sum in fp64
       for (int r = 0; r < g.s; ++r)
         for (int j = 0; j < g.k; ++j) {
           const int tp = fdiv(r + j - pl, g.s) - qmin;
           for (int c = 0; c < g.cin; ++c)
             for (int co = 0; co < g.cout; ++co)
-              bw[(size_t)(tp * g.cin + c) * N + r * g.cout + co] += w[((size_t)j * g.cin + c) * g.cout + co];
+              acc[(size_t)(tp * g.cin + c) * N + r * g.cout + co] += (double)w[((size_t)j * g.cin + c) * g.cout + co];
         }
+      bw.resize(acc.size());
+      for (size_t q = 0; q < acc.size(); ++q) bw[q] = (float)acc[q];
     } else {
       NSW_CHECK(g.k % g.s == 0 && g.k >= g.s, NSW_EINVAL,
                 "deconv layer %d: filter %d must be a multiple of stride %d", i + 1, g.k, g.s);

@@ -228,3 +228,30 @@ def test_cond_vars_helpers_match_oracle(teacher_hp, tmp_path):
     for name, v in cv.items():
         ref = enc.astype(np.float64) @ w[name + '/W'][0, 0].astype(np.float64) + w[name + '/biases']
         assert v.shape == ref.shape and np.abs(v - ref).max() < 2e-5, name
+
+
+@pytest.mark.timeout(600)
+def test_time_chunked_launches_are_bit_identical_to_one_launch(teacher_hp, monkeypatch):
+    """Long utterances run as several launches of the persistent kernel over time chunks (bounded conditioning buffer):
+    resuming from the history rings, the exchange tags and the three carried input samples must reproduce the single
+    launch bit for bit, across chunk sizes that cut through ring wrap-arounds, free-running and teacher-forced."""
+    monkeypatch.setenv('NSW_FASTGEN_ENGINE', 'latency')
+    hp = teacher_hp
+    eng, w = make_engine(hp)
+    rng = np.random.default_rng(77)
+    T = 700
+    enc = rng.uniform(-1, 1, (2, T, 256)).astype(np.float32)
+    wav = rng.uniform(-0.5, 0.5, (2, T)).astype(np.float32)
+    monkeypatch.delenv('NSW_FASTGEN_CHUNK', raising=False)
+    a0, o0 = eng.run_host(enc, seed=13, want_out=True)
+    _, t0 = eng.run_host(enc, teacher_force=wav, want_out=True)
+    for chunk in ('97', '256', '699', '1'):
+        if chunk == '1':
+            sl = slice(0, 40)      # one launch per sample: keep it short
+        else:
+            sl = slice(0, T)
+        monkeypatch.setenv('NSW_FASTGEN_CHUNK', chunk)
+        a1, o1 = eng.run_host(enc[:, sl], seed=13, want_out=True)
+        _, t1 = eng.run_host(enc[:, sl], teacher_force=wav[:, sl], want_out=True)
+        assert np.array_equal(a0[:, sl], a1) and np.array_equal(o0[:, sl], o1), chunk
+        assert np.array_equal(t0[:, sl], t1), chunk

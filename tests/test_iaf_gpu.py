@@ -211,7 +211,8 @@ def test_resize_conv_upsampler_matches_oracle(student_hp, engine):
         ref = O.deconv_stack(mel, w, hp, 'iaf_share/', np.float64)
         got = eng.deconv_device(torch.from_numpy(mel).cuda()).cpu().numpy()
         assert got.shape == ref.shape == (B, F * 200, 256)
-        assert np.abs(got - ref).max() < TOL_FP32, (B, F, np.abs(got - ref).max())
+        # (a resize conv adds up to 20 copies of the same input: outputs of O(10..40), fp32 rounding scales with them)
+        assert np.abs(got - ref).max() < TOL_FP32 * max(1.0, np.abs(ref).max() / 4), (B, F, np.abs(got - ref).max())
     mel, z = synth_inputs(hp, 2, 6)
     ref = O.student_feed_forward(w, hp, mel, z, np.float64)
     out = eng.forward_host(mel, z, quantize=False, want=('x',) + KEYS)
