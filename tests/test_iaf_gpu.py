@@ -215,6 +215,13 @@ def test_resize_conv_upsampler_matches_oracle(student_hp, engine):
         assert np.abs(got - ref).max() < TOL_FP32 * max(1.0, np.abs(ref).max() / 4), (B, F, np.abs(got - ref).max())
     mel, z = synth_inputs(hp, 2, 6)
     ref = O.student_feed_forward(w, hp, mel, z, np.float64)
+    twin = O.student_feed_forward(w, hp, mel, z, np.float32)
     out = eng.forward_host(mel, z, quantize=False, want=('x',) + KEYS)
     for k in KEYS + ('x',):
-        assert np.abs(out[k] - ref[k]).max() < (TOL_FP32 if engine == 'ffma' else TOL), k
+        # conditioning of O(40) drives the stream and the outputs (|mean_tot| ~ 6, |x| ~ 16) 10x above the transposed-conv
+        # init regime, and rounding with them: the bar is the one of test_trained_regime_gpu.py -- the absolute tolerance,
+        # or 8x what the fp32 twin of the same forward loses against fp64 (1.4e-5 on mean_tot here)
+        err = float(np.abs(out[k] - ref[k]).max())
+        cal = float(np.abs(twin[k].astype(np.float64) - ref[k]).max())
+        tol = TOL_FP32 if engine == 'ffma' else TOL
+        assert err <= max(tol, 8 * cal, tol * np.abs(ref[k]).max() / 4), (k, err, cal)
