@@ -609,6 +609,7 @@ struct CondProj {
   const float* bias;
   float* out;  // [N/64] planes of nclips*mclip rows, row-interleaved
   int exp;     // TIMING EXPERIMENTS ONLY (NSW_COND_EXP): 1 = no global stores, 2 = no MMAs (results are wrong)
+  long long* dbg;  // NSW_COND_DEBUG: where the MMA issuer of pair 0 waited (cycles): accumulator, weights, activations, total
 };
 
 // Column-tile visiting order of m-tile group `mtg`: rotated by a group-dependent offset, so that the CTAs (which all
@@ -831,14 +832,20 @@ cond_proj_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_con
 //   BOTH CTAs (the peer's TMA loads name the leader's barrier); commits are multicast to both CTAs; the peer's
 //   epilogue warps release an accumulator stage with a remote arrive on the leader's tmem_empty barrier.
 // ---------------------------------------------------------------------------------------------
-constexpr int CP2_WSTAGES = 6;
-constexpr uint32_t CP2_W_STAGE = TILE_BYTES;          // per CTA: W hi + lo [64 n x 64 k] = 16 KB
-constexpr uint32_t CP2_OFF_BARS = CP_OFF_W + CP2_WSTAGES * CP2_W_STAGE;
+// TN = columns per work item.  TN = 256 is the shape that takes the SM's shared-memory bandwidth out of the picture: an
+// SS MMA reads its A and B operands from shared memory at 128 B/clk, and per 16-deep k-step a CTA reads
+//   1-CTA, N = 128:  4 KB (A) + 4 KB (B) per  64 tensor cycles = 128 B/clk  (exactly the limit, before the TMA fills)
+//   pair,  N = 128:  4 KB     + 2 KB     per  64               =  96 B/clk
+//   pair,  N = 256:  4 KB     + 4 KB     per 128               =  64 B/clk
+// The two accumulator stages of TN = 256 fill the 512 TMEM columns.
+constexpr uint32_t CP2_W_BYTES = 6 * TILE_BYTES;      // weight ring: 96 KB next to the 128 KB activation tile
+constexpr int CP2_MAX_STAGES = 6;
+constexpr uint32_t CP2_OFF_BARS = CP_OFF_W + CP2_W_BYTES;
 constexpr size_t CP2_SMEM_BYTES = CP2_OFF_BARS + 1024 + 1024;
 
 struct Cp2Bars {
   uint64_t x_full[4], x_free[4];
-  uint64_t w_full[CP2_WSTAGES], w_empty[CP2_WSTAGES];
+  uint64_t w_full[CP2_MAX_STAGES], w_empty[CP2_MAX_STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
@@ -882,26 +889,37 @@ __device__ __forceinline__ void cp2_arrive_remote(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
+template <int TN>
 __global__ void __launch_bounds__(CP_THREADS, 1)
 cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                      const __grid_constant__ CUtensorMap map_wh2, const __grid_constant__ CUtensorMap map_wl2, CondProj g) {
+  // per CTA and stage: TN/2 weight rows x 64 k, hi plane then lo plane
+  constexpr uint32_t W_PLANE = (uint32_t)(TN / 2) * TBK * 2;
+  constexpr uint32_t W_STAGE = 2 * W_PLANE;
+  constexpr int WSTAGES = (int)(CP2_W_BYTES / W_STAGE);
+  constexpr uint32_t TM_COLS = 2 * TN;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   Cp2Bars* B = reinterpret_cast<Cp2Bars*>(smem + CP2_OFF_BARS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g.dbg != nullptr && threadIdx.x == 0) {  // NSW_COND_DEBUG: entry / exit time of every CTA
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g.dbg[8 + 2 * blockIdx.x] = (long long)t;
+  }
   const uint32_t sbase = smem_u32(smem);
   const int crank = (int)(blockIdx.x & 1);
   const bool leader = crank == 0;
   if (threadIdx.x == 0) {
     for (int kb = 0; kb < 4; ++kb) { mbar_init(&B->x_full[kb], 1); mbar_init(&B->x_free[kb], 1); }
-    for (int s = 0; s < CP2_WSTAGES; ++s) { mbar_init(&B->w_full[s], 1); mbar_init(&B->w_empty[s], 1); }
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(&B->w_full[s], 1); mbar_init(&B->w_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&B->tmem_full[a], 1); mbar_init(&B->tmem_empty[a], 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&B->tmem_base)),
-                 "r"(TMEM_COLS)
+                 "r"(TM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -940,25 +958,30 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             cp2_tma_3d(sbase + (2 * kb + 1) * TILE_BYTES, &map_xl, xb, kb * TBK, m0 + g.a_off, clip);
           }
           mbar_wait(&B->w_empty[ws], wphase ^ 1);
-          const uint32_t dst = sbase + CP_OFF_W + ws * CP2_W_STAGE;
-          if (leader) mbar_expect_tx(&B->w_full[ws], 2 * CP2_W_STAGE);
+          const uint32_t dst = sbase + CP_OFF_W + ws * W_STAGE;
+          if (leader) mbar_expect_tx(&B->w_full[ws], 2 * W_STAGE);
           const uint32_t wb = cp2_mapa(smem_u32(&B->w_full[ws]), 0);
-          // this CTA's half of the 128 weight rows, hi then lo plane (8 KB each)
-          cp2_tma_2d(dst, &map_wh2, wb, kb * TBK, nt * TBN + crank * 64);
-          cp2_tma_2d(dst + TILE_BYTES / 2, &map_wl2, wb, kb * TBK, nt * TBN + crank * 64);
-          if (++ws == CP2_WSTAGES) { ws = 0; wphase ^= 1; }
+          // this CTA's half of the TN weight rows, hi then lo plane
+          cp2_tma_2d(dst, &map_wh2, wb, kb * TBK, nt * TN + crank * (TN / 2));
+          cp2_tma_2d(dst + W_PLANE, &map_wl2, wb, kb * TBK, nt * TN + crank * (TN / 2));
+          if (++ws == WSTAGES) { ws = 0; wphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (leader) {
-      // instruction descriptor: D = f32, A = B = f16, K-major, M = 256 (128 per CTA), N = TBN
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      // instruction descriptor: D = f32, A = B = f16, K-major, M = 256 (128 per CTA), N = TN
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
       const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase);
       int ws = 0;
       uint32_t wphase = 0;
       int xit = 0, cur_mt = -1, acc_it = 0;
+      const bool dbg = g.dbg != nullptr && blockIdx.x == 0;
+      long long w_acc = 0, w_x = 0, w_w = 0;
+      const long long t_begin = clock64();
+      unsigned long long ns_begin = 0;
+      if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin));
       for (int i = i0; i < i1; ++i, ++acc_it) {
         const int mt = i / g.n_tiles;
         const bool first_of_x = mt != cur_mt;
@@ -968,17 +991,22 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
         }
         const bool last_of_x = (i + 1 == i1) || ((i + 1) / g.n_tiles != mt);
         const int as = acc_it & 1;
+        long long tw = dbg ? clock64() : 0;
         mbar_wait(&B->tmem_empty[as], (uint32_t)(((acc_it >> 1) & 1) ^ 1));
+        if (dbg) { const long long now = clock64(); w_acc += now - tw; }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_u + (uint32_t)(as * TBN);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(as * TN);
         for (int kb = 0; kb < 4; ++kb) {
+          tw = dbg ? clock64() : 0;
           if (first_of_x) mbar_wait(&B->x_full[kb], (uint32_t)((xit - 1) & 1));
+          if (dbg) { const long long now = clock64(); w_x += now - tw; tw = now; }
           mbar_wait(&B->w_full[ws], wphase);
+          if (dbg) { const long long now = clock64(); w_w += now - tw; }
           tc_fence_after();
           const uint64_t xh = umma_desc_sw128(sbase_u + (2 * kb) * TILE_BYTES);
           const uint64_t xl = umma_desc_sw128(sbase_u + (2 * kb + 1) * TILE_BYTES);
-          const uint64_t wh = umma_desc_sw128(sbase_u + CP_OFF_W + ws * CP2_W_STAGE);
-          const uint64_t wl = umma_desc_sw128(sbase_u + CP_OFF_W + ws * CP2_W_STAGE + TILE_BYTES / 2);
+          const uint64_t wh = umma_desc_sw128(sbase_u + CP_OFF_W + ws * W_STAGE);
+          const uint64_t wl = umma_desc_sw128(sbase_u + CP_OFF_W + ws * W_STAGE + W_PLANE);
           if (tc_elect()) {
 #pragma unroll
             for (int k = 0; k < TBK / 16; ++k) {
@@ -992,14 +1020,22 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             if (kb == 3) cp2_commit(&B->tmem_full[as]);
           }
           __syncwarp();
-          if (++ws == CP2_WSTAGES) { ws = 0; wphase ^= 1; }
+          if (++ws == WSTAGES) { ws = 0; wphase ^= 1; }
         }
+      }
+      if (dbg && lane == 0) {
+        unsigned long long ns_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
+        g.dbg[0] = w_acc; g.dbg[1] = w_w; g.dbg[2] = w_x; g.dbg[3] = clock64() - t_begin; g.dbg[4] = i1 - i0;
+        g.dbg[5] = (long long)(ns_end - ns_begin);
       }
     }
   } else {
-    // epilogue: as in the 1-CTA kernel; the accumulator stage is released on the LEADER's barrier
+    // epilogue: warps w and w+4 share a TMEM lane quarter and take half of the TN columns (TN/128 planes) each; the
+    // accumulator stage is released on the LEADER's barrier
     const int q = warp & 3;
     const int colhalf = (warp - 2) >> 2;
+    constexpr int PLANES = TN / 128;  // planes per warp
     const size_t M = (size_t)g.nclips * g.mclip;
     int acc_it = 0;
     for (int i = i0; i < i1; ++i, ++acc_it) {
@@ -1008,14 +1044,18 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
       const size_t tile_base = ((size_t)mt * 8 + q * 2) * 1024;
       const int as = acc_it & 1;
       mbar_wait(&B->tmem_full[as], (uint32_t)((acc_it >> 1) & 1));
+      const long long te0 = (g.dbg != nullptr && blockIdx.x == 0 && warp == 2) ? clock64() : 0;
       tc_fence_after();
-      const int n_plane0 = nt * TBN + colhalf * 64;
-      if (n_plane0 < g.N) {
+#pragma unroll
+      for (int pl = 0; pl < PLANES; ++pl) {
+        const int col0 = colhalf * (TN / 2) + pl * 64;  // first accumulator column of this plane
+        const int n_plane0 = nt * TN + col0;
+        if (n_plane0 >= g.N) continue;
         float* plane = g.out + (size_t)(n_plane0 >> 6) * M * 64 + tile_base;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TBN + colhalf * 64 + h * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TN + col0 + h * 32), v);
           const float4* b4 = reinterpret_cast<const float4*>(g.bias + n_plane0 + h * 32);
           float4* dst = reinterpret_cast<float4*>(plane + h * 1024) + lane;
 #pragma unroll
@@ -1027,6 +1067,7 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
+      if (te0 != 0 && lane == 0) g.dbg[6] += clock64() - te0;  // NSW_COND_DEBUG: epilogue busy cycles of one warp
       if (lane == 0) {
         if (leader) mbar_arrive(&B->tmem_empty[as]);
         else cp2_arrive_remote(cp2_mapa(smem_u32(&B->tmem_empty[as]), 0));
@@ -1040,7 +1081,12 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TM_COLS) : "memory");
+  }
+  if (g.dbg != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g.dbg[8 + 2 * blockIdx.x + 1] = (long long)t;
   }
 }
 
@@ -1150,14 +1196,26 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
   g.bias = bias;
   g.out = out_tiled;
   g.exp = getenv("NSW_COND_EXP") ? atoi(getenv("NSW_COND_EXP")) : 0;
+  g.dbg = nullptr;
+  static long long* dbg_buf = nullptr;  // NSW_COND_DEBUG only (single device)
+  const bool want_dbg = getenv("NSW_COND_DEBUG") != nullptr;
+  if (want_dbg) {
+    if (!dbg_buf) NSW_CUDA(cudaMalloc(&dbg_buf, 512 * sizeof(long long)));
+    NSW_CUDA(cudaMemsetAsync(dbg_buf, 0, 512 * sizeof(long long), stream));
+    g.dbg = dbg_buf;
+  }
   const bool pair = getenv("NSW_COND_NOCLUSTER") == nullptr && (nclips * g.tiles_per_clip) % 2 == 0 && sms >= 2;
   g.cluster = pair ? 2 : 1;
   // cta_group::2 MMAs (cond_proj_tc2_kernel) by default; NSW_COND_1CTA=1 keeps the pair kernel with 1-CTA MMAs
   const bool two = pair && getenv("NSW_COND_1CTA") == nullptr && g.exp == 0;
   if (two) {
-    static std::atomic<uint64_t> attr2_done{0};
-    NSW_TRY(ensure_dynamic_smem((const void*)cond_proj_tc2_kernel, (int)CP2_SMEM_BYTES, attr2_done));
-    const long long pair_items = items / 2;
+    // 256-column work items unless NSW_COND_TN=128 (the earlier shape, kept for the A/B runs under scripts/)
+    static const bool wide = !(getenv("NSW_COND_TN") && atoi(getenv("NSW_COND_TN")) == 128);
+    auto kern = wide ? cond_proj_tc2_kernel<256> : cond_proj_tc2_kernel<128>;
+    static std::atomic<uint64_t> attr2_done{0}, attr2w_done{0};
+    NSW_TRY(ensure_dynamic_smem((const void*)kern, (int)CP2_SMEM_BYTES, wide ? attr2w_done : attr2_done));
+    if (wide) g.n_tiles = (N + 255) / 256;
+    const long long pair_items = (long long)nclips * g.tiles_per_clip * g.n_tiles / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(sms & ~1);
     cfg.blockDim = dim3(CP_THREADS);
@@ -1171,9 +1229,11 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, cond_proj_tc2_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = sms / 2;
     cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(pair_items, std::min(n, sms / 2)));
-    NSW_CUDA(cudaLaunchKernelEx(&cfg, cond_proj_tc2_kernel, mxh, mxl, mwh2, mwl2, g));
+    // each CTA loads TN/2 weight rows per stage: the full-height box for TN = 256, the half-height one for 128
+    if (wide) NSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, g));
+    else NSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh2, mwl2, g));
   } else if (pair) {
     const long long pair_items = items / 2;
     cudaLaunchConfig_t cfg = {};
@@ -1204,6 +1264,25 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
   }
   count_launch();
   NSW_CUDA(cudaGetLastError());
+  if (want_dbg) {
+    long long hb[512];
+    NSW_CUDA(cudaStreamSynchronize(stream));
+    NSW_CUDA(cudaMemcpy(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost));
+    long long t0 = 0, t1 = 0, s_last = 0, e_first = 0;
+    int n_cta = 0;
+    for (int b = 0; b < 250 && hb[8 + 2 * b] != 0; ++b, ++n_cta) {
+      const long long a = hb[8 + 2 * b], z = hb[8 + 2 * b + 1];
+      if (n_cta == 0 || a < t0) t0 = a;
+      if (n_cta == 0 || a > s_last) s_last = a;
+      if (n_cta == 0 || z > t1) t1 = z;
+      if (n_cta == 0 || z < e_first) e_first = z;
+    }
+    fprintf(stderr, "[cond_proj dbg] %d CTAs: first entry -> last exit %lld ns; last entry +%lld ns, first exit +%lld ns\n", n_cta,
+            t1 - t0, s_last - t0, e_first - t0);
+    fprintf(stderr, "[cond_proj dbg N=%d] pair 0: %lld items in %lld cycles = %lld ns (%.0f MHz); issuer waited: accumulator %lld, "
+                    "weights %lld, activations %lld; one epilogue warp busy %lld\n", N, hb[4], hb[3], hb[5],
+            hb[5] > 0 ? 1e3 * (double)hb[3] / (double)hb[5] : 0.0, hb[0], hb[1], hb[2], hb[6]);
+  }
   return NSW_OK;
 }
 

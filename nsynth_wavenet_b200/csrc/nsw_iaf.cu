@@ -448,6 +448,12 @@ struct nsw_iaf {
   int device = 0;
   int num_sms = 148;
   std::vector<FlowWeights> flows;
+  // engine tc3 with a shared upsampling stack: the mel-cond projections of ALL flows are one GEMM (the activation tile
+  // is loaded once per 128 rows instead of once per flow, one launch and one tail instead of four, no column padding:
+  // 64 * sum(L_f + 1) is a multiple of 256 for the shipped configs)
+  DevBuf Wct_all_hi, Wct_all_lo, bc_all;  // the flows' Wct_* / bc back to back
+  std::vector<size_t> plane_off;          // first cond plane of flow f
+  size_t total_planes = 0;                // 0: one projection per flow
   std::vector<DeconvStack> deconvs;
   int max_layers = 0;
   // workspace
@@ -636,6 +642,33 @@ extern "C" int nsw_iaf_create(const nsw_iaf_config* cfg, const nsw_tensor* tenso
     h->flows[f].deconv_index = cfg->share_deconv ? 0 : f;
     h->max_layers = std::max(h->max_layers, cfg->num_iaf_layers[f]);
   }
+  if (rc == NSW_OK && cfg->engine == NSW_ENGINE_TC3 && cfg->share_deconv && cfg->num_flows > 1 &&
+      getenv("NSW_COND_PER_FLOW") == nullptr) {
+    size_t planes = 0;
+    for (int f = 0; f < cfg->num_flows; ++f) {
+      h->plane_off.push_back(planes);
+      planes += (size_t)h->flows[f].L + 1;
+    }
+    rc = h->Wct_all_hi.ensure(planes * C * D * sizeof(__half));
+    if (rc == NSW_OK) rc = h->Wct_all_lo.ensure(planes * C * D * sizeof(__half));
+    if (rc == NSW_OK) rc = h->bc_all.ensure(planes * C * sizeof(float));
+    for (int f = 0; f < cfg->num_flows && rc == NSW_OK; ++f) {
+      const FlowWeights& fw = h->flows[f];
+      const size_t np = (size_t)fw.L + 1, o = h->plane_off[f];
+      cudaError_t e = cudaMemcpy(h->Wct_all_hi.as<__half>() + o * C * D, fw.Wct_hi.as<__half>(), np * C * D * sizeof(__half),
+                                 cudaMemcpyDeviceToDevice);
+      if (e == cudaSuccess)
+        e = cudaMemcpy(h->Wct_all_lo.as<__half>() + o * C * D, fw.Wct_lo.as<__half>(), np * C * D * sizeof(__half),
+                       cudaMemcpyDeviceToDevice);
+      if (e == cudaSuccess)
+        e = cudaMemcpy(h->bc_all.as<float>() + o * C, fw.bc.as<float>(), np * C * sizeof(float), cudaMemcpyDeviceToDevice);
+      if (e != cudaSuccess) {
+        set_error("nsw_iaf_create: %s", cudaGetErrorString(e));
+        rc = NSW_ECUDA;
+      }
+    }
+    if (rc == NSW_OK) h->total_planes = planes;
+  }
   if (rc == NSW_OK) {
     cudaError_t e = cudaFuncSetAttribute(iaf_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(LayerSmem));
@@ -680,7 +713,7 @@ static int ensure_workspace(nsw_iaf* h, int B, int F) {
     NSW_TRY(h->mel_en_split.ensure((size_t)nB * Lc * D * 2 * sizeof(__half)));
   else
     NSW_TRY(h->mel_en.ensure((size_t)nB * Lc * D * sizeof(float)));
-  NSW_TRY(h->cond.ensure((size_t)(h->max_layers + 1) * rows * C * sizeof(float)));
+  NSW_TRY(h->cond.ensure(std::max((size_t)h->max_layers + 1, h->total_planes) * rows * C * sizeof(float)));
   NSW_TRY(h->l0.ensure(rows * C * sizeof(float)));
   NSW_TRY(h->l1.ensure(rows * C * sizeof(float)));
   if (h->cfg.engine >= NSW_ENGINE_TC2) {
@@ -805,8 +838,19 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
       rec(1);
       lap(0, 0, 1);
     }
-    // 2. all mel-cond projections of this flow in one GEMM, centre trim folded into a_off
-    {
+    // 2. all mel-cond projections of this flow in one GEMM, centre trim folded into a_off (tc3 with a shared
+    //    upsampling stack: of all flows, before the first one)
+    const bool cond_all = tc3 && h->total_planes > 0;
+    float* const cond_f = h->cond.as<float>() + (cond_all ? h->plane_off[f] * rows * C : 0);
+    if (cond_all) {
+      if (f == 0) {
+        rec(0);
+        NSW_TRY(cond_proj_tc(B, Lc, T, left, (int)(h->total_planes * C), me_hi, me_lo, h->Wct_all_hi.as<__half>(),
+                             h->Wct_all_lo.as<__half>(), h->bc_all.as<float>(), h->cond.as<float>(), st));
+        rec(1);
+        lap(1, 0, 1);
+      }
+    } else {
       rec(0);
       ConvGemm g;
       g.nclips = B; g.L = Lc; g.cin = D; g.ntaps = 1; g.a_off = left; g.mclip = T;
@@ -870,13 +914,13 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
           FlowStart fs{x_cur, fw.start_w.as<float>(), fw.start_b.as<float>()};
           for (int c0 = 0; c0 < B; c0 += tc3_clips)
             NSW_TRY(flow_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
-                                   h->cond.as<float>() + (size_t)l0 * rows * C, rows * C,
+                                   cond_f + (size_t)l0 * rows * C, rows * C,
                                    fw.br_cum.as<float>(), T, c0, std::min(tc3_clips, B - c0), cur, l0, l1,
                                    cfg.num_stages, h->sync_words.as<unsigned int>(), h->num_sms,
                                    head_fused ? &fh : nullptr, head_fused ? &fs : nullptr, st));
         } else {
           NSW_TRY(layer_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
-                                  h->cond.as<float>() + (size_t)l0 * rows * C, rows * C, ls_hi, ls_lo,
+                                  cond_f + (size_t)l0 * rows * C, rows * C, ls_hi, ls_lo,
                                   fw.br_nat.as<float>(), T, (int)rows, cur, l0, l1, cfg.num_stages,
                                   h->grid_counter.as<unsigned int>(), h->num_sms, st));
         }
@@ -892,7 +936,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     for (int i = 0; i < fw.L; ++i) {
       const int dil = 1 << (i % cfg.num_stages);
       iaf_layer_kernel<<<grid_lk, LK_THREADS, sizeof(LayerSmem), st>>>(
-          l_buf[cur], h->cond.as<float>() + (size_t)i * rows * C, l_buf[cur ^ 1],
+          l_buf[cur], cond_f + (size_t)i * rows * C, l_buf[cur ^ 1],
           fw.Wd.as<float>() + (size_t)i * 3 * C * C, fw.Wr.as<float>() + (size_t)i * HALF * C,
           fw.br.as<float>() + (size_t)i * C, T, dil, n_tiles);
       count_launch();
@@ -916,7 +960,7 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
     hp.l_hi = ls_hi[cur];
     hp.l_lo = ls_lo[cur];
     hp.cond_tiled = tc3 ? 1 : 0;
-    hp.cond = h->cond.as<float>() + (size_t)fw.L * rows * C;
+    hp.cond = cond_f + (size_t)fw.L * rows * C;
     hp.W1 = fw.W1.as<float>();
     hp.wm = fw.wm.as<float>();
     hp.ws = fw.ws.as<float>();
