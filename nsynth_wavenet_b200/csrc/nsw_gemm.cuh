@@ -29,13 +29,31 @@ struct ConvGemm {
   int N;      // GEMM columns (multiple of 64)
   int tap_stride = 1;  // frame = m + a_off + tap * tap_stride (dilated causal conv: stride = d)
   int x_pitch = 0;     // elements between consecutive frames of X (0 = cin)
+  // optional second source in front of K (tensor-core pair kernel only): cin2 more channels read from
+  // X2[clip, m + a_off2, :] (X2 is [nclips, L2, cin2]); Bt has cin2 + ntaps*cin columns, the second source's first.  The
+  // teacher's dilated conv takes its mel conditioning this way (K = 256 + 3*512) instead of adding a separately
+  // projected plane.
+  int cin2 = 0, a_off2 = 0, L2 = 0;
+  // pair kernel: the two small products of the split (lo*hi, hi*lo) accumulate in their own TMEM columns and are added
+  // to the hi*hi sum by the epilogue.  tcgen05 accumulates in fp32 with truncation, an error proportional to the
+  // accumulator's magnitude per instruction; with the small products kept out, the large accumulator takes a third of
+  // the instructions (teacher dilated conv, K = 1792: 112 instead of 336) and the small one is 2^-11 of its size.
+  // Costs the second accumulator stage (the epilogue no longer overlaps the next item's MMAs).
+  int split_acc = 0;
+  // pair kernel: C += Y for a matrix Y held as a split pair [nclips*mclip, ld3] (fp16 hi + lo): its 256-column block of
+  // the work item rides through the tensor core as four more k-blocks against an identity B tile (hi*1 + lo*1, exact),
+  // fetched by TMA like every other operand.  Replaces the epilogue's read-back of the fp32 rows it accumulates onto --
+  // a chain of global loads per 32-column chunk with a few KB in flight per warp, which is what the teacher's
+  // residual/skip GEMM (K = 256: 6 k cycles of MMAs per item) spent 40 k cycles per item on.  In-place (Y = the split
+  // output of the same call) is fine: an item reads exactly the block it later writes.
+  int acc3 = 0, ld3 = 0;
 };
 
 // EPI_ROWS : out[row * ld_out + n] (+)= D + bias[n] (+ addend[row * ld_add + n]); optional relu;
 //            optional fp16 hi/lo copy of the result (relu'd for n >= relu_split_from)
 // EPI_GATE : columns are gate-interleaved (2j = sigmoid half, 2j+1 = tanh half of gate j);
 //            g[row * ld_split + n/2 + j] = sigmoid(D[2j] + c[2j]) * tanh(D[2j+1] + c[2j+1]),
-//            c = addend[row * ld_add + n + ...]; g is written as fp16 hi/lo only
+//            c = addend[row * ld_add + n + ...] (if given) + bias[n + ...] (if given); g is written as fp16 hi/lo only
 enum EpiMode { EPI_PLANES = 0, EPI_DECONV = 1, EPI_ROWS = 2, EPI_GATE = 3 };
 
 struct EpiParams {
@@ -64,7 +82,8 @@ int conv_gemm_ffma(const ConvGemm& g, const float* X, const float* Bw, const Epi
 // fp16 split operands: X_hi/X_lo [nclips, L, cin], Bt_hi/Bt_lo [N, ntaps*cin] (K-major)
 int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
                  const __half* Bt_hi, const __half* Bt_lo, const EpiParams& e,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const __half* X2_hi = nullptr, const __half* X2_lo = nullptr,
+                 const __half* Y_hi = nullptr, const __half* Y_lo = nullptr);
 bool conv_gemm_tc_supported(const ConvGemm& g);
 // X-resident projection of [nclips, L, 256] activations; ALL output planes row-interleaved (tc3 engine)
 int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X_hi, const __half* X_lo,

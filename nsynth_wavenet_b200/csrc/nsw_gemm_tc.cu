@@ -14,6 +14,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <vector>
 
 namespace nsw {
 
@@ -156,10 +157,11 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
-// coalesced read of a [32 rows x 32 floats] block (row pitch `ld` floats) into one row per thread
-__device__ __forceinline__ void load_rows32(const float* base, size_t row0, int ld, int col, int rows_valid,
-                                            uint32_t scr, int lane, float (&out)[32]) {
-  float4 t[8];
+// coalesced read of a [32 rows x 32 floats] block (row pitch `ld` floats) into one row per thread, in two halves so
+// that the global loads can be issued long before their values are needed (rows_issue) and transposed through the
+// warp's scratch later (rows_finish)
+__device__ __forceinline__ void rows_issue(const float* base, size_t row0, int ld, int col, int rows_valid, int lane,
+                                           float4 (&t)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + (lane >> 3);
@@ -167,6 +169,15 @@ __device__ __forceinline__ void load_rows32(const float* base, size_t row0, int 
                ? __ldg(reinterpret_cast<const float4*>(base + (row0 + r) * (size_t)ld + col) + (lane & 7))
                : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+__device__ __forceinline__ void rows_finish(const float4 (&t)[8], uint32_t scr, int lane, float (&out)[32]);
+__device__ __forceinline__ void load_rows32(const float* base, size_t row0, int ld, int col, int rows_valid,
+                                            uint32_t scr, int lane, float (&out)[32]) {
+  float4 t[8];
+  rows_issue(base, row0, ld, col, rows_valid, lane, t);
+  rows_finish(t, scr, lane, out);
+}
+__device__ __forceinline__ void rows_finish(const float4 (&t)[8], uint32_t scr, int lane, float (&out)[32]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + (lane >> 3);
@@ -212,21 +223,53 @@ __device__ __forceinline__ uint4 pack8_f16(const float* a) {
   return r;
 }
 
-// EPI_ROWS / EPI_GATE (see nsw_gemm.cuh) for 32 rows x 32 columns
+// The per-row input an EPI_ROWS / EPI_GATE epilogue reads back from global memory (at most one is prefetched): the
+// rows it accumulates onto, else the addend rows.
+struct RowSrc {
+  const float* base;
+  int ld;
+};
+__device__ __forceinline__ RowSrc primary_rows(const EpiParams& e) {
+  if (e.mode == EPI_GATE) return RowSrc{e.addend, e.ld_add};
+  if (e.mode == EPI_ROWS) return e.accumulate ? RowSrc{e.out_f32, e.ld_out} : RowSrc{e.addend, e.ld_add};
+  return RowSrc{nullptr, 0};
+}
+
+// EPI_ROWS / EPI_GATE (see nsw_gemm.cuh) for 32 rows x 32 columns; `pre` = the primary_rows() block of this tile when
+// the caller has already loaded it (nullptr: loaded here)
 __device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiParams& e, int clip, int m0,
-                                                  int n, const float* v, uint32_t scr, int lane) {
+                                                  int n, const float* v, uint32_t scr, int lane,
+                                                  const float* pre = nullptr) {
   const int rows_valid = min(32, g.mclip - m0);
   if (rows_valid <= 0) return;
   const size_t row0 = (size_t)clip * g.mclip + m0;
   float f[32];
   if (e.mode == EPI_GATE) {
     float c[32];
-    load_rows32(e.addend, row0, e.ld_add, n, rows_valid, scr, lane, c);
+    if (pre) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) c[j] = pre[j];
+    } else if (e.addend) {
+      load_rows32(e.addend, row0, e.ld_add, n, rows_valid, scr, lane, c);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) c[j] = 0.f;
+    }
+    if (e.bias) {  // per-column bias in the same gate-interleaved order as the columns
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        c[4 * j] += b.x; c[4 * j + 1] += b.y; c[4 * j + 2] += b.z; c[4 * j + 3] += b.w;
+      }
+    }
     float gh[16], gl[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float sg = 1.0f / (1.0f + expf(-(v[2 * j] + c[2 * j])));
-      const float gv = sg * tanhf(v[2 * j + 1] + c[2 * j + 1]);
+      // sigmoid(s) * tanh(t) = (1 - b) / ((1 + a)(1 + b)), a = e^-s, b = e^-2t: 3 MUFU ops (the flow kernel's gate)
+      const float a = __expf(fminf(-(v[2 * j] + c[2 * j]), 40.0f));
+      const float b = __expf(fminf(-2.0f * (v[2 * j + 1] + c[2 * j + 1]), 40.0f));
+      const float gv = __fdividef(1.0f - b, (1.0f + a) * (1.0f + b));
       gh[j] = __half2float(__float2half_rn(gv));
       gl[j] = gv - gh[j];
     }
@@ -246,16 +289,26 @@ __device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiPa
     f[4 * j + 2] = v[4 * j + 2] + b.z; f[4 * j + 3] = v[4 * j + 3] + b.w;
   }
   if (e.addend) {
-    float c[32];
-    load_rows32(e.addend, row0, e.ld_add, n, rows_valid, scr, lane, c);
+    if (pre && !e.accumulate) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] += c[j];
+      for (int j = 0; j < 32; ++j) f[j] += pre[j];
+    } else {
+      float c[32];
+      load_rows32(e.addend, row0, e.ld_add, n, rows_valid, scr, lane, c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] += c[j];
+    }
   }
   if (e.accumulate) {
-    float c[32];
-    load_rows32(e.out_f32, row0, e.ld_out, n, rows_valid, scr, lane, c);
+    if (pre) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] += c[j];
+      for (int j = 0; j < 32; ++j) f[j] += pre[j];
+    } else {
+      float c[32];
+      load_rows32(e.out_f32, row0, e.ld_out, n, rows_valid, scr, lane, c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] += c[j];
+    }
   }
   if (e.relu_out) {
 #pragma unroll
@@ -297,10 +350,11 @@ __device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiPa
 // is written with full 128 B lines (8 lanes per row) instead of 32 scattered 16 B pieces per
 // instruction (row-per-thread stores made L1TEX the limiter; profiles/r01).
 __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams& e, int clip, int m0,
-                                             int n, const float* v, uint32_t scr, int lane) {
+                                             int n, const float* v, uint32_t scr, int lane,
+                                             const float* pre = nullptr) {
   if (n >= g.N) return;  // warp-uniform
   if (e.mode == EPI_ROWS || e.mode == EPI_GATE) {
-    store_tile32_rows(g, e, clip, m0, n, v, scr, lane);
+    store_tile32_rows(g, e, clip, m0, n, v, scr, lane, pre);
     return;
   }
   float f[32];
@@ -1090,6 +1144,225 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The general conv-GEMM with cta_group::2 MMAs: M = 256 over a CTA pair (one 128-row m-tile per CTA), N = 256 per
+// work item, each CTA streaming its own A rows and HALF of the B rows (the tensor cores of the pair exchange B).
+// conv_gemm_tc_kernel above (1 CTA, 128 x 128) reads 4 KB of A and 4 KB of B from shared memory per 64 tensor cycles:
+// exactly the 128 B/clk the SM's shared memory delivers, before the TMA fills -- it ran at 48 % of the dense peak on
+// the teacher's layers.  Here a k-step is 4 KB + 4 KB per 128 tensor cycles.  Same ring (3 x 64 KB per CTA), same
+// epilogues (store_tile32), 2 x 256 accumulator columns = all of TMEM.
+//   leader (cluster rank 0) issues; its `full` barriers count the TMA bytes of BOTH CTAs; commits are multicast; the
+//   peer's epilogue warps release accumulator stages with a remote arrive on the leader's barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int TN2 = 256;
+// 8 epilogue warps: warps w and w + 4 share a TMEM lane quarter and take 128 of the 256 columns each.  The epilogues
+// with per-row addends (EPI_ROWS, EPI_GATE) are chains of global load -> shared-memory transpose -> math -> transpose ->
+// store; with one warp per scheduler they, not the tensor pipe, set the pace (the 128 x 128 kernel and a first version
+// of this one with 4 epilogue warps measured the same 13.7 ms on the teacher forward).
+constexpr int TC2_THREADS = 64 + 8 * 32;
+constexpr size_t TC2_SMEM_BYTES = TC_OFF_SCR + 8 * 4096 + 1024;
+
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                     const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                     const __grid_constant__ CUtensorMap map_x2h, const __grid_constant__ CUtensorMap map_x2l,
+                     const __grid_constant__ CUtensorMap map_yh, const __grid_constant__ CUtensorMap map_yl,
+                     const __grid_constant__ CUtensorMap map_id, ConvGemm g, EpiParams e, int tiles_per_clip, int n_tiles,
+                     int total_items) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_per_tap = g.cin / TBK;
+  // the k-blocks of the second source come FIRST: tcgen05's fp32 accumulation truncates, an error proportional to the
+  // accumulator's magnitude per instruction, so the extra instructions are cheapest while the sum is still small
+  const int num_kb2 = g.cin2 / TBK;
+  const int num_kbw = num_kb2 + g.ntaps * kb_per_tap;     // k-blocks against the weights
+  const int num_kb = num_kbw + (g.acc3 ? TN2 / TBK : 0);  // + the identity k-blocks of ConvGemm::acc3
+  const int crank = (int)(blockIdx.x & 1);
+  const bool leader = crank == 0;
+  const int n_pairs = (int)gridDim.x / 2, pair = (int)blockIdx.x / 2;
+  const int total_mt = g.nclips * tiles_per_clip;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tail->tmem_full[a], 1);
+      mbar_init(&tail->tmem_empty[a], 16);  // 8 epilogue warps of each CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                 "r"(2u * TN2)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  // barriers of both CTAs must exist before the peer's TMA completes on / arrives at them
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+  const uint32_t sbase0 = smem_u32(smem);
+
+  // item -> (pair of m-tiles, 256-column block); items are dealt round-robin to the pairs, n fastest, so the pairs
+  // working at the same time share the A rows through L2
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = pair; item < total_items; item += n_pairs) {
+        const int mp = item / n_tiles, nt = item - mp * n_tiles;
+        const int mt = 2 * mp + crank;  // may be one past the end (odd tile count): TMA zero-fills, nothing is stored
+        const int clip = mt / tiles_per_clip;
+        const int m0 = (mt - clip * tiles_per_clip) * TBM;
+        const int nrow = nt * TN2 + crank * (TN2 / 2);  // this CTA's half of the B rows
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail->empty[stage], phase ^ 1);
+          const uint32_t dst = sbase0 + (uint32_t)stage * STAGE_BYTES;
+          if (leader) mbar_expect_tx(&tail->full[stage], 2 * STAGE_BYTES);
+          const uint32_t fb = cp2_mapa(smem_u32(&tail->full[stage]), 0);
+          if (kb >= num_kbw) {
+            // accumulate source: columns [nt * 256 + j * 64, +64) of Y against rows of the 256 x 256 identity
+            const int j = kb - num_kbw;
+            cp2_tma_3d(dst, &map_yh, fb, nt * TN2 + j * TBK, m0, clip);
+            cp2_tma_3d(dst + TILE_BYTES, &map_yl, fb, nt * TN2 + j * TBK, m0, clip);
+            cp2_tma_2d(dst + 2 * TILE_BYTES, &map_id, fb, j * TBK, crank * (TN2 / 2));
+            cp2_tma_2d(dst + 3 * TILE_BYTES, &map_id, fb, j * TBK, crank * (TN2 / 2));  // (unused: keeps the stage size)
+          } else if (kb >= num_kb2) {
+            const int tap = (kb - num_kb2) / kb_per_tap;
+            const int c0 = (kb - num_kb2 - tap * kb_per_tap) * TBK;
+            const int frame0 = m0 + g.a_off + tap * g.tap_stride;  // may be negative: TMA zero-fills
+            cp2_tma_3d(dst, &map_xh, fb, c0, frame0, clip);
+            cp2_tma_3d(dst + TILE_BYTES, &map_xl, fb, c0, frame0, clip);
+          } else {
+            cp2_tma_3d(dst, &map_x2h, fb, kb * TBK, m0 + g.a_off2, clip);
+            cp2_tma_3d(dst + TILE_BYTES, &map_x2l, fb, kb * TBK, m0 + g.a_off2, clip);
+          }
+          if (kb < num_kbw) {
+            cp2_tma_2d(dst + 2 * TILE_BYTES, &map_wh, fb, kb * TBK, nrow);
+            cp2_tma_2d(dst + 3 * TILE_BYTES, &map_wl, fb, kb * TBK, nrow);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // D = f32, A = B = f16, K-major, M = 256 (128 per CTA), N = 256
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(TN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+      const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const bool split = g.split_acc != 0;  // one accumulator stage: [hi*hi | small products]
+      for (int item = pair; item < total_items; item += n_pairs, ++it) {
+        const int as = split ? 0 : (it & 1);
+        const uint32_t use = split ? (uint32_t)it : (uint32_t)(it >> 1);  // how often this stage has been used before
+        mbar_wait(&tail->tmem_empty[as], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + (uint32_t)(as * TN2);
+        const uint32_t d_small = split ? tmem_u + (uint32_t)TN2 : d_tmem;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tail->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sb = sbase_u + (uint32_t)stage * STAGE_BYTES;
+          const uint64_t xh = umma_desc_sw128(sb);
+          const uint64_t xl = umma_desc_sw128(sb + TILE_BYTES);
+          const uint64_t wh = umma_desc_sw128(sb + 2 * TILE_BYTES);
+          const uint64_t wl = umma_desc_sw128(sb + 3 * TILE_BYTES);
+          if (tc_elect()) {
+#pragma unroll
+            for (int k = 0; k < TBK / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+              cp2_mma(d_small, xl + adv, wh + adv, idesc, (kb | k) != 0);
+              if (kb < num_kbw) cp2_mma(d_small, xh + adv, wl + adv, idesc, 1);  // (identity blocks: lo * 1 + hi * 1 only)
+              cp2_mma(d_tmem, xh + adv, wh + adv, idesc, split ? (uint32_t)((kb | k) != 0) : 1u);
+            }
+            cp2_commit(&tail->empty[stage]);
+            if (kb == num_kb - 1) cp2_commit(&tail->tmem_full[as]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const uint32_t scr = sbase0 + TC_OFF_SCR + (uint32_t)(warp - 2) * 4096u;
+    // The rows an EPI_ROWS / EPI_GATE epilogue reads back (accumulate / addend) are requested one 32-column chunk
+    // ahead -- the first chunk of an item before its accumulator is even complete -- so their latency overlaps the
+    // MMAs and the previous chunk's math and stores instead of sitting at the head of every chunk.
+    const RowSrc ps = primary_rows(e);
+    const int cbeg = colhalf * (TN2 / 2), cend = (colhalf + 1) * (TN2 / 2);
+    float4 pre[8];
+    auto issue = [&](int item, int c0) {  // returns through `pre`; false: nothing to load for this chunk
+      const int mp = item / n_tiles, nt = item - mp * n_tiles;
+      const int mt = 2 * mp + crank;
+      const int clip = mt / tiles_per_clip;
+      const int m0 = (mt - clip * tiles_per_clip) * TBM + q * 32;
+      const int n = nt * TN2 + c0;
+      const int rows_valid = min(32, g.mclip - m0);
+      if (ps.base == nullptr || mt >= total_mt || n >= g.N || rows_valid <= 0) return;
+      rows_issue(ps.base, (size_t)clip * g.mclip + m0, ps.ld, n, rows_valid, lane, pre);
+    };
+    int it = 0;
+    if (pair < total_items) issue(pair, cbeg);
+    for (int item = pair; item < total_items; item += n_pairs, ++it) {
+      const int mp = item / n_tiles, nt = item - mp * n_tiles;
+      const int mt = 2 * mp + crank;
+      const int clip = mt / tiles_per_clip;
+      const int m0 = (mt - clip * tiles_per_clip) * TBM + q * 32;
+      const int n0 = nt * TN2;
+      const bool split = g.split_acc != 0;
+      const int as = split ? 0 : (it & 1);
+      mbar_wait(&tail->tmem_full[as], split ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        float v[32], pc[32];
+        const bool live = mt < total_mt && n0 + c0 < g.N && m0 < g.mclip;
+        if (live) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TN2 + c0), v);
+          if (split) {
+            float w[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN2 + c0), w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+          }
+          if (ps.base) rows_finish(pre, scr, lane, pc);
+        }
+        if (c0 + 32 < cend) issue(item, c0 + 32);
+        else if (item + n_pairs < total_items) issue(item + n_pairs, cbeg);
+        if (live) store_tile32(g, e, clip, m0, n0 + c0, v, scr, lane, ps.base ? pc : nullptr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tail->tmem_empty[as]);
+        else cp2_arrive_remote(cp2_mapa(smem_u32(&tail->tmem_empty[as]), 0));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  // do not exit (or free TMEM) while the peer's MMAs / TMA may still touch this CTA
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * TN2) : "memory");
+  }
+}
+
 }  // namespace
 
 bool conv_gemm_tc_supported(const ConvGemm& g) {
@@ -1098,7 +1371,7 @@ bool conv_gemm_tc_supported(const ConvGemm& g) {
 
 int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
                  const __half* Bt_hi, const __half* Bt_lo, const EpiParams& e,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const __half* X2_hi, const __half* X2_lo, const __half* Y_hi, const __half* Y_lo) {
   NSW_CHECK(conv_gemm_tc_supported(g), NSW_EINVAL, "conv_gemm_tc: unsupported shape cin=%d N=%d",
             g.cin, g.N);
   NSW_CHECK(X_hi && X_lo && Bt_hi && Bt_lo, NSW_EINVAL, "conv_gemm_tc: null operand");
@@ -1110,12 +1383,48 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
     NSW_CHECK(e.ld_out % 4 == 0 && e.ld_add % 4 == 0 && e.ld_split % 8 == 0 && e.bias, NSW_EINVAL,
               "conv_gemm_tc: EPI_ROWS leading dimensions must keep 16-byte alignment");
   if (e.mode == EPI_GATE)
-    NSW_CHECK(e.addend && e.out_hi && e.out_lo && e.ld_add % 4 == 0 && e.ld_split % 8 == 0, NSW_EINVAL,
-              "conv_gemm_tc: EPI_GATE needs cond rows and split outputs");
+    NSW_CHECK((e.addend || e.bias) && e.out_hi && e.out_lo && e.ld_add % 4 == 0 && e.ld_split % 8 == 0, NSW_EINVAL,
+              "conv_gemm_tc: EPI_GATE needs cond rows or a bias, and split outputs");
+  const bool second = g.cin2 > 0;
+  if (second)
+    NSW_CHECK(X2_hi && X2_lo && g.cin2 % TBK == 0 && g.L2 > 0, NSW_EINVAL, "conv_gemm_tc: bad second source (cin2=%d)", g.cin2);
   EncodeTiledFn enc;
   NSW_TRY(get_encode_fn(&enc));
-  const int K = g.ntaps * g.cin;
-  CUtensorMap mxh, mxl, mwh, mwl;
+  const int K = g.ntaps * g.cin + g.cin2;
+  CUtensorMap mxh, mxl, mwh, mwl, mx2h, mx2l, myh, myl, mid;
+  if (g.acc3) {
+    NSW_CHECK(Y_hi && Y_lo && g.ld3 % 8 == 0 && g.ld3 >= g.N, NSW_EINVAL, "conv_gemm_tc: bad accumulate source (ld3=%d)", g.ld3);
+    // 256 x 256 fp16 identity, one per device, built on first use
+    static __half* ident[64] = {nullptr};
+    int dv = 0;
+    NSW_CUDA(cudaGetDevice(&dv));
+    if (!ident[dv & 63]) {
+      std::vector<__half> id((size_t)TN2 * TN2, __float2half(0.f));
+      for (int i = 0; i < TN2; ++i) id[(size_t)i * TN2 + i] = __float2half(1.f);
+      __half* d = nullptr;
+      NSW_CUDA(cudaMalloc(&d, id.size() * sizeof(__half)));
+      NSW_CUDA(cudaMemcpy(d, id.data(), id.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      ident[dv & 63] = d;
+    }
+    {
+      const uint64_t dims[2] = {(uint64_t)TN2, (uint64_t)TN2};
+      const uint64_t strides[1] = {(uint64_t)TN2 * 2};
+      const uint32_t box[2] = {TBK, TBN};
+      NSW_TRY(make_map(enc, &mid, ident[dv & 63], 2, dims, strides, box));
+    }
+    const uint64_t dims[3] = {(uint64_t)g.ld3, (uint64_t)g.mclip, (uint64_t)g.nclips};
+    const uint64_t strides[2] = {(uint64_t)g.ld3 * 2, (uint64_t)g.mclip * g.ld3 * 2};
+    const uint32_t box[3] = {TBK, TBM, 1};
+    NSW_TRY(make_map(enc, &myh, Y_hi, 3, dims, strides, box));
+    NSW_TRY(make_map(enc, &myl, Y_lo, 3, dims, strides, box));
+  }
+  if (second) {
+    const uint64_t dims[3] = {(uint64_t)g.cin2, (uint64_t)g.L2, (uint64_t)g.nclips};
+    const uint64_t strides[2] = {(uint64_t)g.cin2 * 2, (uint64_t)g.L2 * g.cin2 * 2};
+    const uint32_t box[3] = {TBK, TBM, 1};
+    NSW_TRY(make_map(enc, &mx2h, X2_hi, 3, dims, strides, box));
+    NSW_TRY(make_map(enc, &mx2l, X2_lo, 3, dims, strides, box));
+  }
   {
     const uint64_t dims[3] = {(uint64_t)g.cin, (uint64_t)g.L, (uint64_t)g.nclips};
     const uint64_t pitch = (uint64_t)(g.x_pitch > 0 ? g.x_pitch : g.cin);
@@ -1137,6 +1446,45 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles_per_clip = (g.mclip + TBM - 1) / TBM;
+  // CTA-pair kernel (M = 256, N = 256 per item) whenever there are more than 128 columns and at least two m-tiles;
+  // NSW_GEMM_1CTA=1 keeps the 128 x 128 kernel (A/B runs)
+  static const bool force_1cta = getenv("NSW_GEMM_1CTA") != nullptr;
+  const int total_mt = g.nclips * tiles_per_clip;
+  const bool pair_ok = g.N > TBN && total_mt >= 2 && sms >= 2;
+  NSW_CHECK(!(second || g.acc3) || pair_ok, NSW_EINVAL,
+            "conv_gemm_tc: a second / accumulate source needs the pair kernel (N > 128, >= 2 m-tiles)");
+  if (!second) { mx2h = mxh; mx2l = mxl; }
+  if (!g.acc3) { myh = mxh; myl = mxl; mid = mwh; }
+  if ((!force_1cta || second || g.acc3) && pair_ok) {
+    static std::atomic<uint64_t> attr2_done{0};
+    NSW_TRY(ensure_dynamic_smem((const void*)conv_gemm_tc2_kernel, (int)TC2_SMEM_BYTES, attr2_done));
+    const int n_tiles2 = (g.N + TN2 - 1) / TN2;
+    const int items = ((total_mt + 1) / 2) * n_tiles2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms & ~1);
+    cfg.blockDim = dim3(TC2_THREADS);
+    cfg.dynamicSmemBytes = TC2_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_pairs[64] = {0};  // per device
+    if (max_pairs[dev & 63] == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc2_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+      max_pairs[dev & 63] = n;
+    }
+    cfg.gridDim = dim3(2 * (unsigned)std::min(items, std::min(max_pairs[dev & 63], sms / 2)));
+    NSW_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel, mxh, mxl, mwh, mwl, mx2h, mx2l, myh, myl, mid, g, e,
+                                tiles_per_clip, n_tiles2, items));
+    count_launch();
+    NSW_CUDA(cudaGetLastError());
+    return NSW_OK;
+  }
   const int n_tiles = (g.N + TBN - 1) / TBN;
   const int total = g.nclips * tiles_per_clip * n_tiles;
   const int grid = std::min(total, sms);

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace nsw {
 namespace {
@@ -166,7 +167,8 @@ gauss_kl_kernel(const float2* __restrict__ te /*[BT] (mean, log-scale param)*/, 
 using namespace nsw;
 
 struct TeacherLayer {
-  DevBuf wd_hi, wd_lo;   // [512 pos][1536]
+  DevBuf wd_hi, wd_lo;   // [512 pos][1536], or [512 pos][1536 + 256] with the mel-cond projection appended along K
+  DevBuf bg;             // [512 pos] dilated-conv + mel-cond biases (fused conditioning only)
   DevBuf wrs_hi, wrs_lo; // [768][256]
   DevBuf brs;            // [768]
 };
@@ -174,6 +176,19 @@ struct TeacherLayer {
 struct nsw_teacher {
   nsw_wavenet_config cfg;
   int device = 0, L = 0, O = 0, NC = 0;
+  // the layers' mel conditioning rides inside the dilated-conv GEMM as 256 extra K columns read straight from mel_en
+  // (no [rows x 30*512] fp32 conditioning plane: 3.4 GB written and read back at the distillation shape, 1.6 of the
+  // 14.7 ms, and a latency-bound addend read in every gate epilogue); NSW_TEACHER_COND_SEPARATE=1 keeps the old scheme
+  bool fuse_cond = true;
+  // residual + skip update: l|s live ONLY as the split pair (22 mantissa bits; no fp32 master to read, add to and
+  // write back) and the update is one GEMM whose accumulate source goes through the tensor core (ConvGemm::acc3);
+  // NSW_TEACHER_FP32_MASTER=1 keeps the fp32 rows and the read-modify-write epilogue
+  bool acc_mma = true;
+  // ConvGemm::split_acc for the dilated-conv GEMMs.  Max-abs error of out_params against the fp64 oracle / forward time at
+  // 7 x 7680 (profiles/r02, run33), conditioning fused:  split 5.6e-5 / 11.45 ms;  no split 1.01e-4 / 10.05 ms (over the
+  // 1e-4 bar: 17 % more instructions into the large accumulator than the separate-conditioning scheme, 8.3e-5 / 11.5 ms).
+  // On unless NSW_TEACHER_SPLIT_ACC=0.
+  bool split_acc = true;
   DeconvStack deconv;
   std::vector<TeacherLayer> layers;
   DevBuf wc_hi, wc_lo, bc;          // cond_all: [NC][256], bias [NC]
@@ -224,6 +239,12 @@ extern "C" int nsw_teacher_create(const nsw_wavenet_config* cfg, const nsw_tenso
   nsw_teacher* h = new nsw_teacher();
   h->cfg = *cfg;
   h->device = device;
+  h->fuse_cond = !(getenv("NSW_TEACHER_COND_SEPARATE") && atoi(getenv("NSW_TEACHER_COND_SEPARATE")) != 0) &&
+                 getenv("NSW_GEMM_1CTA") == nullptr;
+  h->acc_mma = !(getenv("NSW_TEACHER_FP32_MASTER") && atoi(getenv("NSW_TEACHER_FP32_MASTER")) != 0) &&
+               getenv("NSW_GEMM_1CTA") == nullptr;
+  h->split_acc = !(getenv("NSW_TEACHER_SPLIT_ACC") && atoi(getenv("NSW_TEACHER_SPLIT_ACC")) == 0) &&
+                 getenv("NSW_GEMM_1CTA") == nullptr;
   const int L = h->L = cfg->num_layers, O = h->O = cfg->out_width;
   const int G = 2 * TM;
   h->NC = L * G + TS;
@@ -244,13 +265,18 @@ extern "C" int nsw_teacher_create(const nsw_wavenet_config* cfg, const nsw_tenso
     const float* ws = tm.get("skip_" + li + "/W", TM * TS);
     const float* bs = tm.get("skip_" + li + "/biases", TS);
     if (!wd || !bd || !wcd || !bcd || !wr || !br || !ws || !bs) return fail(NSW_EMISSING);
-    std::vector<float> wdt((size_t)G * 3 * TW), wrs((size_t)TLS * TM), brs(TLS);
+    const int K0 = h->fuse_cond ? TD : 0;  // fused conditioning: its 256 K columns come first
+    const int KD = K0 + 3 * TW;
+    std::vector<float> wdt((size_t)G * KD), wrs((size_t)TLS * TM), brs(TLS), bg(G);
     for (int pos = 0; pos < G; ++pos) {
       const int ch = gate_ch(pos);
       for (int tap = 0; tap < 3; ++tap)
-        for (int c = 0; c < TW; ++c) wdt[(size_t)pos * 3 * TW + tap * TW + c] = wd[((size_t)tap * TW + c) * G + ch];
-      for (int k = 0; k < TD; ++k) wc[((size_t)i * G + pos) * TD + k] = wcd[(size_t)k * G + ch];
-      bc[i * G + pos] = bd[ch] + bcd[ch];
+        for (int c = 0; c < TW; ++c) wdt[(size_t)pos * KD + K0 + tap * TW + c] = wd[((size_t)tap * TW + c) * G + ch];
+      for (int k = 0; k < TD; ++k) {
+        wc[((size_t)i * G + pos) * TD + k] = wcd[(size_t)k * G + ch];
+        if (h->fuse_cond) wdt[(size_t)pos * KD + k] = wcd[(size_t)k * G + ch];
+      }
+      bc[i * G + pos] = bg[pos] = bd[ch] + bcd[ch];
     }
     for (int c = 0; c < TW; ++c) {
       for (int j = 0; j < TM; ++j) wrs[(size_t)c * TM + j] = wr[(size_t)j * TW + c];
@@ -262,6 +288,7 @@ extern "C" int nsw_teacher_create(const nsw_wavenet_config* cfg, const nsw_tenso
     }
     TeacherLayer& ly = h->layers[i];
     if ((rc = upload_split(ly.wd_hi, ly.wd_lo, wdt)) != NSW_OK) return fail(rc);
+    if ((rc = upload(ly.bg, bg.data(), bg.size() * 4)) != NSW_OK) return fail(rc);
     if ((rc = upload_split(ly.wrs_hi, ly.wrs_lo, wrs)) != NSW_OK) return fail(rc);
     if ((rc = upload(ly.brs, brs.data(), brs.size() * 4)) != NSW_OK) return fail(rc);
   }
@@ -324,7 +351,9 @@ extern "C" int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, co
   const size_t rows = (size_t)B * T;
   const int L = h->L, NC = h->NC, G = 2 * TM;
   NSW_TRY(h->mel_en.ensure((size_t)B * Lc * TD * 2 * sizeof(__half)));
-  NSW_TRY(h->cond_all.ensure(rows * NC * sizeof(float)));
+  const bool fuse = h->fuse_cond;
+  const int NCb = fuse ? TS : NC;  // columns of the conditioning plane that is still materialised (out1's only)
+  NSW_TRY(h->cond_all.ensure(rows * NCb * sizeof(float)));
   NSW_TRY(h->ls.ensure(rows * TLS * sizeof(float)));
   NSW_TRY(h->ls_split.ensure(rows * TLS * 2 * sizeof(__half)));
   NSW_TRY(h->g_split.ensure(rows * TM * 2 * sizeof(__half)));
@@ -342,10 +371,11 @@ extern "C" int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, co
   float* cond = h->cond_all.as<float>();
   NSW_CUDA(cudaEventRecord(h->ev0, st));
   NSW_TRY(h->deconv.forward(d_mel, B, F, nullptr, me_hi, me_lo, NSW_ENGINE_TC, h->scratch, st));
-  {  // all conditioning projections at once; the centre trim is the row offset
-    ConvGemm g; g.nclips = B; g.L = Lc; g.cin = TD; g.ntaps = 1; g.a_off = left; g.mclip = T; g.N = NC;
-    EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->bc.as<float>(); e.out_f32 = cond; e.ld_out = NC;
-    NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, h->wc_hi.as<__half>(), h->wc_lo.as<__half>(), e, st));
+  {  // conditioning projections hoisted out of the layers (all of them, or only out1's); the centre trim is the row offset
+    const size_t w0 = fuse ? (size_t)L * G * TD : 0;
+    ConvGemm g; g.nclips = B; g.L = Lc; g.cin = TD; g.ntaps = 1; g.a_off = left; g.mclip = T; g.N = NCb;
+    EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->bc.as<float>() + (fuse ? L * G : 0); e.out_f32 = cond; e.ld_out = NCb;
+    NSW_TRY(conv_gemm_tc(g, me_hi, me_lo, h->wc_hi.as<__half>() + w0, h->wc_lo.as<__half>() + w0, e, st));
   }
   teacher_start_kernel<<<(unsigned)((rows * 128 + 255) / 256), 256, 0, st>>>(
       d_wav, h->wcs.as<float>(), h->bcs.as<float>(), ls, ls_hi, ls_lo, T, rows);
@@ -362,21 +392,36 @@ extern "C" int nsw_teacher_forward_device(nsw_teacher* h, const float* d_wav, co
     {  // dilated causal conv + cond + gate  (wavenet.py:244-267)
       ConvGemm g; g.nclips = B; g.L = T; g.cin = TW; g.x_pitch = TLS; g.ntaps = 3; g.tap_stride = d;
       g.a_off = -2 * d; g.mclip = T; g.N = G;
-      EpiParams e{}; e.mode = EPI_GATE; e.addend = cond + (size_t)i * G; e.ld_add = NC;
+      g.split_acc = h->split_acc ? 1 : 0;
+      EpiParams e{}; e.mode = EPI_GATE;
       e.out_hi = g_hi; e.out_lo = g_lo; e.ld_split = TM;
-      NSW_TRY(conv_gemm_tc(g, ls_hi, ls_lo, ly.wd_hi.as<__half>(), ly.wd_lo.as<__half>(), e, st));
+      if (fuse) {
+        g.cin2 = TD; g.a_off2 = left; g.L2 = Lc;
+        e.bias = ly.bg.as<float>();
+        NSW_TRY(conv_gemm_tc(g, ls_hi, ls_lo, ly.wd_hi.as<__half>(), ly.wd_lo.as<__half>(), e, st, me_hi, me_lo));
+      } else {
+        e.addend = cond + (size_t)i * G; e.ld_add = NC;
+        NSW_TRY(conv_gemm_tc(g, ls_hi, ls_lo, ly.wd_hi.as<__half>(), ly.wd_lo.as<__half>(), e, st));
+      }
     }
     {  // l += res(g), s += skip(g) in one GEMM  (wavenet.py:269-274)
       ConvGemm g; g.nclips = B; g.L = T; g.cin = TM; g.ntaps = 1; g.a_off = 0; g.mclip = T; g.N = TLS;
-      EpiParams e{}; e.mode = EPI_ROWS; e.bias = ly.brs.as<float>(); e.out_f32 = ls; e.ld_out = TLS; e.accumulate = 1;
+      EpiParams e{}; e.mode = EPI_ROWS; e.bias = ly.brs.as<float>();
       e.out_hi = ls_hi; e.out_lo = ls_lo; e.ld_split = TLS;
       if (i == L - 1) e.relu_split_from = TW;  // the head consumes relu(s) (wavenet.py:281)
-      NSW_TRY(conv_gemm_tc(g, g_hi, g_lo, ly.wrs_hi.as<__half>(), ly.wrs_lo.as<__half>(), e, st));
+      if (h->acc_mma) {
+        g.acc3 = 1; g.ld3 = TLS;
+        NSW_TRY(conv_gemm_tc(g, g_hi, g_lo, ly.wrs_hi.as<__half>(), ly.wrs_lo.as<__half>(), e, st, nullptr, nullptr, ls_hi,
+                             ls_lo));
+      } else {
+        e.out_f32 = ls; e.ld_out = TLS; e.accumulate = 1;
+        NSW_TRY(conv_gemm_tc(g, g_hi, g_lo, ly.wrs_hi.as<__half>(), ly.wrs_lo.as<__half>(), e, st));
+      }
     }
   }
   {  // h = relu(out1 . relu(s) + cond_out1)  (wavenet.py:281-286)
     ConvGemm g; g.nclips = B; g.L = T; g.cin = TS; g.x_pitch = TLS; g.ntaps = 1; g.a_off = 0; g.mclip = T; g.N = TS;
-    EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->zeros.as<float>(); e.addend = cond + (size_t)L * G; e.ld_add = NC;
+    EpiParams e{}; e.mode = EPI_ROWS; e.bias = h->zeros.as<float>(); e.addend = cond + (fuse ? 0 : (size_t)L * G); e.ld_add = NCb;
     e.relu_out = 1; e.out_hi = h_hi; e.out_lo = h_lo; e.ld_split = TS;
     NSW_TRY(conv_gemm_tc(g, ls_hi + TW, ls_lo + TW, h->wo1_hi.as<__half>(), h->wo1_lo.as<__half>(), e, st));
   }
