@@ -143,6 +143,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load without the wait (several in flight, then one tmem_ld_wait())
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
@@ -1163,13 +1178,18 @@ constexpr int TN2 = 256;
 constexpr int TC2_THREADS = 64 + 8 * 32;
 constexpr size_t TC2_SMEM_BYTES = TC_OFF_SCR + 8 * 4096 + 1024;
 
+// MODE (EpiMode) and SPLIT (ConvGemm::split_acc) are compile-time: with every epilogue inlined behind run-time
+// switches the kernel was 52 k SASS instructions and kept the accumulator chunks in local memory.
+template <int MODE, int SPLIT>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                      const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
                      const __grid_constant__ CUtensorMap map_x2h, const __grid_constant__ CUtensorMap map_x2l,
                      const __grid_constant__ CUtensorMap map_yh, const __grid_constant__ CUtensorMap map_yl,
-                     const __grid_constant__ CUtensorMap map_id, ConvGemm g, EpiParams e, int tiles_per_clip, int n_tiles,
+                     const __grid_constant__ CUtensorMap map_id, ConvGemm g, EpiParams e_in, int tiles_per_clip, int n_tiles,
                      int total_items) {
+  EpiParams e = e_in;
+  e.mode = MODE;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -1262,7 +1282,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      const bool split = g.split_acc != 0;  // one accumulator stage: [hi*hi | small products]
+      constexpr bool split = SPLIT != 0;  // one accumulator stage: [hi*hi | small products]
       for (int item = pair; item < total_items; item += n_pairs, ++it) {
         const int as = split ? 0 : (it & 1);
         const uint32_t use = split ? (uint32_t)it : (uint32_t)(it >> 1);  // how often this stage has been used before
@@ -1322,22 +1342,59 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
       const int clip = mt / tiles_per_clip;
       const int m0 = (mt - clip * tiles_per_clip) * TBM + q * 32;
       const int n0 = nt * TN2;
-      const bool split = g.split_acc != 0;
+      constexpr bool split = SPLIT != 0;
       const int as = split ? 0 : (it & 1);
       mbar_wait(&tail->tmem_full[as], split ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (split) {
+        // one accumulator stage: read this warp's 4 x 32 columns of both accumulators out in one go, hand the stage
+        // back to the MMA issuer, and only then do the math and the stores (they overlap the next item's MMAs)
+        constexpr int NCH = TN2 / 2 / 32;
+        uint32_t acc[NCH][32];  // (raw bits, compile-time indices only: stays in registers)
+        const bool rows_live = mt < total_mt && m0 < g.mclip;
+        if (rows_live) {
+          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tmem_ld32_issue(t0 + (uint32_t)(c * 32), acc[c]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t w[32];
+            tmem_ld32_issue(t0 + (uint32_t)(TN2 + c * 32), w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c][j] = __float_as_uint(__uint_as_float(acc[c][j]) + __uint_as_float(w[j]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tail->tmem_empty[0]);
+          else cp2_arrive_remote(cp2_mapa(smem_u32(&tail->tmem_empty[0]), 0));
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int c0 = cbeg + c * 32;
+          float pc[32];
+          const bool live = rows_live && n0 + c0 < g.N;
+          if (live && ps.base) rows_finish(pre, scr, lane, pc);
+          if (c + 1 < NCH) issue(item, c0 + 32);
+          else if (item + n_pairs < total_items) issue(item + n_pairs, cbeg);
+          if (live) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[c][j]);
+            store_tile32(g, e, clip, m0, n0 + c0, v, scr, lane, ps.base ? pc : nullptr);
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
         float v[32], pc[32];
         const bool live = mt < total_mt && n0 + c0 < g.N && m0 < g.mclip;
         if (live) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TN2 + c0), v);
-          if (split) {
-            float w[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN2 + c0), w);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += w[j];
-          }
           if (ps.base) rows_finish(pre, scr, lane, pc);
         }
         if (c0 + 32 < cend) issue(item, c0 + 32);
@@ -1456,8 +1513,17 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
   if (!second) { mx2h = mxh; mx2l = mxl; }
   if (!g.acc3) { myh = mxh; myl = mxl; mid = mwh; }
   if ((!force_1cta || second || g.acc3) && pair_ok) {
-    static std::atomic<uint64_t> attr2_done{0};
-    NSW_TRY(ensure_dynamic_smem((const void*)conv_gemm_tc2_kernel, (int)TC2_SMEM_BYTES, attr2_done));
+    typedef void (*Tc2Fn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                          CUtensorMap, CUtensorMap, ConvGemm, EpiParams, int, int, int);
+    static const Tc2Fn fns[4][2] = {{conv_gemm_tc2_kernel<EPI_PLANES, 0>, conv_gemm_tc2_kernel<EPI_PLANES, 1>},
+                                    {conv_gemm_tc2_kernel<EPI_DECONV, 0>, conv_gemm_tc2_kernel<EPI_DECONV, 1>},
+                                    {conv_gemm_tc2_kernel<EPI_ROWS, 0>, conv_gemm_tc2_kernel<EPI_ROWS, 1>},
+                                    {conv_gemm_tc2_kernel<EPI_GATE, 0>, conv_gemm_tc2_kernel<EPI_GATE, 1>}};
+    NSW_CHECK(e.mode >= 0 && e.mode < 4, NSW_EINVAL, "conv_gemm_tc: bad epilogue mode %d", e.mode);
+    const int sp = g.split_acc ? 1 : 0;
+    const Tc2Fn kern = fns[e.mode][sp];
+    static std::atomic<uint64_t> attr2_done[4][2];
+    NSW_TRY(ensure_dynamic_smem((const void*)kern, (int)TC2_SMEM_BYTES, attr2_done[e.mode][sp]));
     const int n_tiles2 = (g.N + TN2 - 1) / TN2;
     const int items = ((total_mt + 1) / 2) * n_tiles2;
     cudaLaunchConfig_t cfg = {};
@@ -1475,12 +1541,12 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
     static int max_pairs[64] = {0};  // per device
     if (max_pairs[dev & 63] == 0) {
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc2_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = sms / 2;
       max_pairs[dev & 63] = n;
     }
     cfg.gridDim = dim3(2 * (unsigned)std::min(items, std::min(max_pairs[dev & 63], sms / 2)));
-    NSW_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc2_kernel, mxh, mxl, mwh, mwl, mx2h, mx2l, myh, myl, mid, g, e,
-                                tiles_per_clip, n_tiles2, items));
+    NSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, mx2h, mx2l, myh, myl, mid, g, e, tiles_per_clip, n_tiles2,
+                                items));
     count_launch();
     NSW_CUDA(cudaGetLastError());
     return NSW_OK;
