@@ -184,7 +184,7 @@ struct nsw_teacher {
   // write back) and the update is one GEMM whose accumulate source goes through the tensor core (ConvGemm::acc3);
   // NSW_TEACHER_FP32_MASTER=1 keeps the fp32 rows and the read-modify-write epilogue
   bool acc_mma = true;
-  // ConvGemm::split_acc for the dilated-conv GEMMs.  Max-abs error of out_params against the fp64 oracle / forward time at
+  // ConvGemm::split_acc for the dilated-conv GEMMs.  Max-abs error of out_params against the fp64 reference of tests/test_teacher_gpu.py / forward time at
   // 7 x 7680 (profiles/r02, run33), conditioning fused:  split 5.6e-5 / 11.45 ms;  no split 1.01e-4 / 10.05 ms (over the
   // 1e-4 bar: 17 % more instructions into the large accumulator than the separate-conditioning scheme, 8.3e-5 / 11.5 ms).
   // On unless NSW_TEACHER_SPLIT_ACC=0.
