@@ -238,6 +238,18 @@ int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tenso
 int nsw_fastgen_gn_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tensors, int32_t n_tensors,
                              float* blocks, int64_t blocks_cap, float* cond_w, float* cond_b, int64_t* sizes);
 
+/* KERNEL-LEVEL PARITY HOOK: the tcgen05 conv-GEMM every dense contraction of the path runs on (masked.conv1d as a
+ * GEMM, masked.py:160-232; trans_conv1d phases, masked.py:235-291), with fp32 operands split on the device:
+ *   out[(clip, m), n] = bias[n] + sum_{tap, c} x[clip, m + a_off + tap*tap_stride, c] * w[tap*cin + c, n]
+ *                       + sum_c x2[clip, m + a_off2, c] * w[ntaps*cin + c, n]      (x2 != NULL: second source)
+ *                       + y[(clip, m), n]                                          (y  != NULL: accumulate source)
+ * rows outside [0, L) / [0, L2) read as zeros.  cin, cin2 multiples of 64; N a multiple of 64.  flags: 1 = small split
+ * products in their own accumulator, 2 = the one-CTA 128 x 128 kernel instead of the CTA-pair kernel. */
+int nsw_conv_gemm_device(const float* d_x, int32_t nclips, int32_t L, int32_t cin, int32_t ntaps, int32_t a_off,
+                         int32_t tap_stride, int32_t mclip, const float* d_w, int32_t N, const float* d_bias,
+                         const float* d_x2, int32_t L2, int32_t cin2, int32_t a_off2, const float* d_y, int32_t flags,
+                         float* d_out, void* stream);
+
 /* TEST HOOK (host only, no CUDA): work split and publish / read plan of one launch of the persistent IAF flow kernel
  * (engine NSW_ENGINE_TC3), computed by the same integer functions the kernel uses.  Per CTA: {clip, first tile, tiles,
  * CTAs of the clip} then (l1-l0)*tiles records {published, source of tap t-2d, source of tap t-d} with source >= 0 a

@@ -47,6 +47,7 @@ struct ConvGemm {
   // residual/skip GEMM (K = 256: 6 k cycles of MMAs per item) spent 40 k cycles per item on.  In-place (Y = the split
   // output of the same call) is fine: an item reads exactly the block it later writes.
   int acc3 = 0, ld3 = 0;
+  int one_cta = 0;  // force the 128 x 128 one-CTA kernel (parity hook / A-B runs)
 };
 
 // EPI_ROWS : out[row * ld_out + n] (+)= D + bias[n] (+ addend[row * ld_add + n]); optional relu;

@@ -1518,7 +1518,9 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
             "conv_gemm_tc: a second / accumulate source needs the pair kernel (N > 128, >= 2 m-tiles)");
   if (!second) { mx2h = mxh; mx2l = mxl; }
   if (!g.acc3) { myh = mxh; myl = mxl; mid = mwh; }
-  if ((!force_1cta || second || g.acc3) && pair_ok) {
+  NSW_CHECK(!(g.one_cta && (second || g.acc3 || g.split_acc)), NSW_EINVAL,
+            "conv_gemm_tc: the one-CTA kernel has no second / accumulate source and no split accumulators");
+  if (!g.one_cta && (!force_1cta || second || g.acc3) && pair_ok) {
     typedef void (*Tc2Fn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                           CUtensorMap, CUtensorMap, ConvGemm, EpiParams, int, int, int);
     static const Tc2Fn fns[4][2] = {{conv_gemm_tc2_kernel<EPI_PLANES, 0>, conv_gemm_tc2_kernel<EPI_PLANES, 1>},
@@ -1707,5 +1709,85 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
 }
 
 }  // namespace nsw
+
+
+// ---------------------------------------------------------------------------------------------
+// nsw_conv_gemm_device (include/nsw.h): kernel-level parity hook.  fp32 operands are split / transposed on the
+// device into scratch buffers that live for the call only.
+// ---------------------------------------------------------------------------------------------
+namespace nsw {
+namespace {
+__global__ void hook_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+// w [K rows: taps*cin then cin2][N]  ->  Bt [N][K columns: cin2 first, then taps*cin], split
+__global__ void hook_weight_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int Kmain,
+                                   int K2, int N) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = Kmain + K2;
+  if (i >= (size_t)N * K) return;
+  const int n = (int)(i / K), kc = (int)(i - (size_t)n * K);
+  const int krow = kc < K2 ? Kmain + kc : kc - K2;
+  const float v = w[(size_t)krow * N + n];
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+}  // namespace
+}  // namespace nsw
+
+extern "C" int nsw_conv_gemm_device(const float* d_x, int32_t nclips, int32_t L, int32_t cin, int32_t ntaps, int32_t a_off,
+                                    int32_t tap_stride, int32_t mclip, const float* d_w, int32_t N, const float* d_bias,
+                                    const float* d_x2, int32_t L2, int32_t cin2, int32_t a_off2, const float* d_y,
+                                    int32_t flags, float* d_out, void* stream) {
+  using namespace nsw;
+  NSW_CHECK(d_x && d_w && d_out && nclips >= 1 && L >= 1 && mclip >= 1 && ntaps >= 1, NSW_EINVAL,
+            "nsw_conv_gemm_device: bad argument");
+  NSW_CHECK(cin % 64 == 0 && N % 64 == 0 && (d_x2 == nullptr || (cin2 % 64 == 0 && cin2 > 0 && L2 >= 1)), NSW_EINVAL,
+            "nsw_conv_gemm_device: cin, cin2 and N must be multiples of 64");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K2 = d_x2 ? cin2 : 0, Kmain = ntaps * cin, K = Kmain + K2;
+  const size_t nx = (size_t)nclips * L * cin, nx2 = d_x2 ? (size_t)nclips * L2 * cin2 : 0, nw = (size_t)N * K;
+  const size_t rows = (size_t)nclips * mclip, ny = d_y ? rows * N : 0;
+  DevBuf xs, x2s, ws, ys, zero_bias;
+  NSW_TRY(xs.ensure(nx * 2 * sizeof(__half)));
+  NSW_TRY(ws.ensure(nw * 2 * sizeof(__half)));
+  if (nx2) NSW_TRY(x2s.ensure(nx2 * 2 * sizeof(__half)));
+  if (ny) NSW_TRY(ys.ensure(ny * 2 * sizeof(__half)));
+  auto split = [&](const float* src, DevBuf& dst, size_t n) {
+    hook_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst.as<__half>(), dst.as<__half>() + n, n);
+  };
+  split(d_x, xs, nx);
+  if (nx2) split(d_x2, x2s, nx2);
+  if (ny) split(d_y, ys, ny);
+  hook_weight_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(d_w, ws.as<__half>(), ws.as<__half>() + nw, Kmain, K2, N);
+  NSW_CUDA(cudaGetLastError());
+  if (!d_bias) {
+    NSW_TRY(zero_bias.ensure((size_t)N * sizeof(float)));
+    NSW_CUDA(cudaMemsetAsync(zero_bias.p, 0, (size_t)N * sizeof(float), st));
+  }
+  ConvGemm g;
+  g.nclips = nclips; g.L = L; g.cin = cin; g.ntaps = ntaps; g.a_off = a_off; g.tap_stride = tap_stride; g.mclip = mclip;
+  g.N = N;
+  if (d_x2) { g.cin2 = cin2; g.a_off2 = a_off2; g.L2 = L2; }
+  if (d_y) { g.acc3 = 1; g.ld3 = N; }
+  g.split_acc = (flags & 1) ? 1 : 0;
+  g.one_cta = (flags & 2) ? 1 : 0;
+  EpiParams e{};
+  e.mode = EPI_ROWS;
+  e.bias = d_bias ? d_bias : zero_bias.as<float>();
+  e.out_f32 = d_out;
+  e.ld_out = N;
+  int rc = conv_gemm_tc(g, xs.as<__half>(), xs.as<__half>() + nx, ws.as<__half>(), ws.as<__half>() + nw, e, st,
+                        nx2 ? x2s.as<__half>() : nullptr, nx2 ? x2s.as<__half>() + nx2 : nullptr,
+                        ny ? ys.as<__half>() : nullptr, ny ? ys.as<__half>() + ny : nullptr);
+  cudaStreamSynchronize(st);  // the scratch buffers die with this frame
+  return rc;
+}
 
 NSW_RANGE_GUARD_TU(gemm_tc)
