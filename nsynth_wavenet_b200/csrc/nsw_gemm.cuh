@@ -41,8 +41,8 @@ struct ConvGemm {
   // Costs the second accumulator stage (the epilogue no longer overlaps the next item's MMAs).
   int split_acc = 0;
   // pair kernel: C += Y for a matrix Y held as a split pair [nclips*mclip, ld3] (fp16 hi + lo): its 256-column block of
-  // the work item rides through the tensor core as four more k-blocks against an identity B tile (hi*1 + lo*1, exact),
-  // fetched by TMA like every other operand.  Replaces the epilogue's read-back of the fp32 rows it accumulates onto --
+  // the work item rides through the tensor core as four more k-blocks against a 64 x 64 identity (N = 64 MMAs into the
+  // matching column slice of the accumulator; hi*1 + lo*1, exact), fetched by TMA like every other operand.  Replaces the epilogue's read-back of the fp32 rows it accumulates onto --
   // a chain of global loads per 32-column chunk with a few KB in flight per warp, which is what the teacher's
   // residual/skip GEMM (K = 256: 6 k cycles of MMAs per item) spent 40 k cycles per item on.  In-place (Y = the split
   // output of the same call) is fine: an item reads exactly the block it later writes.

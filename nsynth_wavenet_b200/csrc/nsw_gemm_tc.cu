@@ -1252,15 +1252,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
           const uint32_t dst = sbase0 + (uint32_t)stage * STAGE_BYTES;
-          if (leader) mbar_expect_tx(&tail->full[stage], 2 * STAGE_BYTES);
+          if (leader) mbar_expect_tx(&tail->full[stage], kb >= num_kbw ? 2 * (2 * TILE_BYTES + 32 * TBK * 2) : 2 * STAGE_BYTES);
           const uint32_t fb = cp2_mapa(smem_u32(&tail->full[stage]), 0);
           if (kb >= num_kbw) {
-            // accumulate source: columns [nt * 256 + j * 64, +64) of Y against rows of the 256 x 256 identity
+            // accumulate source: columns [nt * 256 + j * 64, +64) of Y against the 64 x 64 identity (N = 64 MMAs into
+            // that column slice of the accumulator; this CTA holds 32 of the identity's rows: 4 KB per k-block)
             const int j = kb - num_kbw;
             cp2_tma_3d(dst, &map_yh, fb, nt * TN2 + j * TBK, m0, clip);
             cp2_tma_3d(dst + TILE_BYTES, &map_yl, fb, nt * TN2 + j * TBK, m0, clip);
-            cp2_tma_2d(dst + 2 * TILE_BYTES, &map_id, fb, j * TBK, crank * (TN2 / 2));
-            cp2_tma_2d(dst + 3 * TILE_BYTES, &map_id, fb, j * TBK, crank * (TN2 / 2));  // (unused: keeps the stage size)
+            cp2_tma_2d(dst + 2 * TILE_BYTES, &map_id, fb, 0, crank * 32);
           } else if (kb >= num_kb2) {
             const int tap = (kb - num_kb2) / kb_per_tap;
             const int c0 = (kb - num_kb2 - tap * kb_per_tap) * TBK;
@@ -1304,12 +1304,30 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
           const uint64_t xl = umma_desc_sw128(sb + TILE_BYTES);
           const uint64_t wh = umma_desc_sw128(sb + 2 * TILE_BYTES);
           const uint64_t wl = umma_desc_sw128(sb + 3 * TILE_BYTES);
+          if (kb >= num_kbw) {
+            // identity k-block: D[:, 64 j .. 64 j + 63] += Y_lo * I + Y_hi * I (exact), M = 256, N = 64
+            const uint32_t idesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t dj = (uint32_t)((kb - num_kbw) * 64);
+            if (tc_elect()) {
+#pragma unroll
+              for (int k = 0; k < TBK / 16; ++k) {
+                const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+                cp2_mma(d_small + dj, xl + adv, wh + adv, idesc64, 1);
+                cp2_mma(d_tmem + dj, xh + adv, wh + adv, idesc64, 1);
+              }
+              cp2_commit(&tail->empty[stage]);
+              if (kb == num_kb - 1) cp2_commit(&tail->tmem_full[as]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (tc_elect()) {
 #pragma unroll
             for (int k = 0; k < TBK / 16; ++k) {
               const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
               cp2_mma(d_small, xl + adv, wh + adv, idesc, (kb | k) != 0);
-              if (kb < num_kbw) cp2_mma(d_small, xh + adv, wl + adv, idesc, 1);  // (identity blocks: lo * 1 + hi * 1 only)
+              cp2_mma(d_small, xh + adv, wl + adv, idesc, 1);
               cp2_mma(d_tmem, xh + adv, wh + adv, idesc, split ? (uint32_t)((kb | k) != 0) : 1u);
             }
             cp2_commit(&tail->empty[stage]);
@@ -1457,22 +1475,22 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
   CUtensorMap mxh, mxl, mwh, mwl, mx2h, mx2l, myh, myl, mid;
   if (g.acc3) {
     NSW_CHECK(Y_hi && Y_lo && g.ld3 % 8 == 0 && g.ld3 >= g.N, NSW_EINVAL, "conv_gemm_tc: bad accumulate source (ld3=%d)", g.ld3);
-    // 256 x 256 fp16 identity, one per device, built on first use
+    // 64 x 64 fp16 identity, one per device, built on first use
     static __half* ident[64] = {nullptr};
     int dv = 0;
     NSW_CUDA(cudaGetDevice(&dv));
     if (!ident[dv & 63]) {
-      std::vector<__half> id((size_t)TN2 * TN2, __float2half(0.f));
-      for (int i = 0; i < TN2; ++i) id[(size_t)i * TN2 + i] = __float2half(1.f);
+      std::vector<__half> id((size_t)64 * 64, __float2half(0.f));
+      for (int i = 0; i < 64; ++i) id[(size_t)i * 64 + i] = __float2half(1.f);
       __half* d = nullptr;
       NSW_CUDA(cudaMalloc(&d, id.size() * sizeof(__half)));
       NSW_CUDA(cudaMemcpy(d, id.data(), id.size() * sizeof(__half), cudaMemcpyHostToDevice));
       ident[dv & 63] = d;
     }
     {
-      const uint64_t dims[2] = {(uint64_t)TN2, (uint64_t)TN2};
-      const uint64_t strides[1] = {(uint64_t)TN2 * 2};
-      const uint32_t box[2] = {TBK, TBN};
+      const uint64_t dims[2] = {64, 64};
+      const uint64_t strides[1] = {64 * 2};
+      const uint32_t box[2] = {TBK, 32};
       NSW_TRY(make_map(enc, &mid, ident[dv & 63], 2, dims, strides, box));
     }
     const uint64_t dims[3] = {(uint64_t)g.ld3, (uint64_t)g.mclip, (uint64_t)g.nclips};
