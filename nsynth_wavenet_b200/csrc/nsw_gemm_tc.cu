@@ -14,6 +14,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace nsw {
@@ -1477,8 +1478,10 @@ int conv_gemm_tc(const ConvGemm& g, const __half* X_hi, const __half* X_lo,
     NSW_CHECK(Y_hi && Y_lo && g.ld3 % 8 == 0 && g.ld3 >= g.N, NSW_EINVAL, "conv_gemm_tc: bad accumulate source (ld3=%d)", g.ld3);
     // 64 x 64 fp16 identity, one per device, built on first use
     static __half* ident[64] = {nullptr};
+    static std::mutex ident_mu;
     int dv = 0;
     NSW_CUDA(cudaGetDevice(&dv));
+    std::lock_guard<std::mutex> ident_lock(ident_mu);
     if (!ident[dv & 63]) {
       std::vector<__half> id((size_t)64 * 64, __float2half(0.f));
       for (int i = 0; i < 64; ++i) id[(size_t)i * 64 + i] = __float2half(1.f);

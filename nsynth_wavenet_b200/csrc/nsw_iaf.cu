@@ -448,9 +448,10 @@ struct nsw_iaf {
   int device = 0;
   int num_sms = 148;
   std::vector<FlowWeights> flows;
-  // engine tc3 with a shared upsampling stack: the mel-cond projections of ALL flows are one GEMM (the activation tile
-  // is loaded once per 128 rows instead of once per flow, one launch and one tail instead of four, no column padding:
-  // 64 * sum(L_f + 1) is a multiple of 256 for the shipped configs)
+  // NSW_COND_ALL_FLOWS=1 (engine tc3, shared upsampling stack): the mel-cond projections of ALL flows as one GEMM (the
+  // activation tile is loaded once per 128 rows instead of once per flow, one launch and one tail instead of four, no
+  // column padding).  Measured 6 % fewer cycles and the same time (profiles/r02: run25, run44) for twice the plane
+  // memory (1 GB at 8 x 7680), so it is off by default.
   DevBuf Wct_all_hi, Wct_all_lo, bc_all;  // the flows' Wct_* / bc back to back
   std::vector<size_t> plane_off;          // first cond plane of flow f
   size_t total_planes = 0;                // 0: one projection per flow
@@ -643,7 +644,7 @@ extern "C" int nsw_iaf_create(const nsw_iaf_config* cfg, const nsw_tensor* tenso
     h->max_layers = std::max(h->max_layers, cfg->num_iaf_layers[f]);
   }
   if (rc == NSW_OK && cfg->engine == NSW_ENGINE_TC3 && cfg->share_deconv && cfg->num_flows > 1 &&
-      getenv("NSW_COND_PER_FLOW") == nullptr) {
+      getenv("NSW_COND_ALL_FLOWS") != nullptr) {
     size_t planes = 0;
     for (int f = 0; f < cfg->num_flows; ++f) {
       h->plane_off.push_back(planes);
