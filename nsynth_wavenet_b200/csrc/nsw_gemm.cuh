@@ -74,6 +74,12 @@ struct EpiParams {
   //   plane[((row/128)*8 + (row%128)/32*2 + (n%64)/32) * 1024 + ((n%32)/4)*128 + (row%32)*4 + n%4]
   // (a warp-level 16-byte access of one column group is 512 contiguous bytes); needs mclip % 128 == 0
   int tiled_planes = 0;
+  // EPI_DECONV: rows per clip of the OUTPUT buffers (0 = Lout): an intermediate of the upsampling stack is written with
+  // zero rows after every clip so that the next layer can run over all clips as ONE flattened clip (no 128-row tile
+  // padding per clip: 8 x 393 rows are 25 tiles instead of 32), its taps reading the zero rows at the clip boundaries.
+  int out_clip_rows = 0;
+  // EPI_DECONV on such a flattened input: GEMM row m' = clip * flat_rows + m (0: rows are (clip, m) as usual)
+  int flat_rows = 0;
 };
 
 // fp32 X [nclips, L, cin], fp32 Bw [ntaps*cin, N]
@@ -136,7 +142,8 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
 struct DeconvLayer {
   DeconvGeom g;
   DevBuf Bw;              // fp32 [ntaps*cin][s*cout]
-  DevBuf Bt_hi, Bt_lo;    // fp16 [s*cout][ntaps*cin] (tensor-core engine)
+  DevBuf Bt_hi, Bt_lo;    // fp16 [s*cout][ntaps*cin_pad] (tensor-core engine; cin_pad = cin rounded up to 64, zero columns)
+  int cin_pad = 0;
   DevBuf bias;            // [cout]
 };
 

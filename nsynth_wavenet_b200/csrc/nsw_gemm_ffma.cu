@@ -25,7 +25,8 @@ __device__ __forceinline__ void store_epi(const ConvGemm& g, const EpiParams& e,
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     *reinterpret_cast<float4*>(e.out_f32 + (size_t)r * e.ld_out + n) = v;
   } else {
-    const int clip = r / g.mclip, m = r - clip * g.mclip;
+    const int rpc = e.flat_rows > 0 ? e.flat_rows : g.mclip;  // flattened input: the GEMM's "clip" is all clips
+    const int clip = r / rpc, m = r - clip * rpc;
     const int rr = n / e.cout, co = n - rr * e.cout;
     const int o = m * e.s + rr - e.p;
     if (o < 0 || o >= e.Lout) return;
@@ -34,7 +35,7 @@ __device__ __forceinline__ void store_epi(const ConvGemm& g, const EpiParams& e,
     v.y = apply_act(v.y + b.y, e.act);
     v.z = apply_act(v.z + b.z, e.act);
     v.w = apply_act(v.w + b.w, e.act);
-    const size_t off = ((size_t)clip * e.Lout + o) * e.cout + co;
+    const size_t off = ((size_t)clip * (e.out_clip_rows > 0 ? e.out_clip_rows : e.Lout) + o) * e.cout + co;
     if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + off) = v;
     if (e.out_hi) {
       float f[4] = {v.x, v.y, v.z, v.w};
@@ -130,6 +131,23 @@ void split_f16(const float* src, size_t n, __half* hi, __half* lo) {
   }
 }
 
+// mel [B, F, cin] fp32 -> split fp16 [B, rows, cp] with zero channels cin..cp-1 and zero rows F..rows-1
+namespace {
+__global__ void deconv_pad_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int B,
+                                        int F, int cin, int rows, int cp) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)B * rows * cp;
+  if (i >= n) return;
+  const int c = (int)(i % cp);
+  const size_t br = i / cp;
+  const int r = (int)(br % rows), b = (int)(br / rows);
+  const float v = (c < cin && r < F) ? x[((size_t)b * F + r) * cin + c] : 0.f;
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+}  // namespace
+
 // ------------------------------- DeconvStack -------------------------------
 int DeconvStack::init(const TensorMap& tm, const std::string& prefix, int num_mel, int width,
                       int n, const int32_t* filt, const int32_t* stride, int act_kind,
@@ -207,10 +225,15 @@ int DeconvStack::init(const TensorMap& tm, const std::string& prefix, int num_me
     const int K = g.ntaps * g.cin, N = g.s * g.cout;
     NSW_TRY(upload(L.Bw, bw.data(), bw.size() * sizeof(float)));
     NSW_TRY(upload(L.bias, bias, g.cout * sizeof(float)));
+    L.cin_pad = (g.cin + 63) / 64 * 64;
     if (want_tc) {
-      std::vector<float> bt((size_t)N * K);
-      for (int kk = 0; kk < K; ++kk)
-        for (int nn = 0; nn < N; ++nn) bt[(size_t)nn * K + kk] = bw[(size_t)kk * N + nn];
+      // K-major, channels padded to a multiple of 64 with zero columns (layer 1: 80 mel bins -> 128), so that every
+      // layer of the stack can run on the tensor cores
+      const int cp = L.cin_pad, Kp = g.ntaps * cp;
+      std::vector<float> bt((size_t)N * Kp, 0.f);
+      for (int tp = 0; tp < g.ntaps; ++tp)
+        for (int c = 0; c < g.cin; ++c)
+          for (int nn = 0; nn < N; ++nn) bt[(size_t)nn * Kp + tp * cp + c] = bw[(size_t)(tp * g.cin + c) * N + nn];
       std::vector<__half> hi(bt.size()), lo(bt.size());
       split_f16(bt.data(), bt.size(), hi.data(), lo.data());
       NSW_TRY(upload(L.Bt_hi, hi.data(), hi.size() * sizeof(__half)));
@@ -227,21 +250,42 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __hal
   const int n = (int)layers.size();
   NSW_CHECK(n >= 1, NSW_EINVAL, "deconv stack is empty");
   // intermediate activations: layer i output has length Li = F * prod(s_0..s_i)
+  // zero rows the NEXT layer needs after each clip of layer i's output to run over all clips as one flattened clip
+  auto pad_rows = [&](int i, int Lout) {
+    const DeconvGeom& nx = layers[i + 1].g;
+    return std::max(0, std::max(-nx.a_off, nx.mclip(Lout) + nx.a_off + nx.ntaps - 1 - Lout));
+  };
   size_t max_elems = 0;
   {
     int L = F;
     for (int i = 0; i + 1 < n; ++i) {
       L *= layers[i].g.s;
-      max_elems = std::max(max_elems, (size_t)B * L * layers[i].g.cout);
+      max_elems = std::max(max_elems, (size_t)B * (L + pad_rows(i, L)) * layers[i].g.cout);
     }
   }
-  // two ping-pong slots, each big enough for fp32 or (fp16 hi + fp16 lo)
-  NSW_TRY(scratch.ensure(2 * max_elems * sizeof(float) + 256));
+  // tensor-core engine: the mel input itself as a padded split pair, so that layer 1 runs on tensor cores too
+  const DeconvGeom& g0 = layers[0].g;
+  const int cp0 = layers[0].cin_pad;
+  const int P0 = std::max(0, std::max(-g0.a_off, g0.mclip(F) + g0.a_off + g0.ntaps - 1 - F));
+  const bool in_tc = engine == NSW_ENGINE_TC && layers[0].Bt_hi.p != nullptr && (g0.s * g0.cout) % 64 == 0;
+  const size_t in_elems = in_tc ? (size_t)B * (F + P0) * cp0 : 0;  // halves per plane
+  // two ping-pong slots, each big enough for fp32 or (fp16 hi + fp16 lo), + the split input
+  NSW_TRY(scratch.ensure(2 * max_elems * sizeof(float) + 256 + 2 * in_elems * sizeof(__half)));
   float* slot[2] = {scratch.as<float>(), scratch.as<float>() + max_elems};
 
   const float* x_f32 = d_mel;
   const __half *x_hi = nullptr, *x_lo = nullptr;
   int L = F;
+  int in_rows = 0;  // > 0: the input of this layer is padded to in_rows rows per clip (zero rows after the data)
+  if (in_tc) {
+    __half* ih = reinterpret_cast<__half*>(scratch.as<float>() + 2 * max_elems + 64);
+    __half* il = ih + in_elems;
+    deconv_pad_split_kernel<<<(unsigned)((in_elems + 255) / 256), 256, 0, stream>>>(d_mel, ih, il, B, F, g0.cin, F + P0, cp0);
+    count_launch();
+    x_hi = ih;
+    x_lo = il;
+    in_rows = F + P0;
+  }
   for (int i = 0; i < n; ++i) {
     const DeconvLayer& ly = layers[i];
     const DeconvGeom& dg = ly.g;
@@ -249,7 +293,7 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __hal
     ConvGemm g;
     g.nclips = B;
     g.L = L;
-    g.cin = dg.cin;
+    g.cin = (engine == NSW_ENGINE_TC && x_hi != nullptr) ? ly.cin_pad : dg.cin;
     g.ntaps = dg.ntaps;
     g.a_off = dg.a_off;
     g.mclip = dg.mclip(L);
@@ -292,10 +336,29 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __hal
       }
     }
     NSW_CHECK(o_f32 || o_hi, NSW_EINVAL, "deconv: no output buffer for layer %d", i + 1);
+    // an intermediate that the next layer reads as split fp16 on tensor cores is written padded (see EpiParams)
+    int out_rows = 0;
+    if (!last && next_wants_split && !o_f32) {
+      const int P = pad_rows(i, e.Lout);
+      out_rows = e.Lout + P;
+      o_lo = o_hi + (size_t)B * out_rows * dg.cout;
+      e.out_clip_rows = out_rows;
+      if (P > 0) {
+        const size_t pitch = (size_t)out_rows * dg.cout * sizeof(__half), width = (size_t)P * dg.cout * sizeof(__half);
+        NSW_CUDA(cudaMemset2DAsync(o_hi + (size_t)e.Lout * dg.cout, pitch, 0, width, B, stream));
+        NSW_CUDA(cudaMemset2DAsync(o_lo + (size_t)e.Lout * dg.cout, pitch, 0, width, B, stream));
+      }
+    }
     e.out_f32 = o_f32;
     e.out_hi = o_hi;
     e.out_lo = o_lo;
     if (this_tc) {
+      if (in_rows > 0) {  // all clips as one flattened clip
+        g.nclips = 1;
+        g.L = B * in_rows;
+        g.mclip = B * in_rows;
+        e.flat_rows = in_rows;
+      }
       NSW_TRY(conv_gemm_tc(g, x_hi, x_lo, ly.Bt_hi.as<__half>(),
                            ly.Bt_lo.as<__half>(), e, stream));
     } else {
@@ -306,6 +369,7 @@ int DeconvStack::forward(const float* d_mel, int B, int F, float* out_f32, __hal
     x_hi = o_hi;
     x_lo = o_lo;
     L = e.Lout;
+    in_rows = out_rows;
   }
   return NSW_OK;
 }

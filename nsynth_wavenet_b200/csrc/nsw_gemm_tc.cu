@@ -404,9 +404,11 @@ __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams&
       const size_t M = (size_t)g.nclips * g.mclip;
       return reinterpret_cast<float4*>(e.out_f32 + ((size_t)(n >> 6) * M + (size_t)clip * g.mclip + m) * 64 + (n & 63));
     }
-    const int o = m * e.s + rr - e.p;
+    int c = clip, mm = m;
+    if (e.flat_rows > 0) { c = m / e.flat_rows; mm = m - c * e.flat_rows; }  // flattened input (see EpiParams)
+    const int o = mm * e.s + rr - e.p;
     if (o < 0 || o >= e.Lout) return nullptr;
-    return reinterpret_cast<float4*>(e.out_f32 + ((size_t)clip * e.Lout + o) * e.cout + co);
+    return reinterpret_cast<float4*>(e.out_f32 + ((size_t)c * (e.out_clip_rows > 0 ? e.out_clip_rows : e.Lout) + o) * e.cout + co);
   };
   if (e.mode == EPI_PLANES && (n >> 6) < e.tiled_planes) {
     // row-interleaved plane (tc3 layer kernel): lane's row, float4 j -> [j][lane]; 512 B per store
@@ -466,10 +468,12 @@ __device__ __forceinline__ void store_tile32(const ConvGemm& g, const EpiParams&
       for (int i = 0; i < 4; ++i) {
         const int r = 8 * i + (lane >> 2);
         const int m = m0 + r;
-        const int o = m * e.s + rr - e.p;
+        int c = clip, mm = m;
+        if (e.flat_rows > 0) { c = m / e.flat_rows; mm = m - c * e.flat_rows; }
+        const int o = mm * e.s + rr - e.p;
         const float4 val = lds128(scr + (uint32_t)(r * 4 + ((lane & 3) ^ ((r >> 1) & 3))) * 16u);
         if (m < g.mclip && o >= 0 && o < e.Lout)
-          reinterpret_cast<float4*>(base + ((size_t)clip * e.Lout + o) * e.cout + co)[lane & 3] = val;
+          reinterpret_cast<float4*>(base + ((size_t)c * (e.out_clip_rows > 0 ? e.out_clip_rows : e.Lout) + o) * e.cout + co)[lane & 3] = val;
       }
       __syncwarp();
     }
@@ -1671,8 +1675,9 @@ int cond_proj_tc(int nclips, int L, int mclip, int a_off, int N, const __half* X
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+    static int max_pairs2[64][2] = {{0}};  // per device and kernel variant: the query costs tens of microseconds
+    int& n = max_pairs2[dev & 63][wide ? 1 : 0];
+    if (n == 0 && (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1)) n = sms / 2;
     cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(pair_items, std::min(n, sms / 2)));
     // each CTA loads TN/2 weight rows per stage: the full-height box for TN = 256, the half-height one for 128
     if (wide) NSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mxh, mxl, mwh, mwl, g));
