@@ -664,7 +664,7 @@ def main():
             'share_of_step': stage['layers'] / stage['total'],
         },
         'roofline_cond_gemm': {
-            'kernel': 'cond_proj_tc_kernel' if eng.engine == 'tc3' else 'conv_gemm (cond projections)', 'bound': 'tensor',
+            'kernel': 'cond_proj_tc2_kernel<256> (cta_group::2)' if eng.engine == 'tc3' else 'conv_gemm (cond projections)', 'bound': 'tensor',
             'achieved': cond_tflops * SPLIT_PRODUCTS, 'peak': tc_peak, 'unit': 'TFLOP/s',
             'frac': cond_tflops * SPLIT_PRODUCTS / tc_peak, 'achieved_fp32_equivalent': cond_tflops,
             'note': 'issued fp16 tensor flops = 3 x the algorithmic 2*256*64 per (sample, plane)',
