@@ -382,7 +382,7 @@ def distill_bench(device, tc_peak, world, dev, barrier, max_over_ranks):
                       '{} GPU(s): {} clips'.format(world, 7 * world),
             'ms': ms, 'clips_per_s': 7 * world / (ms * 1e-3), 'teacher_forward_ms': te_ms, 'losses': res,
             'roofline_teacher': {
-                'kernel': 'conv_gemm_tc_kernel (teacher layers)', 'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': tc_peak,
+                'kernel': 'conv_gemm_tc2_kernel<EPI_GATE,1> / <EPI_ROWS,0> (teacher layers, cta_group::2)', 'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': tc_peak,
                 'achieved': issued, 'frac': issued / tc_peak,
                 'achieved_fp32_equivalent': issued / SPLIT_PRODUCTS,
                 'note': 'issued fp16 tensor flops = 3 x the algorithmic 67.4 MFLOP per sample (split-fp16 products)'}}
