@@ -361,6 +361,40 @@ __device__ __forceinline__ void store_tile32_rows(const ConvGemm& g, const EpiPa
   }
 }
 
+// EPI_ROWS whose only output is the fp16 split pair (no fp32 rows, no addend: the teacher's residual/skip update), for 32
+// rows x 64 columns: every store instruction writes whole 128-byte lines of a plane (4 rows x 128 B) instead of 64-byte
+// halves (8 rows x 64 B with the 32-column path).
+__device__ __forceinline__ void store_tile64_split(const ConvGemm& g, const EpiParams& e, int clip, int m0, int n,
+                                                   const float* v, uint32_t scr, int lane) {
+  const int rows_valid = min(32, g.mclip - m0);
+  if (rows_valid <= 0 || n >= g.N) return;
+  const size_t row0 = (size_t)clip * g.mclip + m0;
+  const float4* b4 = reinterpret_cast<const float4*>(e.bias + n);
+  const bool relu = n >= e.relu_split_from;
+  uint4 hi[8], lo[8];
+  uint32_t rmx = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
+    float f[8] = {v[8 * j] + b0.x, v[8 * j + 1] + b0.y, v[8 * j + 2] + b0.z, v[8 * j + 3] + b0.w,
+                  v[8 * j + 4] + b1.x, v[8 * j + 5] + b1.y, v[8 * j + 6] + b1.z, v[8 * j + 7] + b1.w};
+    float h[8], l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (relu) f[k] = fmaxf(f[k], 0.f);
+      range_track(rmx, f[k]);
+      h[k] = __half2float(__float2half_rn(f[k]));
+      l[k] = f[k] - h[k];
+    }
+    hi[j] = pack8_f16(h);
+    lo[j] = pack8_f16(l);
+  }
+  range_commit(rmx);
+  const size_t pb = (size_t)e.ld_split * 2;
+  store_rows<8>(reinterpret_cast<unsigned char*>(e.out_hi + n), row0, pb, rows_valid, scr, lane, hi);
+  store_rows<8>(reinterpret_cast<unsigned char*>(e.out_lo + n), row0, pb, rows_valid, scr, lane, lo);
+}
+
 // Epilogue of one warp for 32 rows x 32 consecutive columns (n % 32 == 0).  Thread `lane` holds
 // row m0 + lane in v[32].  Values go through a swizzled 4 KB smem scratch so that global memory
 // is written with full 128 B lines (8 lanes per row) instead of 32 scattered 16 B pieces per
@@ -1415,6 +1449,26 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[c][j]);
             store_tile32(g, e, clip, m0, n0 + c0, v, scr, lane, ps.base ? pc : nullptr);
           }
+        }
+        continue;
+      }
+      if (MODE == EPI_ROWS && e.out_f32 == nullptr && e.out_hi != nullptr && ps.base == nullptr && e.ld_split % 64 == 0 &&
+          (e.relu_split_from % 64 == 0)) {
+        // split-only rows: 64 columns at a time, whole 128-byte lines per store (store_tile64_split)
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cend; c0 += 64) {
+          if (!(mt < total_mt && n0 + c0 < g.N && m0 < g.mclip)) continue;
+          float v[64];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TN2 + c0);
+          tmem_ld32(ta, v);
+          tmem_ld32(ta + 32, v + 32);
+          store_tile64_split(g, e, clip, m0, n0 + c0, v, scr, lane);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tail->tmem_empty[as]);
+          else cp2_arrive_remote(cp2_mapa(smem_u32(&tail->tmem_empty[as]), 0));
         }
         continue;
       }
