@@ -1069,17 +1069,20 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
           const uint32_t dst = sbase + CP_OFF_W + ws * W_STAGE;
           if (leader) mbar_expect_tx(&B->w_full[ws], 2 * W_STAGE);
           const uint32_t wb = cp2_mapa(smem_u32(&B->w_full[ws]), 0);
-          // this CTA's half of the TN weight rows, hi then lo plane
-          cp2_tma_2d(dst, &map_wh2, wb, kb * TBK, nt * TN + crank * (TN / 2));
-          cp2_tma_2d(dst + W_PLANE, &map_wl2, wb, kb * TBK, nt * TN + crank * (TN / 2));
+          // this CTA's half of the item's weight rows, hi then lo plane.  The last item of a row pair may have fewer
+          // than TN valid columns (704 = 2 x 256 + 192): its MMAs run with N = the valid width, so the pair splits
+          // THOSE rows in half (the box still loads TN/2 rows; the extra ones are not read)
+          const int nthis = min(TN, g.N - nt * TN);
+          cp2_tma_2d(dst, &map_wh2, wb, kb * TBK, nt * TN + crank * (nthis / 2));
+          cp2_tma_2d(dst + W_PLANE, &map_wl2, wb, kb * TBK, nt * TN + crank * (nthis / 2));
           if (++ws == WSTAGES) { ws = 0; wphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (leader) {
-      // instruction descriptor: D = f32, A = B = f16, K-major, M = 256 (128 per CTA), N = TN
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      // instruction descriptor: D = f32, A = B = f16, K-major, M = 256 (128 per CTA), N = the item's valid columns
+      const uint32_t idesc_base = (1u << 4) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
       const uint32_t sbase_u = __reduce_or_sync(0xffffffffu, sbase);
       int ws = 0;
@@ -1099,6 +1102,9 @@ cond_proj_tc2_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
         }
         const bool last_of_x = (i + 1 == i1) || ((i + 1) / g.n_tiles != mt);
         const int as = acc_it & 1;
+        const int mtg_i = i / g.n_tiles;
+        const int nthis = min(TN, g.N - cp_ntile(i - mtg_i * g.n_tiles, mtg_i, g.n_tiles) * TN);
+        const uint32_t idesc = idesc_base | ((uint32_t)(nthis >> 3) << 17);
         long long tw = dbg ? clock64() : 0;
         mbar_wait(&B->tmem_empty[as], (uint32_t)(((acc_it >> 1) & 1) ^ 1));
         if (dbg) { const long long now = clock64(); w_acc += now - tw; }
