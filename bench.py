@@ -64,6 +64,15 @@ def measured_peaks():
     return 6650.0, 1590.0, 'fallback'
 
 
+def sustained_tc_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f).get('bf16_tflops_sustained') or 0.0) or None
+    except (OSError, ValueError):
+        return None
+
+
 def ncu_capture(name):
     """Committed ncu --set full summary of a kernel (profiles/r02 first, else r01): dict of metrics or None."""
     for rnd, fname in (('r02', 'flow_cond_ncu.json'), ('r01', 'tc3_ncu_run28.json')):
@@ -647,6 +656,8 @@ def main():
             # bound at 49 instead of 32 cycles; profiles/r02 ncu: shared-memory data pipe vs DRAM), NOT HBM
             'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': tc_peak,
             'achieved': issued_tflops, 'frac': issued_tflops / tc_peak, 'frac_tensor': issued_tflops / tc_peak,
+            # the same against the SUSTAINED dense peak (MEASURED_PEAKS.json: a 4 s GEMM under the power cap)
+            'frac_tensor_vs_sustained_peak': issued_tflops / sustained_tc_peak() if sustained_tc_peak() else None,
             'achieved_fp32_equivalent': issued_tflops / SPLIT_PRODUCTS,
             # SURVEY's per-layer-kernel byte model (768 B per sample and layer) against the HBM peak: a model
             # throughput, kept for continuity with round 1 -- the fused kernel never moves those bytes
