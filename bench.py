@@ -620,17 +620,23 @@ def main():
     # issued tensor-core flops of the same stage: 3 split-fp16 products per algorithmic MAC
     stage_flop = B * T * (LAYER_FLOP_PER_SAMPLE * n_layers + (HEAD_FLOP_PER_SAMPLE * n_flows if fused else 0))
     issued_tflops = stage_flop * SPLIT_PRODUCTS / (stage['layers'] * 1e-3) / 1e12
-    kernel_name = {'tc3': 'iaf_flow_tc_kernel', 'tc2': 'iaf_layer_tc_kernel'}.get(eng.engine, 'iaf_layer_kernel')
+    pair_flow = eng.engine == 'tc3' and os.environ.get('NSW_FLOW_PAIR', '1') != '0' and T % 256 == 0
+    kernel_name = {'tc3': 'iaf_flow_pair_kernel (cta_group::2)' if pair_flow else 'iaf_flow_tc_kernel',
+                   'tc2': 'iaf_layer_tc_kernel'}.get(eng.engine, 'iaf_layer_kernel')
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (one 10-layer flow launch);
     # only valid for the shape and engine it was captured on
     traffic, traffic_src, traffic_alg, frac_dram, ncu_extra = None, None, None, None, None
-    cap, cap_src = ncu_capture('iaf_flow_tc') if fused and (B, T) == (8, 7680) else (None, None)
+    cap, cap_src = (None, None)
+    if fused and (B, T) == (8, 7680):
+        cap, cap_src = ncu_capture('iaf_flow_pair' if pair_flow else 'iaf_flow_tc')
+        if cap is None:
+            cap, cap_src = ncu_capture('iaf_flow_')
     if cap:
         rd, wr = metric_value(cap, 'dram__bytes_read.sum'), metric_value(cap, 'dram__bytes_write.sum')
         scale = 1e6 if rd is not None and rd < 1e5 else 1.0     # r01 summaries are in MB
         traffic = (rd + wr) * scale
         traffic_alg = B * T * (LAYER_BYTES_PER_SAMPLE * 10 + 812)
-        traffic_src = cap_src + ': dram__bytes_read+write of one iaf_flow_tc_kernel launch (10-layer flow incl. start conv and head)'
+        traffic_src = cap_src + ': dram__bytes_read+write of one flow-kernel launch (10-layer flow incl. start conv and head)'
         # the four flows move 60 / 10 x this; divide by the live stage time
         frac_dram = traffic * (n_layers / 10.0) / (stage['layers'] * 1e-3) / 1e9 / hbm_peak
         ncu_extra = {k: metric_value(cap, k) for k in cap

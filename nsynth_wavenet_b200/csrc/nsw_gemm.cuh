@@ -102,7 +102,7 @@ void split_f16(const float* src, size_t n, __half* hi, __half* lo);
 
 // ---- tcgen05 fused IAF residual layer (nsw_iaf_layer_tc.cu); maps are 128-byte CUtensorMaps ----
 int layer_tc_make_act_map(void* map_out, const __half* base, int B, int T);
-int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k);
+int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k, int box_rows = 64);
 int layer_tc_launch(const void* const map_act[2][2], const void* map_wdh, const void* map_wdl,
                     const void* map_wrh, const void* map_wrl, const float* cond, size_t cond_plane,
                     __half* const hi[2], __half* const lo[2], const float* br, int T, int rows, int buf0,
@@ -137,6 +137,14 @@ int flow_tc_launch(const void* const map_act[2][2], const void* map_wdh, const v
                    const float* br, int T, int clip0, int nclips, int buf0, int l0, int l1, int num_stages,
                    unsigned int* sync_words, int num_sms, const FlowHead* head, const FlowStart* start,
                    cudaStream_t stream);
+
+// ---- the same flow on CTA pairs (nsw_iaf_flow_pair.cu): cta_group::2 MMAs, half of every weight tile per SM, the
+//      dilated-conv weights double-buffered.  Weight maps with 32-row boxes.  Whole flow, fused start conv and head only.
+int flow_pair_pairs_per_clip(int T, int nclips, int max_pairs);  // 0 = shape not covered
+int flow_pair_launch(const void* const map_act[2][2], const void* map_wdh32, const void* map_wdl32, const void* map_wrh32,
+                     const void* map_wrl32, const float* cond_tiled, size_t cond_plane, const float* br, int T, int nclips,
+                     int buf0, int nl, int num_stages, unsigned int* sync_words, int num_sms, const FlowHead* head,
+                     const FlowStart* start, cudaStream_t stream);
 
 // ---- transposed-conv upsampling stack (wavenet._deconv_stack, wavenet.py:46-73) ----
 struct DeconvLayer {

@@ -994,7 +994,9 @@ __device__ __forceinline__ void cp2_commit(uint64_t* bar) {  // arrives on the b
       : "memory");
 }
 __device__ __forceinline__ void cp2_arrive_remote(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  // default semantics (release at CTA scope): the accumulator stage this releases lives in TMEM, ordered by
+  // tcgen05.fence::before_thread_sync; a cluster-scope release waits for the warp's outstanding global stores
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
 template <int TN>

@@ -439,6 +439,7 @@ struct FlowWeights {
   DevBuf br_nat;            // [L][64] natural channel order
   DevBuf br_cum;            // [L][64] running sum of br over layers (engine tc3 keeps the biases out of TMEM)
   alignas(64) unsigned char map_wdh[128], map_wdl[128], map_wrh[128], map_wrl[128];
+  alignas(64) unsigned char map_wdh32[128], map_wdl32[128], map_wrh32[128], map_wrl32[128];  // 32-row boxes (pair kernel)
   float bm = 0.f, bs = 0.f;
   int deconv_index = 0;     // which DeconvStack feeds this flow
 };
@@ -584,6 +585,10 @@ static int pack_flow(const nsw_iaf_config& cfg, const TensorMap& tm, int f, Flow
     NSW_TRY(layer_tc_make_weight_map(fw.map_wdl, fw.WdT_lo.as<__half>(), (L * 3 + 1) * C, C));
     NSW_TRY(layer_tc_make_weight_map(fw.map_wrh, fw.WrT_hi.as<__half>(), L * C, HALF));
     NSW_TRY(layer_tc_make_weight_map(fw.map_wrl, fw.WrT_lo.as<__half>(), L * C, HALF));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdh32, fw.WdT_hi.as<__half>(), (L * 3 + 1) * C, C, 32));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wdl32, fw.WdT_lo.as<__half>(), (L * 3 + 1) * C, C, 32));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wrh32, fw.WrT_hi.as<__half>(), L * C, HALF, 32));
+    NSW_TRY(layer_tc_make_weight_map(fw.map_wrl32, fw.WrT_lo.as<__half>(), L * C, HALF, 32));
   }
   if (want_tc) {
     std::vector<float> bt((size_t)NP * D);
@@ -913,6 +918,17 @@ static int iaf_forward_internal(nsw_iaf* h, int B, int F, bool have_z, uint64_t 
           fh.use_mu_law = cfg.use_mu_law; fh.quant_chann = cfg.use_mu_law ? 256.0f : 65536.0f;
           head_fused = fuse_ends && l0 == 0 && l1 == fw.L;  // not when a debug tap wants this flow's rows
           FlowStart fs{x_cur, fw.start_w.as<float>(), fw.start_b.as<float>()};
+          // CTA-pair variant of the flow kernel (nsw_iaf_flow_pair.cu) wherever it covers the launch: whole flow, fused
+          // ends, all clips at once, an even number of tiles per clip.  NSW_FLOW_PAIR=0 keeps the single-CTA kernel
+          // (read per call, so that a test can switch it).
+          const char* pair_env = getenv("NSW_FLOW_PAIR");
+          const bool want_pair = !(pair_env != nullptr && atoi(pair_env) == 0);
+          if (want_pair && head_fused && flow_pair_pairs_per_clip(T, B, h->num_sms / 2 - 2) > 0) {
+            NSW_TRY(flow_pair_launch(maps, fw.map_wdh32, fw.map_wdl32, fw.map_wrh32, fw.map_wrl32,
+                                     cond_f, rows * C,
+                                     fw.br_cum.as<float>(), T, B, cur, fw.L, cfg.num_stages,
+                                     h->sync_words.as<unsigned int>(), h->num_sms, &fh, &fs, st));
+          } else
           for (int c0 = 0; c0 < B; c0 += tc3_clips)
             NSW_TRY(flow_tc_launch(maps, fw.map_wdh, fw.map_wdl, fw.map_wrh, fw.map_wrl,
                                    cond_f + (size_t)l0 * rows * C, rows * C,

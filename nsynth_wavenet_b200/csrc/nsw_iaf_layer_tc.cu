@@ -654,12 +654,12 @@ int layer_tc_make_act_map(void* map_out, const __half* base, int B, int T) {
   return NSW_OK;
 }
 
-int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k) {
+int layer_tc_make_weight_map(void* map_out, const __half* base, int rows, int k, int box_rows) {
   EncodeTiledFn enc;
   NSW_TRY(lt_encode_fn(&enc));
   const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)k, 64}, es[2] = {1, 1};
+  const cuuint32_t box[2] = {(cuuint32_t)k, (cuuint32_t)box_rows}, es[2] = {1, 1};
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<__half*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -107,3 +107,22 @@ def test_tc3_odd_shapes_agree_with_ffma(student_hp, batch, frames):
         assert err < TOL, (batch, frames, k, err)
     # quantised output: identical up to one 16-bit step where x sits on a rounding boundary
     assert np.abs(oa['x'] - ob['x']).max() <= 1.0 / 32768 + 1e-7
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('B,F', [(1, 21), (8, 20), (8, 39)])
+def test_pair_flow_kernel_is_bit_identical_to_the_single_cta_kernel(student_hp, monkeypatch, B, F):
+    """Default (NSW_FLOW_PAIR unset): the flow on CTA pairs (nsw_iaf_flow_pair.cu: cta_group::2 MMAs, half of every weight tile per
+    SM, double-buffered dilated-conv weights, both CTAs in lock step).  Same products in the same order into the same
+    accumulators, so every output must be bit-identical to the single-CTA kernel's (NSW_FLOW_PAIR=0); both are held to the
+    oracle by the other tests (the pair kernel wherever a shape has an even number of tiles per clip).  Shapes: one tile per CTA (1 x 4096), mixed 1 / 2 tiles per CTA (8 x 3584), 3 / 4 tiles per CTA (8 x 7680)."""
+    eng, _ = make_engine(student_hp, 'tc3')
+    mel, z = synth_inputs(student_hp, B, F, seed=77)
+    want = ('x',) + KEYS
+    monkeypatch.setenv('NSW_FLOW_PAIR', '0')                       # single-CTA kernel
+    a = eng.forward_host(mel, z, quantize=False, want=want)
+    monkeypatch.delenv('NSW_FLOW_PAIR', raising=False)             # pair kernel (default)
+    b = eng.forward_host(mel, z, quantize=False, want=want)
+    for k in want:
+        assert np.all(np.isfinite(b[k])), k
+        assert np.array_equal(a[k], b[k]), (k, float(np.abs(a[k] - b[k]).max()))
