@@ -238,6 +238,14 @@ int nsw_fastgen_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tenso
 int nsw_fastgen_gn_pack_host(const nsw_wavenet_config* cfg, const nsw_tensor* tensors, int32_t n_tensors,
                              float* blocks, int64_t blocks_cap, float* cond_w, float* cond_b, int64_t* sizes);
 
+/* TEST HOOK (host only, no CUDA): the same plan for the CTA-pair flow kernel (nsw_iaf_flow_pair.cu; the default
+ * wherever it covers the launch: whole flow, an even number of 128-row tiles per clip, all clips at once).  Per CTA
+ * (cluster rank fastest): {clip, first tile, tiles, CTAs of the clip, index within the clip of the last CTA whose
+ * "consumed" counter this CTA's publisher polls} then nl*tiles records as above.  max_pairs = CTA pairs the device can
+ * hold.  Returns the grid size (>0) or a negative NSW_E* code (shape not covered: NSW_EINVAL). */
+int nsw_flow_pair_plan_host(int32_t T, int32_t nclips, int32_t max_pairs, int32_t nl, int32_t num_stages, int32_t* out,
+                            int64_t cap, int64_t* n_out);
+
 /* KERNEL-LEVEL PARITY HOOK: the tcgen05 conv-GEMM every dense contraction of the path runs on (masked.conv1d as a
  * GEMM, masked.py:160-232; trans_conv1d phases, masked.py:235-291), with fp32 operands split on the device:
  *   out[(clip, m), n] = bias[n] + sum_{tap, c} x[clip, m + a_off + tap*tap_stride, c] * w[tap*cin + c, n]

@@ -113,6 +113,8 @@ PROTOTYPES = {
     'nsw_fastgen_pack_host': (C.c_int, [C.POINTER(nsw_wavenet_config), C.POINTER(nsw_tensor),
                                         C.c_int32, _VP, C.c_int64, _VP, _VP,
                                         C.POINTER(C.c_int64)]),
+    'nsw_flow_pair_plan_host': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                          C.POINTER(C.c_int64)]),
     'nsw_conv_gemm_device': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

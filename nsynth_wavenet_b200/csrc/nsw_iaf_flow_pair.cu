@@ -1128,3 +1128,42 @@ int flow_pair_launch(const void* const map_act[2][2], const void* map_wdh32, con
 }
 
 }  // namespace nsw
+
+// TEST HOOK (host only, no CUDA): work split and publish / read plan of one launch of the CTA-pair flow kernel, from the
+// same integer functions the kernel uses.  Per CTA (cluster rank fastest): {clip, first tile, tiles, CTAs of the clip,
+// index within the clip of the last CTA whose "consumed" counter its publisher polls} then nl*tiles records
+// {published, source of tap t-2d, source of tap t-d} as in nsw_flow_plan_host.  Returns the grid size or a negative code.
+extern "C" int nsw_flow_pair_plan_host(int32_t T, int32_t nclips, int32_t max_pairs, int32_t nl, int32_t num_stages,
+                                       int32_t* out, int64_t cap, int64_t* n_out) {
+  using namespace nsw;
+  NSW_CHECK(nl >= 1 && num_stages >= 1 && n_out, NSW_EINVAL, "nsw_flow_pair_plan_host: bad argument");
+  const int P = flow_pair_pairs_per_clip(T, nclips, max_pairs);
+  NSW_CHECK(P > 0, NSW_EINVAL, "nsw_flow_pair_plan_host: the pair kernel does not cover %d clips of %d samples on %d pairs",
+            nclips, T, max_pairs);
+  const int tiles = T / BM, reach = std::max(1, 2 * (1 << (num_stages - 1)) / BM);
+  int64_t n = 0;
+  auto put = [&](int v) { if (out && n < cap) out[n] = v; ++n; };
+  for (int b = 0; b < 2 * P * nclips; ++b) {
+    const PairRange r = fp_range_of(tiles, P, b >> 1);
+    const int crank = b & 1, K = r.K, tk0 = 2 * r.h0 + crank * K;
+    const int far_tk = std::min(tk0 + K - 1 + reach, tiles - 1);
+    put(r.clip); put(tk0); put(K); put(2 * P); put(fp_owner(tiles, P, far_tk));
+    for (int li = 0; li < nl; ++li) {
+      const int d = 1 << (li % num_stages), dt = d / BM;
+      for (int k = 0; k < K; ++k) {
+        put(fp_published(k, K, li, nl, num_stages) ? 1 : 0);
+        for (int tap = 0; tap < 2; ++tap) {
+          int src;
+          if (2 * d <= BM) src = k == 0 ? (tk0 >= 1 ? tk0 - 1 : -2) : -1;
+          else {
+            const int t = tk0 + k - (2 - tap) * dt;
+            src = t < 0 ? -2 : (t >= tk0 ? -1 : t);
+          }
+          put(src);
+        }
+      }
+    }
+  }
+  *n_out = n;
+  return 2 * P * nclips;
+}

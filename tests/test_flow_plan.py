@@ -125,3 +125,93 @@ def test_plan_rejects_what_one_launch_cannot_hold():
     assert lib.nsw_flow_plan_host(75776 + 128, 1, 148, 0, 10, 10, 1, None, 0, C.byref(n)) < 0   # 593 tiles > 4 x 148
     assert lib.nsw_flow_plan_host(7680, 10, 148, 0, 10, 10, 1, None, 0, C.byref(n)) < 0         # 10 x 15 CTAs > 148
     assert lib.nsw_flow_plan_host(7680 + 64, 1, 148, 0, 10, 10, 1, None, 0, C.byref(n)) < 0      # not whole tiles
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the CTA-pair kernel (nsw_iaf_flow_pair.cu): same properties on its own split (fp_range_of / fp_owner / fp_published)
+def pair_plan(T, nclips, max_pairs, nl, num_stages):
+    from nsynth_wavenet_b200 import _lib
+    lib = _lib.load()
+    n = C.c_int64(0)
+    grid = lib.nsw_flow_pair_plan_host(T, nclips, max_pairs, nl, num_stages, None, 0, C.byref(n))
+    if grid <= 0:
+        return None
+    buf = np.zeros(n.value, np.int32)
+    assert lib.nsw_flow_pair_plan_host(T, nclips, max_pairs, nl, num_stages, buf.ctypes.data_as(C.c_void_p), buf.size,
+                                       C.byref(n)) == grid
+    ctas, pos = [], 0
+    for _ in range(grid):
+        clip, tk0, K, n_c, far = (int(v) for v in buf[pos:pos + 5])
+        pos += 5
+        rec = buf[pos:pos + nl * K * 3].reshape(nl, K, 3)
+        pos += nl * K * 3
+        ctas.append(dict(clip=clip, tk0=tk0, K=K, n_c=n_c, far=far, rec=rec))
+    assert pos == buf.size
+    return ctas
+
+
+PAIR_SHAPES = [
+    # T, clips, CTA pairs on the device, layers, stages
+    (7680, 8, 74, 10, 10),     # the benchmark shape: 9 pairs per clip, 3 + 3 or 4 + 4 tiles
+    (7680, 8, 72, 30, 10),
+    (7680, 7, 74, 30, 10),     # the distillation shard
+    (4096, 1, 74, 10, 10),     # one tile per CTA
+    (3584, 8, 74, 10, 10),     # mixed 1 / 2 tiles per CTA
+    (1024, 2, 74, 30, 10),
+    (512, 1, 74, 10, 10),
+    (7680, 8, 66, 10, 10),     # another device size: 8 pairs per clip, 4 + 4 and 3 + 3
+]
+
+
+@pytest.mark.parametrize('T,nclips,pairs,nl,stages', PAIR_SHAPES)
+def test_pair_kernel_plan(T, nclips, pairs, nl, stages):
+    ctas = pair_plan(T, nclips, pairs, nl, stages)
+    assert ctas is not None
+    tiles = T // BM
+    assert len(ctas) <= 2 * pairs and len(ctas) % 2 == 0
+    seen = np.zeros((nclips, tiles), np.int32)
+    for i, c in enumerate(ctas):
+        assert 1 <= c['K'] <= 4 and c['tk0'] + c['K'] <= tiles
+        seen[c['clip'], c['tk0']:c['tk0'] + c['K']] += 1
+        if i % 2 == 0:                                   # leader and peer: same clip, same tile count, consecutive tiles
+            q = ctas[i + 1]
+            assert q['clip'] == c['clip'] and q['K'] == c['K'] and q['tk0'] == c['tk0'] + c['K']
+    assert np.all(seen == 1)
+    owner = {}
+    for i, c in enumerate(ctas):
+        for k in range(c['K']):
+            owner[(c['clip'], c['tk0'] + k)] = (i, k)
+    first_of_clip = {}
+    for i, c in enumerate(ctas):
+        first_of_clip.setdefault(c['clip'], i)
+    n_foreign = 0
+    for i, c in enumerate(ctas):
+        for li in range(nl):
+            d = 1 << (li % stages)
+            for k in range(c['K']):
+                for tap in (0, 1):
+                    src = int(c['rec'][li, k, 1 + tap])
+                    if src < 0:
+                        continue
+                    assert 0 <= src < c['tk0']
+                    if 2 * d > BM:
+                        assert src == c['tk0'] + k - (2 - tap) * d // BM
+                    else:
+                        assert k == 0 and src == c['tk0'] - 1
+                    n_foreign += 1
+                    j, kj = owner[(c['clip'], src)]
+                    assert j != i
+                    if li >= 1:
+                        assert ctas[j]['rec'][li - 1, kj, 0] == 1, 'tile read by CTA %d is never published' % i
+                    # the publisher of CTA j polls the consumed counters of CTAs (j, far_j] of its clip: the reader is one
+                    assert j < i <= first_of_clip[c['clip']] + ctas[j]['far']
+    if len(ctas) > nclips:
+        assert n_foreign > 0
+    for c in ctas:                                       # the fused head consumes the last layer in place
+        assert np.all(c['rec'][nl - 1, :, 0] == 0)
+
+
+def test_pair_kernel_refuses_what_it_does_not_cover():
+    assert pair_plan(7680 + 128, 8, 74, 10, 10) is None        # odd number of tiles per clip
+    assert pair_plan(7680, 64, 74, 10, 10) is None             # 64 clips: one pair per clip would need 30 tiles per CTA
+    assert pair_plan(154112, 1, 74, 10, 10) is None            # 1204 tiles: more than 8 per pair of ... 72 pairs
